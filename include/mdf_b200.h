@@ -1,0 +1,165 @@
+/*
+ * mdf_b200.h — C ABI of the B200-native structure-branch hot path of Metagenomic-DeepFRI.
+ *
+ * Every entry point is what a reference-side FFI binding for this path would bind
+ * (INTEGRATION.md shows the ctypes stubs).  Plain pointers and sizes only; no torch / CUDA
+ * types in the signatures (streams and device buffers travel as void*).  All functions return
+ * 0 on success or a negative MDF_E* code; `mdf_last_error()` returns a thread-local message.
+ * No exceptions cross the ABI.  The caller owns every buffer it passes in.
+ *
+ * Conventions
+ *   - "host" pointers may be pageable or pinned; copies are asynchronous when pinned.
+ *   - ragged batches use CSR-style int64 offset arrays of n+1 entries.
+ *   - bit-packed contact maps: row i of an L x L map is `mdf_packed_row_words(L)` uint32
+ *     words (rows padded to 128 bits), bit (j & 31) of word (j >> 5) = map[i][j].
+ */
+#ifndef MDF_B200_H
+#define MDF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDF_OK            0
+#define MDF_EINVAL       -1   /* bad argument (shape mismatch, invalid residue, ...) */
+#define MDF_ECUDA        -2   /* CUDA runtime error (see mdf_last_error) */
+#define MDF_ENOMEM       -3   /* workspace arena exhausted */
+#define MDF_EUNSUPPORTED -4   /* model graph not supported by the fused pipeline */
+
+typedef struct mdf_ctx   mdf_ctx;    /* one per device: stream + workspace arena */
+typedef struct mdf_model mdf_model;  /* one per loaded GCN head: weights resident in HBM */
+typedef struct mdf_batch mdf_batch;  /* one uploaded batch of path inputs, resident in HBM */
+
+const char *mdf_last_error(void);
+int mdf_version(void);
+
+/* ---- context --------------------------------------------------------------------------------
+ * `arena`/`arena_bytes`: optional caller-provided device workspace (e.g. a torch uint8 tensor);
+ * NULL lets the library cudaMalloc (and grow) its own.  `stream`: cudaStream_t as void*, NULL =
+ * a private non-blocking stream. */
+int mdf_ctx_create(int device, void *arena, size_t arena_bytes, void *stream, mdf_ctx **out);
+int mdf_ctx_destroy(mdf_ctx *ctx);
+int mdf_ctx_synchronize(mdf_ctx *ctx);
+/* kernels launched by this context since creation (bench.py `gpu_launches`) */
+int64_t mdf_ctx_launch_count(const mdf_ctx *ctx);
+
+/* per-stage CUDA-event profiling: enable (clears old records), run, then fetch a text report with
+ * one "name\tmilliseconds\tunits" line per recorded stage (units = algorithmic flops or bytes). */
+int mdf_ctx_profile(mdf_ctx *ctx, int enable);
+int mdf_ctx_profile_report(mdf_ctx *ctx, char *buf, size_t capacity);
+
+static inline int mdf_packed_row_words(int L) { return ((L + 127) / 128) * 4; }
+
+/* ---- contact_map_utils.pyx:17-37  pairwise_sqeuclidean(X, threads) ---------------------------
+ * X host float32 [n, m] C-contiguous -> D host float32 [n, n].  Bit-exact (unfused fp32). */
+int mdf_pairwise_sqeuclidean(mdf_ctx *ctx, const float *X, int n, int m, float *D);
+
+/* ---- bio_utils.py:196-227  calculate_contact_map(coords, threshold, mode) --------------------
+ * thr2 = float32(threshold**2) computed by the caller (NumPy weak-scalar rule); strict '<'.
+ * matrix mode -> int32 [n, n]. */
+int mdf_contact_map_dense(mdf_ctx *ctx, const float *coords, int n, float thr2, int32_t *cmap);
+/* sparse mode (np.argwhere order).  Call with pairs == NULL to get *nnz, then with a buffer of
+ * capacity >= *nnz pairs. */
+int mdf_contact_map_sparse(mdf_ctx *ctx, const float *coords, int n, float thr2,
+                           int32_t *pairs, int64_t capacity, int64_t *nnz);
+
+/* ---- contact_map_utils.pyx:44-117  align_contact_map(q_aln, t_aln, sparse, gen, threads) -----
+ * `sparse` host int32 [nnz, 2]; `out` host int32 [Lq, Lq] where Lq = non-gap query columns
+ * (returned through *Lq_out; pass out == NULL to only query it). */
+int mdf_align_contact_map(mdf_ctx *ctx, const char *q_aln, const char *t_aln, int aln_len,
+                          const int32_t *sparse, int64_t nnz, int generated_contacts,
+                          int32_t *out, int *Lq_out);
+
+/* ---- bio_utils.py:348-385  build_align_contact_map x n (fused, batched) ----------------------
+ * For protein p: coords rows [coord_off[p], coord_off[p+1]) of `coords` (float32 [*,3]);
+ * alignment columns [aln_off[p], aln_off[p+1]) of q_aln / t_aln; output rows of Lq[p] =
+ * seq_off[p+1]-seq_off[p] residues.  Exactly one of packed_out / dense_out may be non-NULL per
+ * call: packed_out uint32 at word offset packed_off[p]; dense_out int32 [Lq,Lq] at element
+ * offset dense_off[p]. */
+int mdf_cmap_build_transfer(mdf_ctx *ctx, int n,
+                            const float *coords, const int64_t *coord_off,
+                            const char *q_aln, const char *t_aln, const int64_t *aln_off,
+                            const int64_t *seq_off, float thr2, int generated_contacts,
+                            uint32_t *packed_out, const int64_t *packed_off,
+                            int32_t *dense_out, const int64_t *dense_off);
+
+/* ---- predict.pyx:50-73  Predictor.__init__ / _load_model --------------------------------------
+ * The host side parses the .onnx file and hands the initialisers over as fp32 host arrays in
+ * ONNX layout. */
+typedef struct mdf_model_desc {
+    int n_channels;          /* 26 */
+    int lstm_hidden;         /* H */
+    int n_lstm;              /* stacked LSTM layers (2) */
+    const float *lstm_W[4];  /* ONNX [1,4H,in]  gate order i,o,f,c */
+    const float *lstm_R[4];  /* ONNX [1,4H,H] */
+    const float *lstm_B[4];  /* ONNX [1,8H] or NULL */
+    int lm_dim;              /* E */
+    const float *aa_W;       /* [26,E] */
+    const float *lm_W;       /* [H,E] */
+    const float *lm_b;       /* [E] or NULL */
+    int n_gc;                /* GraphConv layers (<= 8) */
+    int gc_dims[8];
+    const float *gc_W[8];    /* [in,out] */
+    const float *gc_b[8];    /* [out] or NULL */
+    int gc_activation;       /* 0 = linear, 1 = relu, 2 = elu */
+    float gc_alpha;          /* elu alpha */
+    float eps;               /* degree normalisation epsilon */
+    int fc_dim;              /* F */
+    const float *fc_W;       /* [sum(gc_dims),F] */
+    const float *fc_b;       /* [F] or NULL */
+    int n_terms;             /* C */
+    const float *out_W;      /* [F,2C] */
+    const float *out_b;      /* [2C] or NULL */
+} mdf_model_desc;
+
+int mdf_model_create(mdf_ctx *ctx, const mdf_model_desc *desc, mdf_model **out);
+int mdf_model_destroy(mdf_model *model);
+/* 0 = fp32 SIMT reference engine, 1 = tcgen05 tensor-core engine */
+int mdf_model_set_engine(mdf_model *model, int engine);
+
+/* ---- predict.pyx:75-102  Predictor.forward_pass(seqres, cmap) ---------------------------------
+ * seq: ASCII residues (alphabet "-DGULNTKHYWCPVSOIEFXQABZRM", anything else -> MDF_EINVAL);
+ * cmap: host int32 [L, L] holding 0/1 (other values -> MDF_EINVAL); scores: host float32 [C]. */
+int mdf_gcn_forward_dense(mdf_model *model, const char *seq, int L, const int32_t *cmap, float *scores);
+
+/* batched GCN forward on bit-packed maps (host buffers): scores host float32 [n, C] */
+int mdf_gcn_forward_packed(mdf_model *model, int n, const char *seq, const int64_t *seq_off,
+                           const uint32_t *packed, const int64_t *packed_off, float *scores);
+
+/* ---- the whole path: pipeline.py:476-481 + :301-319 for n proteins ----------------------------
+ * coords + alignment + query sequence -> GO-term scores, everything in between stays in HBM.
+ * `seq` must equal the gap-stripped query alignment.  Host buffers in, host scores out. */
+int mdf_path_forward(mdf_model *model, int n,
+                     const char *seq, const int64_t *seq_off,
+                     const float *coords, const int64_t *coord_off,
+                     const char *q_aln, const char *t_aln, const int64_t *aln_off,
+                     float thr2, int generated_contacts, float *scores);
+
+/* Same path split into upload / run / fetch so that the compute can be timed with inputs
+ * already resident in HBM (bench.py `value`). */
+int mdf_batch_upload(mdf_ctx *ctx, int n,
+                     const char *seq, const int64_t *seq_off,
+                     const float *coords, const int64_t *coord_off,
+                     const char *q_aln, const char *t_aln, const int64_t *aln_off,
+                     mdf_batch **out);
+int mdf_batch_destroy(mdf_batch *batch);
+int mdf_path_run(mdf_model *model, mdf_batch *batch, float thr2, int generated_contacts);
+/* stage selector for profiling / unit parity: 1 = cmap only, 2 = + LSTM-LM, 3 = + GraphConv, 4 = all */
+int mdf_path_run_stages(mdf_model *model, mdf_batch *batch, float thr2, int generated_contacts, int upto);
+int mdf_batch_fetch_scores(mdf_model *model, mdf_batch *batch, float *scores /* host [n,C] */);
+/* debugging / parity taps: copy an intermediate of the last run to the host.
+ * what: 0 = packed cmaps (uint32 words, offsets as mdf_packed_row_words), 1 = degree vector d,
+ * 2 = LSTM layer-1 output [T,H], 3 = LSTM layer-2 output [T,H], 4 = X0 [T,E],
+ * 5 = pooled [n, sum(gc)], 6 = last GraphConv output [T, g].  fp32 unless noted. */
+int mdf_batch_fetch(mdf_model *model, mdf_batch *batch, int what, void *dst, size_t dst_bytes);
+
+/* device pointer of the scores of the last mdf_path_run ([n, C] float32) */
+const float *mdf_batch_scores_device(const mdf_batch *batch);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MDF_B200_H */

@@ -1,0 +1,191 @@
+"""ctypes binding of `libmdf_b200.so` (C ABI in `include/mdf_b200.h`).
+
+The product path has no CPU implementation: if the shared library has not been built, or no
+sm_100 GPU is visible, every call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+from typing import Dict, Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmdf_b200.so")
+
+MDF_OK, MDF_EINVAL, MDF_ECUDA, MDF_ENOMEM, MDF_EUNSUPPORTED = 0, -1, -2, -3, -4
+
+c_f32p = C.POINTER(C.c_float)
+c_i32p = C.POINTER(C.c_int32)
+c_u32p = C.POINTER(C.c_uint32)
+c_i64p = C.POINTER(C.c_int64)
+
+
+class ModelDesc(C.Structure):
+    _fields_ = [
+        ("n_channels", C.c_int), ("lstm_hidden", C.c_int), ("n_lstm", C.c_int),
+        ("lstm_W", c_f32p * 4), ("lstm_R", c_f32p * 4), ("lstm_B", c_f32p * 4),
+        ("lm_dim", C.c_int), ("aa_W", c_f32p), ("lm_W", c_f32p), ("lm_b", c_f32p),
+        ("n_gc", C.c_int), ("gc_dims", C.c_int * 8), ("gc_W", c_f32p * 8), ("gc_b", c_f32p * 8),
+        ("gc_activation", C.c_int), ("gc_alpha", C.c_float), ("eps", C.c_float),
+        ("fc_dim", C.c_int), ("fc_W", c_f32p), ("fc_b", c_f32p),
+        ("n_terms", C.c_int), ("out_W", c_f32p), ("out_b", c_f32p),
+    ]
+
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def lib() -> C.CDLL:
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build the CUDA extension first "
+                "(python -c 'import __graft_entry__ as g; g.build()'). There is no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        vp = C.c_void_p
+        L.mdf_last_error.restype = C.c_char_p
+        L.mdf_version.restype = C.c_int
+        L.mdf_ctx_create.argtypes = [C.c_int, vp, C.c_size_t, vp, C.POINTER(vp)]
+        L.mdf_ctx_destroy.argtypes = [vp]
+        L.mdf_ctx_synchronize.argtypes = [vp]
+        L.mdf_ctx_launch_count.argtypes = [vp]
+        L.mdf_ctx_launch_count.restype = C.c_int64
+        L.mdf_ctx_profile.argtypes = [vp, C.c_int]
+        L.mdf_ctx_profile.restype = C.c_int
+        L.mdf_ctx_profile_report.argtypes = [vp, C.c_char_p, C.c_size_t]
+        L.mdf_ctx_profile_report.restype = C.c_int
+        L.mdf_pairwise_sqeuclidean.argtypes = [vp, c_f32p, C.c_int, C.c_int, c_f32p]
+        L.mdf_contact_map_dense.argtypes = [vp, c_f32p, C.c_int, C.c_float, c_i32p]
+        L.mdf_contact_map_sparse.argtypes = [vp, c_f32p, C.c_int, C.c_float, c_i32p, C.c_int64, c_i64p]
+        L.mdf_align_contact_map.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_int, c_i32p, C.c_int64, C.c_int,
+                                            c_i32p, C.POINTER(C.c_int)]
+        L.mdf_cmap_build_transfer.argtypes = [vp, C.c_int, c_f32p, c_i64p, C.c_char_p, C.c_char_p, c_i64p, c_i64p,
+                                              C.c_float, C.c_int, c_u32p, c_i64p, c_i32p, c_i64p]
+        L.mdf_model_create.argtypes = [vp, C.POINTER(ModelDesc), C.POINTER(vp)]
+        L.mdf_model_destroy.argtypes = [vp]
+        L.mdf_model_set_engine.argtypes = [vp, C.c_int]
+        L.mdf_gcn_forward_dense.argtypes = [vp, C.c_char_p, C.c_int, c_i32p, c_f32p]
+        L.mdf_gcn_forward_packed.argtypes = [vp, C.c_int, C.c_char_p, c_i64p, c_u32p, c_i64p, c_f32p]
+        L.mdf_path_forward.argtypes = [vp, C.c_int, vp, c_i64p, vp, c_i64p, vp, vp, c_i64p,
+                                       C.c_float, C.c_int, vp]
+        L.mdf_batch_upload.argtypes = [vp, C.c_int, vp, c_i64p, vp, c_i64p, vp, vp, c_i64p, C.POINTER(vp)]
+        L.mdf_batch_destroy.argtypes = [vp]
+        L.mdf_path_run.argtypes = [vp, vp, C.c_float, C.c_int]
+        L.mdf_path_run_stages.argtypes = [vp, vp, C.c_float, C.c_int, C.c_int]
+        L.mdf_batch_fetch_scores.argtypes = [vp, vp, vp]
+        L.mdf_batch_fetch.argtypes = [vp, vp, C.c_int, vp, C.c_size_t]
+        L.mdf_batch_scores_device.argtypes = [vp]
+        L.mdf_batch_scores_device.restype = vp
+        for name in ("mdf_ctx_create", "mdf_ctx_destroy", "mdf_ctx_synchronize", "mdf_pairwise_sqeuclidean",
+                     "mdf_contact_map_dense", "mdf_contact_map_sparse", "mdf_align_contact_map",
+                     "mdf_cmap_build_transfer", "mdf_model_create", "mdf_model_destroy", "mdf_model_set_engine",
+                     "mdf_gcn_forward_dense", "mdf_gcn_forward_packed", "mdf_path_forward", "mdf_batch_upload",
+                     "mdf_batch_destroy", "mdf_path_run", "mdf_path_run_stages", "mdf_batch_fetch_scores",
+                     "mdf_batch_fetch"):
+            getattr(L, name).restype = C.c_int
+        _lib = L
+        return _lib
+
+
+EXPORTED_SYMBOLS = [
+    "mdf_last_error", "mdf_version", "mdf_ctx_create", "mdf_ctx_destroy", "mdf_ctx_synchronize",
+    "mdf_ctx_launch_count", "mdf_ctx_profile", "mdf_ctx_profile_report", "mdf_pairwise_sqeuclidean", "mdf_contact_map_dense", "mdf_contact_map_sparse",
+    "mdf_align_contact_map", "mdf_cmap_build_transfer", "mdf_model_create", "mdf_model_destroy",
+    "mdf_model_set_engine", "mdf_gcn_forward_dense", "mdf_gcn_forward_packed", "mdf_path_forward",
+    "mdf_batch_upload", "mdf_batch_destroy", "mdf_path_run", "mdf_path_run_stages", "mdf_batch_fetch_scores",
+    "mdf_batch_fetch", "mdf_batch_scores_device",
+]
+
+
+def check(rc: int) -> None:
+    if rc == MDF_OK:
+        return
+    msg = (lib().mdf_last_error() or b"").decode("utf-8", "replace")
+    if rc == MDF_EINVAL:
+        raise ValueError(msg)
+    if rc == MDF_ENOMEM:
+        raise MemoryError(msg)
+    if rc == MDF_EUNSUPPORTED:
+        raise NotImplementedError(msg)
+    raise RuntimeError(msg)
+
+
+def packed_row_words(L: int) -> int:
+    return ((L + 127) // 128) * 4
+
+
+def fp(a: np.ndarray):
+    return a.ctypes.data_as(c_f32p)
+
+
+def ip(a: np.ndarray):
+    return a.ctypes.data_as(c_i32p)
+
+
+def up(a: np.ndarray):
+    return a.ctypes.data_as(c_u32p)
+
+
+def lp(a: np.ndarray):
+    return a.ctypes.data_as(c_i64p)
+
+
+class Context:
+    """One per (process, device): owns the stream and the HBM workspace arena."""
+
+    def __init__(self, device: Optional[int] = None, stream: Optional[int] = None):
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0"))
+        self.device = device
+        h = C.c_void_p()
+        check(lib().mdf_ctx_create(device, None, 0, C.c_void_p(stream) if stream else None, C.byref(h)))
+        self.handle = h
+
+    def synchronize(self) -> None:
+        check(lib().mdf_ctx_synchronize(self.handle))
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib().mdf_ctx_launch_count(self.handle))
+
+    def profile(self, enable: bool = True) -> None:
+        check(lib().mdf_ctx_profile(self.handle, 1 if enable else 0))
+
+    def profile_report(self):
+        """[(stage, milliseconds, algorithmic units)] recorded since profile(True)."""
+        buf = C.create_string_buffer(1 << 20)
+        check(lib().mdf_ctx_profile_report(self.handle, buf, len(buf)))
+        out = []
+        for line in buf.value.decode().splitlines():
+            name, ms, units = line.split("\t")
+            out.append((name, float(ms), float(units)))
+        return out
+
+    def close(self) -> None:
+        if getattr(self, "handle", None):
+            lib().mdf_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_contexts: Dict[int, Context] = {}
+
+
+def default_context(device: Optional[int] = None) -> Context:
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    if device not in _contexts:
+        _contexts[device] = Context(device)
+    return _contexts[device]

@@ -1,0 +1,437 @@
+// Contact-map kernels (K1/K2): pairwise-distance threshold -> bit-packed maps, alignment
+// transfer, and the dense/sparse variants behind the reference's low-level functions.
+//
+// Reference semantics (bit-exact):
+//   mDeepFRI/contact_map_utils.pyx:17-37   pairwise_sqeuclidean  (unfused fp32, k order)
+//   mDeepFRI/bio_utils.py:214-223          threshold (strict <, float32(thr**2)), argwhere
+//   mDeepFRI/contact_map_utils.pyx:44-117  align_contact_map     (column walk, diag, generated
+//                                                                 contacts, one-directional transfer)
+//
+// The fused path never materialises the target map: the alignment is scanned once into a
+// query-frame coordinate table (target residue aligned to each query residue, NaN when there
+// is none) and the distance test is evaluated directly on query index pairs.  Because the
+// target->query map is injective on aligned residues, out[qi][qj] = 1 for a target contact
+// (ti,tj) <=> dist(coords[q2t[qi]], coords[q2t[qj]]) < thr2, which is what the gather computes.
+#include "mdf_common.cuh"
+#include "cmap_kernels.cuh"
+
+namespace mdf {
+
+__device__ __forceinline__ float sqdist3(float ax, float ay, float az, float bx, float by, float bz) {
+    // ((0 + dx*dx) + dy*dy) + dz*dz, every operation rounded to fp32, no FMA contraction
+    float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
+    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+// -------------------------------------------------------------------------------------------
+// K2: alignment scan + transfer into the query frame.  One block per protein.
+//   column c:  q gap           -> target index advances (a '-/-' column counts here too)
+//              q res, t gap    -> query residue has no target partner (flag bit0 = "gap": it
+//                                 spawns generated contacts), query index advances
+//              q res, t res    -> query residue maps to the current target index, both advance
+// qc[seq_off[p] + qi] = (x, y, z, flag) of the mapped target residue; xyz = NaN when unmapped
+// or when the target index lies beyond the structure's coordinate rows.
+// -------------------------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 256;
+
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+// block-wide exclusive scan of a packed pair of 16-bit counters; returns exclusive prefix and
+// the block total through `total`
+__device__ __forceinline__ int block_excl_scan(int v, int *total, int *smem /*>= 33 ints*/) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = warp_incl_scan(v, lane);
+    if (lane == 31) smem[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = lane < (SCAN_THREADS / 32) ? smem[lane] : 0;
+        int wi = warp_incl_scan(w, lane);
+        smem[lane] = wi - w;
+        if (lane == 31) smem[32] = wi;
+    }
+    __syncthreads();
+    int excl = incl - v + smem[warp];
+    *total = smem[32];
+    __syncthreads();
+    return excl;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+aln_transfer_kernel(int n, const char *__restrict__ q_aln, const char *__restrict__ t_aln,
+                    const int64_t *__restrict__ aln_off, const int64_t *__restrict__ seq_off,
+                    const float *__restrict__ coords, const int64_t *__restrict__ coord_off,
+                    float4 *__restrict__ qc, int *__restrict__ err)
+{
+    __shared__ int sm[40];
+    const int p = blockIdx.x;
+    if (p >= n) return;
+    const int64_t a0 = aln_off[p];
+    const int La = (int)(aln_off[p + 1] - a0);
+    const int64_t s0 = seq_off[p];
+    const int Lq = (int)(seq_off[p + 1] - s0);
+    const int64_t c0 = coord_off[p];
+    const int nc = (int)(coord_off[p + 1] - c0);
+    const float qnan = __int_as_float(0x7fc00000);
+    int qbase = 0, tbase = 0;
+    for (int base = 0; base < La; base += SCAN_THREADS) {
+        const int c = base + threadIdx.x;
+        int isq = 0, ist = 0, tres = 0;
+        if (c < La) {
+            isq = q_aln[a0 + c] != '-';
+            tres = t_aln[a0 + c] != '-';
+            ist = isq ? tres : 1;
+        }
+        int tot;
+        int ex = block_excl_scan(isq | (ist << 16), &tot, sm);
+        if (isq) {
+            const int qi = qbase + (ex & 0xffff);
+            const int ti = tbase + (ex >> 16);
+            if (qi < Lq) {
+                float4 v = make_float4(qnan, qnan, qnan, __int_as_float(tres ? 0 : 1));
+                if (tres && ti < nc) {
+                    const float *x = coords + (c0 + ti) * 3;
+                    v.x = x[0]; v.y = x[1]; v.z = x[2];
+                }
+                qc[s0 + qi] = v;
+            }
+        }
+        qbase += tot & 0xffff;
+        tbase += tot >> 16;
+    }
+    if (threadIdx.x == 0 && qbase != Lq) atomicCAS(err, 0, MDF_DERR_LQ_MISMATCH);
+}
+
+// identity "alignment": the query frame is the structure itself (standalone contact maps)
+__global__ void coords_to_frame_kernel(int64_t total, const float *__restrict__ coords, float4 *__restrict__ qc)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < total) qc[i] = make_float4(coords[3 * i], coords[3 * i + 1], coords[3 * i + 2], 0.0f);
+}
+
+// -------------------------------------------------------------------------------------------
+// K1: pairwise distance threshold on the query frame -> bit-packed rows.
+// Block = (protein, 32-row block).  Row coordinates are staged in shared memory and broadcast;
+// every lane keeps 4 columns (one per 32-bit word of a 128-column tile) in registers, so a row
+// costs one LDS.128 + 4 x (8 FP32 ops + compare + ballot).  Diagonal and generated contacts are
+// OR-ed in by the storing lane; padding columns compare against NaN and stay 0.
+// -------------------------------------------------------------------------------------------
+constexpr int PAIR_WARPS = 4;
+
+__global__ void __launch_bounds__(PAIR_WARPS * 32)
+cmap_pair_kernel(const int2 *__restrict__ work, const float4 *__restrict__ qc,
+                 const int64_t *__restrict__ seq_off, float thr2, int gen, int diag_val,
+                 uint32_t *__restrict__ packed, const int64_t *__restrict__ packed_off)
+{
+    __shared__ float4 rows[32];
+    const int p = work[blockIdx.x].x, rb = work[blockIdx.x].y;
+    const int64_t s0 = seq_off[p];
+    const int L = (int)(seq_off[p + 1] - s0);
+    const int rw = packed_row_words(L);
+    const float4 *__restrict__ q = qc + s0;
+    const float qnan = __int_as_float(0x7fc00000);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < 32) {
+        const int i = rb * 32 + threadIdx.x;
+        rows[threadIdx.x] = i < L ? q[i] : make_float4(qnan, qnan, qnan, 0.f);
+    }
+    __syncthreads();
+    uint32_t *__restrict__ out = packed + packed_off[p];
+    const int ntile = (L + 127) >> 7;
+    for (int item = warp; item < 4 * ntile; item += PAIR_WARPS) {
+        const int tile = item >> 2, rs = item & 3;
+        const int jlo = tile << 7;
+        float cx[4], cy[4], cz[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int j = jlo + 32 * k + lane;
+            float4 v = j < L ? q[j] : make_float4(qnan, qnan, qnan, 0.f);
+            cx[k] = v.x; cy[k] = v.y; cz[k] = v.z;
+        }
+#pragma unroll 2
+        for (int r = 0; r < 8; ++r) {
+            const int i = rb * 32 + rs * 8 + r;
+            if (i >= L) break;
+            const float4 a = rows[rs * 8 + r];
+            uint32_t w[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                w[k] = __ballot_sync(0xffffffffu, sqdist3(a.x, a.y, a.z, cx[k], cy[k], cz[k]) < thr2);
+            if (lane == 0) {
+                if (i + gen >= jlo && i - gen < jlo + 128) {   // tile touches the diagonal band
+                    const int gi = __float_as_int(a.w) & 1;
+                    for (int dj = -gen; dj <= gen; ++dj) {
+                        const int j = i + dj;
+                        if (j < 0 || j >= L || j < jlo || j >= jlo + 128) continue;
+                        bool set = dj == 0 ? (diag_val != 0) : (gi || (__float_as_int(q[j].w) & 1));
+                        if (set) w[(j - jlo) >> 5] |= 1u << (j & 31);
+                    }
+                }
+                *reinterpret_cast<uint4 *>(out + (size_t)i * rw + tile * 4) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        }
+    }
+}
+
+// packed -> dense int32 [L, L] (the reference's layout; bio_utils.py:220 / contact_map_utils.pyx:82)
+__global__ void unpack_dense_kernel(const int2 *__restrict__ work, const int64_t *__restrict__ seq_off,
+                                    const uint32_t *__restrict__ packed, const int64_t *__restrict__ packed_off,
+                                    int32_t *__restrict__ dense, const int64_t *__restrict__ dense_off)
+{
+    const int p = work[blockIdx.x].x, rb = work[blockIdx.x].y;
+    const int L = (int)(seq_off[p + 1] - seq_off[p]);
+    const int rw = packed_row_words(L);
+    const uint32_t *src = packed + packed_off[p];
+    int32_t *dst = dense + dense_off[p];
+    for (int r = 0; r < 32; ++r) {
+        const int i = rb * 32 + r;
+        if (i >= L) break;
+        for (int j = threadIdx.x; j < L; j += blockDim.x)
+            dst[(size_t)i * L + j] = (src[(size_t)i * rw + (j >> 5)] >> (j & 31)) & 1u;
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// contact_map_utils.pyx:17-37, any m.  D[i][i] = 0 (never computed by the reference).
+// -------------------------------------------------------------------------------------------
+__global__ void pairwise_sq_kernel(const float *__restrict__ X, int n, int m, float *__restrict__ D)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (j >= n) return;
+    float d = 0.0f;
+    if (i != j) {
+        const float *a = X + (size_t)min(i, j) * m, *b = X + (size_t)max(i, j) * m;
+        for (int k = 0; k < m; ++k) {
+            float diff = __fsub_rn(a[k], b[k]);
+            d = __fadd_rn(d, __fmul_rn(diff, diff));
+        }
+    }
+    D[(size_t)i * n + j] = d;
+}
+
+// -------------------------------------------------------------------------------------------
+// sparse (argwhere) output: row popcounts -> exclusive scan -> ordered emit
+// -------------------------------------------------------------------------------------------
+__global__ void row_popcount_kernel(const uint32_t *__restrict__ packed, int L, int rw, int64_t *__restrict__ counts)
+{
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (i >= L) return;
+    int c = 0;
+    for (int w = lane; w < rw; w += 32) c += __popc(packed[(size_t)i * rw + w]);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) counts[i] = c;
+}
+
+// single block: exclusive scan of `counts[0..n)` in place, total to counts[n]
+__global__ void excl_scan64_kernel(int64_t *counts, int n)
+{
+    __shared__ int64_t carry;
+    __shared__ int64_t wsum[32];
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int base = 0; base < n; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        int64_t v = i < n ? counts[i] : 0, incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int64_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        int64_t woff = 0;
+        for (int w = 0; w < warp; ++w) woff += wsum[w];
+        int64_t tot = 0;
+        for (int w = 0; w < nw; ++w) tot += wsum[w];
+        if (i < n) counts[i] = carry + woff + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) counts[n] = carry;
+}
+
+__global__ void emit_pairs_kernel(const uint32_t *__restrict__ packed, int L, int rw,
+                                  const int64_t *__restrict__ row_start, int32_t *__restrict__ pairs)
+{
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (i >= L) return;
+    int64_t base = row_start[i];
+    for (int w0 = 0; w0 < rw; w0 += 32) {
+        const int w = w0 + lane;
+        uint32_t bits = w < rw ? packed[(size_t)i * rw + w] : 0u;
+        int c = __popc(bits), incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        int64_t pos = base + incl - c;
+        while (bits) {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            pairs[2 * pos] = i;
+            pairs[2 * pos + 1] = (w << 5) + b;
+            ++pos;
+        }
+        base += __shfl_sync(0xffffffffu, incl, 31);
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// contact_map_utils.pyx:44-117 with an explicit sparse target map (drop-in align_contact_map).
+// Step 1: scan the alignment -> t2q[] (target index -> query index or -1), gapq[] flags.
+// Step 2: diagonal + generated contacts.  Step 3: scatter target contacts (idempotent stores,
+// same benign race as the reference's prange, :105-115).
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SCAN_THREADS)
+aln_t2q_kernel(const char *__restrict__ q_aln, const char *__restrict__ t_aln, int La,
+               int *__restrict__ t2q, int *__restrict__ gapq, int *__restrict__ totals /*[2] = Lq, nt*/)
+{
+    __shared__ int sm[40];
+    int qbase = 0, tbase = 0;
+    for (int base = 0; base < La; base += SCAN_THREADS) {
+        const int c = base + threadIdx.x;
+        int isq = 0, ist = 0, tres = 0;
+        if (c < La) {
+            isq = q_aln[c] != '-';
+            tres = t_aln[c] != '-';
+            ist = isq ? tres : 1;
+        }
+        int tot;
+        int ex = block_excl_scan(isq | (ist << 16), &tot, sm);
+        const int qi = qbase + (ex & 0xffff), ti = tbase + (ex >> 16);
+        if (c < La) {
+            if (ist) t2q[ti] = isq ? qi : -1;
+            if (isq) gapq[qi] = tres ? 0 : 1;
+        }
+        qbase += tot & 0xffff;
+        tbase += tot >> 16;
+    }
+    if (threadIdx.x == 0) { totals[0] = qbase; totals[1] = tbase; }
+}
+
+__global__ void align_diag_gen_kernel(int Lq, int gen, const int *__restrict__ gapq, int32_t *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Lq) return;
+    out[(size_t)i * Lq + i] = 1;
+    if (gapq[i]) {
+        for (int j = 1; j <= gen; ++j) {
+            if (i + j < Lq) { out[(size_t)(i + j) * Lq + i] = 1; out[(size_t)i * Lq + i + j] = 1; }
+            if (i - j >= 0) { out[(size_t)(i - j) * Lq + i] = 1; out[(size_t)i * Lq + i - j] = 1; }
+        }
+    }
+}
+
+__global__ void align_scatter_kernel(const int32_t *__restrict__ sparse, int64_t nnz, const int *__restrict__ t2q,
+                                     int nt, int Lq, int32_t *__restrict__ out)
+{
+    int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= nnz) return;
+    const int ti = sparse[2 * r], tj = sparse[2 * r + 1];
+    if ((unsigned)ti < (unsigned)nt && (unsigned)tj < (unsigned)nt) {   // negatives fail, like size_t compare
+        const int a = t2q[ti], b = t2q[tj];
+        if (a != -1 && b != -1) out[(size_t)a * Lq + b] = 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------- host launchers
+int launch_aln_transfer(mdf_ctx *ctx, int n, const char *q_aln, const char *t_aln, const int64_t *aln_off,
+                        const int64_t *seq_off, const float *coords, const int64_t *coord_off, float4 *qc)
+{
+    if (n <= 0) return MDF_OK;
+    aln_transfer_kernel<<<n, SCAN_THREADS, 0, ctx->stream>>>(n, q_aln, t_aln, aln_off, seq_off, coords,
+                                                              coord_off, qc, ctx->d_err);
+    MDF_LAUNCH_CHECK(ctx);
+    return MDF_OK;
+}
+
+int launch_coords_to_frame(mdf_ctx *ctx, int64_t total, const float *coords, float4 *qc)
+{
+    if (total <= 0) return MDF_OK;
+    coords_to_frame_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, ctx->stream>>>(total, coords, qc);
+    MDF_LAUNCH_CHECK(ctx);
+    return MDF_OK;
+}
+
+int launch_cmap_pair(mdf_ctx *ctx, int nwork, const int2 *work, const float4 *qc, const int64_t *seq_off,
+                     float thr2, int gen, int diag_val, uint32_t *packed, const int64_t *packed_off)
+{
+    if (nwork <= 0) return MDF_OK;
+    cmap_pair_kernel<<<nwork, PAIR_WARPS * 32, 0, ctx->stream>>>(work, qc, seq_off, thr2, gen < 0 ? 0 : gen,
+                                                                 diag_val, packed, packed_off);
+    MDF_LAUNCH_CHECK(ctx);
+    return MDF_OK;
+}
+
+int launch_unpack_dense(mdf_ctx *ctx, int nwork, const int2 *work, const int64_t *seq_off, const uint32_t *packed,
+                        const int64_t *packed_off, int32_t *dense, const int64_t *dense_off)
+{
+    if (nwork <= 0) return MDF_OK;
+    unpack_dense_kernel<<<nwork, 256, 0, ctx->stream>>>(work, seq_off, packed, packed_off, dense, dense_off);
+    MDF_LAUNCH_CHECK(ctx);
+    return MDF_OK;
+}
+
+int launch_pairwise_sq(mdf_ctx *ctx, const float *X, int n, int m, float *D)
+{
+    if (n <= 0) return MDF_OK;
+    dim3 grid(cdiv(n, 256), n);
+    pairwise_sq_kernel<<<grid, 256, 0, ctx->stream>>>(X, n, m, D);
+    MDF_LAUNCH_CHECK(ctx);
+    return MDF_OK;
+}
+
+int launch_sparse_count(mdf_ctx *ctx, const uint32_t *packed, int L, int64_t *counts /*[L+1]*/)
+{
+    const int rw = packed_row_words(L);
+    if (L > 0) {
+        row_popcount_kernel<<<cdiv(L, 8), 256, 0, ctx->stream>>>(packed, L, rw, counts);
+        MDF_LAUNCH_CHECK(ctx);
+    }
+    excl_scan64_kernel<<<1, 1024, 0, ctx->stream>>>(counts, L);
+    MDF_LAUNCH_CHECK(ctx);
+    return MDF_OK;
+}
+
+int launch_sparse_emit(mdf_ctx *ctx, const uint32_t *packed, int L, const int64_t *row_start, int32_t *pairs)
+{
+    if (L <= 0) return MDF_OK;
+    emit_pairs_kernel<<<cdiv(L, 8), 256, 0, ctx->stream>>>(packed, L, packed_row_words(L), row_start, pairs);
+    MDF_LAUNCH_CHECK(ctx);
+    return MDF_OK;
+}
+
+int launch_aln_t2q(mdf_ctx *ctx, const char *q_aln, const char *t_aln, int La, int *t2q, int *gapq, int *totals)
+{
+    aln_t2q_kernel<<<1, SCAN_THREADS, 0, ctx->stream>>>(q_aln, t_aln, La, t2q, gapq, totals);
+    MDF_LAUNCH_CHECK(ctx);
+    return MDF_OK;
+}
+
+int launch_align_scatter(mdf_ctx *ctx, int Lq, int gen, const int *gapq, const int32_t *sparse, int64_t nnz,
+                         const int *t2q, int nt, int32_t *out)
+{
+    if (Lq <= 0) return MDF_OK;
+    align_diag_gen_kernel<<<cdiv(Lq, 256), 256, 0, ctx->stream>>>(Lq, gen < 0 ? 0 : gen, gapq, out);
+    MDF_LAUNCH_CHECK(ctx);
+    if (nnz > 0) {
+        align_scatter_kernel<<<(unsigned)cdiv64(nnz, 256), 256, 0, ctx->stream>>>(sparse, nnz, t2q, nt, Lq, out);
+        MDF_LAUNCH_CHECK(ctx);
+    }
+    return MDF_OK;
+}
+
+}  // namespace mdf

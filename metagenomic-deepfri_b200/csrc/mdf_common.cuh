@@ -1,0 +1,116 @@
+// Shared host-side plumbing for libmdf_b200: error handling, context, workspace arena.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/mdf_b200.h"
+
+namespace mdf {
+
+void set_error(const char *fmt, ...);
+
+#define MDF_CUDA(call)                                                                         \
+    do {                                                                                       \
+        cudaError_t _e = (call);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            mdf::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call,                  \
+                           cudaGetErrorString(_e));                                            \
+            return MDF_ECUDA;                                                                  \
+        }                                                                                      \
+    } while (0)
+
+#define MDF_TRY(call)                                                                          \
+    do {                                                                                       \
+        int _r = (call);                                                                       \
+        if (_r != MDF_OK) return _r;                                                           \
+    } while (0)
+
+#define MDF_REQUIRE(cond, ...)                                                                 \
+    do {                                                                                       \
+        if (!(cond)) {                                                                         \
+            mdf::set_error(__VA_ARGS__);                                                       \
+            return MDF_EINVAL;                                                                 \
+        }                                                                                      \
+    } while (0)
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+__host__ __device__ __forceinline__ int packed_row_words(int L) { return ((L + 127) >> 7) << 2; }  // == mdf_packed_row_words
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+}  // namespace mdf
+
+// Device workspace: one big allocation, bump-allocated, reset per API call (stack discipline).
+struct mdf_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    char *arena = nullptr;
+    size_t arena_bytes = 0;
+    size_t arena_top = 0;
+    bool own_arena = true;
+    int sm_count = 148;
+    int64_t launches = 0;
+    // device-side error flag (invalid residue, non-0/1 cmap, Lq mismatch ...)
+    int *d_err = nullptr;
+    int *h_err = nullptr;  // pinned
+
+    // optional per-stage CUDA-event profiling (bench.py roofline leg)
+    struct ProfEntry { const char *name; cudaEvent_t start, stop; double units; };
+    bool profiling = false;
+    std::vector<ProfEntry> prof;
+
+    int alloc(void **out, size_t bytes);  // arena bump allocation (256 B aligned)
+    template <typename T>
+    int alloc_n(T **out, size_t count) { return alloc((void **)out, count * sizeof(T)); }
+    int reserve(size_t bytes);            // make sure `bytes` are available above arena_top
+    int check_device_error(const char *where);
+};
+
+struct ArenaScope {
+    mdf_ctx *ctx;
+    size_t mark;
+    explicit ArenaScope(mdf_ctx *c) : ctx(c), mark(c->arena_top) {}
+    ~ArenaScope() { ctx->arena_top = mark; }
+};
+
+// Records start/stop events around a stage when ctx->profiling is on; `units` = algorithmic
+// flops (or bytes) of the stage, reported back by mdf_ctx_profile_report.
+struct ProfScope {
+    mdf_ctx *ctx;
+    int idx = -1;
+    ProfScope(mdf_ctx *c, const char *name, double units = 0.0) : ctx(c)
+    {
+        if (!c->profiling) return;
+        mdf_ctx::ProfEntry e{name, nullptr, nullptr, units};
+        if (cudaEventCreate(&e.start) != cudaSuccess || cudaEventCreate(&e.stop) != cudaSuccess) return;
+        cudaEventRecord(e.start, c->stream);
+        c->prof.push_back(e);
+        idx = (int)c->prof.size() - 1;
+    }
+    ~ProfScope()
+    {
+        if (idx >= 0) cudaEventRecord(ctx->prof[idx].stop, ctx->stream);
+    }
+};
+
+#define MDF_LAUNCH_CHECK(ctx)                                                                  \
+    do {                                                                                       \
+        (ctx)->launches++;                                                                     \
+        cudaError_t _e = cudaGetLastError();                                                   \
+        if (_e != cudaSuccess) {                                                               \
+            mdf::set_error("%s:%d: kernel launch failed: %s", __FILE__, __LINE__,              \
+                           cudaGetErrorString(_e));                                            \
+            return MDF_ECUDA;                                                                  \
+        }                                                                                      \
+    } while (0)
+
+// device error codes written to ctx->d_err (first error wins)
+#define MDF_DERR_BAD_RESIDUE 1
+#define MDF_DERR_BAD_CMAP 2
+#define MDF_DERR_LQ_MISMATCH 3

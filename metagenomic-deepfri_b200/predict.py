@@ -1,0 +1,239 @@
+"""Drop-in for `mDeepFRI.predict` (`predict.pyx`): `seq2onehot` and `Predictor`.
+
+`Predictor(model_path, threads)` keeps the reference constructor and public attributes
+(`model_path`, `threads`, `session`, `input_names`, `predict.pyx:50-60`) and
+`forward_pass(seqres, cmap)` keeps its contract (`predict.pyx:75-102`): a float32 vector with
+one score per GO term (channel 0 of the [1, C, 2] softmax output).  Instead of an onnxruntime
+session, the `.onnx` file is recognised by `onnx_plan` and executed by the fused CUDA pipeline
+behind the C ABI.  Batched entry points (`forward_batch`, `forward_structures`) run the same
+kernels over many proteins per launch; `forward_pass` is a batch of one.
+
+`cmap=None` selects the reference's sequence-only CNN branch, which is out of scope here and
+raises `NotImplementedError` (there is no CPU or library fallback).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from .batching import pack_sequences, pack_structures, packed_offsets
+from .onnx_plan import GCNPlan, load_plan
+
+_ALPHABET = b"-DGULNTKHYWCPVSOIEFXQABZRM"          # predict.pyx:26
+_LUT = np.full(256, -1, np.int16)
+_LUT[np.frombuffer(_ALPHABET, np.uint8)] = np.arange(26)
+
+
+def _encode(seq: str) -> bytes:
+    b = seq.encode("ascii")                         # UnicodeEncodeError like predict.pyx:19
+    codes = _LUT[np.frombuffer(b, np.uint8)]
+    bad = np.flatnonzero(codes < 0)
+    if bad.size:
+        raise ValueError(f"Invalid character in sequence: {seq[int(bad[0])]}")
+    return b
+
+
+def seq2onehot(seq: str) -> np.ndarray:
+    """`predict.pyx:17-48`: float32 [L, 26] one-hot over "-DGULNTKHYWCPVSOIEFXQABZRM"."""
+    b = _encode(seq)
+    out = np.zeros((len(b), 26), np.float32)
+    if len(b):
+        out[np.arange(len(b)), _LUT[np.frombuffer(b, np.uint8)]] = 1.0
+    return out
+
+
+class _Session:
+    """Stands where the reference keeps its `onnxruntime.InferenceSession` (`predict.pyx:67-72`)."""
+
+    class _Arg:
+        def __init__(self, name):
+            self.name = name
+
+    def __init__(self, plan: GCNPlan, handle, ctx: _lib.Context):
+        self.plan = plan
+        self.handle = handle
+        self.ctx = ctx
+
+    def get_inputs(self):
+        return [self._Arg(n) for n in self.plan.input_names]
+
+    def get_providers(self):
+        return ["B200ExecutionProvider"]
+
+
+class PathBatch:
+    """A batch of path inputs uploaded once and kept resident in HBM (`mdf_batch_upload`)."""
+
+    def __init__(self, ctx: _lib.Context, seqs: Sequence[str], gapped_query: Sequence[str],
+                 gapped_target: Sequence[str], coords: Sequence[np.ndarray]):
+        ps = pack_structures(gapped_query, gapped_target, coords)
+        seq_bytes, seq_off = pack_sequences([_encode(s).decode() for s in seqs])
+        if not np.array_equal(seq_off, ps.seq_off):
+            raise ValueError("query sequences do not match the gap-stripped query alignments")
+        self.n = len(seqs)
+        self.ctx = ctx
+        self._keep = (ps, seq_bytes, seq_off)
+        h = C.c_void_p()
+        _lib.check(_lib.lib().mdf_batch_upload(
+            ctx.handle, self.n, seq_bytes, _lib.lp(seq_off), ps.coords.ctypes.data, _lib.lp(ps.coord_off),
+            ps.q_aln, ps.t_aln, _lib.lp(ps.aln_off), C.byref(h)))
+        self.handle = h
+        self.seq_off = seq_off
+        self.packed_off = ps.packed_off
+        self.h2d_bytes = (len(seq_bytes) + ps.coords.nbytes + 2 * len(ps.q_aln)
+                          + 8 * (seq_off.size + ps.coord_off.size + ps.aln_off.size))
+
+    def close(self):
+        if getattr(self, "handle", None):
+            _lib.lib().mdf_batch_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Predictor:
+    def __init__(self, model_path: str, threads: int = 1, device: Optional[int] = None,
+                 context: Optional[_lib.Context] = None):
+        self.model_path = model_path
+        self.threads = threads          # accepted for compatibility; the GPU path ignores it
+        self._ctx = context if context is not None else _lib.default_context(device)
+        self.session = None
+        self.input_names: List[str] = []
+        self._load_model()
+
+    # -- predict.pyx:62-73
+    def _load_model(self):
+        plan = load_plan(self.model_path)        # FileNotFoundError / RuntimeError on bad files
+        d = _lib.ModelDesc()
+        keep = []
+
+        def ptr(a):
+            if a is None:
+                return None
+            a = np.ascontiguousarray(a, np.float32)
+            keep.append(a)
+            return _lib.fp(a)
+
+        d.n_channels, d.lstm_hidden, d.n_lstm = plan.n_channels, plan.lstm_hidden, len(plan.lstm_W)
+        if d.n_lstm > 4 or len(plan.gc_W) > 8:
+            raise NotImplementedError("model deeper than the fused pipeline supports")
+        for l in range(d.n_lstm):
+            d.lstm_W[l], d.lstm_R[l], d.lstm_B[l] = ptr(plan.lstm_W[l]), ptr(plan.lstm_R[l]), ptr(plan.lstm_B[l])
+        d.lm_dim, d.aa_W, d.lm_W, d.lm_b = plan.lm_dim, ptr(plan.aa_W), ptr(plan.lm_W), ptr(plan.lm_b)
+        d.n_gc = len(plan.gc_W)
+        for l, w in enumerate(plan.gc_W):
+            d.gc_dims[l], d.gc_W[l], d.gc_b[l] = w.shape[1], ptr(w), ptr(plan.gc_b[l])
+        d.gc_activation, d.gc_alpha, d.eps = plan.gc_activation, plan.gc_alpha, plan.eps
+        d.fc_dim, d.fc_W, d.fc_b = plan.fc_W.shape[1], ptr(plan.fc_W), ptr(plan.fc_b)
+        d.n_terms, d.out_W, d.out_b = plan.n_terms, ptr(plan.out_W), ptr(plan.out_b)
+        h = C.c_void_p()
+        _lib.check(_lib.lib().mdf_model_create(self._ctx.handle, C.byref(d), C.byref(h)))
+        self._handle = h
+        self.n_terms = plan.n_terms
+        self.plan = plan
+        self.session = _Session(plan, h, self._ctx)
+        self.input_names = list(plan.input_names)
+
+    def set_engine(self, engine: str) -> None:
+        """'simt' = exact-fp32 CUDA-core engine, 'tc' = tcgen05 tensor-core engine."""
+        _lib.check(_lib.lib().mdf_model_set_engine(self._handle, {"simt": 0, "tc": 1}[engine]))
+
+    # -- predict.pyx:75-102
+    def forward_pass(self, seqres: str, cmap=None) -> np.ndarray:
+        seq = _encode(seqres)
+        if cmap is None:
+            raise NotImplementedError(
+                "Predictor.forward_pass(seqres, cmap=None) selects the sequence-only CNN branch "
+                "(predict.pyx:91-95), which the B200 structure-branch path does not implement")
+        A = cmap.reshape(cmap.shape[0], cmap.shape[1])
+        L = len(seq)
+        if A.shape != (L, L):
+            raise ValueError(f"cmap shape {A.shape} does not match sequence length {L}")
+        if A.dtype != np.int32:
+            Ai = A.astype(np.int32)
+            if not np.array_equal(Ai, A):
+                raise ValueError("forward_pass: contact map holds values other than 0/1")
+            A = Ai
+        A = np.ascontiguousarray(A)
+        y = np.empty(self.n_terms, np.float32)
+        _lib.check(_lib.lib().mdf_gcn_forward_dense(self._handle, seq, L, _lib.ip(A), _lib.fp(y)))
+        return y
+
+    def forward_batch(self, seqs: Sequence[str], packed_cmaps: Sequence[np.ndarray]) -> np.ndarray:
+        """GCN forward for n proteins with bit-packed maps (uint32 [L, row_words] each)."""
+        n = len(seqs)
+        seq_bytes, seq_off = pack_sequences([_encode(s).decode() for s in seqs])
+        poff = packed_offsets(np.diff(seq_off))
+        flat = np.concatenate([np.ascontiguousarray(c, np.uint32).reshape(-1) for c in packed_cmaps]) \
+            if n else np.zeros(0, np.uint32)
+        if flat.size != poff[-1]:
+            raise ValueError("packed contact maps do not match the sequence lengths")
+        out = np.empty((n, self.n_terms), np.float32)
+        _lib.check(_lib.lib().mdf_gcn_forward_packed(self._handle, n, seq_bytes, _lib.lp(seq_off), _lib.up(flat),
+                                                     _lib.lp(poff), _lib.fp(out)))
+        return out
+
+    def forward_structures(self, seqs: Sequence[str], gapped_query: Sequence[str], gapped_target: Sequence[str],
+                           coords: Sequence[np.ndarray], threshold: float = 6, generated_contacts: int = 2,
+                           out: Optional[np.ndarray] = None) -> np.ndarray:
+        """The whole path for n proteins (contact map build + alignment transfer + GCN), host
+        buffers in, host scores out: what `pipeline.py:476-481` + `:301-319` compute together."""
+        from .bio_utils import threshold_sq
+        n = len(seqs)
+        ps = pack_structures(gapped_query, gapped_target, coords)
+        seq_bytes, seq_off = pack_sequences([_encode(s).decode() for s in seqs])
+        if not np.array_equal(seq_off, ps.seq_off):
+            raise ValueError("query sequences do not match the gap-stripped query alignments")
+        if out is None:
+            out = np.empty((n, self.n_terms), np.float32)
+        _lib.check(_lib.lib().mdf_path_forward(
+            self._handle, n, seq_bytes, _lib.lp(seq_off), ps.coords.ctypes.data, _lib.lp(ps.coord_off), ps.q_aln,
+            ps.t_aln, _lib.lp(ps.aln_off), float(threshold_sq(threshold)), int(generated_contacts), out.ctypes.data))
+        return out
+
+    # -- resident-batch interface (bench / multi-head reuse)
+    def upload(self, seqs, gapped_query, gapped_target, coords) -> PathBatch:
+        return PathBatch(self._ctx, seqs, gapped_query, gapped_target, coords)
+
+    def run(self, batch: PathBatch, threshold: float = 6, generated_contacts: int = 2, upto: int = 4) -> None:
+        from .bio_utils import threshold_sq
+        _lib.check(_lib.lib().mdf_path_run_stages(self._handle, batch.handle, float(threshold_sq(threshold)),
+                                                  int(generated_contacts), upto))
+
+    def fetch_scores(self, batch: PathBatch, out: Optional[np.ndarray] = None) -> np.ndarray:
+        if out is None:
+            out = np.empty((batch.n, self.n_terms), np.float32)
+        _lib.check(_lib.lib().mdf_batch_fetch_scores(self._handle, batch.handle, out.ctypes.data))
+        return out
+
+    _TAPS = {"packed": 0, "deg": 1, "lstm1": 2, "lstm2": 3, "x0": 4, "pooled": 5, "gc_last": 6}
+
+    def fetch(self, batch: PathBatch, what: str) -> np.ndarray:
+        T = int(batch.seq_off[-1])
+        p = self.plan
+        shape, dt = {
+            "packed": ((int(batch.packed_off[-1]),), np.uint32), "deg": ((T,), np.float32),
+            "lstm1": ((T, p.lstm_hidden), np.float32), "lstm2": ((T, p.lstm_hidden), np.float32),
+            "x0": ((T, p.lm_dim), np.float32), "pooled": ((batch.n, sum(w.shape[1] for w in p.gc_W)), np.float32),
+            "gc_last": ((T, p.gc_W[-1].shape[1]), np.float32)}[what]
+        out = np.empty(shape, dt)
+        _lib.check(_lib.lib().mdf_batch_fetch(self._handle, batch.handle, self._TAPS[what], out.ctypes.data, out.nbytes))
+        return out
+
+    def close(self):
+        if getattr(self, "_handle", None):
+            _lib.lib().mdf_model_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,304 @@
+"""Synthetic models and workloads.
+
+Nothing here is on the product path: it writes random-init DeepFRI GCN heads *in the
+reference's ONNX layout* (the file `mDeepFRI.predict.Predictor` hands to onnxruntime,
+`predict.pyx:62-73`; model family `DeepFRI-MERGED_GraphConv_gcd_512-512-512_fcd_1024_ca_10.0_*`,
+`mDeepFRI/__init__.py:73`) and generates seeded proteins / structures / alignments for the
+BASELINE.json configs.  The real `.onnx` files are not redistributable offline, so the graph
+below restates upstream DeepFRI (LSTM-LM -> GraphConv x3 -> sum-pool -> dense -> FuncPredictor)
+with standard ONNX ops the way tf2onnx lowers a Keras model (Transpose/LSTM/Squeeze,
+MatMul/Add, Elu, ReduceSum, Reshape, Softmax).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import onnx_lite as ox
+
+AA20 = "ACDEFGHIKLMNPQRSTVWY"
+# head sizes of the v1.0 "MERGED" models
+HEAD_SIZES = {"mf": 489, "bp": 1943, "cc": 320, "ec": 538}
+
+
+@dataclass
+class GCNConfig:
+    n_channels: int = 26
+    lstm_hidden: int = 512          # LSTM-LM hidden size H (both layers)
+    lm_dim: int = 1024              # embedding width E
+    gc_dims: Tuple[int, ...] = (512, 512, 512)
+    fc_dim: int = 1024
+    n_terms: int = 489              # C
+    gc_activation: str = "Elu"      # upstream GraphConv uses elu; north-star text says ReLU
+    gc_bias: bool = False
+    eps: float = 1e-6
+    logit_scale: float = 0.0125      # multiplies the FuncPredictor dense so scores are not saturated
+
+
+def _uniform(rng, a, shape):
+    return rng.uniform(-a, a, size=shape).astype(np.float32)
+
+
+def make_weights(cfg: GCNConfig, seed: int = 1234, lm_seed: int = 99) -> Dict[str, np.ndarray]:
+    """Random-init weights with gains chosen so that activations are O(0.1-1) like a trained
+    network (plain Glorot leaves the LSTM-LM output ~1e-2 and would hide LSTM / GraphConv
+    arithmetic errors from the parity tests).  LSTM biases 0 with forget gate 1 (Keras).
+
+    The LSTM-LM uses its own seed so that every head shares byte-identical LM weights,
+    as upstream freezes the language model."""
+    H, E, I = cfg.lstm_hidden, cfg.lm_dim, cfg.n_channels
+    lm = np.random.default_rng(lm_seed)
+    rng = np.random.default_rng(seed)
+    w: Dict[str, np.ndarray] = {}
+    rec = np.sqrt(3.0 / H) * 1.5
+    for l, inp in ((1, I), (2, H)):
+        # ONNX LSTM layout: W[1,4H,in], R[1,4H,H], B[1,8H]; gate order i,o,f,c
+        w[f"lstm{l}_W"] = _uniform(lm, 1.5 if l == 1 else rec * 2.0, (1, 4 * H, inp))
+        w[f"lstm{l}_R"] = _uniform(lm, rec, (1, 4 * H, H))
+        b = _uniform(lm, 0.1, (1, 8 * H))
+        b[0, 2 * H:3 * H] += 1.0     # forget-gate bias (input half)
+        w[f"lstm{l}_B"] = b
+    w["AA_embedding_W"] = _uniform(rng, 0.5, (I, E))
+    w["LM_embedding_W"] = _uniform(rng, np.sqrt(6.0 / H), (H, E))
+    w["LM_embedding_b"] = _uniform(rng, 0.1, (E,))
+    prev = E
+    for l, g in enumerate(cfg.gc_dims, 1):
+        w[f"GraphConv_{l}_W"] = _uniform(rng, np.sqrt(6.0 / prev) * 1.4, (prev, g))
+        if cfg.gc_bias:
+            w[f"GraphConv_{l}_b"] = _uniform(rng, 0.1, (g,))
+        prev = g
+    G = int(sum(cfg.gc_dims))
+    w["dense_W"] = _uniform(rng, np.sqrt(6.0 / (G + cfg.fc_dim)), (G, cfg.fc_dim))
+    w["dense_b"] = _uniform(rng, 0.1, (cfg.fc_dim,))
+    w["labels_W"] = _uniform(rng, np.sqrt(6.0 / (cfg.fc_dim + 2 * cfg.n_terms)) * cfg.logit_scale,
+                             (cfg.fc_dim, 2 * cfg.n_terms))
+    w["labels_b"] = _uniform(rng, 1.0, (2 * cfg.n_terms,))
+    return w
+
+
+def build_gcn_model(cfg: GCNConfig, weights: Optional[Dict[str, np.ndarray]] = None,
+                    seed: int = 1234) -> ox.Model:
+    """DeepFRI GCN head as an ONNX graph. Inputs are ordered (cmap, seq) as the reference
+    feeds them (`predict.pyx:87-90`); output is [1, C, 2] with the score in channel 0
+    (`predict.pyx:100`)."""
+    w = dict(weights) if weights is not None else make_weights(cfg, seed)
+    g = ox.Graph(name="DeepFRI_GraphConv")
+    g.inputs = [ox.ValueInfo("cmap", ox.FLOAT, ("unk__b", "unk__l", "unk__l")),
+                ox.ValueInfo("seq", ox.FLOAT, ("unk__b", "unk__l", cfg.n_channels))]
+    g.outputs = [ox.ValueInfo("labels", ox.FLOAT, ("unk__b", cfg.n_terms, 2))]
+    init = g.initializers
+    N = g.nodes
+    for k, v in w.items():
+        init[k] = v
+    init["const_axes_0"] = np.array([0], np.int64)
+    init["const_axes_1"] = np.array([1], np.int64)
+    init["const_axes_2"] = np.array([2], np.int64)
+    init["const_one"] = np.array(1.0, np.float32)
+    init["const_eps"] = np.array(cfg.eps, np.float32)
+    init["const_out_shape"] = np.array([-1, cfg.n_terms, 2], np.int64)
+
+    def add(op, ins, outs, **attrs):
+        N.append(ox.Node(op, list(ins), list(outs), name=f"{op}__{len(N)}", attrs=attrs))
+        return outs[0]
+
+    # ---- LSTM language model (tf2onnx: Transpose -> LSTM -> Squeeze, time-major)
+    H = cfg.lstm_hidden
+    x = add("Transpose", ["seq"], ["lm/seq_tm"], perm=[1, 0, 2])
+    for l in (1, 2):
+        y = add("LSTM", [x, f"lstm{l}_W", f"lstm{l}_R", f"lstm{l}_B"],
+                [f"lm/LSTM{l}_Y"], hidden_size=H, direction="forward")
+        x = add("Squeeze", [y, "const_axes_1"], [f"lm/LSTM{l}_out"])
+    lm_out = add("Transpose", [x], ["lm/LSTM2_bm"], perm=[1, 0, 2])
+    x_lm = add("MatMul", [lm_out, "LM_embedding_W"], ["LM_embedding/MatMul"])
+    x_lm = add("Add", [x_lm, "LM_embedding_b"], ["LM_embedding/BiasAdd"])
+    x_aa = add("MatMul", ["seq", "AA_embedding_W"], ["AA_embedding/MatMul"])
+    x = add("Add", [x_lm, x_aa], ["Embedding/add"])
+    x = add("Relu", [x], ["activation/Relu"])
+
+    # ---- adjacency normalisation (GraphConv._normalize upstream)
+    a2 = add("Squeeze", ["cmap", "const_axes_0"], ["norm/A2d"])
+    eye = add("EyeLike", [a2], ["norm/eye2d"])
+    eye = add("Unsqueeze", [eye, "const_axes_0"], ["norm/eye"])
+    dg = add("Mul", ["cmap", eye], ["norm/diagA"])
+    a0 = add("Sub", ["cmap", dg], ["norm/A_nodiag"])
+    ah = add("Add", [a0, eye], ["norm/A_hat"])
+    rs = add("ReduceSum", [ah, "const_axes_2"], ["norm/rowsum"], keepdims=0)
+    sq = add("Sqrt", [rs], ["norm/sqrt"])
+    dn = add("Add", [sq, "const_eps"], ["norm/denom"])
+    d = add("Div", ["const_one", dn], ["norm/d"])
+    dc = add("Unsqueeze", [d, "const_axes_2"], ["norm/d_col"])
+    dr = add("Unsqueeze", [d, "const_axes_1"], ["norm/d_row"])
+    an = add("Mul", [dc, ah], ["norm/DA"])
+    an = add("Mul", [an, dr], ["norm/DAD"])
+
+    # ---- GraphConv stack: act((A_n . X) . W [+ b])
+    outs = []
+    for l, gdim in enumerate(cfg.gc_dims, 1):
+        t = add("MatMul", [an, x], [f"GraphConv_{l}/batch_dot"])
+        t = add("MatMul", [t, f"GraphConv_{l}_W"], [f"GraphConv_{l}/MatMul"])
+        if cfg.gc_bias:
+            t = add("Add", [t, f"GraphConv_{l}_b"], [f"GraphConv_{l}/BiasAdd"])
+        if cfg.gc_activation == "Elu":
+            x = add("Elu", [t], [f"GraphConv_{l}/Elu"], alpha=1.0)
+        else:
+            x = add(cfg.gc_activation, [t], [f"GraphConv_{l}/{cfg.gc_activation}"])
+        outs.append(x)
+    cat = add("Concat", outs, ["GCNN_concatenate/concat"], axis=2) if len(outs) > 1 else outs[0]
+    pooled = add("ReduceSum", [cat, "const_axes_1"], ["SumPooling/Sum"], keepdims=0)
+    h = add("MatMul", [pooled, "dense_W"], ["dense/MatMul"])
+    h = add("Add", [h, "dense_b"], ["dense/BiasAdd"])
+    h = add("Relu", [h], ["dense/Relu"])
+    o = add("MatMul", [h, "labels_W"], ["labels/dense/MatMul"])
+    o = add("Add", [o, "labels_b"], ["labels/dense/BiasAdd"])
+    o = add("Reshape", [o, "const_out_shape"], ["labels/reshape"])
+    add("Softmax", [o], ["labels"], axis=-1)
+    return ox.Model(g, ir_version=8, opset=15, producer_name="mdf-b200-synth",
+                    producer_version="1")
+
+
+def write_gcn_model(path: str, cfg: GCNConfig, seed: int = 1234) -> None:
+    ox.save(build_gcn_model(cfg, seed=seed), path)
+
+
+# ----------------------------------------------------------------------------- workloads
+def random_sequences(rng: np.random.Generator, lengths: Sequence[int]) -> List[str]:
+    """Uniform over the 20 standard residues."""
+    table = np.frombuffer(AA20.encode(), dtype=np.uint8)
+    flat = table[rng.integers(0, 20, size=int(np.sum(lengths)))]
+    out, p = [], 0
+    for L in lengths:
+        out.append(flat[p:p + L].tobytes().decode())
+        p += L
+    return out
+
+
+def random_walk_coords(rng: np.random.Generator, lengths: Sequence[int],
+                       step: float = 3.8, pull: float = 0.0, persist: float = 0.5) -> List[np.ndarray]:
+    """Calpha random walks: 3.8 A steps, direction = random + `persist` x previous direction
+    (+ optional weak pull toward the running centroid), rounded to 3 decimals (PDB
+    precision).  Defaults give protein-like contact density: ~13-21 contacts per residue at
+    10 A and ~5-8 at 6 A.  Vectorised over proteins, sequential over residues."""
+    lengths = np.asarray(lengths, dtype=np.int64)
+    n, Lmax = len(lengths), int(lengths.max()) if len(lengths) else 0
+    pos = np.zeros((n, 3), np.float64)
+    csum = np.zeros((n, 3), np.float64)
+    vprev = np.zeros((n, 3), np.float64)
+    out = np.zeros((Lmax, n, 3), np.float32)
+    for t in range(Lmax):
+        if t:
+            v = rng.standard_normal((n, 3))
+            v /= np.linalg.norm(v, axis=1, keepdims=True) + 1e-12
+            v = v + persist * vprev + pull * (csum / t - pos)
+            v /= np.linalg.norm(v, axis=1, keepdims=True) + 1e-12
+            pos = pos + step * v
+            vprev = v
+        csum += pos
+        out[t] = np.round(pos, 3).astype(np.float32)
+    return [np.ascontiguousarray(out[:L, i]) for i, L in enumerate(lengths)]
+
+
+def markov_alignments(rng: np.random.Generator, queries: Sequence[str],
+                      p_open: float = 0.02, p_ext: float = 0.5, p_match: float = 0.6
+                      ) -> Tuple[List[str], List[str], List[str]]:
+    """MMseqs2/PyOpal-style pairwise alignments from a 3-state Markov chain over
+    {M, I, D}.  `I` puts '-' in the query, `D` puts '-' in the target — the dialect of
+    `mDeepFRI.alignment.insert_gaps` (`alignment.py:38-62`).  Returns
+    (gapped_query, gapped_target, target_sequence)."""
+    gq_all, gt_all, tgt_all = [], [], []
+    aa = np.frombuffer(AA20.encode(), dtype=np.uint8)
+    for q in queries:
+        Lq = len(q)
+        qb = np.frombuffer(q.encode(), dtype=np.uint8)
+        # run-length form of the chain: M-run, gap-run (I or D), M-run, ...; more runs than
+        # needed are drawn, then the columns are cut where the query is consumed
+        k = int(Lq * 2 * p_open * 1.5) + 8
+        m_len = rng.geometric(2 * p_open, size=k)
+        if rng.random() < 0.05:
+            m_len[0] = 0                                   # leading gap
+        g_len = rng.geometric(1.0 - p_ext, size=k)
+        g_typ = rng.integers(1, 3, size=k).astype(np.int8)  # 1=I 2=D
+        runs_state = np.empty(2 * k, np.int8)
+        runs_state[0::2] = 0
+        runs_state[1::2] = g_typ
+        runs_len = np.empty(2 * k, np.int64)
+        runs_len[0::2] = m_len
+        runs_len[1::2] = g_len
+        state = np.repeat(runs_state, runs_len)            # 0=M 1=I 2=D per column
+        consumes_q = state != 1
+        cq = np.cumsum(consumes_q)
+        if cq[-1] < Lq:                                    # (rare) not enough columns: pad with M
+            state = np.concatenate([state, np.zeros(Lq - cq[-1], np.int8)])
+            consumes_q = state != 1
+            cq = np.cumsum(consumes_q)
+        end = int(np.searchsorted(cq, Lq)) + 1
+        if rng.random() < 0.05:                            # trailing query gap
+            state = np.concatenate([state[:end], np.ones(int(rng.integers(1, 4)), np.int8)])
+            end = len(state)
+        state = state[:end]
+        consumes_q = state != 1
+        assert int(consumes_q.sum()) == Lq
+        qi = np.cumsum(consumes_q) - 1
+        gq = np.where(consumes_q, qb[np.clip(qi, 0, Lq - 1)], ord("-")).astype(np.uint8)
+        rnd = aa[rng.integers(0, 20, size=end)]
+        keep = rng.random(end) < p_match
+        tcol = np.where((state == 0) & keep, gq, rnd)
+        gt = np.where(state == 2, ord("-"), tcol).astype(np.uint8)
+        gq_all.append(gq.tobytes().decode())
+        gt_all.append(gt.tobytes().decode())
+        tgt_all.append(gt[gt != ord("-")].tobytes().decode())
+    return gq_all, gt_all, tgt_all
+
+
+@dataclass
+class Workload:
+    """One batch of the hot path's inputs (what `pipeline.py:476-481` + `:301-319` consume)."""
+    query_seqs: List[str]
+    gapped_query: List[str]
+    gapped_target: List[str]
+    coords: List[np.ndarray]          # float32 [Lt, 3] per target structure
+    threshold: float = 10.0
+    generated_contacts: int = 2
+    name: str = ""
+
+    def __len__(self):
+        return len(self.query_seqs)
+
+
+def make_workload(n: int, lmin: int, lmax: int, seed: int, *, gapped: bool = True,
+                  threshold: float = 10.0, generated_contacts: int = 2,
+                  dist: str = "uniform", name: str = "") -> Workload:
+    rng = np.random.default_rng(seed)
+    if dist == "uniform":
+        lengths = rng.integers(lmin, lmax + 1, size=n)
+    elif dist == "lognormal":       # metagenomic length distribution, SURVEY.md §8d config 3
+        lengths = np.clip(np.exp(rng.normal(np.log(250.0), 0.6, size=n)), lmin, lmax).astype(np.int64)
+    else:
+        raise ValueError(dist)
+    seqs = random_sequences(rng, lengths)
+    if gapped:
+        gq, gt, tgt = markov_alignments(rng, seqs)
+    else:
+        gq, gt, tgt = list(seqs), list(seqs), list(seqs)
+    coords = random_walk_coords(rng, [len(t) for t in tgt])
+    return Workload(seqs, gq, gt, coords, threshold, generated_contacts,
+                    name or f"n{n}_L{lmin}-{lmax}_{dist}_seed{seed}")
+
+
+def config_workload(idx: int, scale: float = 1.0) -> Workload:
+    """BASELINE.json `configs[idx]`; `scale` shrinks the protein count for tests."""
+    if idx == 0:
+        return make_workload(max(1, int(1000 * scale)), 100, 500, seed=1, name="config0_1k_L100-500_MF")
+    if idx == 1:
+        return make_workload(max(1, int(100_000 * scale)), 50, 1000, seed=2, threshold=6.0,
+                             name="config1_100k_pairs_cmap_transfer")
+    if idx == 2:
+        return make_workload(max(1, int(10_000 * scale)), 50, 1000, seed=3, dist="lognormal",
+                             name="config2_10k_L50-1000_4heads")
+    if idx == 3:
+        return make_workload(max(1, int(2000 * scale)), 1000, 2500, seed=4, name="config3_2k_L1000-2500")
+    if idx == 4:
+        return make_workload(max(1, int(1_000_000 * scale)), 50, 1000, seed=5, dist="lognormal",
+                             name="config4_1M_MF_sharded")
+    raise ValueError(idx)
