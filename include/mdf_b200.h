@@ -119,6 +119,7 @@ int mdf_model_create(mdf_ctx *ctx, const mdf_model_desc *desc, mdf_model **out);
 int mdf_model_destroy(mdf_model *model);
 /* 0 = fp32 SIMT reference engine, 1 = tcgen05 tensor-core engine */
 int mdf_model_set_engine(mdf_model *model, int engine);
+int mdf_model_get_engine(const mdf_model *model);
 
 /* ---- predict.pyx:75-102  Predictor.forward_pass(seqres, cmap) ---------------------------------
  * seq: ASCII residues (alphabet "-DGULNTKHYWCPVSOIEFXQABZRM", anything else -> MDF_EINVAL);

@@ -71,6 +71,8 @@ def lib() -> C.CDLL:
         L.mdf_model_create.argtypes = [vp, C.POINTER(ModelDesc), C.POINTER(vp)]
         L.mdf_model_destroy.argtypes = [vp]
         L.mdf_model_set_engine.argtypes = [vp, C.c_int]
+        L.mdf_model_get_engine.argtypes = [vp]
+        L.mdf_model_get_engine.restype = C.c_int
         L.mdf_gcn_forward_dense.argtypes = [vp, C.c_char_p, C.c_int, c_i32p, c_f32p]
         L.mdf_gcn_forward_packed.argtypes = [vp, C.c_int, C.c_char_p, c_i64p, c_u32p, c_i64p, c_f32p]
         L.mdf_path_forward.argtypes = [vp, C.c_int, vp, c_i64p, vp, c_i64p, vp, vp, c_i64p,
@@ -98,7 +100,7 @@ EXPORTED_SYMBOLS = [
     "mdf_last_error", "mdf_version", "mdf_ctx_create", "mdf_ctx_destroy", "mdf_ctx_synchronize",
     "mdf_ctx_launch_count", "mdf_ctx_profile", "mdf_ctx_profile_report", "mdf_pairwise_sqeuclidean", "mdf_contact_map_dense", "mdf_contact_map_sparse",
     "mdf_align_contact_map", "mdf_cmap_build_transfer", "mdf_model_create", "mdf_model_destroy",
-    "mdf_model_set_engine", "mdf_gcn_forward_dense", "mdf_gcn_forward_packed", "mdf_path_forward",
+    "mdf_model_set_engine", "mdf_model_get_engine", "mdf_gcn_forward_dense", "mdf_gcn_forward_packed", "mdf_path_forward",
     "mdf_batch_upload", "mdf_batch_destroy", "mdf_path_run", "mdf_path_run_stages", "mdf_batch_fetch_scores",
     "mdf_batch_fetch", "mdf_batch_scores_device",
 ]

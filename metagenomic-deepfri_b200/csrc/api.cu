@@ -777,3 +777,5 @@ extern "C" int mdf_model_set_engine(mdf_model *m, int engine)
     m->engine = engine;
     return MDF_OK;
 }
+
+extern "C" int mdf_model_get_engine(const mdf_model *m) { return m ? m->engine : -1; }

@@ -64,6 +64,47 @@ class _Session:
         return ["B200ExecutionProvider"]
 
 
+class PathInputs:
+    """Path inputs of n proteins packed once into flat host arrays (optionally pinned through
+    torch so that the per-call host->device copies are truly asynchronous)."""
+
+    def __init__(self, seqs: Sequence[str], gapped_query: Sequence[str], gapped_target: Sequence[str],
+                 coords: Sequence[np.ndarray], pin: bool = False):
+        ps = pack_structures(gapped_query, gapped_target, coords)
+        seq_bytes, seq_off = pack_sequences([_encode(s).decode() for s in seqs])
+        if not np.array_equal(seq_off, ps.seq_off):
+            raise ValueError("query sequences do not match the gap-stripped query alignments")
+        self.n = len(seqs)
+        self._pinned = []
+
+        def host(a: np.ndarray) -> np.ndarray:
+            if not pin or a.nbytes == 0:
+                return np.ascontiguousarray(a)
+            import torch
+            t = torch.empty(a.nbytes, dtype=torch.uint8, pin_memory=True)
+            self._pinned.append(t)
+            v = t.numpy().view(a.dtype).reshape(a.shape)
+            v[...] = a
+            return v
+        self.seq = host(np.frombuffer(seq_bytes, np.uint8))
+        self.q_aln = host(np.frombuffer(ps.q_aln, np.uint8))
+        self.t_aln = host(np.frombuffer(ps.t_aln, np.uint8))
+        self.coords = host(ps.coords)
+        self.seq_off, self.coord_off, self.aln_off = seq_off, ps.coord_off, ps.aln_off
+        self.packed_off = ps.packed_off
+        self.pin = pin
+        self.h2d_bytes = int(self.seq.nbytes + self.q_aln.nbytes + self.t_aln.nbytes + self.coords.nbytes
+                             + 8 * (seq_off.size + ps.coord_off.size + ps.aln_off.size))
+
+    def output_buffer(self, n_terms: int) -> np.ndarray:
+        if not self.pin:
+            return np.empty((self.n, n_terms), np.float32)
+        import torch
+        t = torch.empty((self.n, n_terms), dtype=torch.float32, pin_memory=True)
+        self._pinned.append(t)
+        return t.numpy()
+
+
 class PathBatch:
     """A batch of path inputs uploaded once and kept resident in HBM (`mdf_batch_upload`)."""
 
@@ -145,6 +186,10 @@ class Predictor:
         """'simt' = exact-fp32 CUDA-core engine, 'tc' = tcgen05 tensor-core engine."""
         _lib.check(_lib.lib().mdf_model_set_engine(self._handle, {"simt": 0, "tc": 1}[engine]))
 
+    @property
+    def engine(self) -> str:
+        return {0: "simt", 1: "tc"}[_lib.lib().mdf_model_get_engine(self._handle)]
+
     # -- predict.pyx:75-102
     def forward_pass(self, seqres: str, cmap=None) -> np.ndarray:
         seq = _encode(seqres)
@@ -196,6 +241,19 @@ class Predictor:
         _lib.check(_lib.lib().mdf_path_forward(
             self._handle, n, seq_bytes, _lib.lp(seq_off), ps.coords.ctypes.data, _lib.lp(ps.coord_off), ps.q_aln,
             ps.t_aln, _lib.lp(ps.aln_off), float(threshold_sq(threshold)), int(generated_contacts), out.ctypes.data))
+        return out
+
+    def forward_inputs(self, inputs: PathInputs, threshold: float = 6, generated_contacts: int = 2,
+                       out: Optional[np.ndarray] = None) -> np.ndarray:
+        """`forward_structures` on pre-packed (optionally pinned) host buffers: per call this does
+        the host->device copies, every kernel of the path and the device->host copy of the scores."""
+        from .bio_utils import threshold_sq
+        if out is None:
+            out = inputs.output_buffer(self.n_terms)
+        _lib.check(_lib.lib().mdf_path_forward(
+            self._handle, inputs.n, inputs.seq.ctypes.data, _lib.lp(inputs.seq_off), inputs.coords.ctypes.data,
+            _lib.lp(inputs.coord_off), inputs.q_aln.ctypes.data, inputs.t_aln.ctypes.data, _lib.lp(inputs.aln_off),
+            float(threshold_sq(threshold)), int(generated_contacts), out.ctypes.data))
         return out
 
     # -- resident-batch interface (bench / multi-head reuse)
