@@ -175,7 +175,8 @@ def run_b200(args, rank, world, local_rank):
     import torch.distributed as dist
     from metagenomic_deepfri_b200 import _lib, predict
     torch.cuda.set_device(local_rank)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()             # a real (non-NULL) stream shared by torch and the library
+    torch.cuda.set_stream(stream)
     ctx = _lib.Context(local_rank, stream=stream.cuda_stream)
     wl = synth.make_workload(args.proteins, 100, 500, seed=1 + rank, threshold=THRESHOLD)
     tmp = tempfile.mkdtemp()

@@ -441,9 +441,10 @@ static int run_cmap(mdf_ctx *ctx, mdf_batch *b, float thr2, int gen)
     return launch_cmap_pair(ctx, b->nwork, b->d_work, b->d_qc, b->d_seq_off, thr2, gen, 1, b->d_packed, b->d_packed_off);
 }
 
-static size_t engine_workspace(const mdf_model *m, int n, int64_t T)
+static size_t engine_workspace(const mdf_model *m, int n, const int64_t *seq_off)
 {
-    return m->engine == 1 ? tc_workspace_bytes(m, n, T) : simt_workspace_bytes(m, n, T);
+    if (n <= 0 || !seq_off) return 4096;
+    return m->engine == 1 ? tc_workspace_bytes(m, n, seq_off) : simt_workspace_bytes(m, n, seq_off[n]);
 }
 
 // stages: 1 cmap, 2 LSTM-LM+embedding, 3 GraphConv+pool, 4 head.  Arena must already be reserved.
@@ -496,6 +497,7 @@ extern "C" int mdf_batch_destroy(mdf_batch *b)
         cudaFree(b->block);
         if (b->out_block) cudaFree(b->out_block);
     }
+    tc_batch_free(b);
     delete b;
     return MDF_OK;
 }
@@ -517,7 +519,7 @@ extern "C" int mdf_path_run_stages(mdf_model *m, mdf_batch *b, float thr2, int g
         b->out_G = m->G; b->out_C = m->C;
     }
     ArenaScope scope(ctx);
-    MDF_TRY(ctx->reserve(engine_workspace(m, b->n, b->T)));
+    MDF_TRY(ctx->reserve(engine_workspace(m, b->n, b->h_seq_off.data())));
     return run_path(m, b, thr2, gen, upto, b->has_structure);
 }
 
@@ -569,9 +571,8 @@ extern "C" int mdf_path_forward(mdf_model *m, int n, const char *seq, const int6
     MDF_CUDA(cudaSetDevice(ctx->device));
     ArenaScope scope(ctx);
     mdf_batch b;
-    const int64_t T = seq_off ? seq_off[n] : 0;
     MDF_TRY(batch_build(ctx, &b, false, n, seq, seq_off, coords, coord_off, q_aln, t_aln, aln_off, nullptr, m->G, m->C,
-                        engine_workspace(m, n, T)));
+                        engine_workspace(m, n, seq_off)));
     MDF_TRY(run_path(m, &b, thr2, gen, 4, true));
     return fetch_scores(m, &b, scores);
 }
@@ -584,7 +585,6 @@ extern "C" int mdf_gcn_forward_packed(mdf_model *m, int n, const char *seq, cons
     MDF_CUDA(cudaSetDevice(ctx->device));
     ArenaScope scope(ctx);
     mdf_batch b;
-    const int64_t T = seq_off ? seq_off[n] : 0;
     // packed_off must follow the canonical layout (contiguous, mdf_packed_row_words)
     int64_t off = 0;
     for (int p = 0; p < n; ++p) {
@@ -593,7 +593,7 @@ extern "C" int mdf_gcn_forward_packed(mdf_model *m, int n, const char *seq, cons
         off += L * mdf_packed_row_words((int)L);
     }
     MDF_TRY(batch_build(ctx, &b, false, n, seq, seq_off, nullptr, nullptr, nullptr, nullptr, nullptr, packed, m->G, m->C,
-                        engine_workspace(m, n, T)));
+                        engine_workspace(m, n, seq_off)));
     MDF_TRY(run_path(m, &b, 0.f, 0, 4, false));
     return fetch_scores(m, &b, scores);
 }
@@ -608,7 +608,7 @@ extern "C" int mdf_gcn_forward_dense(mdf_model *m, const char *seq, int L, const
     const int64_t seq_off[2] = {0, L};
     const size_t dense_bytes = (size_t)L * L * 4;
     MDF_TRY(batch_build(ctx, &b, false, 1, seq, seq_off, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, m->G, m->C,
-                        engine_workspace(m, 1, L) + dense_bytes + 4096));
+                        engine_workspace(m, 1, seq_off) + dense_bytes + 4096));
     int32_t *dd;
     MDF_TRY(ctx->alloc_n(&dd, (size_t)L * L + 1));
     if (L) MDF_CUDA(cudaMemcpyAsync(dd, cmap, dense_bytes, cudaMemcpyHostToDevice, ctx->stream));

@@ -58,11 +58,13 @@ struct mdf_batch {
     // taps into the arena of the last run (valid until the next run)
     float *tap_h[MDF_MAX_LSTM] = {nullptr};
     float *tap_x0 = nullptr, *tap_gc_last = nullptr;
+    void *tc_meta = nullptr;     // tensor-core engine metadata of persistent batches (tc_engine.cu)
 };
 
 namespace mdf {
 
 size_t simt_workspace_bytes(const mdf_model *m, int n, int64_t T);
+int simt_lstm_stack(mdf_model *m, mdf_batch *b, float **Hl, float *pre, float *Cst, unsigned *barrier);
 // stages: 2 = LSTM-LM + embedding, 3 = + GraphConv + pooling, 4 = + head
 int simt_forward(mdf_model *m, mdf_batch *b, int upto);
 

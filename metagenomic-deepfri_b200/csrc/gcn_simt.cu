@@ -334,7 +334,7 @@ static int lstm_layer(mdf_model *m, mdf_batch *b, int layer, const float *pre, f
     a.Hout = Hout; a.Cst = Cst; a.order = b->d_order; a.seq_off = b->d_seq_off; a.barrier = barrier;
     const size_t smem = ((size_t)m->H * LSTM_UNITS * 4 + (size_t)LSTM_CHUNK * (m->H + 4)) * sizeof(float);
     MDF_CUDA(cudaFuncSetAttribute(lstm_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MDF_CUDA(cudaMemsetAsync(barrier, 0, sizeof(unsigned) * 16, ctx->stream));
+    MDF_CUDA(cudaMemsetAsync(barrier, 0, sizeof(unsigned) * 256, ctx->stream));
     void *args[] = {&a};
     MDF_CUDA(cudaLaunchCooperativeKernel((void *)lstm_simt_kernel, dim3(a.n_groups * a.ctas_per_group),
                                          dim3(LSTM_THREADS), args, smem, ctx->stream));
@@ -428,12 +428,32 @@ size_t simt_workspace_bytes(const mdf_model *m, int n, int64_t T)
     for (int l = 0; l < m->n_lstm; ++l) add((size_t)T * m->H * 4);   // H_l
     add((size_t)T * 4 * m->H * 4);                                    // pre (layers >= 2)
     add((size_t)n * m->H * 4);                                        // cell state
-    add(256);                                                         // barriers
+    add(1024);                                                        // barriers
     add((size_t)T * m->E * 4);                                        // X0
     add((size_t)T * gmax * 4 * 3);                                    // Y, Xa, Xb
     add((size_t)n * m->F * 4);
     add((size_t)n * 2 * m->C * 4);
     return b + 4096;
+}
+
+// LSTM stack on the fp32 kernels: layer l >= 1 gets its input pre-activations from an SGEMM.
+int simt_lstm_stack(mdf_model *m, mdf_batch *b, float **Hl, float *pre, float *Cst, unsigned *barrier)
+{
+    mdf_ctx *ctx = m->ctx;
+    const int64_t T = b->T;
+    for (int l = 0; l < m->n_lstm; ++l) {
+        if (l > 0) {
+            ProfScope ps(ctx, "lstm_input_gemm", 2.0 * T * 4 * m->H * m->H);
+            Epilogue e; e.bias = m->lstm_b[l];
+            MDF_TRY(sgemm(ctx, T, 4 * m->H, m->H, Hl[l - 1], m->H, m->lstm_Wt[l], 4 * m->H, pre, 4 * m->H, e));
+        }
+        {
+            ProfScope ps(ctx, "lstm_recurrent", 2.0 * T * 4 * m->H * m->H);
+            MDF_TRY(lstm_layer(m, b, l, l > 0 ? pre : nullptr, Hl[l], Cst, barrier));
+        }
+        b->tap_h[l] = Hl[l];
+    }
+    return MDF_OK;
 }
 
 int simt_forward(mdf_model *m, mdf_batch *b, int upto)
@@ -447,21 +467,10 @@ int simt_forward(mdf_model *m, mdf_batch *b, int upto)
     for (int l = 0; l < m->n_lstm; ++l) MDF_TRY(ctx->alloc_n(&Hl[l], (size_t)T * m->H));
     MDF_TRY(ctx->alloc_n(&pre, (size_t)T * 4 * m->H));
     MDF_TRY(ctx->alloc_n(&Cst, (size_t)n * m->H));
-    MDF_TRY(ctx->alloc_n(&barrier, 64));
+    MDF_TRY(ctx->alloc_n(&barrier, 256));
     MDF_TRY(ctx->alloc_n(&X0, (size_t)T * m->E));
     // ---- LSTM language model
-    for (int l = 0; l < m->n_lstm; ++l) {
-        if (l > 0) {
-            ProfScope ps(ctx, "lstm_input_gemm", 2.0 * T * 4 * m->H * m->H);
-            Epilogue e; e.bias = m->lstm_b[l];
-            MDF_TRY(sgemm(ctx, T, 4 * m->H, m->H, Hl[l - 1], m->H, m->lstm_Wt[l], 4 * m->H, pre, 4 * m->H, e));
-        }
-        {
-            ProfScope ps(ctx, "lstm_recurrent", 2.0 * T * 4 * m->H * m->H);
-            MDF_TRY(lstm_layer(m, b, l, l > 0 ? pre : nullptr, Hl[l], Cst, barrier));
-        }
-        b->tap_h[l] = Hl[l];
-    }
+    MDF_TRY(simt_lstm_stack(m, b, Hl, pre, Cst, barrier));
     // ---- embedding: relu(H2 W_lm + b_lm + W_aa[idx])
     {
         ProfScope ps(ctx, "embedding_gemm", 2.0 * T * m->H * m->E);

@@ -1,0 +1,235 @@
+// tcgen05 GEMM kernel (see gemm_tc.cuh).
+#include "gemm_tc.cuh"
+
+namespace mdf {
+namespace tc {
+
+constexpr int GEMM_THREADS = 192;   // warp 0 producer, warp 1 MMA, warps 2-5 epilogue
+
+struct __align__(8) GemmBarriers {
+    uint64_t full[8], empty[8], tmem_full[2], tmem_empty[2];
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ float act_f(float v, int act, float alpha)
+{
+    if (act == 1) return fmaxf(v, 0.0f);
+    if (act == 2) return v > 0.0f ? v : alpha * (__expf(v) - 1.0f);
+    return v;
+}
+
+template <int EPI, int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_kernel(GemmArgs g, int a_terms, int b_terms, int stages)
+{
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    constexpr int NSUB = BN / 128;                 // B sub-tiles (one 128x128x16 MMA each)
+    __shared__ GemmBarriers bars;
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int a_bytes = a_terms * TILE_BYTES;
+    const int stage_bytes = a_bytes + b_terms * NSUB * TILE_BYTES;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total_tiles = g.m_tiles * g.n_tiles;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) { mbar_init(&bars.full[s], 1); mbar_init(&bars.empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&bars.tmem_full[s], 1); mbar_init(&bars.tmem_empty[s], 4); }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<2 * BN>(&bars.tmem_base);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = bars.tmem_base;
+
+    if (warp == 0) {
+        // ===================== producer: bulk-TMA tile images into the stage ring
+        if (lane == 0) {
+            int st = 0; uint32_t ph = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int mt = t / g.n_tiles, nt = t % g.n_tiles;
+                int a_tile0, b_kb0, nkb;
+                if (g.tile_info) { const int4 ti = g.tile_info[mt]; a_tile0 = ti.x; b_kb0 = ti.y; nkb = ti.z; }
+                else { a_tile0 = mt * g.KB_A; b_kb0 = 0; nkb = g.nkb; }
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(&bars.empty[st], ph ^ 1);
+                    mbar_arrive_expect_tx(&bars.full[st], (uint32_t)stage_bytes);
+                    uint8_t *dst = smem + (size_t)st * stage_bytes;
+                    for (int ta = 0; ta < a_terms; ++ta)
+                        bulk_g2s(dst + ta * TILE_BYTES,
+                                 reinterpret_cast<const uint8_t *>(g.A[ta]) + (size_t)(a_tile0 + kb) * TILE_BYTES,
+                                 TILE_BYTES, &bars.full[st]);
+                    for (int tb = 0; tb < b_terms; ++tb)
+                        for (int j = 0; j < NSUB; ++j)
+                            bulk_g2s(dst + a_bytes + (tb * NSUB + j) * TILE_BYTES,
+                                     reinterpret_cast<const uint8_t *>(g.B[tb]) +
+                                         ((size_t)(nt * NSUB + j) * g.KB_B + b_kb0 + kb) * TILE_BYTES,
+                                     TILE_BYTES, &bars.full[st]);
+                    if (++st == stages) { st = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_f16(128, 128);
+            int st = 0; uint32_t ph = 0;
+            int acc = 0; uint32_t acc_ph = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int mt = t / g.n_tiles;
+                const int nkb = g.tile_info ? g.tile_info[mt].z : g.nkb;
+                mbar_wait(&bars.tmem_empty[acc], acc_ph ^ 1);
+                tcgen05_fence_after();
+                const uint32_t d0 = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(&bars.full[st], ph);
+                    tcgen05_fence_after();
+                    const uint32_t sa = smem_u32(smem + (size_t)st * stage_bytes);
+                    const uint32_t sb = sa + a_bytes;
+                    // every (A term, B term) pair contributes; at most one side has two terms
+                    for (int ta = 0; ta < a_terms; ++ta)
+                        for (int tb = 0; tb < b_terms; ++tb)
+#pragma unroll
+                            for (int ks = 0; ks < TILE_K / 16; ++ks) {
+                                const uint64_t ad = umma_smem_desc(sa + ta * TILE_BYTES + ks * 2 * TILE_LBO, TILE_LBO, TILE_SBO);
+#pragma unroll
+                                for (int j = 0; j < NSUB; ++j) {
+                                    const uint64_t bd = umma_smem_desc(sb + (tb * NSUB + j) * TILE_BYTES + ks * 2 * TILE_LBO,
+                                                                       TILE_LBO, TILE_SBO);
+                                    umma_f16(d0 + j * 128, ad, bd, idesc, (kb | ks | ta | tb) != 0);
+                                }
+                            }
+                    umma_commit(&bars.empty[st]);                 // frees the smem stage when the MMAs retire
+                    if (kb == nkb - 1) umma_commit(&bars.tmem_full[acc]);
+                    if (++st == stages) { st = 0; ph ^= 1; }
+                }
+                if (nkb == 0) umma_commit(&bars.tmem_full[acc]);
+                if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue: TMEM -> registers -> global
+        const int lb = (warp & 3) * 32;          // this warp's TMEM lane block = output rows
+        int acc = 0; uint32_t acc_ph = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const int mt = t / g.n_tiles, nt = t % g.n_tiles;
+            const int nkb = g.tile_info ? g.tile_info[mt].z : g.nkb;
+            mbar_wait(&bars.tmem_full[acc], acc_ph);
+            tcgen05_fence_after();
+            const int64_t m = (int64_t)mt * 128 + lb + lane;
+            const uint32_t trow = tmem_base + ((uint32_t)lb << 16) + (uint32_t)(acc * BN);
+            float rs = 1.0f;
+            const float *grow = nullptr;
+            if (EPI == EPI_IMG_ROWSCALE) rs = g.rowscale[m];
+            if (EPI == EPI_IMG_EMBED) grow = g.gtab + (size_t)g.gidx[m] * g.ldg;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t r[32];
+                if (nkb > 0) {
+                    tmem_ld_32x32b_x32(trow + c0, r);
+                    tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] = 0u;
+                }
+                const int n0 = nt * BN + c0;
+                if (EPI == EPI_F32_BIAS) {
+                    if (m < g.m_valid) {
+                        float *dst = g.out_f32 + (size_t)m * g.ldc + n0;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            if (n0 + 4 * q < g.n_valid) {
+                                float4 v;
+                                const float4 b = g.bias ? *reinterpret_cast<const float4 *>(g.bias + n0 + 4 * q) : make_float4(0, 0, 0, 0);
+                                v.x = __uint_as_float(r[4 * q + 0]) + b.x; v.y = __uint_as_float(r[4 * q + 1]) + b.y;
+                                v.z = __uint_as_float(r[4 * q + 2]) + b.z; v.w = __uint_as_float(r[4 * q + 3]) + b.w;
+                                *reinterpret_cast<float4 *>(dst + 4 * q) = v;
+                            }
+                        }
+                    }
+                } else {
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                    if (EPI == EPI_IMG_COLSCALE) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float cs = g.colscale[n0 + j];
+                            v[j] = cs != 0.0f ? v[j] * cs : 0.0f;
+                        }
+                    } else if (EPI == EPI_IMG_ROWSCALE) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            v[j] = act_f(v[j] * rs + (g.bias ? g.bias[n0 + j] : 0.0f), g.act, g.alpha);
+                    } else if (EPI == EPI_IMG_EMBED) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 b = *reinterpret_cast<const float4 *>(g.bias + n0 + 4 * q);
+                            const float4 a = *reinterpret_cast<const float4 *>(grow + n0 + 4 * q);
+                            v[4 * q + 0] = fmaxf(v[4 * q + 0] + b.x + a.x, 0.0f);
+                            v[4 * q + 1] = fmaxf(v[4 * q + 1] + b.y + a.y, 0.0f);
+                            v[4 * q + 2] = fmaxf(v[4 * q + 2] + b.z + a.z, 0.0f);
+                            v[4 * q + 3] = fmaxf(v[4 * q + 3] + b.w + a.w, 0.0f);
+                        }
+                    }
+                    uint8_t *img = reinterpret_cast<uint8_t *>(g.out_img);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint4 pk;
+                        pk.x = pack_half2(v[8 * q + 0], v[8 * q + 1]); pk.y = pack_half2(v[8 * q + 2], v[8 * q + 3]);
+                        pk.z = pack_half2(v[8 * q + 4], v[8 * q + 5]); pk.w = pack_half2(v[8 * q + 6], v[8 * q + 7]);
+                        *reinterpret_cast<uint4 *>(img + image_offset_bytes(m, n0 + 8 * q, g.KB_out)) = pk;
+                    }
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars.tmem_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<2 * BN>(tmem_base);
+}
+
+template <int EPI, int BN>
+static int launch_one(mdf_ctx *ctx, int a_terms, int b_terms, const GemmArgs &args)
+{
+    const int stage_bytes = (a_terms + b_terms * (BN / 128)) * TILE_BYTES;
+    int stages = (int)((200 * 1024) / stage_bytes);
+    if (stages > 8) stages = 8;
+    if (stages < 2) { set_error("gemm_tc: stage of %d bytes does not fit twice in shared memory", stage_bytes); return MDF_EUNSUPPORTED; }
+    const size_t smem = (size_t)stages * stage_bytes + 1024;
+    auto kern = gemm_tc_kernel<EPI, BN>;
+    MDF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int total = args.m_tiles * args.n_tiles;
+    if (total <= 0) return MDF_OK;
+    const int grid = total < ctx->sm_count ? total : ctx->sm_count;
+    kern<<<grid, GEMM_THREADS, smem, ctx->stream>>>(args, a_terms, b_terms, stages);
+    MDF_LAUNCH_CHECK(ctx);
+    return MDF_OK;
+}
+
+int launch_gemm_tc(mdf_ctx *ctx, int epi, int bn, int a_terms, int b_terms, const GemmArgs &args)
+{
+    if (a_terms < 1 || a_terms > 2 || b_terms < 1 || b_terms > 2 || (a_terms == 2 && b_terms == 2)) {
+        set_error("gemm_tc: unsupported term split %d x %d", a_terms, b_terms);
+        return MDF_EUNSUPPORTED;
+    }
+#define MDF_GEMM_CASE(E, N) if (epi == E && bn == N) return launch_one<E, N>(ctx, a_terms, b_terms, args)
+    MDF_GEMM_CASE(EPI_F32_BIAS, 128);
+    MDF_GEMM_CASE(EPI_F32_BIAS, 256);
+    MDF_GEMM_CASE(EPI_IMG_COLSCALE, 128);
+    MDF_GEMM_CASE(EPI_IMG_COLSCALE, 256);
+    MDF_GEMM_CASE(EPI_IMG_ROWSCALE, 128);
+    MDF_GEMM_CASE(EPI_IMG_ROWSCALE, 256);
+    MDF_GEMM_CASE(EPI_IMG_EMBED, 128);
+    MDF_GEMM_CASE(EPI_IMG_EMBED, 256);
+#undef MDF_GEMM_CASE
+    set_error("gemm_tc: no kernel for epilogue %d / BN %d", epi, bn);
+    return MDF_EUNSUPPORTED;
+}
+
+}  // namespace tc
+}  // namespace mdf

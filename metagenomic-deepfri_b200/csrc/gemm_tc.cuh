@@ -1,0 +1,48 @@
+// tcgen05 GEMM over fp16 operand tile images (see tc_ptx.cuh) with fused epilogues.
+//   D[M x N] (fp32, TMEM) = sum_terms A_t[M x K] . B_t[N x K]^T
+// Persistent, warp-specialised: warp 0 = bulk-TMA producer, warp 1 = MMA issuer (one elected lane),
+// warps 2..5 = epilogue (TMEM -> registers -> global).  Accumulators are double-buffered in TMEM so
+// the epilogue of tile i overlaps the MMAs of tile i+1.
+#pragma once
+#include "mdf_common.cuh"
+#include "tc_ptx.cuh"
+
+namespace mdf {
+namespace tc {
+
+enum Epi : int {
+    EPI_F32_BIAS = 0,   // out_f32[m * ldc + n] = acc + bias[n]
+    EPI_IMG_COLSCALE,   // out image (rows = m, k = n): colscale[n] != 0 ? acc * colscale[n] : 0
+    EPI_IMG_ROWSCALE,   // out image: act(acc * rowscale[m] + bias[n])
+    EPI_IMG_EMBED,      // out image: relu(acc + bias[n] + gtab[gidx[m] * ldg + n])
+};
+
+struct GemmArgs {
+    const __half *A[2] = {nullptr, nullptr};
+    const __half *B[2] = {nullptr, nullptr};
+    int KB_A = 0, KB_B = 0;          // k-blocks per row tile of the A / B images
+    int m_tiles = 0, n_tiles = 0;    // output tiles (128 rows x BN columns)
+    int nkb = 0;                     // k-blocks per output tile (regular case)
+    // grouped case (adjacency product): per m-tile {A tile index of its first k-block, first k-block
+    // on the B side, number of k-blocks, unused}
+    const int4 *tile_info = nullptr;
+    // epilogue
+    float *out_f32 = nullptr;
+    int ldc = 0;
+    __half *out_img = nullptr;
+    int KB_out = 0;
+    const float *bias = nullptr;
+    const float *rowscale = nullptr;
+    const float *colscale = nullptr;
+    const float *gtab = nullptr;
+    const uint8_t *gidx = nullptr;
+    int ldg = 0;
+    int act = 0;
+    float alpha = 1.0f;
+    int m_valid = 0, n_valid = 0;    // bounds for the fp32 epilogue
+};
+
+int launch_gemm_tc(mdf_ctx *ctx, int epi, int bn, int a_terms, int b_terms, const GemmArgs &args);
+
+}  // namespace tc
+}  // namespace mdf

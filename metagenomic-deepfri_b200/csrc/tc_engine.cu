@@ -1,16 +1,437 @@
-// Tensor-core engine — placeholder until gemm_tc.cu / lstm_tc.cu land.
+// Tensor-core engine (engine 1) of the GCN half of the path.
+//
+// Precision plan (measured against the fp32 oracle, DESIGN.md "precision"): every GEMM runs on
+// tcgen05 with fp16 operands and fp32 accumulation in TMEM.  Activations are a single fp16 term;
+// *weights* are split into hi + lo fp16 terms (two MMAs per k-step) because their rounding error is
+// coherent across residues and would otherwise survive the sum-pool readout.  The adjacency A_hat is
+// 0/1 and exact in fp16.
+//
+// Layout: the residue axis is padded per protein to a multiple of 128 rows ("segments"); all
+// per-residue activations are fp16 operand tile images over that padded axis (tc_ptx.cuh).
+//   H2 image [Tp x H] --embed GEMM--> X0 image [Tp x E]
+//   per GraphConv layer:  Y^T image [g x Tp] = (W^T hi/lo) . X^T, columns scaled by d_j (pads -> 0)
+//                         X_l image [Tp x g] = act(d_i * A_hat . Y + b)     (grouped per protein)
+//                         pooled[p] += sum over valid rows of X_l
+#include <algorithm>
+
+#include "gemm_tc.cuh"
 #include "tc_engine.cuh"
 
 namespace mdf {
 
-int tc_model_init(mdf_model *, const mdf_model_desc *) { return MDF_OK; }
-void tc_model_free(mdf_model *) {}
-bool tc_available(const mdf_model *) { return false; }
-size_t tc_workspace_bytes(const mdf_model *, int, int64_t) { return 0; }
-int tc_forward(mdf_model *, mdf_batch *, int)
+int head_forward(mdf_model *m, int n, const float *pooled, float *fc, float *logits, float *scores);
+int simt_lstm_stack(mdf_model *m, mdf_batch *b, float **Hl, float *pre, float *Cst, unsigned *barrier);
+
+using namespace tc;
+
+struct TcModel {
+    __half *lm_W[2] = {nullptr, nullptr};                  // [E rows x H k]  (B operand of the embed GEMM)
+    __half *gc_W[MDF_MAX_GC][2] = {{nullptr}};             // [g rows x k_in] (A operand of X.W, transposed)
+    bool ok = false;
+};
+
+struct TcBatchMeta {
+    int64_t Tp = 0;             // padded residue rows (multiple of 256)
+    int n_adj_tiles = 0;        // tiles of all A_hat images
+    int m_tiles = 0;            // Tp / 128
+    int *rowmap = nullptr;      // [Tp] padded row -> packed residue index, -1 on pads
+    int4 *tile_info = nullptr;  // [m_tiles] grouped-GEMM info per 128-row tile
+    int4 *exp_tiles = nullptr;  // [n_adj_tiles] {protein, local m-tile, k-block, first tile of protein}
+    int64_t *seg_off = nullptr; // [n+1] padded row offsets
+    void *block = nullptr;
+    bool persistent = false;
+};
+
+// ------------------------------------------------------------------------------------------- weight images
+static void build_image_host(const float *src, int rows, int K, bool transposed_src, int ld,
+                             std::vector<__half> &hi, std::vector<__half> &lo)
 {
-    set_error("tensor-core engine not built");
-    return MDF_EUNSUPPORTED;
+    // element (r, k) = transposed_src ? src[k * ld + r] : src[r * ld + k]
+    const int RT = cdiv(rows, TILE_ROWS), KB = cdiv(K, TILE_K);
+    const size_t total = (size_t)RT * KB * (TILE_BYTES / 2);
+    hi.assign(total, __float2half(0.0f));
+    lo.assign(total, __float2half(0.0f));
+    for (int r = 0; r < rows; ++r)
+        for (int k = 0; k < K; ++k) {
+            const float v = transposed_src ? src[(size_t)k * ld + r] : src[(size_t)r * ld + k];
+            const __half h = __float2half_rn(v);
+            const __half l = __float2half_rn(v - __half2float(h));
+            const size_t off = image_offset_bytes(r, k, KB) / 2;
+            hi[off] = h;
+            lo[off] = l;
+        }
+}
+
+static int upload_half(mdf_model *m, __half **dst, const std::vector<__half> &src)
+{
+    MDF_CUDA(cudaMalloc((void **)dst, src.size() * sizeof(__half)));
+    m->owned.push_back(*dst);
+    MDF_CUDA(cudaMemcpy(*dst, src.data(), src.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    return MDF_OK;
+}
+
+int tc_model_init(mdf_model *m, const mdf_model_desc *d)
+{
+    TcModel *t = new TcModel();
+    m->tc = t;
+    // shape constraints of the tile-image GEMMs
+    bool ok = m->H % 64 == 0 && m->E % 128 == 0;
+    for (int l = 0; l < m->n_gc; ++l) ok = ok && m->gc[l] % 128 == 0;
+    if (!ok) return MDF_OK;           // engine stays unavailable; the SIMT engine serves this model
+    std::vector<__half> hi, lo;
+    build_image_host(d->lm_W, m->E, m->H, true, m->E, hi, lo);       // rows = E (n), k = H : lm_W[k][n]
+    MDF_TRY(upload_half(m, &t->lm_W[0], hi));
+    MDF_TRY(upload_half(m, &t->lm_W[1], lo));
+    int prev = m->E;
+    for (int l = 0; l < m->n_gc; ++l) {
+        build_image_host(d->gc_W[l], m->gc[l], prev, true, m->gc[l], hi, lo);   // rows = out, k = in : W[k][out]
+        MDF_TRY(upload_half(m, &t->gc_W[l][0], hi));
+        MDF_TRY(upload_half(m, &t->gc_W[l][1], lo));
+        prev = m->gc[l];
+    }
+    t->ok = true;
+    return MDF_OK;
+}
+
+void tc_model_free(mdf_model *m)
+{
+    delete static_cast<TcModel *>(m->tc);
+    m->tc = nullptr;
+}
+
+bool tc_available(const mdf_model *m) { return m->tc && static_cast<TcModel *>(m->tc)->ok; }
+
+// ------------------------------------------------------------------------------------------- small kernels
+// fp32 row-major [T, K] (packed residues) -> fp16 image over the padded axis; pad rows are zero
+__global__ void f32_to_image_kernel(const float *__restrict__ src, int K, const int *__restrict__ rowmap, int64_t Tp,
+                                    __half *__restrict__ img)
+{
+    const int KB = K / TILE_K;
+    const int64_t chunk = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;    // one 16-byte chunk (8 k) per thread
+    const int64_t total = Tp * (K / 8);
+    if (chunk >= total) return;
+    const int64_t r = chunk / (K / 8);
+    const int k = (int)(chunk % (K / 8)) * 8;
+    const int s = rowmap[r];
+    uint4 pk = make_uint4(0, 0, 0, 0);
+    if (s >= 0) {
+        const float4 a = *reinterpret_cast<const float4 *>(src + (size_t)s * K + k);
+        const float4 b = *reinterpret_cast<const float4 *>(src + (size_t)s * K + k + 4);
+        pk.x = pack_half2(a.x, a.y); pk.y = pack_half2(a.z, a.w);
+        pk.z = pack_half2(b.x, b.y); pk.w = pack_half2(b.z, b.w);
+    }
+    *reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(img) + image_offset_bytes(r, k, KB)) = pk;
+}
+
+// fp16 image over the padded axis -> fp32 row-major over packed residues (taps only)
+__global__ void image_to_f32_kernel(const __half *__restrict__ img, int K, const int *__restrict__ rowmap, int64_t Tp,
+                                    float *__restrict__ dst)
+{
+    const int KB = K / TILE_K;
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= Tp * K) return;
+    const int64_t r = e / K;
+    const int k = (int)(e % K);
+    const int s = rowmap[r];
+    if (s >= 0) dst[(size_t)s * K + k] = __half2float(*reinterpret_cast<const __half *>(
+                    reinterpret_cast<const uint8_t *>(img) + image_offset_bytes(r, k, KB)));
+}
+
+// padded-axis copies of the degree vector (0 on pads) and residue codes (0 on pads)
+__global__ void pad_vectors_kernel(int64_t Tp, const int *__restrict__ rowmap, const float *__restrict__ deg,
+                                   const uint8_t *__restrict__ idx, float *__restrict__ deg_pad, uint8_t *__restrict__ idx_pad)
+{
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= Tp) return;
+    const int s = rowmap[r];
+    deg_pad[r] = s >= 0 ? deg[s] : 0.0f;
+    idx_pad[r] = s >= 0 ? idx[s] : (uint8_t)0;
+}
+
+// bit-packed A_hat -> fp16 operand tiles.  One block per 128 x 64 tile.
+__global__ void __launch_bounds__(256)
+expand_adjacency_kernel(const int4 *__restrict__ tiles, const int64_t *__restrict__ seq_off,
+                        const uint32_t *__restrict__ packed, const int64_t *__restrict__ packed_off,
+                        __half *__restrict__ img)
+{
+    const int4 t = tiles[blockIdx.x];            // {protein, local m-tile, k-block, first tile of the protein}
+    const int p = t.x, lmt = t.y, kb = t.z;
+    const int L = (int)(seq_off[p + 1] - seq_off[p]);
+    const int rw = packed_row_words(L);
+    const int KBp = (L + TILE_K - 1) / TILE_K;
+    const uint32_t *A = packed + packed_off[p];
+    uint8_t *dst = reinterpret_cast<uint8_t *>(img) + ((size_t)t.w + (size_t)lmt * KBp + kb) * TILE_BYTES;
+    const int r = threadIdx.x >> 1, half = threadIdx.x & 1;     // row in tile, 32-column half
+    const int i = lmt * 128 + r;
+    const int w = kb * 2 + half;                                 // 32-bit word of the packed row
+    const uint32_t bits = (i < L && w < rw) ? A[(size_t)i * rw + w] : 0u;
+    const uint32_t one = 0x3C00u;                                // fp16 1.0
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint32_t b8 = (bits >> (8 * q)) & 0xFFu;
+        uint4 pk;
+        pk.x = ((b8 & 1u) ? one : 0u) | ((b8 & 2u) ? one << 16 : 0u);
+        pk.y = ((b8 & 4u) ? one : 0u) | ((b8 & 8u) ? one << 16 : 0u);
+        pk.z = ((b8 & 16u) ? one : 0u) | ((b8 & 32u) ? one << 16 : 0u);
+        pk.w = ((b8 & 64u) ? one : 0u) | ((b8 & 128u) ? one << 16 : 0u);
+        const int k8 = half * 4 + q;
+        *reinterpret_cast<uint4 *>(dst + (k8 * 16 + (r >> 3)) * 128 + (r & 7) * 16) = pk;
+    }
+}
+
+// pooled[p, goff + k] += sum over the valid rows of one 128-row tile of an X image
+__global__ void __launch_bounds__(256)
+pool_image_kernel(const __half *__restrict__ img, int K, const int *__restrict__ rowmap, const int *__restrict__ res_prot,
+                  float *__restrict__ pooled, int G, int goff)
+{
+    const int KB = K / TILE_K;
+    const int rt = blockIdx.x, kb = blockIdx.y;
+    const int s0 = rowmap[(int64_t)rt * 128];
+    if (s0 < 0) return;                                          // a tile starts on a valid row or is all padding
+    const int p = res_prot[s0];
+    const uint8_t *tile = reinterpret_cast<const uint8_t *>(img) + ((size_t)rt * KB + kb) * TILE_BYTES;
+    const int k8 = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float acc[8] = {};
+    for (int r = lane; r < 128; r += 32) {
+        if (rowmap[(int64_t)rt * 128 + r] < 0) continue;
+        const uint4 v = *reinterpret_cast<const uint4 *>(tile + (k8 * 16 + (r >> 3)) * 128 + (r & 7) * 16);
+        const __half2 *h = reinterpret_cast<const __half2 *>(&v);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float2 f = __half22float2(h[q]);
+            acc[2 * q] += f.x; acc[2 * q + 1] += f.y;
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+    }
+    if (lane == 0) {
+        float *dst = pooled + (size_t)p * G + goff + kb * TILE_K + k8 * 8;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) atomicAdd(dst + q, acc[q]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------- batch metadata
+static int build_meta(mdf_ctx *ctx, mdf_batch *b, TcBatchMeta &meta)
+{
+    const int n = b->n;
+    std::vector<int64_t> seg_off(n + 1, 0);
+    for (int p = 0; p < n; ++p) {
+        const int64_t L = b->h_seq_off[p + 1] - b->h_seq_off[p];
+        seg_off[p + 1] = seg_off[p] + (L + 127) / 128 * 128;
+    }
+    const int64_t Tp = (seg_off[n] + 255) / 256 * 256;
+    std::vector<int> rowmap((size_t)Tp, -1);
+    std::vector<int4> tile_info((size_t)(Tp / 128), make_int4(0, 0, 0, 0));
+    std::vector<int4> exp_tiles;
+    int tile_base = 0;
+    for (int p = 0; p < n; ++p) {
+        const int L = (int)(b->h_seq_off[p + 1] - b->h_seq_off[p]);
+        for (int i = 0; i < L; ++i) rowmap[(size_t)seg_off[p] + i] = (int)(b->h_seq_off[p] + i);
+        const int KBp = (L + TILE_K - 1) / TILE_K, MT = (L + 127) / 128;
+        for (int mt = 0; mt < MT; ++mt) {
+            tile_info[(size_t)(seg_off[p] / 128) + mt] = make_int4(tile_base + mt * KBp, (int)(seg_off[p] / TILE_K), KBp, p);
+            for (int kb = 0; kb < KBp; ++kb) exp_tiles.push_back(make_int4(p, mt, kb, tile_base));
+        }
+        tile_base += MT * KBp;
+    }
+    meta.Tp = Tp;
+    meta.m_tiles = (int)(Tp / 128);
+    meta.n_adj_tiles = tile_base;
+    const size_t bytes = align_up((size_t)Tp * 4, 256) + align_up(tile_info.size() * 16, 256) +
+                         align_up(exp_tiles.size() * 16 + 16, 256) + align_up((size_t)(n + 1) * 8, 256);
+    char *base = nullptr;
+    if (b->owns_memory) {
+        MDF_CUDA(cudaMalloc((void **)&base, bytes));
+        meta.persistent = true;
+    } else {
+        MDF_TRY(ctx->alloc((void **)&base, bytes));
+    }
+    meta.block = base;
+    meta.rowmap = (int *)base; base += align_up((size_t)Tp * 4, 256);
+    meta.tile_info = (int4 *)base; base += align_up(tile_info.size() * 16, 256);
+    meta.exp_tiles = (int4 *)base; base += align_up(exp_tiles.size() * 16 + 16, 256);
+    meta.seg_off = (int64_t *)base;
+    cudaStream_t s = ctx->stream;
+    MDF_CUDA(cudaMemcpyAsync(meta.rowmap, rowmap.data(), (size_t)Tp * 4, cudaMemcpyHostToDevice, s));
+    MDF_CUDA(cudaMemcpyAsync(meta.tile_info, tile_info.data(), tile_info.size() * 16, cudaMemcpyHostToDevice, s));
+    if (!exp_tiles.empty())
+        MDF_CUDA(cudaMemcpyAsync(meta.exp_tiles, exp_tiles.data(), exp_tiles.size() * 16, cudaMemcpyHostToDevice, s));
+    MDF_CUDA(cudaMemcpyAsync(meta.seg_off, seg_off.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, s));
+    MDF_CUDA(cudaStreamSynchronize(s));      // host vectors are pageable
+    return MDF_OK;
+}
+
+size_t tc_workspace_bytes(const mdf_model *m, int n, const int64_t *seq_off)
+{
+    int64_t rows = 0, tiles = 0;
+    for (int p = 0; p < n; ++p) {
+        const int64_t L = seq_off[p + 1] - seq_off[p];
+        rows += (L + 127) / 128 * 128;
+        tiles += ((L + 127) / 128) * ((L + TILE_K - 1) / TILE_K);
+    }
+    const int64_t T = seq_off[n];
+    const int64_t Tp = (rows + 255) / 256 * 256;
+    int gmax = 0;
+    for (int l = 0; l < m->n_gc; ++l) gmax = std::max(gmax, m->gc[l]);
+    size_t b = simt_workspace_bytes(m, n, T);        // the LSTM stack still runs on the fp32 kernels
+    auto add = [&](size_t x) { b += align_up(x, 256) + 256; };
+    add((size_t)Tp * 4 + (size_t)Tp / 128 * 16 + (size_t)(tiles + 1) * 16 + (size_t)(n + 1) * 8 + 1024);   // metadata
+    add((size_t)Tp * 4); add((size_t)Tp);             // deg_pad, idx_pad
+    add((size_t)Tp * m->H * 2);                       // H image
+    add((size_t)Tp * m->E * 2);                       // X0 image
+    add((size_t)Tp * gmax * 2); add((size_t)Tp * gmax * 2); add((size_t)Tp * gmax * 2);   // Y^T, X_a, X_b images
+    add((size_t)tiles * TILE_BYTES + 256);            // A_hat images
+    add((size_t)T * gmax * 4);                        // fp32 tap of the last GraphConv layer
+    return b + 8192;
+}
+
+// ------------------------------------------------------------------------------------------- forward
+int tc_forward(mdf_model *m, mdf_batch *b, int upto)
+{
+    mdf_ctx *ctx = m->ctx;
+    TcModel *tm = static_cast<TcModel *>(m->tc);
+    const int n = b->n;
+    const int64_t T = b->T;
+    if (n == 0) return MDF_OK;
+    cudaStream_t s = ctx->stream;
+
+    // ---- LSTM language model (fp32 kernels for now), outputs packed [T, H]
+    float *Hl[MDF_MAX_LSTM] = {nullptr}, *pre = nullptr, *Cst = nullptr;
+    unsigned *barrier = nullptr;
+    for (int l = 0; l < m->n_lstm; ++l) MDF_TRY(ctx->alloc_n(&Hl[l], (size_t)T * m->H));
+    MDF_TRY(ctx->alloc_n(&pre, (size_t)T * 4 * m->H));
+    MDF_TRY(ctx->alloc_n(&Cst, (size_t)n * m->H));
+    MDF_TRY(ctx->alloc_n(&barrier, 256));
+    MDF_TRY(simt_lstm_stack(m, b, Hl, pre, Cst, barrier));
+
+    // ---- padded-axis metadata
+    TcBatchMeta local_meta;
+    TcBatchMeta *meta = &local_meta;
+    if (b->owns_memory) {
+        if (!b->tc_meta) {
+            TcBatchMeta *pm = new TcBatchMeta();
+            int r = build_meta(ctx, b, *pm);
+            if (r != MDF_OK) { delete pm; return r; }
+            b->tc_meta = pm;
+        }
+        meta = static_cast<TcBatchMeta *>(b->tc_meta);
+    } else {
+        MDF_TRY(build_meta(ctx, b, local_meta));
+    }
+    const int64_t Tp = meta->Tp;
+    int gmax = 0;
+    for (int l = 0; l < m->n_gc; ++l) gmax = std::max(gmax, m->gc[l]);
+
+    float *deg_pad; uint8_t *idx_pad; __half *Himg, *X0img, *Yt, *Xa, *Xb, *Aimg;
+    MDF_TRY(ctx->alloc_n(&deg_pad, (size_t)Tp));
+    MDF_TRY(ctx->alloc_n(&idx_pad, (size_t)Tp));
+    MDF_TRY(ctx->alloc_n(&Himg, (size_t)Tp * m->H));
+    MDF_TRY(ctx->alloc_n(&X0img, (size_t)Tp * m->E));
+    MDF_TRY(ctx->alloc_n(&Yt, (size_t)Tp * gmax));
+    MDF_TRY(ctx->alloc_n(&Xa, (size_t)Tp * gmax));
+    MDF_TRY(ctx->alloc_n(&Xb, (size_t)Tp * gmax));
+    {
+        // A_hat images can exceed the static workspace estimate for very long proteins: check explicitly
+        const size_t need = (size_t)meta->n_adj_tiles * TILE_BYTES;
+        if (align_up(ctx->arena_top, 256) + need > ctx->arena_bytes) {
+            set_error("workspace arena too small for the adjacency images (%zu bytes)", need);
+            return MDF_ENOMEM;
+        }
+        MDF_TRY(ctx->alloc((void **)&Aimg, need + 256));
+    }
+    pad_vectors_kernel<<<(unsigned)cdiv64(Tp, 256), 256, 0, s>>>(Tp, meta->rowmap, b->d_deg, b->d_idx, deg_pad, idx_pad);
+    MDF_LAUNCH_CHECK(ctx);
+    {
+        const int64_t chunks = Tp * (m->H / 8);
+        f32_to_image_kernel<<<(unsigned)cdiv64(chunks, 256), 256, 0, s>>>(Hl[m->n_lstm - 1], m->H, meta->rowmap, Tp, Himg);
+        MDF_LAUNCH_CHECK(ctx);
+    }
+    // ---- embedding: X0 = relu(H2 . W_lm + b + W_aa[idx])
+    {
+        ProfScope ps(ctx, "embedding_gemm", 2.0 * T * m->H * m->E);
+        GemmArgs g;
+        g.A[0] = Himg; g.KB_A = m->H / TILE_K;
+        g.B[0] = tm->lm_W[0]; g.B[1] = tm->lm_W[1]; g.KB_B = m->H / TILE_K;
+        g.m_tiles = meta->m_tiles; g.n_tiles = m->E / 128; g.nkb = m->H / TILE_K;
+        g.out_img = X0img; g.KB_out = m->E / TILE_K;
+        g.bias = m->lm_b; g.gtab = m->aa_W; g.gidx = idx_pad; g.ldg = m->E;
+        MDF_TRY(launch_gemm_tc(ctx, EPI_IMG_EMBED, 128, 1, 2, g));
+    }
+    if (upto < 3) return MDF_OK;
+    // ---- adjacency operand tiles
+    if (meta->n_adj_tiles > 0) {
+        ProfScope ps(ctx, "expand_adjacency", 0.0);
+        expand_adjacency_kernel<<<meta->n_adj_tiles, 256, 0, s>>>(meta->exp_tiles, b->d_seq_off, b->d_packed,
+                                                                  b->d_packed_off, Aimg);
+        MDF_LAUNCH_CHECK(ctx);
+    }
+    MDF_CUDA(cudaMemsetAsync(b->d_pooled, 0, (size_t)n * m->G * sizeof(float), s));
+    double l2 = 0.0;
+    for (int p = 0; p < n; ++p) { const double L = (double)(b->h_seq_off[p + 1] - b->h_seq_off[p]); l2 += L * L; }
+    const __half *Xin = X0img;
+    int kin = m->E, goff = 0;
+    __half *Xlast = nullptr;
+    for (int l = 0; l < m->n_gc; ++l) {
+        const int gd = m->gc[l];
+        {
+            ProfScope ps(ctx, "graphconv_xw_gemm", 2.0 * T * kin * gd);
+            GemmArgs g;                                   // Y^T[gd x Tp] = W^T . X^T, columns scaled by d_j
+            g.A[0] = tm->gc_W[l][0]; g.A[1] = tm->gc_W[l][1]; g.KB_A = kin / TILE_K;
+            g.B[0] = Xin; g.KB_B = kin / TILE_K;
+            g.m_tiles = gd / 128; g.n_tiles = (int)(Tp / 256); g.nkb = kin / TILE_K;
+            g.out_img = Yt; g.KB_out = (int)(Tp / TILE_K);
+            g.colscale = deg_pad;
+            MDF_TRY(launch_gemm_tc(ctx, EPI_IMG_COLSCALE, 256, 2, 1, g));
+        }
+        __half *Xout = (l & 1) ? Xb : Xa;
+        {
+            ProfScope ps(ctx, "graphconv_adj", 2.0 * l2 * gd);
+            GemmArgs g;                                   // X_l[Tp x gd] = act(d_i * A_hat . Y + b), grouped per protein
+            g.A[0] = Aimg; g.B[0] = Yt; g.KB_B = (int)(Tp / TILE_K);
+            g.tile_info = meta->tile_info;
+            const int bn = gd % 256 == 0 ? 256 : 128;
+            g.m_tiles = meta->m_tiles; g.n_tiles = gd / bn;
+            g.out_img = Xout; g.KB_out = gd / TILE_K;
+            g.rowscale = deg_pad; g.bias = m->gc_b[l]; g.act = m->act; g.alpha = m->alpha;
+            MDF_TRY(launch_gemm_tc(ctx, EPI_IMG_ROWSCALE, bn, 1, 1, g));
+        }
+        {
+            ProfScope ps(ctx, "pool", 0.0);
+            dim3 grid(meta->m_tiles, gd / TILE_K);
+            pool_image_kernel<<<grid, 256, 0, s>>>(Xout, gd, meta->rowmap, b->d_res_prot, b->d_pooled, m->G, goff);
+            MDF_LAUNCH_CHECK(ctx);
+        }
+        Xin = Xout; kin = gd; goff += gd; Xlast = Xout;
+    }
+    // fp32 taps (debug / parity API): X0 and the last GraphConv output over packed residues
+    b->tap_x0 = nullptr;
+    {
+        float *tap = nullptr;
+        MDF_TRY(ctx->alloc_n(&tap, (size_t)T * m->gc[m->n_gc - 1]));
+        const int K = m->gc[m->n_gc - 1];
+        image_to_f32_kernel<<<(unsigned)cdiv64(Tp * K, 256), 256, 0, s>>>(Xlast, K, meta->rowmap, Tp, tap);
+        MDF_LAUNCH_CHECK(ctx);
+        b->tap_gc_last = tap;
+    }
+    if (upto < 4) return MDF_OK;
+    float *fc = nullptr, *logits = nullptr;
+    ProfScope ps(ctx, "head", 2.0 * n * ((double)m->G * m->F + (double)m->F * 2 * m->C));
+    MDF_TRY(ctx->alloc_n(&fc, (size_t)n * m->F));
+    MDF_TRY(ctx->alloc_n(&logits, (size_t)n * 2 * m->C));
+    return head_forward(m, n, b->d_pooled, fc, logits, b->d_scores);
+}
+
+void tc_batch_free(mdf_batch *b)
+{
+    if (!b->tc_meta) return;
+    TcBatchMeta *meta = static_cast<TcBatchMeta *>(b->tc_meta);
+    if (meta->persistent && meta->block) cudaFree(meta->block);
+    delete meta;
+    b->tc_meta = nullptr;
 }
 
 }  // namespace mdf

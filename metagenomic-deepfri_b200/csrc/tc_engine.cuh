@@ -7,7 +7,8 @@ namespace mdf {
 int tc_model_init(mdf_model *m, const mdf_model_desc *d);   // builds fp16 hi/lo operand images
 void tc_model_free(mdf_model *m);
 bool tc_available(const mdf_model *m);
-size_t tc_workspace_bytes(const mdf_model *m, int n, int64_t T);
+size_t tc_workspace_bytes(const mdf_model *m, int n, const int64_t *seq_off);
+void tc_batch_free(mdf_batch *b);
 int tc_forward(mdf_model *m, mdf_batch *b, int upto);
 
 }  // namespace mdf

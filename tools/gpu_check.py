@@ -166,8 +166,52 @@ def check_gcn():
     print("  launches:", ctx.launch_count)
 
 
+def check_tc():
+    section("tensor-core engine vs oracle / simt")
+    import tempfile
+    d = tempfile.mkdtemp()
+    path = os.path.join(d, "mf.onnx")
+    synth.write_gcn_model(path, synth.GCNConfig())
+    pred = predict.Predictor(path)
+    oracle = go.Predictor(path)
+    wl = synth.make_workload(10, 30, 330, seed=11, threshold=10.0)
+    cms = [co.build_align_contact_map(wl.gapped_query[i], wl.gapped_target[i], wl.coords[i], 10.0, 2) for i in range(len(wl))]
+    want = np.stack([oracle.forward_pass(wl.query_seqs[i], cms[i]) for i in range(len(wl))])
+    b = pred.upload(wl.query_seqs, wl.gapped_query, wl.gapped_target, wl.coords)
+    res = {}
+    for eng in ("simt", "tc"):
+        pred.set_engine(eng)
+        pred.run(b, 10.0, 2)
+        res[eng] = (pred.fetch_scores(b), pred.fetch(b, "pooled"), pred.fetch(b, "gc_last"))
+        print(f"engine {eng}: scores max err vs oracle {np.abs(res[eng][0] - want).max():.3e}  per-protein {np.abs(res[eng][0] - want).max(1)}")
+    for k, name in ((1, "pooled"), (2, "gc_last")):
+        a, t = res["simt"][k], res["tc"][k]
+        print(f"  {name}: tc vs simt max abs {np.abs(a - t).max():.3e} (absmax {np.abs(a).max():.3f}) nan {np.isnan(t).sum()}")
+    off = b.seq_off
+    a, t = res["simt"][2], res["tc"][2]
+    for i in range(len(wl)):
+        e = np.abs(a[off[i]:off[i + 1]] - t[off[i]:off[i + 1]])
+        print(f"    protein {i} L={off[i + 1] - off[i]} gc_last err max {e.max():.3e} rows>1e-2: {(e.max(1) > 1e-2).sum()} cols>1e-2: {(e.max(0) > 1e-2).sum()}")
+    pred.set_engine("tc")
+    wl = synth.config_workload(0, 1.0)
+    b2 = pred.upload(wl.query_seqs, wl.gapped_query, wl.gapped_target, wl.coords)
+    ctx = _lib.default_context()
+    for it in range(3):
+        ctx.synchronize(); t0 = time.time()
+        pred.run(b2, 10.0, 2)
+        ctx.synchronize(); dt = time.time() - t0
+        print(f"  tc run {it}: n={len(wl)} {dt * 1e3:.1f} ms -> {len(wl) / dt:.0f} proteins/s")
+    ctx.profile(True)
+    pred.run(b2, 10.0, 2)
+    for name, ms, units in ctx.profile_report():
+        print(f"    {name:24s} {ms:9.3f} ms  {units / (ms * 1e-3) / 1e12 if ms > 0 else 0:9.2f} T(units)/s")
+    ctx.profile(False)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["cmap", "gcn"]
+    if "tc" in which:
+        run(check_tc)
     if "cmap" in which:
         run(check_cmap)
     if "gcn" in which:
