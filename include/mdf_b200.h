@@ -50,6 +50,8 @@ int64_t mdf_ctx_launch_count(const mdf_ctx *ctx);
  * one "name\tmilliseconds\tunits" line per recorded stage (units = algorithmic flops or bytes). */
 int mdf_ctx_profile(mdf_ctx *ctx, int enable);
 int mdf_ctx_profile_report(mdf_ctx *ctx, char *buf, size_t capacity);
+/* also keep fp32 copies of the tensor-core engine's intermediates for mdf_batch_fetch (parity tests) */
+int mdf_ctx_set_debug_taps(mdf_ctx *ctx, int enable);
 
 static inline int mdf_packed_row_words(int L) { return ((L + 127) / 128) * 4; }
 

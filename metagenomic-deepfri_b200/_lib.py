@@ -61,6 +61,8 @@ def lib() -> C.CDLL:
         L.mdf_ctx_profile.restype = C.c_int
         L.mdf_ctx_profile_report.argtypes = [vp, C.c_char_p, C.c_size_t]
         L.mdf_ctx_profile_report.restype = C.c_int
+        L.mdf_ctx_set_debug_taps.argtypes = [vp, C.c_int]
+        L.mdf_ctx_set_debug_taps.restype = C.c_int
         L.mdf_pairwise_sqeuclidean.argtypes = [vp, c_f32p, C.c_int, C.c_int, c_f32p]
         L.mdf_contact_map_dense.argtypes = [vp, c_f32p, C.c_int, C.c_float, c_i32p]
         L.mdf_contact_map_sparse.argtypes = [vp, c_f32p, C.c_int, C.c_float, c_i32p, C.c_int64, c_i64p]
@@ -98,7 +100,7 @@ def lib() -> C.CDLL:
 
 EXPORTED_SYMBOLS = [
     "mdf_last_error", "mdf_version", "mdf_ctx_create", "mdf_ctx_destroy", "mdf_ctx_synchronize",
-    "mdf_ctx_launch_count", "mdf_ctx_profile", "mdf_ctx_profile_report", "mdf_pairwise_sqeuclidean", "mdf_contact_map_dense", "mdf_contact_map_sparse",
+    "mdf_ctx_launch_count", "mdf_ctx_profile", "mdf_ctx_profile_report", "mdf_ctx_set_debug_taps", "mdf_pairwise_sqeuclidean", "mdf_contact_map_dense", "mdf_contact_map_sparse",
     "mdf_align_contact_map", "mdf_cmap_build_transfer", "mdf_model_create", "mdf_model_destroy",
     "mdf_model_set_engine", "mdf_model_get_engine", "mdf_gcn_forward_dense", "mdf_gcn_forward_packed", "mdf_path_forward",
     "mdf_batch_upload", "mdf_batch_destroy", "mdf_path_run", "mdf_path_run_stages", "mdf_batch_fetch_scores",
@@ -159,6 +161,9 @@ class Context:
 
     def profile(self, enable: bool = True) -> None:
         check(lib().mdf_ctx_profile(self.handle, 1 if enable else 0))
+
+    def set_debug_taps(self, enable: bool = True) -> None:
+        check(lib().mdf_ctx_set_debug_taps(self.handle, 1 if enable else 0))
 
     def profile_report(self):
         """[(stage, milliseconds, algorithmic units)] recorded since profile(True)."""

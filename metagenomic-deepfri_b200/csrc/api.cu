@@ -151,6 +151,13 @@ extern "C" int mdf_ctx_profile(mdf_ctx *c, int enable)
     return MDF_OK;
 }
 
+extern "C" int mdf_ctx_set_debug_taps(mdf_ctx *c, int enable)
+{
+    MDF_REQUIRE(c, "ctx is NULL");
+    c->debug_taps = enable != 0;
+    return MDF_OK;
+}
+
 extern "C" int mdf_ctx_profile_report(mdf_ctx *c, char *buf, size_t capacity)
 {
     MDF_REQUIRE(c && buf && capacity > 0, "mdf_ctx_profile_report: bad arguments");

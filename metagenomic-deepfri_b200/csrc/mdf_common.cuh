@@ -63,6 +63,7 @@ struct mdf_ctx {
     // optional per-stage CUDA-event profiling (bench.py roofline leg)
     struct ProfEntry { const char *name; cudaEvent_t start, stop; double units; };
     bool profiling = false;
+    bool debug_taps = false;   // tensor-core engine: also produce fp32 copies of intermediates for mdf_batch_fetch
     std::vector<ProfEntry> prof;
 
     int alloc(void **out, size_t bytes);  // arena bump allocation (256 B aligned)

@@ -15,6 +15,7 @@
 #include <algorithm>
 
 #include "gemm_tc.cuh"
+#include "lstm_tc.cuh"
 #include "tc_engine.cuh"
 
 namespace mdf {
@@ -27,6 +28,10 @@ using namespace tc;
 struct TcModel {
     __half *lm_W[2] = {nullptr, nullptr};                  // [E rows x H k]  (B operand of the embed GEMM)
     __half *gc_W[MDF_MAX_GC][2] = {{nullptr}};             // [g rows x k_in] (A operand of X.W, transposed)
+    __half *lstm_R[MDF_MAX_LSTM] = {nullptr};              // [H/16][2][64 x H] resident recurrent slices (hi, lo)
+    float *lstm_tab = nullptr;                             // [H/16][26][16][4] layer-1 input table (bias folded)
+    __half *lstm_Win[MDF_MAX_LSTM][2] = {{nullptr}};       // layers >= 2: [4H rows in (unit,gate) order x H k]
+    float *lstm_bperm[MDF_MAX_LSTM] = {nullptr};           // layers >= 2: bias in (unit,gate) order
     bool ok = false;
 };
 
@@ -89,6 +94,57 @@ int tc_model_init(mdf_model *m, const mdf_model_desc *d)
         MDF_TRY(upload_half(m, &t->gc_W[l][1], lo));
         prev = m->gc[l];
     }
+    // ---- LSTM: resident recurrent slices, layer-1 table, input-GEMM weights of the upper layers
+    const int H = m->H, H4 = 4 * H, cpg = H / 16;
+    for (int l = 0; l < m->n_lstm; ++l) {
+        const float *R = d->lstm_R[l];                                  // ONNX [4H][H], gate order i,o,f,c
+        std::vector<__half> img((size_t)cpg * 2 * 64 * H, __float2half(0.0f));
+        for (int s = 0; s < cpg; ++s)
+            for (int r = 0; r < 64; ++r) {
+                const int gate = r >> 4, u = r & 15;
+                const float *src = R + (size_t)(gate * H + s * 16 + u) * H;
+                for (int k = 0; k < H; ++k) {
+                    const __half h = __float2half_rn(src[k]);
+                    const __half lo2 = __float2half_rn(src[k] - __half2float(h));
+                    const size_t off = (size_t)(((k >> 3) * 8 + (r >> 3)) * 128 + (r & 7) * 16 + (k & 7) * 2) / 2;
+                    img[((size_t)s * 2 + 0) * 64 * H + off] = h;
+                    img[((size_t)s * 2 + 1) * 64 * H + off] = lo2;
+                }
+            }
+        MDF_TRY(upload_half(m, &t->lstm_R[l], img));
+        std::vector<float> bsum(H4, 0.0f);
+        if (d->lstm_B[l])
+            for (int r = 0; r < H4; ++r) bsum[r] = d->lstm_B[l][r] + d->lstm_B[l][H4 + r];
+        if (l == 0) {
+            std::vector<float> tab((size_t)cpg * 26 * 64);
+            for (int s = 0; s < cpg; ++s)
+                for (int aa = 0; aa < 26; ++aa)
+                    for (int u = 0; u < 16; ++u)
+                        for (int gate = 0; gate < 4; ++gate) {
+                            const int row = gate * H + s * 16 + u;
+                            tab[(((size_t)s * 26 + aa) * 16 + u) * 4 + gate] = d->lstm_W[0][(size_t)row * m->I + aa] + bsum[row];
+                        }
+            MDF_CUDA(cudaMalloc((void **)&t->lstm_tab, tab.size() * sizeof(float)));
+            m->owned.push_back(t->lstm_tab);
+            MDF_CUDA(cudaMemcpy(t->lstm_tab, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice));
+        } else {
+            // B operand rows n' = unit*4 + gate  <-  ONNX row gate*H + unit ; k = input feature
+            std::vector<float> Wp((size_t)H4 * H), bp(H4);
+            for (int unit = 0; unit < H; ++unit)
+                for (int gate = 0; gate < 4; ++gate) {
+                    const int np = unit * 4 + gate, row = gate * H + unit;
+                    std::copy(d->lstm_W[l] + (size_t)row * H, d->lstm_W[l] + (size_t)(row + 1) * H, Wp.begin() + (size_t)np * H);
+                    bp[np] = bsum[row];
+                }
+            build_image_host(Wp.data(), H4, H, false, H, hi, lo);
+            MDF_TRY(upload_half(m, &t->lstm_Win[l][0], hi));
+            MDF_TRY(upload_half(m, &t->lstm_Win[l][1], lo));
+            MDF_CUDA(cudaMalloc((void **)&t->lstm_bperm[l], bp.size() * sizeof(float)));
+            m->owned.push_back(t->lstm_bperm[l]);
+            MDF_CUDA(cudaMemcpy(t->lstm_bperm[l], bp.data(), bp.size() * sizeof(float), cudaMemcpyHostToDevice));
+        }
+    }
+    if (lstm_tc_smem_bytes(H) > 227 * 1024) return MDF_OK;   // cannot keep the slices resident: engine unavailable
     t->ok = true;
     return MDF_OK;
 }
@@ -277,11 +333,14 @@ size_t tc_workspace_bytes(const mdf_model *m, int n, const int64_t *seq_off)
     const int64_t Tp = (rows + 255) / 256 * 256;
     int gmax = 0;
     for (int l = 0; l < m->n_gc; ++l) gmax = std::max(gmax, m->gc[l]);
-    size_t b = simt_workspace_bytes(m, n, T);        // the LSTM stack still runs on the fp32 kernels
+    size_t b = 0;
     auto add = [&](size_t x) { b += align_up(x, 256) + 256; };
+    for (int l = 0; l < m->n_lstm; ++l) add((size_t)Tp * m->H * 2);   // H_l images
+    add((size_t)Tp * 4 * m->H * 4);                   // input pre-activations of the upper LSTM layers
+    add(lstm_tc_scratch_bytes(m->ctx, m->H));
+    for (int l = 0; l < m->n_lstm; ++l) add((size_t)T * m->H * 4);    // optional fp32 taps
     add((size_t)Tp * 4 + (size_t)Tp / 128 * 16 + (size_t)(tiles + 1) * 16 + (size_t)(n + 1) * 8 + 1024);   // metadata
     add((size_t)Tp * 4); add((size_t)Tp);             // deg_pad, idx_pad
-    add((size_t)Tp * m->H * 2);                       // H image
     add((size_t)Tp * m->E * 2);                       // X0 image
     add((size_t)Tp * gmax * 2); add((size_t)Tp * gmax * 2); add((size_t)Tp * gmax * 2);   // Y^T, X_a, X_b images
     add((size_t)tiles * TILE_BYTES + 256);            // A_hat images
@@ -298,15 +357,6 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto)
     const int64_t T = b->T;
     if (n == 0) return MDF_OK;
     cudaStream_t s = ctx->stream;
-
-    // ---- LSTM language model (fp32 kernels for now), outputs packed [T, H]
-    float *Hl[MDF_MAX_LSTM] = {nullptr}, *pre = nullptr, *Cst = nullptr;
-    unsigned *barrier = nullptr;
-    for (int l = 0; l < m->n_lstm; ++l) MDF_TRY(ctx->alloc_n(&Hl[l], (size_t)T * m->H));
-    MDF_TRY(ctx->alloc_n(&pre, (size_t)T * 4 * m->H));
-    MDF_TRY(ctx->alloc_n(&Cst, (size_t)n * m->H));
-    MDF_TRY(ctx->alloc_n(&barrier, 256));
-    MDF_TRY(simt_lstm_stack(m, b, Hl, pre, Cst, barrier));
 
     // ---- padded-axis metadata
     TcBatchMeta local_meta;
@@ -326,30 +376,52 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto)
     int gmax = 0;
     for (int l = 0; l < m->n_gc; ++l) gmax = std::max(gmax, m->gc[l]);
 
-    float *deg_pad; uint8_t *idx_pad; __half *Himg, *X0img, *Yt, *Xa, *Xb, *Aimg;
+    float *deg_pad; uint8_t *idx_pad; __half *X0img, *Yt, *Xa, *Xb, *Aimg;
+    __half *Hlimg[MDF_MAX_LSTM] = {nullptr};
+    float *pre = nullptr;
+    void *scratch = nullptr;
     MDF_TRY(ctx->alloc_n(&deg_pad, (size_t)Tp));
     MDF_TRY(ctx->alloc_n(&idx_pad, (size_t)Tp));
-    MDF_TRY(ctx->alloc_n(&Himg, (size_t)Tp * m->H));
+    for (int l = 0; l < m->n_lstm; ++l) MDF_TRY(ctx->alloc_n(&Hlimg[l], (size_t)Tp * m->H));
+    if (m->n_lstm > 1) MDF_TRY(ctx->alloc_n(&pre, (size_t)Tp * 4 * m->H));
+    MDF_TRY(ctx->alloc(&scratch, lstm_tc_scratch_bytes(ctx, m->H)));
     MDF_TRY(ctx->alloc_n(&X0img, (size_t)Tp * m->E));
     MDF_TRY(ctx->alloc_n(&Yt, (size_t)Tp * gmax));
     MDF_TRY(ctx->alloc_n(&Xa, (size_t)Tp * gmax));
     MDF_TRY(ctx->alloc_n(&Xb, (size_t)Tp * gmax));
-    {
-        // A_hat images can exceed the static workspace estimate for very long proteins: check explicitly
-        const size_t need = (size_t)meta->n_adj_tiles * TILE_BYTES;
-        if (align_up(ctx->arena_top, 256) + need > ctx->arena_bytes) {
-            set_error("workspace arena too small for the adjacency images (%zu bytes)", need);
-            return MDF_ENOMEM;
-        }
-        MDF_TRY(ctx->alloc((void **)&Aimg, need + 256));
-    }
+    MDF_TRY(ctx->alloc((void **)&Aimg, (size_t)meta->n_adj_tiles * TILE_BYTES + 256));
     pad_vectors_kernel<<<(unsigned)cdiv64(Tp, 256), 256, 0, s>>>(Tp, meta->rowmap, b->d_deg, b->d_idx, deg_pad, idx_pad);
     MDF_LAUNCH_CHECK(ctx);
-    {
-        const int64_t chunks = Tp * (m->H / 8);
-        f32_to_image_kernel<<<(unsigned)cdiv64(chunks, 256), 256, 0, s>>>(Hl[m->n_lstm - 1], m->H, meta->rowmap, Tp, Himg);
-        MDF_LAUNCH_CHECK(ctx);
+
+    // ---- LSTM language model: persistent tcgen05 recurrence per layer, input GEMM between layers
+    for (int l = 0; l < m->n_lstm; ++l) {
+        if (l > 0) {
+            ProfScope ps(ctx, "lstm_input_gemm", 2.0 * T * 4 * m->H * m->H);
+            GemmArgs g;                                   // pre[Tp x 4H] = H_{l-1} . W_in^T + b   ([unit][gate] columns)
+            g.A[0] = Hlimg[l - 1]; g.KB_A = m->H / TILE_K;
+            g.B[0] = tm->lstm_Win[l][0]; g.B[1] = tm->lstm_Win[l][1]; g.KB_B = m->H / TILE_K;
+            g.m_tiles = meta->m_tiles; g.n_tiles = 4 * m->H / 128; g.nkb = m->H / TILE_K;
+            g.out_f32 = pre; g.ldc = 4 * m->H; g.bias = tm->lstm_bperm[l];
+            g.m_valid = (int)Tp; g.n_valid = 4 * m->H;
+            MDF_TRY(launch_gemm_tc(ctx, EPI_F32_BIAS, 128, 1, 2, g));
+        }
+        {
+            ProfScope ps(ctx, "lstm_recurrent", 2.0 * T * 4 * m->H * m->H);
+            MDF_TRY(launch_lstm_tc(ctx, m->H, n, tm->lstm_R[l], l == 0 ? tm->lstm_tab : nullptr, l > 0 ? pre : nullptr,
+                                   idx_pad, b->d_order, b->d_seq_off, meta->seg_off, Hlimg[l], scratch));
+        }
+        b->tap_h[l] = nullptr;
     }
+    if (ctx->debug_taps) {                                // fp32 copies of the LSTM outputs over packed residues
+        for (int l = 0; l < m->n_lstm; ++l) {
+            float *tap = nullptr;
+            MDF_TRY(ctx->alloc_n(&tap, (size_t)T * m->H));
+            image_to_f32_kernel<<<(unsigned)cdiv64(Tp * m->H, 256), 256, 0, s>>>(Hlimg[l], m->H, meta->rowmap, Tp, tap);
+            MDF_LAUNCH_CHECK(ctx);
+            b->tap_h[l] = tap;
+        }
+    }
+    __half *Himg = Hlimg[m->n_lstm - 1];
     // ---- embedding: X0 = relu(H2 . W_lm + b + W_aa[idx])
     {
         ProfScope ps(ctx, "embedding_gemm", 2.0 * T * m->H * m->E);

@@ -173,8 +173,9 @@ def check_tc():
     path = os.path.join(d, "mf.onnx")
     synth.write_gcn_model(path, synth.GCNConfig())
     pred = predict.Predictor(path)
+    _lib.default_context().set_debug_taps(True)
     oracle = go.Predictor(path)
-    wl = synth.make_workload(10, 30, 330, seed=11, threshold=10.0)
+    wl = synth.make_workload(int(os.environ.get("TC_N", "10")), 30, 330, seed=11, threshold=10.0)
     cms = [co.build_align_contact_map(wl.gapped_query[i], wl.gapped_target[i], wl.coords[i], 10.0, 2) for i in range(len(wl))]
     want = np.stack([oracle.forward_pass(wl.query_seqs[i], cms[i]) for i in range(len(wl))])
     b = pred.upload(wl.query_seqs, wl.gapped_query, wl.gapped_target, wl.coords)
@@ -182,8 +183,18 @@ def check_tc():
     for eng in ("simt", "tc"):
         pred.set_engine(eng)
         pred.run(b, 10.0, 2)
-        res[eng] = (pred.fetch_scores(b), pred.fetch(b, "pooled"), pred.fetch(b, "gc_last"))
+        res[eng] = (pred.fetch_scores(b), pred.fetch(b, "pooled"), pred.fetch(b, "gc_last"), pred.fetch(b, "lstm1"), pred.fetch(b, "lstm2"))
         print(f"engine {eng}: scores max err vs oracle {np.abs(res[eng][0] - want).max():.3e}  per-protein {np.abs(res[eng][0] - want).max(1)}")
+    for k, name in ((3, "lstm1"), (4, "lstm2")):
+        a, t = res["simt"][k], res["tc"][k]
+        e = np.abs(a - t)
+        print(f"  {name}: tc vs simt max abs {e.max():.3e} nan {np.isnan(t).sum()} rows>1e-2 {(e.max(1) > 1e-2).sum()}/{len(e)} cols>1e-2 {(e.max(0) > 1e-2).sum()}")
+        if e.max() > 1e-2:
+            off = b.seq_off
+            for i in range(len(wl)):
+                ei = e[off[i]:off[i + 1]]
+                bad_t = np.flatnonzero(ei.max(1) > 1e-2)
+                print(f"    protein {i} L={off[i+1]-off[i]} first bad step {bad_t[:3]} bad units at that step {np.flatnonzero(ei[bad_t[0]] > 1e-2)[:8] if len(bad_t) else ''}")
     for k, name in ((1, "pooled"), (2, "gc_last")):
         a, t = res["simt"][k], res["tc"][k]
         print(f"  {name}: tc vs simt max abs {np.abs(a - t).max():.3e} (absmax {np.abs(a).max():.3f}) nan {np.isnan(t).sum()}")
@@ -193,6 +204,7 @@ def check_tc():
         e = np.abs(a[off[i]:off[i + 1]] - t[off[i]:off[i + 1]])
         print(f"    protein {i} L={off[i + 1] - off[i]} gc_last err max {e.max():.3e} rows>1e-2: {(e.max(1) > 1e-2).sum()} cols>1e-2: {(e.max(0) > 1e-2).sum()}")
     pred.set_engine("tc")
+    _lib.default_context().set_debug_taps(False)
     wl = synth.config_workload(0, 1.0)
     b2 = pred.upload(wl.query_seqs, wl.gapped_query, wl.gapped_target, wl.coords)
     ctx = _lib.default_context()
