@@ -13,6 +13,7 @@
 //                         X_l image [Tp x g] = act(d_i * A_hat . Y + b)     (grouped per protein)
 //                         pooled[p] += sum over valid rows of X_l
 #include <algorithm>
+#include <stdlib.h>
 
 #include "gemm_tc.cuh"
 #include "lstm_tc.cuh"
@@ -29,6 +30,8 @@ struct TcModel {
     __half *lm_W[2] = {nullptr, nullptr};                  // [E rows x H k]  (B operand of the embed GEMM)
     __half *gc_W[MDF_MAX_GC][2] = {{nullptr}};             // [g rows x k_in] (A operand of X.W, transposed)
     __half *lstm_R[MDF_MAX_LSTM] = {nullptr};              // [H/16][2][64 x H] resident recurrent slices (hi, lo)
+    __half *lstm_Ralt[MDF_MAX_LSTM] = {nullptr};           // same, time-dithered pair (R_a, R_b = fp16(2R - R_a))
+    int lstm_alternate = 1;
     float *lstm_tab = nullptr;                             // [H/16][26][16][4] layer-1 input table (bias folded)
     __half *lstm_Win[MDF_MAX_LSTM][2] = {{nullptr}};       // layers >= 2: [4H rows in (unit,gate) order x H k]
     float *lstm_bperm[MDF_MAX_LSTM] = {nullptr};           // layers >= 2: bias in (unit,gate) order
@@ -79,6 +82,7 @@ int tc_model_init(mdf_model *m, const mdf_model_desc *d)
 {
     TcModel *t = new TcModel();
     m->tc = t;
+    if (const char *e = getenv("MDF_LSTM_HILO")) t->lstm_alternate = atoi(e) ? 0 : 1;   // 1 = hi+lo on every step
     // shape constraints of the tile-image GEMMs
     bool ok = m->H % 64 == 0 && m->E % 128 == 0;
     for (int l = 0; l < m->n_gc; ++l) ok = ok && m->gc[l] % 128 == 0;
@@ -98,7 +102,7 @@ int tc_model_init(mdf_model *m, const mdf_model_desc *d)
     const int H = m->H, H4 = 4 * H, cpg = H / 16;
     for (int l = 0; l < m->n_lstm; ++l) {
         const float *R = d->lstm_R[l];                                  // ONNX [4H][H], gate order i,o,f,c
-        std::vector<__half> img((size_t)cpg * 2 * 64 * H, __float2half(0.0f));
+        std::vector<__half> img((size_t)cpg * 2 * 64 * H, __float2half(0.0f)), alt((size_t)cpg * 2 * 64 * H, __float2half(0.0f));
         for (int s = 0; s < cpg; ++s)
             for (int r = 0; r < 64; ++r) {
                 const int gate = r >> 4, u = r & 15;
@@ -109,9 +113,12 @@ int tc_model_init(mdf_model *m, const mdf_model_desc *d)
                     const size_t off = (size_t)(((k >> 3) * 8 + (r >> 3)) * 128 + (r & 7) * 16 + (k & 7) * 2) / 2;
                     img[((size_t)s * 2 + 0) * 64 * H + off] = h;
                     img[((size_t)s * 2 + 1) * 64 * H + off] = lo2;
+                    alt[((size_t)s * 2 + 0) * 64 * H + off] = h;
+                    alt[((size_t)s * 2 + 1) * 64 * H + off] = __float2half_rn(2.0f * src[k] - __half2float(h));
                 }
             }
         MDF_TRY(upload_half(m, &t->lstm_R[l], img));
+        MDF_TRY(upload_half(m, &t->lstm_Ralt[l], alt));
         std::vector<float> bsum(H4, 0.0f);
         if (d->lstm_B[l])
             for (int r = 0; r < H4; ++r) bsum[r] = d->lstm_B[l][r] + d->lstm_B[l][H4 + r];
@@ -407,8 +414,9 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto)
         }
         {
             ProfScope ps(ctx, "lstm_recurrent", 2.0 * T * 4 * m->H * m->H);
-            MDF_TRY(launch_lstm_tc(ctx, m->H, n, tm->lstm_R[l], l == 0 ? tm->lstm_tab : nullptr, l > 0 ? pre : nullptr,
-                                   idx_pad, b->d_order, b->d_seq_off, meta->seg_off, Hlimg[l], scratch));
+            MDF_TRY(launch_lstm_tc(ctx, m->H, n, tm->lstm_alternate ? tm->lstm_Ralt[l] : tm->lstm_R[l],
+                                   l == 0 ? tm->lstm_tab : nullptr, l > 0 ? pre : nullptr, idx_pad, b->d_order,
+                                   b->d_seq_off, meta->seg_off, Hlimg[l], scratch, tm->lstm_alternate));
         }
         b->tap_h[l] = nullptr;
     }
