@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--proteins", type=int, default=1000, help="proteins per step per GPU")
     ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tc"])
-    ap.add_argument("--cpu-sample", type=int, default=48, help="proteins in the cpu_baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=400, help="proteins in the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 

@@ -4,7 +4,7 @@
 namespace mdf {
 namespace tc {
 
-constexpr int GEMM_THREADS = 192;   // warp 0 producer, warp 1 MMA, warps 2-5 epilogue
+constexpr int GEMM_THREADS = 320;   // warp 0 producer, warp 1 MMA, warps 2-9 epilogue
 
 struct __align__(8) GemmBarriers {
     uint64_t full[8], empty[8], tmem_full[2], tmem_empty[2];
@@ -33,7 +33,7 @@ gemm_tc_kernel(GemmArgs g, int a_terms, int b_terms, int stages)
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) { mbar_init(&bars.full[s], 1); mbar_init(&bars.empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&bars.tmem_full[s], 1); mbar_init(&bars.tmem_empty[s], 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&bars.tmem_full[s], 1); mbar_init(&bars.tmem_empty[s], 8); }
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc<2 * BN>(&bars.tmem_base);
@@ -47,7 +47,7 @@ gemm_tc_kernel(GemmArgs g, int a_terms, int b_terms, int stages)
         if (lane == 0) {
             int st = 0; uint32_t ph = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const int mt = t / g.n_tiles, nt = t % g.n_tiles;
+                const int mt = g.m_fastest ? t % g.m_tiles : t / g.n_tiles, nt = g.m_fastest ? t / g.m_tiles : t % g.n_tiles;
                 int a_tile0, b_kb0, nkb;
                 if (g.tile_info) { const int4 ti = g.tile_info[mt]; a_tile0 = ti.x; b_kb0 = ti.y; nkb = ti.z; }
                 else { a_tile0 = mt * g.KB_A; b_kb0 = 0; nkb = g.nkb; }
@@ -76,7 +76,7 @@ gemm_tc_kernel(GemmArgs g, int a_terms, int b_terms, int stages)
             int st = 0; uint32_t ph = 0;
             int acc = 0; uint32_t acc_ph = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const int mt = t / g.n_tiles;
+                const int mt = g.m_fastest ? t % g.m_tiles : t / g.n_tiles;
                 const int nkb = g.tile_info ? g.tile_info[mt].z : g.nkb;
                 mbar_wait(&bars.tmem_empty[acc], acc_ph ^ 1);
                 tcgen05_fence_after();
@@ -108,11 +108,12 @@ gemm_tc_kernel(GemmArgs g, int a_terms, int b_terms, int stages)
             }
         }
     } else {
-        // ===================== epilogue: TMEM -> registers -> global
+        // ===================== epilogue: TMEM -> registers -> global (8 warps: 4 lane blocks x 2 column halves)
         const int lb = (warp & 3) * 32;          // this warp's TMEM lane block = output rows
+        const int ch = (warp - 2) >> 2;          // column half handled by this warp
         int acc = 0; uint32_t acc_ph = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-            const int mt = t / g.n_tiles, nt = t % g.n_tiles;
+            const int mt = g.m_fastest ? t % g.m_tiles : t / g.n_tiles, nt = g.m_fastest ? t / g.m_tiles : t % g.n_tiles;
             const int nkb = g.tile_info ? g.tile_info[mt].z : g.nkb;
             mbar_wait(&bars.tmem_full[acc], acc_ph);
             tcgen05_fence_after();
@@ -122,8 +123,11 @@ gemm_tc_kernel(GemmArgs g, int a_terms, int b_terms, int stages)
             const float *grow = nullptr;
             if (EPI == EPI_IMG_ROWSCALE) rs = g.rowscale[m];
             if (EPI == EPI_IMG_EMBED) grow = g.gtab + (size_t)g.gidx[m] * g.ldg;
+            // byte address of (row m, k = 0) in the output image; a 32-column chunk stays inside one k-block
+            uint8_t *row_ptr = reinterpret_cast<uint8_t *>(g.out_img) + (size_t)(m >> 7) * g.KB_out * TILE_BYTES +
+                               (size_t)((((int)m & 127) >> 3) * 128 + ((int)m & 7) * 16);
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            for (int c0 = ch * (BN / 2); c0 < (ch + 1) * (BN / 2); c0 += 32) {
                 uint32_t r[32];
                 if (nkb > 0) {
                     tmem_ld_32x32b_x32(trow + c0, r);
@@ -140,7 +144,7 @@ gemm_tc_kernel(GemmArgs g, int a_terms, int b_terms, int stages)
                         for (int q = 0; q < 8; ++q) {
                             if (n0 + 4 * q < g.n_valid) {
                                 float4 v;
-                                const float4 b = g.bias ? *reinterpret_cast<const float4 *>(g.bias + n0 + 4 * q) : make_float4(0, 0, 0, 0);
+                                const float4 b = g.bias ? __ldg(reinterpret_cast<const float4 *>(g.bias + n0 + 4 * q)) : make_float4(0, 0, 0, 0);
                                 v.x = __uint_as_float(r[4 * q + 0]) + b.x; v.y = __uint_as_float(r[4 * q + 1]) + b.y;
                                 v.z = __uint_as_float(r[4 * q + 2]) + b.z; v.w = __uint_as_float(r[4 * q + 3]) + b.w;
                                 *reinterpret_cast<float4 *>(dst + 4 * q) = v;
@@ -153,32 +157,54 @@ gemm_tc_kernel(GemmArgs g, int a_terms, int b_terms, int stages)
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
                     if (EPI == EPI_IMG_COLSCALE) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float cs = g.colscale[n0 + j];
-                            v[j] = cs != 0.0f ? v[j] * cs : 0.0f;
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 cs = __ldg(reinterpret_cast<const float4 *>(g.colscale + n0 + 4 * q));
+                            v[4 * q + 0] = cs.x != 0.0f ? v[4 * q + 0] * cs.x : 0.0f;
+                            v[4 * q + 1] = cs.y != 0.0f ? v[4 * q + 1] * cs.y : 0.0f;
+                            v[4 * q + 2] = cs.z != 0.0f ? v[4 * q + 2] * cs.z : 0.0f;
+                            v[4 * q + 3] = cs.w != 0.0f ? v[4 * q + 3] * cs.w : 0.0f;
                         }
                     } else if (EPI == EPI_IMG_ROWSCALE) {
+                        if (g.bias) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            v[j] = act_f(v[j] * rs + (g.bias ? g.bias[n0 + j] : 0.0f), g.act, g.alpha);
+                            for (int q = 0; q < 8; ++q) {
+                                const float4 b = __ldg(reinterpret_cast<const float4 *>(g.bias + n0 + 4 * q));
+                                v[4 * q + 0] = fmaf(v[4 * q + 0], rs, b.x); v[4 * q + 1] = fmaf(v[4 * q + 1], rs, b.y);
+                                v[4 * q + 2] = fmaf(v[4 * q + 2], rs, b.z); v[4 * q + 3] = fmaf(v[4 * q + 3], rs, b.w);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] *= rs;
+                        }
+                        if (g.act == 1) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+                        } else if (g.act == 2) {
+                            const float alpha = g.alpha;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const float e = alpha * (__expf(fminf(v[j], 0.0f)) - 1.0f);   // branch-free ELU
+                                v[j] = v[j] > 0.0f ? v[j] : e;
+                            }
+                        }
                     } else if (EPI == EPI_IMG_EMBED) {
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
-                            const float4 b = *reinterpret_cast<const float4 *>(g.bias + n0 + 4 * q);
-                            const float4 a = *reinterpret_cast<const float4 *>(grow + n0 + 4 * q);
+                            const float4 b = __ldg(reinterpret_cast<const float4 *>(g.bias + n0 + 4 * q));
+                            const float4 a = __ldg(reinterpret_cast<const float4 *>(grow + n0 + 4 * q));
                             v[4 * q + 0] = fmaxf(v[4 * q + 0] + b.x + a.x, 0.0f);
                             v[4 * q + 1] = fmaxf(v[4 * q + 1] + b.y + a.y, 0.0f);
                             v[4 * q + 2] = fmaxf(v[4 * q + 2] + b.z + a.z, 0.0f);
                             v[4 * q + 3] = fmaxf(v[4 * q + 3] + b.w + a.w, 0.0f);
                         }
                     }
-                    uint8_t *img = reinterpret_cast<uint8_t *>(g.out_img);
+                    uint8_t *dst = row_ptr + (size_t)(n0 >> 6) * TILE_BYTES + (((n0 & 63) >> 3) * 2048);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         uint4 pk;
                         pk.x = pack_half2(v[8 * q + 0], v[8 * q + 1]); pk.y = pack_half2(v[8 * q + 2], v[8 * q + 3]);
                         pk.z = pack_half2(v[8 * q + 4], v[8 * q + 5]); pk.w = pack_half2(v[8 * q + 6], v[8 * q + 7]);
-                        *reinterpret_cast<uint4 *>(img + image_offset_bytes(m, n0 + 8 * q, g.KB_out)) = pk;
+                        *reinterpret_cast<uint4 *>(dst + q * 2048) = pk;
                     }
                 }
             }

@@ -23,6 +23,7 @@ struct GemmArgs {
     int KB_A = 0, KB_B = 0;          // k-blocks per row tile of the A / B images
     int m_tiles = 0, n_tiles = 0;    // output tiles (128 rows x BN columns)
     int nkb = 0;                     // k-blocks per output tile (regular case)
+    int m_fastest = 0;               // tile order: consecutive CTAs walk M first (B tile shared in L2) instead of N first
     // grouped case (adjacency product): per m-tile {A tile index of its first k-block, first k-block
     // on the B side, number of k-blocks, unused}
     const int4 *tile_info = nullptr;

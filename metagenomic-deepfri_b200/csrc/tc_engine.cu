@@ -465,6 +465,7 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto)
             g.m_tiles = gd / 128; g.n_tiles = (int)(Tp / 256); g.nkb = kin / TILE_K;
             g.out_img = Yt; g.KB_out = (int)(Tp / TILE_K);
             g.colscale = deg_pad;
+            g.m_fastest = 1;                              // the 4 feature tiles of one residue block run back to back: X is read once
             MDF_TRY(launch_gemm_tc(ctx, EPI_IMG_COLSCALE, 256, 2, 1, g));
         }
         __half *Xout = (l & 1) ? Xb : Xa;
@@ -489,7 +490,8 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto)
     }
     // fp32 taps (debug / parity API): X0 and the last GraphConv output over packed residues
     b->tap_x0 = nullptr;
-    {
+    b->tap_gc_last = nullptr;
+    if (ctx->debug_taps) {
         float *tap = nullptr;
         MDF_TRY(ctx->alloc_n(&tap, (size_t)T * m->gc[m->n_gc - 1]));
         const int K = m->gc[m->n_gc - 1];
