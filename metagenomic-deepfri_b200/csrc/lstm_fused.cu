@@ -1,0 +1,619 @@
+// Fused two-layer LSTM language model on tcgen05: both recurrences AND the layer-2 input projection in
+// one persistent kernel, run as a wavefront (layer 2 lags layer 1 by one step).
+//
+// Why: run layer by layer, the LM costs two latency-bound recurrences plus a [T x 4H] fp32 input GEMM
+// whose output (8 KiB per residue) has to be written to and re-read from HBM.  Here nothing but h
+// leaves the chip:
+//   * a group of CTAs covers the hidden units of BOTH layers; slice s owns units [64s, 64s+64), i.e.
+//     256 gate rows of each of the three matrices R1, W2 (layer-2 input weights), R2;
+//   * a CTA works on 128 proteins (MMA M, TMEM lane = protein).  The step operand (h1_{t-1} or h2_{t-2},
+//     [128 x H] fp16, 128 KiB) lives in shared memory as the MMA A operand in 8 k-block chunks; the
+//     weight slices stream from L2 through a bulk-TMA ring as the B operand.  The weight stream does not
+//     depend on h and is prefetched across ticks;
+//   * PAIR mode (default): two CTAs of a cluster share one weight slice through cta_group::2 MMAs
+//     (M = 256: 128 proteins from each CTA, N = 256 gate rows: 128 from each CTA's ring), so every SM
+//     pulls only HALF of the slice from L2 - the stream, not the tensor pipe, is what bounds the
+//     single-CTA form.  The leader CTA issues the MMAs; the peer relays its "data landed" barriers;
+//   * TMEM holds two accumulators of 256 columns: g1 = gates of layer 1, g2 = gates of layer 2
+//     (column = gate * 64 + unit), so an epilogue thread finds the four gates of its cells in its own lane;
+//   * tick tau:  P1: g1  = R1 . h1_{tau-1}          -> E1: cell update of layer 1, step tau   -> h1_tau
+//                P2: g2  = W2 . h1_{tau-1}             (same smem operand as P1)
+//                P3: g2 += R2 . h2_{tau-2}          -> E2: cell update of layer 2, step tau-1 -> h2_{tau-1}
+//     E1 overlaps P2/P3 and E2 overlaps the next tick's P1.  The operand chunks are recycled k-block by
+//     k-block (h2 chunk kb is fetched as soon as P2 has retired chunk kb of h1, and so on);
+//   * h_t is exchanged through a per-group buffer in global memory (L2) in operand-tile layout: slice s
+//     writes exactly k-block s of the next operand and bumps a per-tile release counter; every CTA's
+//     loader acquires the counter and bulk-copies the tile.
+// Layer-1 input pre-activations are a 26-row table slice resident in shared memory (one-hot matmul =
+// gather, bias folded); layer-2 biases likewise.  Weights are the time-dithered fp16 pair (R_a on odd
+// steps, R_b = fp16(2R - R_a) on even steps) - streaming makes the alternation free.
+#include <algorithm>
+#include <cuda.h>
+#include <stdlib.h>
+#include <vector>
+
+#include "gemm_tc.cuh"
+#include "lstm_tc.cuh"
+
+namespace mdf {
+namespace tc {
+
+constexpr int LF_M = 128;            // proteins per CTA
+constexpr int LF_U = 64;             // hidden units per slice
+constexpr int LF_STAGES = 4;         // weight ring (16 KiB tiles: 128 gate rows x 64 k)
+constexpr int LF_THREADS = 352;      // warp 0: weight producer, 1: operand loader, 2: MMA issuer / relay, 3-10: epilogue
+constexpr int LF_TAB_STRIDE = 260;   // floats per residue row of the layer-1 table slice (64 units x 4 gates + pad)
+constexpr int LF_MAX_KB = 8;
+
+struct LstmFusedArgs {
+    int H, n, n_groups, cpg, n_sub;
+    int cell_mode;            // 0: exp/rcp cell (fp32-accurate), 1: tanh.approx cell
+    const __half *W[3][2];    // R1, W2, R2: [4H rows (slice, gate, unit) x H] operand images, indexed by step parity
+    const float *tab;         // [26][H][4] layer-1 pre-activation table ([unit][gate] order, bias folded)
+    const float *b2;          // [H][4] layer-2 bias ([unit][gate] order)
+    const uint8_t *idx_pad;   // [Tp]
+    const int *order;         // [n] protein ids, length-descending
+    const int64_t *seq_off;   // [n+1]
+    const int64_t *seg_off;   // [n+1] padded row offsets
+    __half *H1img;            // [Tp x H] layer-1 output image (debug taps only) or nullptr
+    __half *H2img;            // [Tp x H] layer-2 output image
+    __half *hbuf;             // [n_groups][halves][2 layers][2 parities][128 x H] exchange buffers (operand tile images)
+    unsigned *flags;          // [n_groups][halves][2 layers][LF_MAX_KB] release counters, one per operand tile
+    long long *trace;         // optional clock64 stamps of CTA 0 (MDF_LSTM_TRACE=1)
+    int trace_items;
+    // PAIR mode: flat [bytes/512][256] u16 tensor maps (one 16 KiB tile = a [32 x 256] box) over the six weight
+    // images and the exchange buffer - tensor-map TMA is the form that can credit the leader CTA's barrier
+    alignas(64) CUtensorMap tmW[3][2];
+    alignas(64) CUtensorMap tmH;
+};
+
+__device__ __forceinline__ unsigned lf_ld_acquire(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void lf_red_release(unsigned *p, unsigned v)
+{
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void lf_bar_sync(int id, int nthreads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// LSTM cell, ONNX gate order (i, o, f, g).
+// MODE 0: shared denominators, 5 ex2 + 2 rcp, errors ~1e-7:
+//   c' = sigmoid(f) c + sigmoid(i) tanh(g) = [c B C + (C - 2) A] / (A B C),  A = 1+e^-f, B = 1+e^-i, C = e^2g + 1
+//   h  = sigmoid(o) tanh(c')             = (E - 2) / (D E),                  D = 1+e^-o, E = e^2c' + 1
+//   The exponents are capped at 2^40 so that the triple products stay finite (sigmoid/tanh change by < 1e-12).
+// MODE 1: 5 tanh.approx (sigmoid(x) = 0.5 + 0.5 tanh(x/2)); absolute error ~2^-11 per activation.
+template <int MODE>
+__device__ __forceinline__ void lf_cell(float xi, float xo, float xf, float xg, float c_prev, float &c_out, float &h_out)
+{
+    if (MODE == 0) {
+        constexpr float L2E = 1.4426950408889634f;
+        const float A = 1.0f + ex2_ftz(fminf(xf * -L2E, 40.0f));
+        const float B = 1.0f + ex2_ftz(fminf(xi * -L2E, 40.0f));
+        const float C = 1.0f + ex2_ftz(fminf(xg * (2.0f * L2E), 40.0f));
+        const float BC = B * C;
+        const float c = fmaf(C - 2.0f, A, c_prev * BC) * rcp_ftz(A * BC);
+        const float D = 1.0f + ex2_ftz(fminf(xo * -L2E, 40.0f));
+        const float E = 1.0f + ex2_ftz(fminf(c * (2.0f * L2E), 40.0f));
+        c_out = c;
+        h_out = (E - 2.0f) * rcp_ftz(D * E);
+    } else {
+        const float si = fmaf(tanh_approx(0.5f * xi), 0.5f, 0.5f);
+        const float sf = fmaf(tanh_approx(0.5f * xf), 0.5f, 0.5f);
+        const float so = fmaf(tanh_approx(0.5f * xo), 0.5f, 0.5f);
+        const float c = fmaf(sf, c_prev, si * tanh_approx(xg));
+        c_out = c;
+        h_out = so * tanh_approx(c);
+    }
+}
+
+struct LfSub {
+    int sb, Lmax;
+};
+template <bool PAIR>
+__device__ __forceinline__ LfSub lf_next(int &cursor, const LstmFusedArgs &a)
+{
+    LfSub r{-1, 0};
+    if (cursor < a.n_sub) {
+        const int p0 = a.order[cursor * (PAIR ? 2 * LF_M : LF_M)];   // longest protein of the sub-batch
+        r.Lmax = (int)(a.seq_off[p0 + 1] - a.seq_off[p0]);
+        if (r.Lmax > 0) r.sb = cursor;                               // sorted descending: zero length = nothing left
+        cursor += a.n_groups;
+    }
+    return r;
+}
+
+// one layer's cell update for this thread's 32 units: TMEM (gates) + pre-activations -> c, h -> exchange tile (+ image)
+template <int MODE>
+__device__ __forceinline__ void lf_epilogue(uint32_t tgates, bool have_gates, bool active, const float4 *pre4, float (&cst)[32],
+                                            uint8_t *xd, uint8_t *id)
+{
+#pragma unroll
+    for (int c0 = 0; c0 < 32; c0 += 8) {
+        uint32_t gi[8], go[8], gf[8], gc[8];
+        if (have_gates) {                                     // warp-uniform: tcgen05.ld is .sync.aligned
+            tmem_ld_32x32b_x8(tgates + 0 * 64 + c0, gi);
+            tmem_ld_32x32b_x8(tgates + 1 * 64 + c0, go);
+            tmem_ld_32x32b_x8(tgates + 2 * 64 + c0, gf);
+            tmem_ld_32x32b_x8(tgates + 3 * 64 + c0, gc);
+            tmem_ld_wait();
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) gi[j] = go[j] = gf[j] = gc[j] = 0u;
+        }
+        if (active) {
+            float hv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 pre = pre4[c0 + j];
+                float c;
+                lf_cell<MODE>(__uint_as_float(gi[j]) + pre.x, __uint_as_float(go[j]) + pre.y, __uint_as_float(gf[j]) + pre.z,
+                              __uint_as_float(gc[j]) + pre.w, cst[c0 + j], c, hv[j]);
+                cst[c0 + j] = c;
+            }
+            uint4 pk;
+            pk.x = pack_half2(hv[0], hv[1]); pk.y = pack_half2(hv[2], hv[3]);
+            pk.z = pack_half2(hv[4], hv[5]); pk.w = pack_half2(hv[6], hv[7]);
+            *reinterpret_cast<uint4 *>(xd + (c0 >> 3) * 2048) = pk;
+            if (id) *reinterpret_cast<uint4 *>(id + (c0 >> 3) * 2048) = pk;
+        }
+    }
+}
+
+template <bool PAIR, int MODE>
+__global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_constant__ LstmFusedArgs a)
+{
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ uint64_t bar_full[LF_STAGES], bar_empty[LF_STAGES];     // weight ring
+    __shared__ uint64_t bar_hfull[LF_MAX_KB], bar_hfree[LF_MAX_KB];    // operand chunks
+    __shared__ uint64_t bar_gfull[2], bar_gfree[2];                    // TMEM accumulators g1, g2
+    __shared__ uint32_t tmem_slot;
+
+    constexpr int HALVES = PAIR ? 2 : 1;
+    constexpr int TPK = PAIR ? 1 : 2;                                  // weight tiles this CTA loads per k-block
+    const int H = a.H, KB = H / TILE_K;
+    const int cta_in_group = blockIdx.x % (a.cpg * HALVES);
+    const int g = blockIdx.x / (a.cpg * HALVES);
+    const int s = PAIR ? cta_in_group >> 1 : cta_in_group;             // unit slice
+    const int r = PAIR ? (int)cluster_ctarank() : 0;                   // protein half = rank in the CTA pair
+    const bool leader = r == 0;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *sH = smem;                                               // [KB][16 KiB] operand, rows = proteins
+    uint8_t *sW = sH + (size_t)KB * TILE_BYTES;                       // [LF_STAGES][16 KiB] weight ring
+    float *tabS = reinterpret_cast<float *>(sW + (size_t)LF_STAGES * TILE_BYTES);   // [26][LF_TAB_STRIDE]
+    float *b2S = tabS + 26 * LF_TAB_STRIDE;                           // [64][4]
+    const uint32_t h_bytes = (uint32_t)KB * TILE_BYTES;
+
+    // ---- one-time setup
+    for (int e = tid; e < 26 * LF_U; e += LF_THREADS) {               // one float4 (unit) per iteration
+        const int aa = e / LF_U, u = e % LF_U;
+        *reinterpret_cast<float4 *>(tabS + aa * LF_TAB_STRIDE + u * 4) =
+            __ldg(reinterpret_cast<const float4 *>(a.tab) + (size_t)aa * H + s * LF_U + u);
+    }
+    for (int e = tid; e < LF_U; e += LF_THREADS)
+        *reinterpret_cast<float4 *>(b2S + e * 4) = __ldg(reinterpret_cast<const float4 *>(a.b2) + s * LF_U + e);
+    if (tid == 0) {
+        // PAIR: only the leader's full barriers are used; they collect the bytes of both CTAs' TMA loads
+        for (int i = 0; i < LF_STAGES; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
+        for (int i = 0; i < LF_MAX_KB; ++i) { mbar_init(&bar_hfull[i], 1); mbar_init(&bar_hfree[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&bar_gfull[i], 1); mbar_init(&bar_gfree[i], 8 * HALVES); }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        if (PAIR) tmem_alloc_pair<512>(&tmem_slot); else tmem_alloc<512>(&tmem_slot);
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (PAIR) cluster_sync_all();          // the peer's barriers and TMEM exist before anything crosses the pair
+    tcgen05_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    unsigned *flags = a.flags + (size_t)(g * HALVES + r) * 2 * LF_MAX_KB;
+    uint8_t *hb = reinterpret_cast<uint8_t *>(a.hbuf) + (size_t)(g * HALVES + r) * 4 * h_bytes;    // [layer][parity][h_bytes]
+
+    if (warp == 0) {
+        // =========================================================== weight producer
+        if (lane == 0) {
+            int st = 0; uint32_t ph = 0;
+            int fill = 0;
+            const bool tr2 = a.trace && blockIdx.x < 2;
+            long long *t2 = a.trace + (size_t)a.trace_items * 8 + (size_t)blockIdx.x * a.trace_items * 2;
+            auto stream = [&](int mi, int par) {
+                const uint8_t *src = reinterpret_cast<const uint8_t *>(a.W[mi][par]) + (size_t)(2 * s) * KB * TILE_BYTES;
+                for (int kb = 0; kb < KB; ++kb)
+                    for (int jj = 0; jj < TPK; ++jj) {
+                        const int j = PAIR ? r : jj;                  // row tile of the slice: gates {2j, 2j+1}
+                        mbar_wait(&bar_empty[st], ph ^ 1);
+                        if (tr2 && fill < a.trace_items) t2[fill * 2] = clock64();
+                        ++fill;
+                        if (PAIR) {
+                            if (leader) mbar_arrive_expect_tx(&bar_full[st], 2 * TILE_BYTES);     // my rows + the peer's rows
+                            tma_tile_g2s_pair(sW + (size_t)st * TILE_BYTES, &a.tmW[mi][par], (((2 * s + j) * KB) + kb) * (TILE_BYTES / 512),
+                                              &bar_full[st]);
+                        } else {
+                            mbar_arrive_expect_tx(&bar_full[st], TILE_BYTES);
+                            bulk_g2s(sW + (size_t)st * TILE_BYTES, src + ((size_t)j * KB + kb) * TILE_BYTES, TILE_BYTES, &bar_full[st]);
+                        }
+                        if (++st == LF_STAGES) { st = 0; ph ^= 1; }
+                    }
+            };
+            int cursor = g;
+            for (LfSub sbt = lf_next<PAIR>(cursor, a); sbt.sb >= 0; sbt = lf_next<PAIR>(cursor, a)) {
+                for (int tau = 0; tau <= sbt.Lmax; ++tau) {
+                    if (tau >= 1 && tau < sbt.Lmax) stream(0, tau & 1);               // P1: layer-1 step tau
+                    if (tau >= 1) stream(1, (tau - 1) & 1);                           // P2: layer-2 step tau-1, input part
+                    if (tau >= 2) stream(2, (tau - 1) & 1);                           // P3: layer-2 step tau-1, recurrent part
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =========================================================== operand loader (h1_{tau-1}, then h2_{tau-2})
+        if (lane == 0) {
+            uint32_t hph = 0;
+            unsigned done = 0;
+            auto load = [&](int layer, int step, unsigned target) {
+                const uint8_t *src = hb + (size_t)(layer * 2 + (step & 1)) * h_bytes;
+                for (int kb = 0; kb < KB; ++kb) {
+                    mbar_wait(&bar_hfree[kb], hph ^ 1);                  // the MMAs reading the previous operand retired
+                    const unsigned *f = flags + layer * LF_MAX_KB + kb;
+                    while (lf_ld_acquire(f) < target) { }                // slice kb of the group has published this tile
+                    asm volatile("fence.proxy.async;" ::: "memory");     // peers' generic stores -> this async-proxy read
+                    if (PAIR) {
+                        if (leader) mbar_arrive_expect_tx(&bar_hfull[kb], 2 * TILE_BYTES);       // my proteins + the peer's
+                        tma_tile_g2s_pair(sH + (size_t)kb * TILE_BYTES, &a.tmH,
+                                          (int32_t)((size_t)(src - reinterpret_cast<const uint8_t *>(a.hbuf)) / 512) + kb * (TILE_BYTES / 512),
+                                          &bar_hfull[kb]);
+                    } else {
+                        mbar_arrive_expect_tx(&bar_hfull[kb], TILE_BYTES);
+                        bulk_g2s(sH + (size_t)kb * TILE_BYTES, src + (size_t)kb * TILE_BYTES, TILE_BYTES, &bar_hfull[kb]);
+                    }
+                }
+                hph ^= 1;
+            };
+            int cursor = g;
+            for (LfSub sbt = lf_next<PAIR>(cursor, a); sbt.sb >= 0; sbt = lf_next<PAIR>(cursor, a)) {
+                for (int tau = 1; tau <= sbt.Lmax; ++tau) {
+                    load(0, tau - 1, done + (unsigned)tau);                        // h1_{tau-1}: published at tick tau-1
+                    if (tau >= 2) load(1, tau - 2, done + (unsigned)(tau - 1));    // h2_{tau-2}: published at tick tau-1
+                }
+                done += (unsigned)sbt.Lmax;
+            }
+        }
+    } else if (warp == 2) {
+        // =========================================================== MMA issuer (PAIR: leader CTA only)
+        if (lane == 0 && leader) {
+            constexpr uint32_t idesc = PAIR ? umma_idesc_f16(256, 256) : umma_idesc_f16(128, 128);
+            int st = 0; uint32_t ph = 0, hph = 0;
+            uint32_t rounds[2] = {0, 0};
+            const uint32_t sh_addr = smem_u32(sH);
+            int item = 0;
+            int fill = 0;
+            const bool tr2 = a.trace && blockIdx.x < 2;
+            long long *t2 = a.trace + (size_t)a.trace_items * 8 + (size_t)blockIdx.x * a.trace_items * 2;
+            // one pass over the operand in shared memory: gates[acc] (+)= W_slice . operand
+            auto pass = [&](uint32_t d0, bool accumulate, bool wait_h, bool release_chunks) {
+                for (int kb = 0; kb < KB; ++kb) {
+                    if (wait_h) mbar_wait(&bar_hfull[kb], hph);
+                    tcgen05_fence_after();
+                    const uint64_t hd = umma_smem_desc(sh_addr + kb * TILE_BYTES, TILE_LBO, TILE_SBO);   // A: proteins x 64 k
+                    for (int jj = 0; jj < TPK; ++jj) {
+                        mbar_wait(&bar_full[st], ph);
+                        if (tr2 && fill < a.trace_items) t2[fill * 2 + 1] = clock64();
+                        ++fill;
+                        tcgen05_fence_after();
+                        const uint64_t wd = umma_smem_desc(smem_u32(sW + (size_t)st * TILE_BYTES), TILE_LBO, TILE_SBO);   // B: gate rows x 64 k
+#pragma unroll
+                        for (int ks = 0; ks < TILE_K / 16; ++ks) {
+                            if (PAIR)
+                                umma_f16_pair(tmem_base + d0, hd + (uint64_t)(ks * 256), wd + (uint64_t)(ks * 256), idesc,
+                                              accumulate || (kb | ks) != 0);
+                            else
+                                umma_f16(tmem_base + d0 + (uint32_t)(jj * 128), hd + (uint64_t)(ks * 256), wd + (uint64_t)(ks * 256), idesc,
+                                         accumulate || (kb | ks) != 0);
+                        }
+                        if (PAIR) umma_commit_pair(&bar_empty[st], 3); else umma_commit(&bar_empty[st]);
+                        if (++st == LF_STAGES) { st = 0; ph ^= 1; }
+                    }
+                    if (release_chunks) {
+                        if (PAIR) umma_commit_pair(&bar_hfree[kb], 3); else umma_commit(&bar_hfree[kb]);
+                    }
+                }
+            };
+            auto wait_gfree = [&](int acc) {
+                mbar_wait(&bar_gfree[acc], (rounds[acc] & 1) ^ 1);
+                tcgen05_fence_after();
+            };
+            auto commit_gfull = [&](int acc) {
+                if (PAIR) umma_commit_pair(&bar_gfull[acc], 3); else umma_commit(&bar_gfull[acc]);
+                ++rounds[acc];
+            };
+            int cursor = g;
+            for (LfSub sbt = lf_next<PAIR>(cursor, a); sbt.sb >= 0; sbt = lf_next<PAIR>(cursor, a)) {
+                for (int tau = 1; tau <= sbt.Lmax; ++tau, ++item) {
+                    const bool tr = a.trace && blockIdx.x == 0 && item < a.trace_items;
+                    if (tr) a.trace[item * 8 + 0] = clock64();
+                    const bool p1 = tau < sbt.Lmax;
+                    if (p1) {                                             // P1
+                        wait_gfree(0);
+                        pass(0u, false, true, false);
+                        commit_gfull(0);
+                    }
+                    if (tr) a.trace[item * 8 + 1] = clock64();
+                    wait_gfree(1);                                        // P2
+                    pass(256u, false, !p1, true);
+                    hph ^= 1;
+                    if (tr) a.trace[item * 8 + 2] = clock64();
+                    if (tau >= 2) {                                       // P3
+                        pass(256u, true, true, true);
+                        hph ^= 1;
+                    }
+                    commit_gfull(1);
+                    if (tr) a.trace[item * 8 + 3] = clock64();
+                }
+            }
+        }
+    } else {
+        // =========================================================== epilogue: thread = one protein x 32 units x both layers
+        const int et = tid - 96;
+        const int q = warp & 3;                                // TMEM lane quarter this warp may access
+        const int half = (warp - 3) >> 2;                      // units [32*half, 32*half + 32) of this slice
+        const int p = q * 32 + lane;                           // protein inside this CTA's 128 = TMEM lane
+        const int ub = half * 32;                              // first unit (within the slice) of this thread
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)ub;
+        // byte offset of (row p, k-chunk ub/8) inside an exchange tile
+        const uint32_t xoff = (uint32_t)((ub >> 3) * 2048 + (p >> 3) * 128 + (p & 7) * 16);
+        uint8_t *x1 = hb + (size_t)s * TILE_BYTES + xoff;                       // layer 1, parity 0
+        uint8_t *x2 = hb + (size_t)2 * h_bytes + (size_t)s * TILE_BYTES + xoff; // layer 2, parity 0
+        float c1[32], c2[32];
+        unsigned done = 0;
+        uint32_t rounds[2] = {0, 0};
+        int cursor = g;
+        int item = 0;
+        for (LfSub sbt = lf_next<PAIR>(cursor, a); sbt.sb >= 0; sbt = lf_next<PAIR>(cursor, a)) {
+            // The exchange buffers are reused: every CTA of this half-group must have finished the previous
+            // sub-batch (its last operand loads precede its last layer-2 publish) before tick 0 writes them.
+            if (et < KB) {
+                const unsigned *f = flags + LF_MAX_KB + et;
+                while (lf_ld_acquire(f) < done) { }
+            }
+            lf_bar_sync(1, 256);
+            int len = 0;
+            long long row0 = 0;
+            {
+                const int j = sbt.sb * (HALVES * LF_M) + r * LF_M + p;
+                if (j < a.n) {
+                    const int pid = a.order[j];
+                    len = (int)(a.seq_off[pid + 1] - a.seq_off[pid]);
+                    row0 = a.seg_off[pid];
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { c1[j] = 0.0f; c2[j] = 0.0f; }
+            int aa_next = len > 0 ? (int)a.idx_pad[row0] : 0;
+            for (int tau = 0; tau <= sbt.Lmax; ++tau) {
+                const bool tr = a.trace && blockIdx.x == 0 && et == 0 && tau >= 1 && item < a.trace_items;
+                // ---------------------------------------------------------------- E1: layer 1, step tau
+                if (tau < sbt.Lmax) {
+                    const bool active = tau < len;
+                    const int aa = aa_next;
+                    if (tau + 1 < len) aa_next = (int)a.idx_pad[row0 + tau + 1];
+                    const float4 *pre4 = reinterpret_cast<const float4 *>(tabS + aa * LF_TAB_STRIDE + ub * 4);
+                    if (tau >= 1) {
+                        mbar_wait(&bar_gfull[0], rounds[0] & 1);
+                        ++rounds[0];
+                        tcgen05_fence_after();
+                    }
+                    if (tr) a.trace[item * 8 + 4] = clock64();
+                    uint8_t *id = nullptr;
+                    if (a.H1img) {
+                        const long long row = row0 + tau;
+                        id = reinterpret_cast<uint8_t *>(a.H1img) + ((size_t)(row >> 7) * KB + s) * TILE_BYTES +
+                             (size_t)((ub >> 3) * 2048 + (((int)row & 127) >> 3) * 128 + ((int)row & 7) * 16);
+                    }
+                    lf_epilogue<MODE>(trow, tau >= 1, active, pre4, c1, x1 + (size_t)(tau & 1) * h_bytes, id);
+                    if (tau >= 1) {
+                        tcgen05_fence_before();
+                        __syncwarp();
+                        if (lane == 0) {                                  // g1 drained by this warp
+                            if (PAIR && !leader) mbar_arrive_remote(&bar_gfree[0], 0); else mbar_arrive(&bar_gfree[0]);
+                        }
+                    }
+                    lf_bar_sync(1, 256);                                  // all h1_tau stores of this CTA issued
+                    if (et == 0) lf_red_release(flags + s, 1u);
+                    if (tr) a.trace[item * 8 + 5] = clock64();
+                }
+                // ---------------------------------------------------------------- E2: layer 2, step tau-1
+                if (tau >= 1) {
+                    const int t2 = tau - 1;
+                    const bool active = t2 < len;
+                    mbar_wait(&bar_gfull[1], rounds[1] & 1);
+                    ++rounds[1];
+                    tcgen05_fence_after();
+                    if (tr) a.trace[item * 8 + 6] = clock64();
+                    const long long row = row0 + t2;
+                    uint8_t *id = reinterpret_cast<uint8_t *>(a.H2img) + ((size_t)(row >> 7) * KB + s) * TILE_BYTES +
+                                  (size_t)((ub >> 3) * 2048 + (((int)row & 127) >> 3) * 128 + ((int)row & 7) * 16);
+                    lf_epilogue<MODE>(trow + 256, true, active, reinterpret_cast<const float4 *>(b2S + ub * 4), c2,
+                                      x2 + (size_t)(t2 & 1) * h_bytes, id);
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {                                      // g2 drained by this warp
+                        if (PAIR && !leader) mbar_arrive_remote(&bar_gfree[1], 0); else mbar_arrive(&bar_gfree[1]);
+                    }
+                    lf_bar_sync(1, 256);                                  // all h2 stores of this CTA issued
+                    if (et == 0) lf_red_release(flags + LF_MAX_KB + s, 1u);
+                    if (tr) a.trace[item * 8 + 7] = clock64();
+                    ++item;
+                }
+            }
+            done += (unsigned)sbt.Lmax;
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (PAIR) cluster_sync_all();          // no MMA, commit or remote arrive of the pair is still in flight
+    if (warp == 2) {
+        if (PAIR) tmem_dealloc_pair<512>(tmem_base); else tmem_dealloc<512>(tmem_base);
+    }
+}
+
+static size_t lstm_fused_smem_bytes(int H)
+{
+    return (size_t)(H / TILE_K + LF_STAGES) * TILE_BYTES + (size_t)26 * LF_TAB_STRIDE * 4 + LF_U * 16 + 1024;
+}
+
+bool lstm_fused_supported(int H, int n_lstm)
+{
+    return n_lstm == 2 && H % LF_U == 0 && H / TILE_K <= LF_MAX_KB && lstm_fused_smem_bytes(H) <= 227 * 1024;
+}
+
+size_t lstm_fused_scratch_bytes(const mdf_ctx *ctx, int H)
+{
+    const int ctas_per_unit_cover = std::max(1, H / LF_U);             // CTAs (of 128 proteins each) covering all units once
+    const int covers = std::max(1, ctx->sm_count / ctas_per_unit_cover);
+    return (size_t)covers * 4 * LF_M * H * 2 + 8192;
+}
+
+// flat u16 tensor map whose [32 x 256] boxes are the 16 KiB operand tiles of an image
+static int make_tile_map(CUtensorMap *map, const void *base, size_t bytes)
+{
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        MDF_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        if (!fn || q != cudaDriverEntryPointSuccess) { set_error("lstm_fused: cuTensorMapEncodeTiled is unavailable"); return MDF_ECUDA; }
+        encode = reinterpret_cast<EncodeFn>(fn);
+    }
+    const cuuint64_t dims[2] = {256, (cuuint64_t)(bytes / 512)};
+    const cuuint64_t strides[1] = {512};
+    const cuuint32_t box[2] = {256, 32};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("lstm_fused: cuTensorMapEncodeTiled failed (%d)", (int)r); return MDF_ECUDA; }
+    return MDF_OK;
+}
+
+template <bool PAIR, int MODE>
+static int launch_variant(mdf_ctx *ctx, LstmFusedArgs &a, size_t smem)
+{
+    auto kern = lstm_fused_kernel<PAIR, MODE>;
+    MDF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(a.n_groups * a.cpg * (PAIR ? 2 : 1));
+    cfg.blockDim = dim3(LF_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attrs[2];
+    int na = 0;
+    attrs[na].id = cudaLaunchAttributeCooperative;      // co-residency: the CTAs spin on each other's release counters
+    attrs[na].val.cooperative = 1;
+    ++na;
+    if (PAIR) {
+        attrs[na].id = cudaLaunchAttributeClusterDimension;
+        attrs[na].val.clusterDim.x = 2; attrs[na].val.clusterDim.y = 1; attrs[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    cfg.attrs = attrs;
+    cfg.numAttrs = na;
+    MDF_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
+    ctx->launches++;
+    return MDF_OK;
+}
+
+int launch_lstm_fused(mdf_ctx *ctx, int H, int n, const __half *const W[3][2], const float *tab, const float *b2,
+                      const uint8_t *idx_pad, const int *order, const int64_t *seq_off, const int64_t *seg_off,
+                      __half *H1img, __half *H2img, void *scratch)
+{
+    if (n <= 0) return MDF_OK;
+    static const int pair_env = getenv("MDF_LSTM_PAIR") ? atoi(getenv("MDF_LSTM_PAIR")) : 1;
+    static const int cell_env = getenv("MDF_LSTM_CELL") ? atoi(getenv("MDF_LSTM_CELL")) : 0;
+    const bool pair = pair_env != 0;
+    LstmFusedArgs a;
+    a.H = H; a.n = n;
+    a.cell_mode = cell_env;
+    a.cpg = H / LF_U;
+    const int sub_n = pair ? 2 * LF_M : LF_M;
+    a.n_sub = cdiv(n, sub_n);
+    const int max_groups = std::max(1, ctx->sm_count / (a.cpg * (pair ? 2 : 1)));
+    a.n_groups = std::min(max_groups, a.n_sub);
+    for (int m = 0; m < 3; ++m) {
+        a.W[m][1] = W[m][0];              // odd steps use R_a, even steps R_b (same convention as lstm_tc.cu)
+        a.W[m][0] = W[m][1];
+    }
+    a.tab = tab; a.b2 = b2; a.idx_pad = idx_pad; a.order = order;
+    a.seq_off = seq_off; a.seg_off = seg_off; a.H1img = H1img; a.H2img = H2img;
+    if ((size_t)a.n_groups * 2 * 2 * LF_MAX_KB * sizeof(unsigned) > 8192) { set_error("lstm_fused: too many groups"); return MDF_EUNSUPPORTED; }
+    a.flags = reinterpret_cast<unsigned *>(scratch);
+    a.hbuf = reinterpret_cast<__half *>(reinterpret_cast<uint8_t *>(scratch) + 8192);
+    MDF_CUDA(cudaMemsetAsync(scratch, 0, 8192, ctx->stream));
+    memset(a.tmW, 0, sizeof(a.tmW));
+    memset(&a.tmH, 0, sizeof(a.tmH));
+    if (pair) {
+        for (int m = 0; m < 3; ++m)
+            for (int q = 0; q < 2; ++q) MDF_TRY(make_tile_map(&a.tmW[m][q], a.W[m][q], (size_t)4 * H * H * 2));
+        MDF_TRY(make_tile_map(&a.tmH, a.hbuf, (size_t)a.n_groups * 2 * 4 * LF_M * H * 2));
+    }
+    a.trace = nullptr; a.trace_items = 0;
+    const bool want_trace = getenv("MDF_LSTM_TRACE") != nullptr;
+    if (want_trace) {
+        a.trace_items = 2048;
+        MDF_CUDA(cudaMalloc((void **)&a.trace, (size_t)a.trace_items * 12 * sizeof(long long)));
+        MDF_CUDA(cudaMemsetAsync(a.trace, 0, (size_t)a.trace_items * 12 * sizeof(long long), ctx->stream));
+    }
+    const size_t smem = lstm_fused_smem_bytes(H);
+    if (pair) {
+        if (a.cell_mode) MDF_TRY((launch_variant<true, 1>(ctx, a, smem))); else MDF_TRY((launch_variant<true, 0>(ctx, a, smem)));
+    } else {
+        if (a.cell_mode) MDF_TRY((launch_variant<false, 1>(ctx, a, smem))); else MDF_TRY((launch_variant<false, 0>(ctx, a, smem)));
+    }
+    if (want_trace) {
+        std::vector<long long> h((size_t)a.trace_items * 12);
+        MDF_CUDA(cudaStreamSynchronize(ctx->stream));
+        MDF_CUDA(cudaMemcpy(h.data(), a.trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        cudaFree(a.trace);
+        double sum[8] = {0}; int cnt = 0;
+        for (int i = 32; i < a.trace_items; ++i) {
+            const long long *t = &h[(size_t)i * 8];
+            const long long *pv = &h[(size_t)(i - 1) * 8];
+            if (!t[7] || !t[3] || !t[5] || !pv[0]) continue;
+            sum[0] += t[0] - pv[0];  // tick (issuer, start to start)
+            sum[1] += t[1] - t[0];   // P1 issue (incl. operand + weight waits)
+            sum[2] += t[2] - t[1];   // P2 issue
+            sum[3] += t[3] - t[2];   // P3 issue
+            sum[4] += t[4] - t[1];   // P1 issued -> E1 sees g1
+            sum[5] += t[5] - t[4];   // E1
+            sum[6] += t[6] - t[3];   // P3 issued -> E2 sees g2
+            sum[7] += t[7] - t[6];   // E2
+            ++cnt;
+        }
+        for (int c = 0; c < 2; ++c) {             // weight-ring stamps of CTA 0 and 1: {TMA issued, data seen by issuer/relay}
+            const long long *t2 = &h[(size_t)a.trace_items * 8 + (size_t)c * a.trace_items * 2];
+            double land = 0, turn = 0; int k = 0;
+            for (int f = 256; f + LF_STAGES < a.trace_items; ++f) {
+                if (!t2[f * 2] || !t2[f * 2 + 1] || !t2[(f + LF_STAGES) * 2]) continue;
+                land += t2[f * 2 + 1] - t2[f * 2];                      // TMA issue -> consumer saw the stage full
+                turn += t2[(f + LF_STAGES) * 2] - t2[f * 2 + 1];        // consumer saw it -> producer re-issued the same stage
+                ++k;
+            }
+            if (k) fprintf(stderr, "[lstm fused trace] cta %d weight ring: issue->seen %.0f cyc, seen->reissue %.0f cyc (avg over %d fills)\n", c, land / k, turn / k, k);
+        }
+        if (cnt)
+            fprintf(stderr, "[lstm fused trace] pair %d cell %d, avg over %d ticks: tick %.0f cyc | P1 %.0f P2 %.0f P3 %.0f | P1->g1 %.0f E1 %.0f | P3->g2 %.0f E2 %.0f\n",
+                    (int)pair, a.cell_mode, cnt, sum[0] / cnt, sum[1] / cnt, sum[2] / cnt, sum[3] / cnt, sum[4] / cnt, sum[5] / cnt, sum[6] / cnt, sum[7] / cnt);
+    }
+    return MDF_OK;
+}
+
+}  // namespace tc
+}  // namespace mdf

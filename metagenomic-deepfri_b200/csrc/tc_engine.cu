@@ -32,6 +32,11 @@ struct TcModel {
     __half *lstm_R[MDF_MAX_LSTM] = {nullptr};              // [H/16][2][64 x H] resident recurrent slices (hi, lo)
     __half *lstm_Ralt[MDF_MAX_LSTM] = {nullptr};           // same, time-dithered pair (R_a, R_b = fp16(2R - R_a))
     int lstm_alternate = 1;
+    __half *lstm_Rstream[MDF_MAX_LSTM][2] = {{nullptr}};   // streamed kernel: [4H rows (cta,gate,unit) x H], (R_a, R_b)
+    float *lstm_tab_full = nullptr;                        // [26][H][4] layer-1 table over all units
+    int lstm_stream_min = 2048;                            // proteins per batch from which the streamed kernel is used
+    __half *lstm_fused_W[3][2] = {{nullptr}};              // fused kernel: R1, W2, R2 as [4H rows (cta64, gate, unit) x H], (R_a, R_b)
+    int lstm_fused = 1;                                    // use the fused two-layer wavefront kernel when supported
     float *lstm_tab = nullptr;                             // [H/16][26][16][4] layer-1 input table (bias folded)
     __half *lstm_Win[MDF_MAX_LSTM][2] = {{nullptr}};       // layers >= 2: [4H rows in (unit,gate) order x H k]
     float *lstm_bperm[MDF_MAX_LSTM] = {nullptr};           // layers >= 2: bias in (unit,gate) order
@@ -52,8 +57,9 @@ struct TcBatchMeta {
 
 // ------------------------------------------------------------------------------------------- weight images
 static void build_image_host(const float *src, int rows, int K, bool transposed_src, int ld,
-                             std::vector<__half> &hi, std::vector<__half> &lo)
+                             std::vector<__half> &hi, std::vector<__half> &lo, bool dither = false)
 {
+    // dither = false: (hi, lo) with hi + lo ~ v;  dither = true: (a, b) with a + b ~ 2v (time-dithered pair)
     // element (r, k) = transposed_src ? src[k * ld + r] : src[r * ld + k]
     const int RT = cdiv(rows, TILE_ROWS), KB = cdiv(K, TILE_K);
     const size_t total = (size_t)RT * KB * (TILE_BYTES / 2);
@@ -63,7 +69,7 @@ static void build_image_host(const float *src, int rows, int K, bool transposed_
         for (int k = 0; k < K; ++k) {
             const float v = transposed_src ? src[(size_t)k * ld + r] : src[(size_t)r * ld + k];
             const __half h = __float2half_rn(v);
-            const __half l = __float2half_rn(v - __half2float(h));
+            const __half l = dither ? __float2half_rn(2.0f * v - __half2float(h)) : __float2half_rn(v - __half2float(h));
             const size_t off = image_offset_bytes(r, k, KB) / 2;
             hi[off] = h;
             lo[off] = l;
@@ -83,6 +89,8 @@ int tc_model_init(mdf_model *m, const mdf_model_desc *d)
     TcModel *t = new TcModel();
     m->tc = t;
     if (const char *e = getenv("MDF_LSTM_HILO")) t->lstm_alternate = atoi(e) ? 0 : 1;   // 1 = hi+lo on every step
+    if (const char *e = getenv("MDF_LSTM_STREAM_MIN")) t->lstm_stream_min = atoi(e);
+    if (const char *e = getenv("MDF_LSTM_FUSED")) t->lstm_fused = atoi(e);
     // shape constraints of the tile-image GEMMs
     bool ok = m->H % 64 == 0 && m->E % 128 == 0;
     for (int l = 0; l < m->n_gc; ++l) ok = ok && m->gc[l] % 128 == 0;
@@ -119,6 +127,20 @@ int tc_model_init(mdf_model *m, const mdf_model_desc *d)
             }
         MDF_TRY(upload_half(m, &t->lstm_R[l], img));
         MDF_TRY(upload_half(m, &t->lstm_Ralt[l], alt));
+        if (lstm_stream_supported(H)) {
+            // streamed kernel: CTA s owns units [128s, 128s+128); its rows are ordered (gate, unit) so that the
+            // four gates of a unit share a TMEM lane: image row s*512 + gate*128 + u <- ONNX row gate*H + s*128 + u
+            std::vector<float> Rp((size_t)H4 * H);
+            for (int s = 0; s < H / 128; ++s)
+                for (int gate = 0; gate < 4; ++gate)
+                    for (int u = 0; u < 128; ++u)
+                        std::copy(R + (size_t)(gate * H + s * 128 + u) * H, R + (size_t)(gate * H + s * 128 + u + 1) * H,
+                                  Rp.begin() + (size_t)(s * 512 + gate * 128 + u) * H);
+            std::vector<__half> ra, rb;
+            build_image_host(Rp.data(), H4, H, false, H, ra, rb, true);
+            MDF_TRY(upload_half(m, &t->lstm_Rstream[l][0], ra));
+            MDF_TRY(upload_half(m, &t->lstm_Rstream[l][1], rb));
+        }
         std::vector<float> bsum(H4, 0.0f);
         if (d->lstm_B[l])
             for (int r = 0; r < H4; ++r) bsum[r] = d->lstm_B[l][r] + d->lstm_B[l][H4 + r];
@@ -134,6 +156,14 @@ int tc_model_init(mdf_model *m, const mdf_model_desc *d)
             MDF_CUDA(cudaMalloc((void **)&t->lstm_tab, tab.size() * sizeof(float)));
             m->owned.push_back(t->lstm_tab);
             MDF_CUDA(cudaMemcpy(t->lstm_tab, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice));
+            std::vector<float> full((size_t)26 * H * 4);                 // [aa][unit][gate]
+            for (int aa = 0; aa < 26; ++aa)
+                for (int unit = 0; unit < H; ++unit)
+                    for (int gate = 0; gate < 4; ++gate)
+                        full[((size_t)aa * H + unit) * 4 + gate] = d->lstm_W[0][(size_t)(gate * H + unit) * m->I + aa] + bsum[gate * H + unit];
+            MDF_CUDA(cudaMalloc((void **)&t->lstm_tab_full, full.size() * sizeof(float)));
+            m->owned.push_back(t->lstm_tab_full);
+            MDF_CUDA(cudaMemcpy(t->lstm_tab_full, full.data(), full.size() * sizeof(float), cudaMemcpyHostToDevice));
         } else {
             // B operand rows n' = unit*4 + gate  <-  ONNX row gate*H + unit ; k = input feature
             std::vector<float> Wp((size_t)H4 * H), bp(H4);
@@ -149,6 +179,23 @@ int tc_model_init(mdf_model *m, const mdf_model_desc *d)
             MDF_CUDA(cudaMalloc((void **)&t->lstm_bperm[l], bp.size() * sizeof(float)));
             m->owned.push_back(t->lstm_bperm[l]);
             MDF_CUDA(cudaMemcpy(t->lstm_bperm[l], bp.data(), bp.size() * sizeof(float), cudaMemcpyHostToDevice));
+        }
+    }
+    if (lstm_fused_supported(H, m->n_lstm)) {
+        // fused kernel: CTA s owns units [64s, 64s+64) of both layers; rows ordered (cta, gate, unit) so that
+        // TMEM column = gate*64 + unit: image row s*256 + gate*64 + u <- ONNX row gate*H + s*64 + u
+        const float *src[3] = {d->lstm_R[0], d->lstm_W[1], d->lstm_R[1]};
+        std::vector<float> Wp((size_t)H4 * H);
+        for (int mi = 0; mi < 3; ++mi) {
+            for (int s = 0; s < H / 64; ++s)
+                for (int gate = 0; gate < 4; ++gate)
+                    for (int u = 0; u < 64; ++u)
+                        std::copy(src[mi] + (size_t)(gate * H + s * 64 + u) * H, src[mi] + (size_t)(gate * H + s * 64 + u + 1) * H,
+                                  Wp.begin() + (size_t)(s * 256 + gate * 64 + u) * H);
+            std::vector<__half> wa, wb;
+            build_image_host(Wp.data(), H4, H, false, H, wa, wb, true);
+            MDF_TRY(upload_half(m, &t->lstm_fused_W[mi][0], wa));
+            MDF_TRY(upload_half(m, &t->lstm_fused_W[mi][1], wb));
         }
     }
     if (lstm_tc_smem_bytes(H) > 227 * 1024) return MDF_OK;   // cannot keep the slices resident: engine unavailable
@@ -344,7 +391,7 @@ size_t tc_workspace_bytes(const mdf_model *m, int n, const int64_t *seq_off)
     auto add = [&](size_t x) { b += align_up(x, 256) + 256; };
     for (int l = 0; l < m->n_lstm; ++l) add((size_t)Tp * m->H * 2);   // H_l images
     add((size_t)Tp * 4 * m->H * 4);                   // input pre-activations of the upper LSTM layers
-    add(lstm_tc_scratch_bytes(m->ctx, m->H));
+    add(std::max({lstm_tc_scratch_bytes(m->ctx, m->H), lstm_stream_scratch_bytes(m->ctx, m->H), lstm_fused_scratch_bytes(m->ctx, m->H)}));
     for (int l = 0; l < m->n_lstm; ++l) add((size_t)T * m->H * 4);    // optional fp32 taps
     add((size_t)Tp * 4 + (size_t)Tp / 128 * 16 + (size_t)(tiles + 1) * 16 + (size_t)(n + 1) * 8 + 1024);   // metadata
     add((size_t)Tp * 4); add((size_t)Tp);             // deg_pad, idx_pad
@@ -390,8 +437,10 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto)
     MDF_TRY(ctx->alloc_n(&deg_pad, (size_t)Tp));
     MDF_TRY(ctx->alloc_n(&idx_pad, (size_t)Tp));
     for (int l = 0; l < m->n_lstm; ++l) MDF_TRY(ctx->alloc_n(&Hlimg[l], (size_t)Tp * m->H));
-    if (m->n_lstm > 1) MDF_TRY(ctx->alloc_n(&pre, (size_t)Tp * 4 * m->H));
-    MDF_TRY(ctx->alloc(&scratch, lstm_tc_scratch_bytes(ctx, m->H)));
+    if (m->n_lstm > 1 && !(tm->lstm_fused && tm->lstm_fused_W[0][0])) MDF_TRY(ctx->alloc_n(&pre, (size_t)Tp * 4 * m->H));
+    const bool fused = tm->lstm_fused && tm->lstm_fused_W[0][0] != nullptr;
+    MDF_TRY(ctx->alloc(&scratch, std::max({lstm_tc_scratch_bytes(ctx, m->H), lstm_stream_scratch_bytes(ctx, m->H),
+                                           lstm_fused_scratch_bytes(ctx, m->H)})));
     MDF_TRY(ctx->alloc_n(&X0img, (size_t)Tp * m->E));
     MDF_TRY(ctx->alloc_n(&Yt, (size_t)Tp * gmax));
     MDF_TRY(ctx->alloc_n(&Xa, (size_t)Tp * gmax));
@@ -400,8 +449,16 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto)
     pad_vectors_kernel<<<(unsigned)cdiv64(Tp, 256), 256, 0, s>>>(Tp, meta->rowmap, b->d_deg, b->d_idx, deg_pad, idx_pad);
     MDF_LAUNCH_CHECK(ctx);
 
-    // ---- LSTM language model: persistent tcgen05 recurrence per layer, input GEMM between layers
-    for (int l = 0; l < m->n_lstm; ++l) {
+    // ---- LSTM language model
+    if (fused) {
+        // both layers + the layer-2 input projection in one persistent wavefront kernel (lstm_fused.cu)
+        ProfScope ps(ctx, "lstm_fused", 3.0 * 2.0 * T * 4 * m->H * m->H);
+        MDF_TRY(launch_lstm_fused(ctx, m->H, n, tm->lstm_fused_W, tm->lstm_tab_full, tm->lstm_bperm[1], idx_pad, b->d_order,
+                                  b->d_seq_off, meta->seg_off, ctx->debug_taps ? Hlimg[0] : nullptr, Hlimg[1], scratch));
+        b->tap_h[0] = b->tap_h[1] = nullptr;
+    }
+    // fallback: persistent tcgen05 recurrence per layer, input GEMM between layers
+    for (int l = 0; l < (fused ? 0 : m->n_lstm); ++l) {
         if (l > 0) {
             ProfScope ps(ctx, "lstm_input_gemm", 2.0 * T * 4 * m->H * m->H);
             GemmArgs g;                                   // pre[Tp x 4H] = H_{l-1} . W_in^T + b   ([unit][gate] columns)
@@ -414,9 +471,14 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto)
         }
         {
             ProfScope ps(ctx, "lstm_recurrent", 2.0 * T * 4 * m->H * m->H);
-            MDF_TRY(launch_lstm_tc(ctx, m->H, n, tm->lstm_alternate ? tm->lstm_Ralt[l] : tm->lstm_R[l],
-                                   l == 0 ? tm->lstm_tab : nullptr, l > 0 ? pre : nullptr, idx_pad, b->d_order,
-                                   b->d_seq_off, meta->seg_off, Hlimg[l], scratch, tm->lstm_alternate));
+            if (tm->lstm_Rstream[l][0] && n >= tm->lstm_stream_min)      // large batch: streamed weights, N = 128
+                MDF_TRY(launch_lstm_stream(ctx, m->H, n, tm->lstm_Rstream[l][0], tm->lstm_Rstream[l][1],
+                                           l == 0 ? tm->lstm_tab_full : nullptr, l > 0 ? pre : nullptr, idx_pad, b->d_order,
+                                           b->d_seq_off, meta->seg_off, Hlimg[l], scratch));
+            else                                                         // small batch: weights resident in smem, N = 32
+                MDF_TRY(launch_lstm_tc(ctx, m->H, n, tm->lstm_alternate ? tm->lstm_Ralt[l] : tm->lstm_R[l],
+                                       l == 0 ? tm->lstm_tab : nullptr, l > 0 ? pre : nullptr, idx_pad, b->d_order,
+                                       b->d_seq_off, meta->seg_off, Hlimg[l], scratch, tm->lstm_alternate));
         }
         b->tap_h[l] = nullptr;
     }

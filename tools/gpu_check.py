@@ -205,7 +205,7 @@ def check_tc():
         print(f"    protein {i} L={off[i + 1] - off[i]} gc_last err max {e.max():.3e} rows>1e-2: {(e.max(1) > 1e-2).sum()} cols>1e-2: {(e.max(0) > 1e-2).sum()}")
     pred.set_engine("tc")
     _lib.default_context().set_debug_taps(False)
-    wl = synth.config_workload(0, 1.0)
+    wl = synth.make_workload(int(os.environ.get("TC_TIMING_N", "1000")), 100, 500, seed=1, threshold=10.0)
     b2 = pred.upload(wl.query_seqs, wl.gapped_query, wl.gapped_target, wl.coords)
     ctx = _lib.default_context()
     for it in range(3):
