@@ -41,7 +41,12 @@ namespace tc {
 constexpr int LF_M = 128;            // proteins per CTA
 constexpr int LF_U = 64;             // hidden units per slice
 constexpr int LF_STAGES = 4;         // weight ring (16 KiB tiles: 128 gate rows x 64 k)
-constexpr int LF_THREADS = 352;      // warp 0: weight producer, 1: operand loader, 2: MMA issuer / relay, 3-10: epilogue
+#ifndef LF_EPI_WARPS
+#define LF_EPI_WARPS 16
+#endif
+constexpr int LF_EW = LF_EPI_WARPS;                  // epilogue warps (8 or 16): 4 TMEM lane quarters x LF_EW/4 unit ranges
+constexpr int LF_UPT = LF_U / (LF_EW / 4);           // units per epilogue thread (per layer)
+constexpr int LF_THREADS = (3 + LF_EW) * 32;         // warp 0: weight producer, 1: operand loader, 2: MMA issuer, 3..: epilogue
 constexpr int LF_TAB_STRIDE = 260;   // floats per residue row of the layer-1 table slice (64 units x 4 gates + pad)
 constexpr int LF_MAX_KB = 8;
 
@@ -76,6 +81,12 @@ __device__ __forceinline__ unsigned lf_ld_acquire(const unsigned *p)
 __device__ __forceinline__ void lf_red_release(unsigned *p, unsigned v)
 {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ long long lf_gtime()
+{
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
 }
 __device__ __forceinline__ void lf_bar_sync(int id, int nthreads)
 {
@@ -128,13 +139,13 @@ __device__ __forceinline__ LfSub lf_next(int &cursor, const LstmFusedArgs &a)
     return r;
 }
 
-// one layer's cell update for this thread's 32 units: TMEM (gates) + pre-activations -> c, h -> exchange tile (+ image)
+// one layer's cell update for this thread's LF_UPT units: TMEM (gates) + pre-activations -> c, h -> exchange tile (+ image)
 template <int MODE>
-__device__ __forceinline__ void lf_epilogue(uint32_t tgates, bool have_gates, bool active, const float4 *pre4, float (&cst)[32],
+__device__ __forceinline__ void lf_epilogue(uint32_t tgates, bool have_gates, bool active, const float4 *pre4, float (&cst)[LF_UPT],
                                             uint8_t *xd, uint8_t *id)
 {
 #pragma unroll
-    for (int c0 = 0; c0 < 32; c0 += 8) {
+    for (int c0 = 0; c0 < LF_UPT; c0 += 8) {
         uint32_t gi[8], go[8], gf[8], gc[8];
         if (have_gates) {                                     // warp-uniform: tcgen05.ld is .sync.aligned
             tmem_ld_32x32b_x8(tgates + 0 * 64 + c0, gi);
@@ -202,7 +213,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
         // PAIR: only the leader's full barriers are used; they collect the bytes of both CTAs' TMA loads
         for (int i = 0; i < LF_STAGES; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
         for (int i = 0; i < LF_MAX_KB; ++i) { mbar_init(&bar_hfull[i], 1); mbar_init(&bar_hfree[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&bar_gfull[i], 1); mbar_init(&bar_gfree[i], 8 * HALVES); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&bar_gfull[i], 1); mbar_init(&bar_gfree[i], LF_EW * HALVES); }
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -220,17 +231,12 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
         // =========================================================== weight producer
         if (lane == 0) {
             int st = 0; uint32_t ph = 0;
-            int fill = 0;
-            const bool tr2 = a.trace && blockIdx.x < 2;
-            long long *t2 = a.trace + (size_t)a.trace_items * 8 + (size_t)blockIdx.x * a.trace_items * 2;
             auto stream = [&](int mi, int par) {
                 const uint8_t *src = reinterpret_cast<const uint8_t *>(a.W[mi][par]) + (size_t)(2 * s) * KB * TILE_BYTES;
                 for (int kb = 0; kb < KB; ++kb)
                     for (int jj = 0; jj < TPK; ++jj) {
                         const int j = PAIR ? r : jj;                  // row tile of the slice: gates {2j, 2j+1}
                         mbar_wait(&bar_empty[st], ph ^ 1);
-                        if (tr2 && fill < a.trace_items) t2[fill * 2] = clock64();
-                        ++fill;
                         if (PAIR) {
                             if (leader) mbar_arrive_expect_tx(&bar_full[st], 2 * TILE_BYTES);     // my rows + the peer's rows
                             tma_tile_g2s_pair(sW + (size_t)st * TILE_BYTES, &a.tmW[mi][par], (((2 * s + j) * KB) + kb) * (TILE_BYTES / 512),
@@ -256,13 +262,23 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
         if (lane == 0) {
             uint32_t hph = 0;
             unsigned done = 0;
+            int item = 0;
+            long long *th = a.trace + (size_t)a.trace_items * 12;    // [item][16] globaltimer stamps of the layer-1 operand, CTAs 0/1
             auto load = [&](int layer, int step, unsigned target) {
                 const uint8_t *src = hb + (size_t)(layer * 2 + (step & 1)) * h_bytes;
+                const bool trh = a.trace && blockIdx.x < 2 && layer == 0 && item < a.trace_items;
+                // every slice of the group has published its tile of this operand ...
+                for (int kb = 0; kb < KB; ++kb) {
+                    const unsigned *f = flags + layer * LF_MAX_KB + kb;
+                    while (lf_ld_acquire(f) < target) { }
+                }
+                if (trh) th[item * 16 + blockIdx.x * 8 + 1] = lf_gtime();
+                // ... and ONE proxy fence orders those generic-proxy stores before the async-proxy reads below (a fence
+                // per chunk serialises the chunk loads: it waits for this thread's TMA copies already in flight)
+                asm volatile("fence.proxy.async.global;" ::: "memory");
                 for (int kb = 0; kb < KB; ++kb) {
                     mbar_wait(&bar_hfree[kb], hph ^ 1);                  // the MMAs reading the previous operand retired
-                    const unsigned *f = flags + layer * LF_MAX_KB + kb;
-                    while (lf_ld_acquire(f) < target) { }                // slice kb of the group has published this tile
-                    asm volatile("fence.proxy.async;" ::: "memory");     // peers' generic stores -> this async-proxy read
+                    if (trh && (kb == 0 || kb == KB - 1)) th[item * 16 + blockIdx.x * 8 + (kb ? 4 : 0) + 0] = lf_gtime();
                     if (PAIR) {
                         if (leader) mbar_arrive_expect_tx(&bar_hfull[kb], 2 * TILE_BYTES);       // my proteins + the peer's
                         tma_tile_g2s_pair(sH + (size_t)kb * TILE_BYTES, &a.tmH,
@@ -277,7 +293,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
             };
             int cursor = g;
             for (LfSub sbt = lf_next<PAIR>(cursor, a); sbt.sb >= 0; sbt = lf_next<PAIR>(cursor, a)) {
-                for (int tau = 1; tau <= sbt.Lmax; ++tau) {
+                for (int tau = 1; tau <= sbt.Lmax; ++tau, ++item) {
                     load(0, tau - 1, done + (unsigned)tau);                        // h1_{tau-1}: published at tick tau-1
                     if (tau >= 2) load(1, tau - 2, done + (unsigned)(tau - 1));    // h2_{tau-2}: published at tick tau-1
                 }
@@ -292,19 +308,27 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
             uint32_t rounds[2] = {0, 0};
             const uint32_t sh_addr = smem_u32(sH);
             int item = 0;
-            int fill = 0;
-            const bool tr2 = a.trace && blockIdx.x < 2;
-            long long *t2 = a.trace + (size_t)a.trace_items * 8 + (size_t)blockIdx.x * a.trace_items * 2;
+            const bool trw = a.trace && blockIdx.x == 0;
+            long long *tw = a.trace + (size_t)a.trace_items * 8;     // [item][4]: per tick cycles waiting on operand chunks, weights, g1/g2 drain
+            long long acc_h = 0, acc_w = 0, acc_g = 0;
             // one pass over the operand in shared memory: gates[acc] (+)= W_slice . operand
             auto pass = [&](uint32_t d0, bool accumulate, bool wait_h, bool release_chunks) {
                 for (int kb = 0; kb < KB; ++kb) {
-                    if (wait_h) mbar_wait(&bar_hfull[kb], hph);
+                    if (wait_h) {
+                        const long long c0 = trw ? clock64() : 0;
+                        mbar_wait(&bar_hfull[kb], hph);
+                        if (trw) acc_h += clock64() - c0;
+                        if (trw && d0 == 0u && item < a.trace_items && (kb == 0 || kb == KB - 1))
+                            a.trace[(size_t)a.trace_items * 12 + item * 16 + (kb ? 4 : 0) + 2] = lf_gtime();
+                    }
                     tcgen05_fence_after();
                     const uint64_t hd = umma_smem_desc(sh_addr + kb * TILE_BYTES, TILE_LBO, TILE_SBO);   // A: proteins x 64 k
                     for (int jj = 0; jj < TPK; ++jj) {
-                        mbar_wait(&bar_full[st], ph);
-                        if (tr2 && fill < a.trace_items) t2[fill * 2 + 1] = clock64();
-                        ++fill;
+                        {
+                            const long long c0 = trw ? clock64() : 0;
+                            mbar_wait(&bar_full[st], ph);
+                            if (trw) acc_w += clock64() - c0;
+                        }
                         tcgen05_fence_after();
                         const uint64_t wd = umma_smem_desc(smem_u32(sW + (size_t)st * TILE_BYTES), TILE_LBO, TILE_SBO);   // B: gate rows x 64 k
 #pragma unroll
@@ -325,7 +349,9 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
                 }
             };
             auto wait_gfree = [&](int acc) {
+                const long long c0 = trw ? clock64() : 0;
                 mbar_wait(&bar_gfree[acc], (rounds[acc] & 1) ^ 1);
+                if (trw) acc_g += clock64() - c0;
                 tcgen05_fence_after();
             };
             auto commit_gfull = [&](int acc) {
@@ -336,14 +362,14 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
             for (LfSub sbt = lf_next<PAIR>(cursor, a); sbt.sb >= 0; sbt = lf_next<PAIR>(cursor, a)) {
                 for (int tau = 1; tau <= sbt.Lmax; ++tau, ++item) {
                     const bool tr = a.trace && blockIdx.x == 0 && item < a.trace_items;
-                    if (tr) a.trace[item * 8 + 0] = clock64();
+                    if (tr) { a.trace[item * 8 + 0] = clock64(); a.trace[(size_t)a.trace_items * 12 + item * 16 + 3] = lf_gtime(); }
                     const bool p1 = tau < sbt.Lmax;
                     if (p1) {                                             // P1
                         wait_gfree(0);
                         pass(0u, false, true, false);
                         commit_gfull(0);
                     }
-                    if (tr) a.trace[item * 8 + 1] = clock64();
+                    if (tr) { a.trace[item * 8 + 1] = clock64(); tw[item * 4 + 0] = acc_h; }
                     wait_gfree(1);                                        // P2
                     pass(256u, false, !p1, true);
                     hph ^= 1;
@@ -353,23 +379,24 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
                         hph ^= 1;
                     }
                     commit_gfull(1);
-                    if (tr) a.trace[item * 8 + 3] = clock64();
+                    if (tr) { a.trace[item * 8 + 3] = clock64(); tw[item * 4 + 1] = acc_h; tw[item * 4 + 2] = acc_w; tw[item * 4 + 3] = acc_g; }
+                    acc_h = acc_w = acc_g = 0;
                 }
             }
         }
     } else {
-        // =========================================================== epilogue: thread = one protein x 32 units x both layers
+        // =========================================================== epilogue: thread = one protein x LF_UPT units x both layers
         const int et = tid - 96;
         const int q = warp & 3;                                // TMEM lane quarter this warp may access
-        const int half = (warp - 3) >> 2;                      // units [32*half, 32*half + 32) of this slice
+        const int part = (warp - 3) >> 2;                      // units [LF_UPT*part, LF_UPT*(part+1)) of this slice
         const int p = q * 32 + lane;                           // protein inside this CTA's 128 = TMEM lane
-        const int ub = half * 32;                              // first unit (within the slice) of this thread
+        const int ub = part * LF_UPT;                          // first unit (within the slice) of this thread
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)ub;
         // byte offset of (row p, k-chunk ub/8) inside an exchange tile
         const uint32_t xoff = (uint32_t)((ub >> 3) * 2048 + (p >> 3) * 128 + (p & 7) * 16);
         uint8_t *x1 = hb + (size_t)s * TILE_BYTES + xoff;                       // layer 1, parity 0
         uint8_t *x2 = hb + (size_t)2 * h_bytes + (size_t)s * TILE_BYTES + xoff; // layer 2, parity 0
-        float c1[32], c2[32];
+        float c1[LF_UPT], c2[LF_UPT];
         unsigned done = 0;
         uint32_t rounds[2] = {0, 0};
         int cursor = g;
@@ -381,7 +408,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
                 const unsigned *f = flags + LF_MAX_KB + et;
                 while (lf_ld_acquire(f) < done) { }
             }
-            lf_bar_sync(1, 256);
+            lf_bar_sync(1, LF_EW * 32);
             int len = 0;
             long long row0 = 0;
             {
@@ -393,7 +420,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
                 }
             }
 #pragma unroll
-            for (int j = 0; j < 32; ++j) { c1[j] = 0.0f; c2[j] = 0.0f; }
+            for (int j = 0; j < LF_UPT; ++j) { c1[j] = 0.0f; c2[j] = 0.0f; }
             int aa_next = len > 0 ? (int)a.idx_pad[row0] : 0;
             for (int tau = 0; tau <= sbt.Lmax; ++tau) {
                 const bool tr = a.trace && blockIdx.x == 0 && et == 0 && tau >= 1 && item < a.trace_items;
@@ -416,6 +443,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
                              (size_t)((ub >> 3) * 2048 + (((int)row & 127) >> 3) * 128 + ((int)row & 7) * 16);
                     }
                     lf_epilogue<MODE>(trow, tau >= 1, active, pre4, c1, x1 + (size_t)(tau & 1) * h_bytes, id);
+                    if (tr) a.trace[item * 8 + 5] = clock64();
                     if (tau >= 1) {
                         tcgen05_fence_before();
                         __syncwarp();
@@ -423,9 +451,10 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
                             if (PAIR && !leader) mbar_arrive_remote(&bar_gfree[0], 0); else mbar_arrive(&bar_gfree[0]);
                         }
                     }
-                    lf_bar_sync(1, 256);                                  // all h1_tau stores of this CTA issued
+                    lf_bar_sync(1, LF_EW * 32);                                  // all h1_tau stores of this CTA issued
+                    if (tr) a.trace[item * 8 + 6] = clock64();
                     if (et == 0) lf_red_release(flags + s, 1u);
-                    if (tr) a.trace[item * 8 + 5] = clock64();
+                    if (tr) { a.trace[item * 8 + 7] = clock64(); a.trace[(size_t)a.trace_items * 12 + item * 16 + 7] = lf_gtime(); }
                 }
                 // ---------------------------------------------------------------- E2: layer 2, step tau-1
                 if (tau >= 1) {
@@ -434,7 +463,6 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
                     mbar_wait(&bar_gfull[1], rounds[1] & 1);
                     ++rounds[1];
                     tcgen05_fence_after();
-                    if (tr) a.trace[item * 8 + 6] = clock64();
                     const long long row = row0 + t2;
                     uint8_t *id = reinterpret_cast<uint8_t *>(a.H2img) + ((size_t)(row >> 7) * KB + s) * TILE_BYTES +
                                   (size_t)((ub >> 3) * 2048 + (((int)row & 127) >> 3) * 128 + ((int)row & 7) * 16);
@@ -445,9 +473,8 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
                     if (lane == 0) {                                      // g2 drained by this warp
                         if (PAIR && !leader) mbar_arrive_remote(&bar_gfree[1], 0); else mbar_arrive(&bar_gfree[1]);
                     }
-                    lf_bar_sync(1, 256);                                  // all h2 stores of this CTA issued
+                    lf_bar_sync(1, LF_EW * 32);                                  // all h2 stores of this CTA issued
                     if (et == 0) lf_red_release(flags + LF_MAX_KB + s, 1u);
-                    if (tr) a.trace[item * 8 + 7] = clock64();
                     ++item;
                 }
             }
@@ -568,8 +595,8 @@ int launch_lstm_fused(mdf_ctx *ctx, int H, int n, const __half *const W[3][2], c
     const bool want_trace = getenv("MDF_LSTM_TRACE") != nullptr;
     if (want_trace) {
         a.trace_items = 2048;
-        MDF_CUDA(cudaMalloc((void **)&a.trace, (size_t)a.trace_items * 12 * sizeof(long long)));
-        MDF_CUDA(cudaMemsetAsync(a.trace, 0, (size_t)a.trace_items * 12 * sizeof(long long), ctx->stream));
+        MDF_CUDA(cudaMalloc((void **)&a.trace, (size_t)a.trace_items * 28 * sizeof(long long)));
+        MDF_CUDA(cudaMemsetAsync(a.trace, 0, (size_t)a.trace_items * 28 * sizeof(long long), ctx->stream));
     }
     const size_t smem = lstm_fused_smem_bytes(H);
     if (pair) {
@@ -578,7 +605,7 @@ int launch_lstm_fused(mdf_ctx *ctx, int H, int n, const __half *const W[3][2], c
         if (a.cell_mode) MDF_TRY((launch_variant<false, 1>(ctx, a, smem))); else MDF_TRY((launch_variant<false, 0>(ctx, a, smem)));
     }
     if (want_trace) {
-        std::vector<long long> h((size_t)a.trace_items * 12);
+        std::vector<long long> h((size_t)a.trace_items * 28);
         MDF_CUDA(cudaStreamSynchronize(ctx->stream));
         MDF_CUDA(cudaMemcpy(h.data(), a.trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
         cudaFree(a.trace);
@@ -592,24 +619,44 @@ int launch_lstm_fused(mdf_ctx *ctx, int H, int n, const __half *const W[3][2], c
             sum[2] += t[2] - t[1];   // P2 issue
             sum[3] += t[3] - t[2];   // P3 issue
             sum[4] += t[4] - t[1];   // P1 issued -> E1 sees g1
-            sum[5] += t[5] - t[4];   // E1
-            sum[6] += t[6] - t[3];   // P3 issued -> E2 sees g2
-            sum[7] += t[7] - t[6];   // E2
+            sum[5] += t[5] - t[4];   // E1 compute (thread 0)
+            sum[6] += t[6] - t[5];   // E1: gfree arrive + CTA barrier
+            sum[7] += t[7] - t[6];   // E1: release
             ++cnt;
         }
-        for (int c = 0; c < 2; ++c) {             // weight-ring stamps of CTA 0 and 1: {TMA issued, data seen by issuer/relay}
-            const long long *t2 = &h[(size_t)a.trace_items * 8 + (size_t)c * a.trace_items * 2];
-            double land = 0, turn = 0; int k = 0;
-            for (int f = 256; f + LF_STAGES < a.trace_items; ++f) {
-                if (!t2[f * 2] || !t2[f * 2 + 1] || !t2[(f + LF_STAGES) * 2]) continue;
-                land += t2[f * 2 + 1] - t2[f * 2];                      // TMA issue -> consumer saw the stage full
-                turn += t2[(f + LF_STAGES) * 2] - t2[f * 2 + 1];        // consumer saw it -> producer re-issued the same stage
+        {
+            const long long *tw = &h[(size_t)a.trace_items * 8];
+            double w[4] = {0}; int k = 0;
+            for (int i = 32; i < a.trace_items; ++i) {
+                if (!h[(size_t)i * 8 + 3]) continue;
+                for (int j = 0; j < 4; ++j) w[j] += tw[i * 4 + j];
                 ++k;
             }
-            if (k) fprintf(stderr, "[lstm fused trace] cta %d weight ring: issue->seen %.0f cyc, seen->reissue %.0f cyc (avg over %d fills)\n", c, land / k, turn / k, k);
+            if (k) fprintf(stderr, "[lstm fused trace] issuer waits per tick: operand chunks %.0f cyc (of which in P1 %.0f), weights %.0f, accumulator drain %.0f\n",
+                           w[1] / k, w[0] / k, w[2] / k, w[3] / k);
+        }
+        {
+            // layer-1 operand of tick i (h1_{i-1}), relative to the issuer's start of tick i (ns, globaltimer):
+            // when E1 of tick i-1 published, when chunk 0 / 7 became free, had their flag, were seen by the issuer
+            const long long *th = &h[(size_t)a.trace_items * 12];
+            double v[12] = {0}; int k = 0;
+            for (int i = 40; i < a.trace_items - 1; ++i) {
+                const long long *t = th + (size_t)i * 16, *pv = th + (size_t)(i - 1) * 16;
+                const long long t0 = t[3];
+                if (!t0 || !t[2] || !t[6] || !pv[7] || !t[0]) continue;
+                v[0] += pv[7] - t0;                                   // E1 publish of previous tick (CTA 0)
+                v[1] += t[0] - t0; v[2] += t[1] - t0; v[3] += t[2] - t0;          // cta0 chunk0: free, flag, seen
+                v[4] += t[4] - t0; v[5] += t[5] - t0; v[6] += t[6] - t0;          // cta0 chunk7
+                v[7] += t[8] - t0; v[8] += t[9] - t0;                             // cta1 chunk0: free, flag
+                v[9] += t[12] - t0; v[10] += t[13] - t0;                          // cta1 chunk7
+                ++k;
+            }
+            if (k) fprintf(stderr, "[lstm fused trace] h1 operand vs tick start (ns): E1 publish %.0f | cta0 chunk0 free %.0f all-flags %.0f seen %.0f | chunk7 free %.0f (-) %.0f seen %.0f | "
+                           "cta1 chunk0 free %.0f all-flags %.0f | chunk7 free %.0f (-) %.0f\n", v[0] / k, v[1] / k, v[2] / k, v[3] / k, v[4] / k, v[5] / k, v[6] / k,
+                           v[7] / k, v[8] / k, v[9] / k, v[10] / k);
         }
         if (cnt)
-            fprintf(stderr, "[lstm fused trace] pair %d cell %d, avg over %d ticks: tick %.0f cyc | P1 %.0f P2 %.0f P3 %.0f | P1->g1 %.0f E1 %.0f | P3->g2 %.0f E2 %.0f\n",
+            fprintf(stderr, "[lstm fused trace] pair %d cell %d, avg over %d ticks: tick %.0f cyc | P1 %.0f P2 %.0f P3 %.0f | P1->g1 %.0f E1 compute %.0f barrier %.0f release %.0f\n",
                     (int)pair, a.cell_mode, cnt, sum[0] / cnt, sum[1] / cnt, sum[2] / cnt, sum[3] / cnt, sum[4] / cnt, sum[5] / cnt, sum[6] / cnt, sum[7] / cnt);
     }
     return MDF_OK;
