@@ -53,7 +53,8 @@ constexpr int LF_MAX_KB = 8;
 struct LstmFusedArgs {
     int H, n, n_groups, cpg, n_sub;
     int cell_mode;            // 0: exp/rcp cell (fp32-accurate), 1: tanh.approx cell
-    const __half *W[3][2];    // R1, W2, R2: [4H rows (slice, gate, unit) x H] operand images, indexed by step parity
+    const __half *W;          // [R1, W2, R2][phase][4H rows (slice, gate, unit) x H] operand images (time-dither phases)
+    int phases;
     const float *tab;         // [26][H][4] layer-1 pre-activation table ([unit][gate] order, bias folded)
     const float *b2;          // [H][4] layer-2 bias ([unit][gate] order)
     const uint8_t *idx_pad;   // [Tp]
@@ -68,7 +69,7 @@ struct LstmFusedArgs {
     int trace_items;
     // PAIR mode: flat [bytes/512][256] u16 tensor maps (one 16 KiB tile = a [32 x 256] box) over the six weight
     // images and the exchange buffer - tensor-map TMA is the form that can credit the leader CTA's barrier
-    alignas(64) CUtensorMap tmW[3][2];
+    alignas(64) CUtensorMap tmW;
     alignas(64) CUtensorMap tmH;
 };
 
@@ -231,16 +232,18 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
         // =========================================================== weight producer
         if (lane == 0) {
             int st = 0; uint32_t ph = 0;
-            auto stream = [&](int mi, int par) {
-                const uint8_t *src = reinterpret_cast<const uint8_t *>(a.W[mi][par]) + (size_t)(2 * s) * KB * TILE_BYTES;
+            const int tiles_per_img = 4 * H / TILE_ROWS * KB;
+            auto stream = [&](int mi, int step) {                 // weights of matrix mi for (layer) step `step`
+                const int img = mi * a.phases + step % a.phases;
+                const uint8_t *src = reinterpret_cast<const uint8_t *>(a.W) + ((size_t)img * tiles_per_img + (size_t)(2 * s) * KB) * TILE_BYTES;
                 for (int kb = 0; kb < KB; ++kb)
                     for (int jj = 0; jj < TPK; ++jj) {
                         const int j = PAIR ? r : jj;                  // row tile of the slice: gates {2j, 2j+1}
                         mbar_wait(&bar_empty[st], ph ^ 1);
                         if (PAIR) {
                             if (leader) mbar_arrive_expect_tx(&bar_full[st], 2 * TILE_BYTES);     // my rows + the peer's rows
-                            tma_tile_g2s_pair(sW + (size_t)st * TILE_BYTES, &a.tmW[mi][par], (((2 * s + j) * KB) + kb) * (TILE_BYTES / 512),
-                                              &bar_full[st]);
+                            tma_tile_g2s_pair(sW + (size_t)st * TILE_BYTES, &a.tmW,
+                                              (img * tiles_per_img + (2 * s + j) * KB + kb) * (TILE_BYTES / 512), &bar_full[st]);
                         } else {
                             mbar_arrive_expect_tx(&bar_full[st], TILE_BYTES);
                             bulk_g2s(sW + (size_t)st * TILE_BYTES, src + ((size_t)j * KB + kb) * TILE_BYTES, TILE_BYTES, &bar_full[st]);
@@ -251,9 +254,9 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
             int cursor = g;
             for (LfSub sbt = lf_next<PAIR>(cursor, a); sbt.sb >= 0; sbt = lf_next<PAIR>(cursor, a)) {
                 for (int tau = 0; tau <= sbt.Lmax; ++tau) {
-                    if (tau >= 1 && tau < sbt.Lmax) stream(0, tau & 1);               // P1: layer-1 step tau
-                    if (tau >= 1) stream(1, (tau - 1) & 1);                           // P2: layer-2 step tau-1, input part
-                    if (tau >= 2) stream(2, (tau - 1) & 1);                           // P3: layer-2 step tau-1, recurrent part
+                    if (tau >= 1 && tau < sbt.Lmax) stream(0, tau);                   // P1: layer-1 step tau
+                    if (tau >= 1) stream(1, tau - 1);                                 // P2: layer-2 step tau-1, input part
+                    if (tau >= 2) stream(2, tau - 1);                                 // P3: layer-2 step tau-1, recurrent part
                 }
             }
         }
@@ -558,7 +561,7 @@ static int launch_variant(mdf_ctx *ctx, LstmFusedArgs &a, size_t smem)
     return MDF_OK;
 }
 
-int launch_lstm_fused(mdf_ctx *ctx, int H, int n, const __half *const W[3][2], const float *tab, const float *b2,
+int launch_lstm_fused(mdf_ctx *ctx, int H, int n, const __half *W, int phases, const float *tab, const float *b2,
                       const uint8_t *idx_pad, const int *order, const int64_t *seq_off, const int64_t *seg_off,
                       __half *H1img, __half *H2img, void *scratch)
 {
@@ -574,21 +577,17 @@ int launch_lstm_fused(mdf_ctx *ctx, int H, int n, const __half *const W[3][2], c
     a.n_sub = cdiv(n, sub_n);
     const int max_groups = std::max(1, ctx->sm_count / (a.cpg * (pair ? 2 : 1)));
     a.n_groups = std::min(max_groups, a.n_sub);
-    for (int m = 0; m < 3; ++m) {
-        a.W[m][1] = W[m][0];              // odd steps use R_a, even steps R_b (same convention as lstm_tc.cu)
-        a.W[m][0] = W[m][1];
-    }
+    a.W = W; a.phases = phases;
     a.tab = tab; a.b2 = b2; a.idx_pad = idx_pad; a.order = order;
     a.seq_off = seq_off; a.seg_off = seg_off; a.H1img = H1img; a.H2img = H2img;
     if ((size_t)a.n_groups * 2 * 2 * LF_MAX_KB * sizeof(unsigned) > 8192) { set_error("lstm_fused: too many groups"); return MDF_EUNSUPPORTED; }
     a.flags = reinterpret_cast<unsigned *>(scratch);
     a.hbuf = reinterpret_cast<__half *>(reinterpret_cast<uint8_t *>(scratch) + 8192);
     MDF_CUDA(cudaMemsetAsync(scratch, 0, 8192, ctx->stream));
-    memset(a.tmW, 0, sizeof(a.tmW));
+    memset(&a.tmW, 0, sizeof(a.tmW));
     memset(&a.tmH, 0, sizeof(a.tmH));
     if (pair) {
-        for (int m = 0; m < 3; ++m)
-            for (int q = 0; q < 2; ++q) MDF_TRY(make_tile_map(&a.tmW[m][q], a.W[m][q], (size_t)4 * H * H * 2));
+        MDF_TRY(make_tile_map(&a.tmW, a.W, (size_t)3 * phases * 4 * H * H * 2));
         MDF_TRY(make_tile_map(&a.tmH, a.hbuf, (size_t)a.n_groups * 2 * 4 * LF_M * H * 2));
     }
     a.trace = nullptr; a.trace_items = 0;

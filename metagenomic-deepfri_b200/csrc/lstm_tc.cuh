@@ -21,11 +21,12 @@ int launch_lstm_stream(mdf_ctx *ctx, int H, int n, const __half *Ra, const __hal
                        const uint8_t *idx_pad, const int *order, const int64_t *seq_off, const int64_t *seg_off,
                        __half *Himg, void *scratch);
 
-// fused two-layer wavefront kernel (lstm_fused.cu): W = {R1, W2, R2} x (R_a, R_b) images with rows ordered
-// (cta, gate, unit) for 64-unit CTA slices; tab = [26][H][4] fp32, b2 = [H][4] fp32 ([unit][gate] order)
+// fused two-layer wavefront kernel (lstm_fused.cu): W = [R1, W2, R2][phase][4H x H] contiguous images with rows ordered
+// (slice, gate, unit) for 64-unit slices, `phases` time-dither roundings each; tab = [26][H][4] fp32, b2 = [H][4] fp32
+// ([unit][gate] order)
 bool lstm_fused_supported(int H, int n_lstm);
 size_t lstm_fused_scratch_bytes(const mdf_ctx *ctx, int H);
-int launch_lstm_fused(mdf_ctx *ctx, int H, int n, const __half *const W[3][2], const float *tab, const float *b2,
+int launch_lstm_fused(mdf_ctx *ctx, int H, int n, const __half *W, int phases, const float *tab, const float *b2,
                       const uint8_t *idx_pad, const int *order, const int64_t *seq_off, const int64_t *seg_off,
                       __half *H1img, __half *H2img, void *scratch);
 

@@ -35,7 +35,8 @@ struct TcModel {
     __half *lstm_Rstream[MDF_MAX_LSTM][2] = {{nullptr}};   // streamed kernel: [4H rows (cta,gate,unit) x H], (R_a, R_b)
     float *lstm_tab_full = nullptr;                        // [26][H][4] layer-1 table over all units
     int lstm_stream_min = 2048;                            // proteins per batch from which the streamed kernel is used
-    __half *lstm_fused_W[3][2] = {{nullptr}};              // fused kernel: R1, W2, R2 as [4H rows (cta64, gate, unit) x H], (R_a, R_b)
+    __half *lstm_fused_W = nullptr;                        // fused kernel: [R1, W2, R2][phase][4H rows (slice, gate, unit) x H] images
+    int lstm_phases = 8;                                   // time-dither period of the fused kernel's weights (sigma-delta rounding)
     int lstm_fused = 1;                                    // use the fused two-layer wavefront kernel when supported
     float *lstm_tab = nullptr;                             // [H/16][26][16][4] layer-1 input table (bias folded)
     __half *lstm_Win[MDF_MAX_LSTM][2] = {{nullptr}};       // layers >= 2: [4H rows in (unit,gate) order x H k]
@@ -76,6 +77,28 @@ static void build_image_host(const float *src, int rows, int K, bool transposed_
         }
 }
 
+// Time-dithered weight images: P fp16 roundings q_1..q_P of every weight, chosen by first-order error feedback
+// (q_k = fp16(k v - sum_{j<k} q_j)) so that their MEAN equals v to ulp/(2P).  A kernel that uses image t mod P on
+// step t sees rounding errors that cancel over every window of P steps instead of accumulating coherently along
+// the sequence - log2(P) extra mantissa bits for the price of P images in L2, no extra MMAs.
+static void build_dither_images_host(const float *src, int rows, int K, int P, __half *out)
+{
+    const int KB = cdiv(K, TILE_K);
+    const size_t img = (size_t)cdiv(rows, TILE_ROWS) * KB * (TILE_BYTES / 2);
+    for (size_t i = 0; i < img * P; ++i) out[i] = __float2half(0.0f);
+    for (int r = 0; r < rows; ++r)
+        for (int k = 0; k < K; ++k) {
+            const double v = src[(size_t)r * K + k];
+            const size_t off = image_offset_bytes(r, k, KB) / 2;
+            double acc = 0.0;
+            for (int p = 0; p < P; ++p) {
+                const __half q = __float2half_rn((float)((p + 1) * v - acc));
+                acc += (double)__half2float(q);
+                out[(size_t)p * img + off] = q;
+            }
+        }
+}
+
 static int upload_half(mdf_model *m, __half **dst, const std::vector<__half> &src)
 {
     MDF_CUDA(cudaMalloc((void **)dst, src.size() * sizeof(__half)));
@@ -91,6 +114,7 @@ int tc_model_init(mdf_model *m, const mdf_model_desc *d)
     if (const char *e = getenv("MDF_LSTM_HILO")) t->lstm_alternate = atoi(e) ? 0 : 1;   // 1 = hi+lo on every step
     if (const char *e = getenv("MDF_LSTM_STREAM_MIN")) t->lstm_stream_min = atoi(e);
     if (const char *e = getenv("MDF_LSTM_FUSED")) t->lstm_fused = atoi(e);
+    if (const char *e = getenv("MDF_LSTM_PHASES")) t->lstm_phases = std::min(64, std::max(1, atoi(e)));
     // shape constraints of the tile-image GEMMs
     bool ok = m->H % 64 == 0 && m->E % 128 == 0;
     for (int l = 0; l < m->n_gc; ++l) ok = ok && m->gc[l] % 128 == 0;
@@ -182,21 +206,23 @@ int tc_model_init(mdf_model *m, const mdf_model_desc *d)
         }
     }
     if (lstm_fused_supported(H, m->n_lstm)) {
-        // fused kernel: CTA s owns units [64s, 64s+64) of both layers; rows ordered (cta, gate, unit) so that
-        // TMEM column = gate*64 + unit: image row s*256 + gate*64 + u <- ONNX row gate*H + s*64 + u
+        // fused kernel: slice s owns units [64s, 64s+64) of both layers; rows ordered (slice, gate, unit) so that
+        // TMEM column = gate*64 + unit: image row s*256 + gate*64 + u <- ONNX row gate*H + s*64 + u.
+        // One image per matrix and dither phase, contiguous: [R1, W2, R2][phase][4H x H].
         const float *src[3] = {d->lstm_R[0], d->lstm_W[1], d->lstm_R[1]};
-        std::vector<float> Wp((size_t)H4 * H);
+        const int P = t->lstm_phases;
+        const size_t img_elems = (size_t)H4 * H;
+        std::vector<__half> all(3 * (size_t)P * img_elems);
+        std::vector<float> Wp(img_elems);
         for (int mi = 0; mi < 3; ++mi) {
             for (int s = 0; s < H / 64; ++s)
                 for (int gate = 0; gate < 4; ++gate)
                     for (int u = 0; u < 64; ++u)
                         std::copy(src[mi] + (size_t)(gate * H + s * 64 + u) * H, src[mi] + (size_t)(gate * H + s * 64 + u + 1) * H,
                                   Wp.begin() + (size_t)(s * 256 + gate * 64 + u) * H);
-            std::vector<__half> wa, wb;
-            build_image_host(Wp.data(), H4, H, false, H, wa, wb, true);
-            MDF_TRY(upload_half(m, &t->lstm_fused_W[mi][0], wa));
-            MDF_TRY(upload_half(m, &t->lstm_fused_W[mi][1], wb));
+            build_dither_images_host(Wp.data(), H4, H, P, all.data() + (size_t)mi * P * img_elems);
         }
+        MDF_TRY(upload_half(m, &t->lstm_fused_W, all));
     }
     if (lstm_tc_smem_bytes(H) > 227 * 1024) return MDF_OK;   // cannot keep the slices resident: engine unavailable
     t->ok = true;
@@ -398,7 +424,7 @@ size_t tc_workspace_bytes(const mdf_model *m, int n, const int64_t *seq_off)
     add((size_t)Tp * m->E * 2);                       // X0 image
     add((size_t)Tp * gmax * 2); add((size_t)Tp * gmax * 2); add((size_t)Tp * gmax * 2);   // Y^T, X_a, X_b images
     add((size_t)tiles * TILE_BYTES + 256);            // A_hat images
-    add((size_t)T * gmax * 4);                        // fp32 tap of the last GraphConv layer
+    add((size_t)T * gmax * 4); add((size_t)T * m->E * 4);   // fp32 taps of the last GraphConv layer and of X0
     return b + 8192;
 }
 
@@ -437,8 +463,8 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto)
     MDF_TRY(ctx->alloc_n(&deg_pad, (size_t)Tp));
     MDF_TRY(ctx->alloc_n(&idx_pad, (size_t)Tp));
     for (int l = 0; l < m->n_lstm; ++l) MDF_TRY(ctx->alloc_n(&Hlimg[l], (size_t)Tp * m->H));
-    if (m->n_lstm > 1 && !(tm->lstm_fused && tm->lstm_fused_W[0][0])) MDF_TRY(ctx->alloc_n(&pre, (size_t)Tp * 4 * m->H));
-    const bool fused = tm->lstm_fused && tm->lstm_fused_W[0][0] != nullptr;
+    if (m->n_lstm > 1 && !(tm->lstm_fused && tm->lstm_fused_W)) MDF_TRY(ctx->alloc_n(&pre, (size_t)Tp * 4 * m->H));
+    const bool fused = tm->lstm_fused && tm->lstm_fused_W != nullptr;
     MDF_TRY(ctx->alloc(&scratch, std::max({lstm_tc_scratch_bytes(ctx, m->H), lstm_stream_scratch_bytes(ctx, m->H),
                                            lstm_fused_scratch_bytes(ctx, m->H)})));
     MDF_TRY(ctx->alloc_n(&X0img, (size_t)Tp * m->E));
@@ -453,7 +479,7 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto)
     if (fused) {
         // both layers + the layer-2 input projection in one persistent wavefront kernel (lstm_fused.cu)
         ProfScope ps(ctx, "lstm_fused", 3.0 * 2.0 * T * 4 * m->H * m->H);
-        MDF_TRY(launch_lstm_fused(ctx, m->H, n, tm->lstm_fused_W, tm->lstm_tab_full, tm->lstm_bperm[1], idx_pad, b->d_order,
+        MDF_TRY(launch_lstm_fused(ctx, m->H, n, tm->lstm_fused_W, tm->lstm_phases, tm->lstm_tab_full, tm->lstm_bperm[1], idx_pad, b->d_order,
                                   b->d_seq_off, meta->seg_off, ctx->debug_taps ? Hlimg[0] : nullptr, Hlimg[1], scratch));
         b->tap_h[0] = b->tap_h[1] = nullptr;
     }
@@ -503,6 +529,14 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto)
         g.bias = m->lm_b; g.gtab = m->aa_W; g.gidx = idx_pad; g.ldg = m->E;
         MDF_TRY(launch_gemm_tc(ctx, EPI_IMG_EMBED, 128, 1, 2, g));
     }
+    b->tap_x0 = nullptr;
+    if (ctx->debug_taps) {                                // fp32 copy of X0 over packed residues
+        float *tap = nullptr;
+        MDF_TRY(ctx->alloc_n(&tap, (size_t)T * m->E));
+        image_to_f32_kernel<<<(unsigned)cdiv64(Tp * m->E, 256), 256, 0, s>>>(X0img, m->E, meta->rowmap, Tp, tap);
+        MDF_LAUNCH_CHECK(ctx);
+        b->tap_x0 = tap;
+    }
     if (upto < 3) return MDF_OK;
     // ---- adjacency operand tiles
     if (meta->n_adj_tiles > 0) {
@@ -550,8 +584,7 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto)
         }
         Xin = Xout; kin = gd; goff += gd; Xlast = Xout;
     }
-    // fp32 taps (debug / parity API): X0 and the last GraphConv output over packed residues
-    b->tap_x0 = nullptr;
+    // fp32 tap (debug / parity API): the last GraphConv output over packed residues
     b->tap_gc_last = nullptr;
     if (ctx->debug_taps) {
         float *tap = nullptr;
