@@ -5,11 +5,14 @@ DeepFRI GCN MF forward) on N B200s of one node, one process per GPU.
   python bench.py --gpus 1 --steps K --warmup W            # this repo's CUDA path
   python bench.py --impl reference ...                     # the reference's CPU path (oracle) on host cores
 
-One "step" = one pass of the whole path over one batch of BASELINE.json configs[0]
-(1,000 synthetic proteins, L~U{100..500}, Markov-gapped alignments, random-walk C-alpha structures,
-10 A contact maps, random-init MF head C=489 in the reference's ONNX layout).  Weak scaling: every
-rank processes its own 1,000-protein batch (seed 1 + rank); no collective on the compute path, one
-final host gather of the score matrices.
+One "step" = one pass of the whole path over one batch of synthetic proteins.  The default workload is
+the configuration BASELINE.json's metric is quoted on, configs[4] (the 1M-protein metagenomic MF job,
+L ~ LogNormal(median 250, sigma 0.6) clipped to [50, 1000]), processed the way the sharded job runs it:
+in batches of 16,384 proteins per GPU (Markov-gapped alignments, random-walk C-alpha structures, 10 A
+contact maps, random-init MF head C=489 in the reference's ONNX layout).  `--workload config0` selects
+configs[0] (1,000 proteins, L~U{100..500}), the reference's own CPU-runnable case.  Weak scaling: every
+rank processes its own batch (seed + rank); no collective on the compute path, one final gather of the
+score matrices.
 
 Prints ONE JSON line on rank 0 (contract in the task statement).
 """
@@ -33,7 +36,21 @@ mdf_pkg.load()
 from metagenomic_deepfri_b200 import synth  # noqa: E402
 
 THRESHOLD, GEN = 10.0, 2
-WORKLOAD = "BASELINE configs[0]: 1000 synthetic proteins L~U{100..500}, gapped alignments, 10A maps, MF head C=489"
+WORKLOADS = {
+    # name: (description, default proteins per step per GPU, generator)
+    "config4": ("BASELINE configs[4]: 1M-protein metagenomic MF job, L~LogNormal(250, 0.6) clipped [50,1000], run in "
+                "batches of {n} proteins per GPU per step; gapped alignments, 10A maps, MF head C=489", 16384,
+                lambda n, seed: synth.make_workload(n, 50, 1000, seed=seed, dist="lognormal", threshold=THRESHOLD)),
+    "config0": ("BASELINE configs[0]: {n} synthetic proteins L~U{{100..500}}, gapped alignments, 10A maps, MF head C=489", 1000,
+                lambda n, seed: synth.make_workload(n, 100, 500, seed=seed, threshold=THRESHOLD)),
+}
+
+
+def make_batch(args, rank):
+    desc, default_n, gen = WORKLOADS[args.workload]
+    n = args.proteins or default_n
+    base_seed = 5 if args.workload == "config4" else 1
+    return gen(n, base_seed + rank), desc.format(n=n)
 
 
 def parse():
@@ -42,7 +59,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--proteins", type=int, default=1000, help="proteins per step per GPU")
+    ap.add_argument("--workload", default="config4", choices=sorted(WORKLOADS))
+    ap.add_argument("--proteins", type=int, default=0, help="proteins per step per GPU (0 = the workload's default)")
     ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tc"])
     ap.add_argument("--cpu-sample", type=int, default=400, help="proteins in the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -56,6 +74,15 @@ def measured_peaks():
         return {"hbm_gbs": d["hbm_gbs"], "tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
                 "tflops_burst": d["bf16_tflops"], "source": "measured (MEASURED_PEAKS.json)"}
     return {"hbm_gbs": 6650.0, "tflops": 1400.0, "tflops_burst": 1590.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def ncu_traffic(stage):
+    """dram bytes (read + write) per launch of the stage's kernel from the committed `ncu --set full` capture of this
+    same command (profiles/ncu_traffic.json, written by tools/ncu_summary.py), or None."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get(stage)
+    return None
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
@@ -95,7 +122,7 @@ def blas_threads():
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    wl = synth.make_workload(args.proteins, 100, 500, seed=1, threshold=THRESHOLD)
+    wl, workload = make_batch(args, 0)
     per_step = 6
     with tempfile.TemporaryDirectory() as d:
         path = os.path.join(d, "mf.onnx")
@@ -114,7 +141,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "proteins/sec (GCN MF fwd incl. cmap)", "value": value, "unit": "proteins/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": f"{per_step} proteins per step drawn from the 1000-protein batch",
+        "config": {"workload": workload, "sample": f"{per_step} proteins per step drawn from one {len(wl)}-protein batch",
                    "cmap": cm_impl, "gcn": "fp32 NumPy ONNX interpreter (onnxruntime absent)"},
         "cpu_baseline": {"value": value, "unit": "proteins/s", "cores": cores, "kind": "port",
                          "sample": f"{per_step * args.steps} proteins, batch=1 per call, host has {os.cpu_count()} cpus"},
@@ -178,7 +205,7 @@ def run_b200(args, rank, world, local_rank):
     stream = torch.cuda.Stream()             # a real (non-NULL) stream shared by torch and the library
     torch.cuda.set_stream(stream)
     ctx = _lib.Context(local_rank, stream=stream.cuda_stream)
-    wl = synth.make_workload(args.proteins, 100, 500, seed=1 + rank, threshold=THRESHOLD)
+    wl, workload = make_batch(args, rank)
     tmp = tempfile.mkdtemp()
     path = os.path.join(tmp, f"mf_{rank}.onnx")
     synth.write_gcn_model(path, synth.GCNConfig())
@@ -245,15 +272,20 @@ def run_b200(args, rank, world, local_rank):
     dev_ms, e2e_ms = float(t[0]), float(t[1])
 
     # ---- per-stage profile (separate, untimed pass) for the roofline object
-    ctx.profile(True)
-    pred.run(batch, THRESHOLD, GEN)
-    stages = ctx.profile_report()
-    ctx.profile(False)
-    peaks = measured_peaks()
+    PROF_PASSES = 3
     agg = {}
-    for name, ms, units in stages:
-        a = agg.setdefault(name, [0.0, 0.0, 0])
-        a[0] += ms; a[1] += units; a[2] += 1
+    for _ in range(PROF_PASSES):
+        flush.zero_()
+        ctx.profile(True)
+        pred.run(batch, THRESHOLD, GEN)
+        stages = ctx.profile_report()
+        ctx.profile(False)
+        for name, ms, units in stages:
+            a = agg.setdefault(name, [0.0, 0.0, 0])
+            a[0] += ms / PROF_PASSES; a[1] += units / PROF_PASSES; a[2] += 1
+    for a in agg.values():
+        a[2] //= PROF_PASSES
+    peaks = measured_peaks()
     stage_total = sum(a[0] for a in agg.values())
     dom = max(agg.items(), key=lambda kv: kv[1][0])
     dname, (dms, dunits, dcount) = dom
@@ -262,7 +294,7 @@ def run_b200(args, rank, world, local_rank):
     else:
         roof = {"bound": "tensor", "achieved": dunits / (dms * 1e-3) / 1e12, "peak": peaks["tflops"], "unit": "TFLOP/s"}
     roof["frac"] = roof["achieved"] / roof["peak"]
-    roof["traffic"] = None
+    roof["traffic"] = ncu_traffic(dname)
     roof["kernel"] = dname
     roof["launches_per_step"] = dcount
     roof["share_of_step"] = dms / stage_total if stage_total else None
@@ -285,7 +317,7 @@ def run_b200(args, rank, world, local_rank):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32" if pred.engine == "simt" else "f16 (hi/lo split weights) with f32 accumulate",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "proteins_per_step_per_gpu": n, "residues_per_step_per_gpu": T,
+        "config": {"workload": workload, "proteins_per_step_per_gpu": n, "residues_per_step_per_gpu": T,
                    "threshold_A": THRESHOLD, "generated_contacts": GEN, "engine": pred.engine,
                    "l2": "flushed between timed iterations (256 MiB memset outside the event pairs)",
                    "timing": "per-step CUDA events on the launch stream, summed over steps, max over ranks"},

@@ -26,7 +26,8 @@ gemm_tc_kernel(GemmArgs g, int a_terms, int b_terms, int stages)
     constexpr int NSUB = BN / 128;                 // B sub-tiles (one 128x128x16 MMA each)
     __shared__ GemmBarriers bars;
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int a_bytes = a_terms * TILE_BYTES;
+    const bool a_per_sub = g.a_phases > 0;                  // one A tile per 128-column sub-tile (dither phase follows the residue tile)
+    const int a_bytes = (a_per_sub ? NSUB : a_terms) * TILE_BYTES;
     const int stage_bytes = a_bytes + b_terms * NSUB * TILE_BYTES;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = g.m_tiles * g.n_tiles;
@@ -55,14 +56,23 @@ gemm_tc_kernel(GemmArgs g, int a_terms, int b_terms, int stages)
                     mbar_wait(&bars.empty[st], ph ^ 1);
                     mbar_arrive_expect_tx(&bars.full[st], (uint32_t)stage_bytes);
                     uint8_t *dst = smem + (size_t)st * stage_bytes;
-                    for (int ta = 0; ta < a_terms; ++ta)
-                        bulk_g2s(dst + ta * TILE_BYTES,
-                                 reinterpret_cast<const uint8_t *>(g.A[ta]) + (size_t)(a_tile0 + kb) * TILE_BYTES,
-                                 TILE_BYTES, &bars.full[st]);
+                    if (a_per_sub) {
+                        for (int j = 0; j < NSUB; ++j)
+                            bulk_g2s(dst + j * TILE_BYTES,
+                                     reinterpret_cast<const uint8_t *>(g.A[0]) + (size_t)((nt * NSUB + j) % g.a_phases) * g.a_phase_stride +
+                                         (size_t)(a_tile0 + kb) * TILE_BYTES,
+                                     TILE_BYTES, &bars.full[st]);
+                    } else {
+                        for (int ta = 0; ta < a_terms; ++ta)
+                            bulk_g2s(dst + ta * TILE_BYTES,
+                                     reinterpret_cast<const uint8_t *>(g.A[ta]) + (size_t)(a_tile0 + kb) * TILE_BYTES,
+                                     TILE_BYTES, &bars.full[st]);
+                    }
+                    const size_t b_phase_off = g.b_phases > 0 ? (size_t)(mt % g.b_phases) * g.b_phase_stride : 0;
                     for (int tb = 0; tb < b_terms; ++tb)
                         for (int j = 0; j < NSUB; ++j)
                             bulk_g2s(dst + a_bytes + (tb * NSUB + j) * TILE_BYTES,
-                                     reinterpret_cast<const uint8_t *>(g.B[tb]) +
+                                     reinterpret_cast<const uint8_t *>(g.B[tb]) + b_phase_off +
                                          ((size_t)(nt * NSUB + j) * g.KB_B + b_kb0 + kb) * TILE_BYTES,
                                      TILE_BYTES, &bars.full[st]);
                     if (++st == stages) { st = 0; ph ^= 1; }
@@ -86,6 +96,16 @@ gemm_tc_kernel(GemmArgs g, int a_terms, int b_terms, int stages)
                     tcgen05_fence_after();
                     const uint32_t sa = smem_u32(smem + (size_t)st * stage_bytes);
                     const uint32_t sb = sa + a_bytes;
+                    if (a_per_sub) {
+#pragma unroll
+                        for (int ks = 0; ks < TILE_K / 16; ++ks)
+#pragma unroll
+                            for (int j = 0; j < NSUB; ++j) {
+                                const uint64_t ad = umma_smem_desc(sa + j * TILE_BYTES + ks * 2 * TILE_LBO, TILE_LBO, TILE_SBO);
+                                const uint64_t bd = umma_smem_desc(sb + j * TILE_BYTES + ks * 2 * TILE_LBO, TILE_LBO, TILE_SBO);
+                                umma_f16(d0 + j * 128, ad, bd, idesc, (kb | ks) != 0);
+                            }
+                    } else
                     // every (A term, B term) pair contributes; at most one side has two terms
                     for (int ta = 0; ta < a_terms; ++ta)
                         for (int tb = 0; tb < b_terms; ++tb)
@@ -222,7 +242,7 @@ gemm_tc_kernel(GemmArgs g, int a_terms, int b_terms, int stages)
 template <int EPI, int BN>
 static int launch_one(mdf_ctx *ctx, int a_terms, int b_terms, const GemmArgs &args)
 {
-    const int stage_bytes = (a_terms + b_terms * (BN / 128)) * TILE_BYTES;
+    const int stage_bytes = ((args.a_phases > 0 ? BN / 128 : a_terms) + b_terms * (BN / 128)) * TILE_BYTES;
     int stages = (int)((200 * 1024) / stage_bytes);
     if (stages > 8) stages = 8;
     if (stages < 2) { set_error("gemm_tc: stage of %d bytes does not fit twice in shared memory", stage_bytes); return MDF_EUNSUPPORTED; }

@@ -24,6 +24,14 @@ struct GemmArgs {
     int m_tiles = 0, n_tiles = 0;    // output tiles (128 rows x BN columns)
     int nkb = 0;                     // k-blocks per output tile (regular case)
     int m_fastest = 0;               // tile order: consecutive CTAs walk M first (B tile shared in L2) instead of N first
+    // Dithered single-term weights (tc_engine.cu build_dither_images_host): the weight operand exists as `phases`
+    // roundings whose mean is exact; the phase follows the 128-row residue tile, so the rounding error cancels
+    // across the tiles of a protein instead of accumulating in the sum-pool (half the MMAs of a hi+lo split).
+    //   b_phases > 0: B = weights, phase = m-tile % b_phases           (B[0] + phase * b_phase_stride bytes)
+    //   a_phases > 0: A = weights, phase = (nt*NSUB + j) % a_phases per 128-column sub-tile j: the stage holds one
+    //                 A tile per sub-tile and MMA j pairs A_j with B sub-tile j   (A[0] + phase * a_phase_stride bytes)
+    int a_phases = 0, b_phases = 0;
+    size_t a_phase_stride = 0, b_phase_stride = 0;
     // grouped case (adjacency product): per m-tile {A tile index of its first k-block, first k-block
     // on the B side, number of k-blocks, unused}
     const int4 *tile_info = nullptr;

@@ -27,8 +27,13 @@ int simt_lstm_stack(mdf_model *m, mdf_batch *b, float **Hl, float *pre, float *C
 using namespace tc;
 
 struct TcModel {
-    __half *lm_W[2] = {nullptr, nullptr};                  // [E rows x H k]  (B operand of the embed GEMM)
-    __half *gc_W[MDF_MAX_GC][2] = {{nullptr}};             // [g rows x k_in] (A operand of X.W, transposed)
+    __half *lm_W[2] = {nullptr, nullptr};                  // [E rows x H k]  (B operand of the embed GEMM), hi / lo terms
+    __half *gc_W[MDF_MAX_GC][2] = {{nullptr}};             // [g rows x k_in] (A operand of X.W, transposed), hi / lo terms
+    int gemm_phases = 0;                                   // > 0 (MDF_GEMM_PHASES, experiment): single-term dithered weights, phase = residue tile
+                                                           // % phases.  Measured and rejected as default: a short protein spans 1-3 tiles, so
+                                                           // the rounding error does not cancel (6.7e-4 at L~128) and scores depend on the batch
+    __half *lm_Wd = nullptr;                               // [phases][E rows x H k]
+    __half *gc_Wd[MDF_MAX_GC] = {nullptr};                 // [phases][g rows x k_in]
     __half *lstm_R[MDF_MAX_LSTM] = {nullptr};              // [H/16][2][64 x H] resident recurrent slices (hi, lo)
     __half *lstm_Ralt[MDF_MAX_LSTM] = {nullptr};           // same, time-dithered pair (R_a, R_b = fp16(2R - R_a))
     int lstm_alternate = 1;
@@ -115,6 +120,7 @@ int tc_model_init(mdf_model *m, const mdf_model_desc *d)
     if (const char *e = getenv("MDF_LSTM_STREAM_MIN")) t->lstm_stream_min = atoi(e);
     if (const char *e = getenv("MDF_LSTM_FUSED")) t->lstm_fused = atoi(e);
     if (const char *e = getenv("MDF_LSTM_PHASES")) t->lstm_phases = std::min(64, std::max(1, atoi(e)));
+    if (const char *e = getenv("MDF_GEMM_PHASES")) t->gemm_phases = std::min(64, std::max(0, atoi(e)));   // 0: hi+lo split on every tile
     // shape constraints of the tile-image GEMMs
     bool ok = m->H % 64 == 0 && m->E % 128 == 0;
     for (int l = 0; l < m->n_gc; ++l) ok = ok && m->gc[l] % 128 == 0;
@@ -123,11 +129,21 @@ int tc_model_init(mdf_model *m, const mdf_model_desc *d)
     build_image_host(d->lm_W, m->E, m->H, true, m->E, hi, lo);       // rows = E (n), k = H : lm_W[k][n]
     MDF_TRY(upload_half(m, &t->lm_W[0], hi));
     MDF_TRY(upload_half(m, &t->lm_W[1], lo));
+    auto upload_dithered = [&](const float *src_kn, int rows, int K, __half **dst) -> int {   // src[k][row] -> [phases][rows x K] images
+        std::vector<float> tr((size_t)rows * K);
+        for (int r = 0; r < rows; ++r)
+            for (int k = 0; k < K; ++k) tr[(size_t)r * K + k] = src_kn[(size_t)k * rows + r];
+        std::vector<__half> all((size_t)t->gemm_phases * cdiv(rows, TILE_ROWS) * cdiv(K, TILE_K) * (TILE_BYTES / 2));
+        build_dither_images_host(tr.data(), rows, K, t->gemm_phases, all.data());
+        return upload_half(m, dst, all);
+    };
+    if (t->gemm_phases > 0) MDF_TRY(upload_dithered(d->lm_W, m->E, m->H, &t->lm_Wd));
     int prev = m->E;
     for (int l = 0; l < m->n_gc; ++l) {
         build_image_host(d->gc_W[l], m->gc[l], prev, true, m->gc[l], hi, lo);   // rows = out, k = in : W[k][out]
         MDF_TRY(upload_half(m, &t->gc_W[l][0], hi));
         MDF_TRY(upload_half(m, &t->gc_W[l][1], lo));
+        if (t->gemm_phases > 0) MDF_TRY(upload_dithered(d->gc_W[l], m->gc[l], prev, &t->gc_Wd[l]));
         prev = m->gc[l];
     }
     // ---- LSTM: resident recurrent slices, layer-1 table, input-GEMM weights of the upper layers
@@ -527,7 +543,13 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto)
         g.m_tiles = meta->m_tiles; g.n_tiles = m->E / 128; g.nkb = m->H / TILE_K;
         g.out_img = X0img; g.KB_out = m->E / TILE_K;
         g.bias = m->lm_b; g.gtab = m->aa_W; g.gidx = idx_pad; g.ldg = m->E;
-        MDF_TRY(launch_gemm_tc(ctx, EPI_IMG_EMBED, 128, 1, 2, g));
+        if (tm->lm_Wd) {                                  // single-term weights, dither phase = residue tile
+            g.B[0] = tm->lm_Wd; g.B[1] = nullptr;
+            g.b_phases = tm->gemm_phases; g.b_phase_stride = (size_t)m->E * m->H * 2;
+            MDF_TRY(launch_gemm_tc(ctx, EPI_IMG_EMBED, 128, 1, 1, g));
+        } else {
+            MDF_TRY(launch_gemm_tc(ctx, EPI_IMG_EMBED, 128, 1, 2, g));
+        }
     }
     b->tap_x0 = nullptr;
     if (ctx->debug_taps) {                                // fp32 copy of X0 over packed residues
@@ -562,7 +584,13 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto)
             g.out_img = Yt; g.KB_out = (int)(Tp / TILE_K);
             g.colscale = deg_pad;
             g.m_fastest = 1;                              // the 4 feature tiles of one residue block run back to back: X is read once
-            MDF_TRY(launch_gemm_tc(ctx, EPI_IMG_COLSCALE, 256, 2, 1, g));
+            if (tm->gc_Wd[l]) {                           // single-term weights, dither phase = residue tile
+                g.A[0] = tm->gc_Wd[l]; g.A[1] = nullptr;
+                g.a_phases = tm->gemm_phases; g.a_phase_stride = (size_t)gd * kin * 2;
+                MDF_TRY(launch_gemm_tc(ctx, EPI_IMG_COLSCALE, 256, 1, 1, g));
+            } else {
+                MDF_TRY(launch_gemm_tc(ctx, EPI_IMG_COLSCALE, 256, 2, 1, g));
+            }
         }
         __half *Xout = (l & 1) ? Xb : Xa;
         {
