@@ -53,8 +53,9 @@ constexpr int LF_MAX_KB = 8;
 struct LstmFusedArgs {
     int H, n, n_groups, cpg, n_sub;
     int cell_mode;            // 0: exp/rcp cell (fp32-accurate), 1: tanh.approx cell
-    const __half *W;          // [R1, W2, R2][phase][4H rows (slice, gate, unit) x H] operand images (time-dither phases)
-    int phases;
+    const __half *W;          // [R1, W2, R2][phases + 2][4H rows (slice, gate, unit) x H] operand images: `phases` time-dither
+    int phases;               //   roundings, then the exact split (hi, lo)
+    int precise_len;          // sub-batches whose longest protein exceeds this run both split terms on every step
     const float *tab;         // [26][H][4] layer-1 pre-activation table ([unit][gate] order, bias folded)
     const float *b2;          // [H][4] layer-2 bias ([unit][gate] order)
     const uint8_t *idx_pad;   // [Tp]
@@ -233,10 +234,13 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
         if (lane == 0) {
             int st = 0; uint32_t ph = 0;
             const int tiles_per_img = 4 * H / TILE_ROWS * KB;
+            bool precise = false;
             auto stream = [&](int mi, int step) {                 // weights of matrix mi for (layer) step `step`
-                const int img = mi * a.phases + step % a.phases;
-                const uint8_t *src = reinterpret_cast<const uint8_t *>(a.W) + ((size_t)img * tiles_per_img + (size_t)(2 * s) * KB) * TILE_BYTES;
+                const int img0 = mi * (a.phases + 2) + (precise ? a.phases : step % a.phases);
                 for (int kb = 0; kb < KB; ++kb)
+                  for (int term = 0; term < (precise ? 2 : 1); ++term) {
+                    const int img = img0 + term;
+                    const uint8_t *src = reinterpret_cast<const uint8_t *>(a.W) + ((size_t)img * tiles_per_img + (size_t)(2 * s) * KB) * TILE_BYTES;
                     for (int jj = 0; jj < TPK; ++jj) {
                         const int j = PAIR ? r : jj;                  // row tile of the slice: gates {2j, 2j+1}
                         mbar_wait(&bar_empty[st], ph ^ 1);
@@ -250,9 +254,11 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
                         }
                         if (++st == LF_STAGES) { st = 0; ph ^= 1; }
                     }
+                  }
             };
             int cursor = g;
             for (LfSub sbt = lf_next<PAIR>(cursor, a); sbt.sb >= 0; sbt = lf_next<PAIR>(cursor, a)) {
+                precise = sbt.Lmax > a.precise_len;
                 for (int tau = 0; tau <= sbt.Lmax; ++tau) {
                     if (tau >= 1 && tau < sbt.Lmax) stream(0, tau);                   // P1: layer-1 step tau
                     if (tau >= 1) stream(1, tau - 1);                                 // P2: layer-2 step tau-1, input part
@@ -315,6 +321,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
             long long *tw = a.trace + (size_t)a.trace_items * 8;     // [item][4]: per tick cycles waiting on operand chunks, weights, g1/g2 drain
             long long acc_h = 0, acc_w = 0, acc_g = 0;
             // one pass over the operand in shared memory: gates[acc] (+)= W_slice . operand
+            int nterms = 1;
             auto pass = [&](uint32_t d0, bool accumulate, bool wait_h, bool release_chunks) {
                 for (int kb = 0; kb < KB; ++kb) {
                     if (wait_h) {
@@ -326,7 +333,8 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
                     }
                     tcgen05_fence_after();
                     const uint64_t hd = umma_smem_desc(sh_addr + kb * TILE_BYTES, TILE_LBO, TILE_SBO);   // A: proteins x 64 k
-                    for (int jj = 0; jj < TPK; ++jj) {
+                    for (int tj = 0; tj < nterms * TPK; ++tj) {
+                        const int term = tj / TPK, jj = tj % TPK;
                         {
                             const long long c0 = trw ? clock64() : 0;
                             mbar_wait(&bar_full[st], ph);
@@ -338,10 +346,10 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
                         for (int ks = 0; ks < TILE_K / 16; ++ks) {
                             if (PAIR)
                                 umma_f16_pair(tmem_base + d0, hd + (uint64_t)(ks * 256), wd + (uint64_t)(ks * 256), idesc,
-                                              accumulate || (kb | ks) != 0);
+                                              accumulate || (kb | ks | term) != 0);
                             else
                                 umma_f16(tmem_base + d0 + (uint32_t)(jj * 128), hd + (uint64_t)(ks * 256), wd + (uint64_t)(ks * 256), idesc,
-                                         accumulate || (kb | ks) != 0);
+                                         accumulate || (kb | ks | term) != 0);
                         }
                         if (PAIR) umma_commit_pair(&bar_empty[st], 3); else umma_commit(&bar_empty[st]);
                         if (++st == LF_STAGES) { st = 0; ph ^= 1; }
@@ -363,6 +371,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
             };
             int cursor = g;
             for (LfSub sbt = lf_next<PAIR>(cursor, a); sbt.sb >= 0; sbt = lf_next<PAIR>(cursor, a)) {
+                nterms = sbt.Lmax > a.precise_len ? 2 : 1;
                 for (int tau = 1; tau <= sbt.Lmax; ++tau, ++item) {
                     const bool tr = a.trace && blockIdx.x == 0 && item < a.trace_items;
                     if (tr) { a.trace[item * 8 + 0] = clock64(); a.trace[(size_t)a.trace_items * 12 + item * 16 + 3] = lf_gtime(); }
@@ -578,6 +587,8 @@ int launch_lstm_fused(mdf_ctx *ctx, int H, int n, const __half *W, int phases, c
     const int max_groups = std::max(1, ctx->sm_count / (a.cpg * (pair ? 2 : 1)));
     a.n_groups = std::min(max_groups, a.n_sub);
     a.W = W; a.phases = phases;
+    static const int precise_env = getenv("MDF_LSTM_PRECISE_LEN") ? atoi(getenv("MDF_LSTM_PRECISE_LEN")) : 1000;
+    a.precise_len = precise_env;
     a.tab = tab; a.b2 = b2; a.idx_pad = idx_pad; a.order = order;
     a.seq_off = seq_off; a.seg_off = seg_off; a.H1img = H1img; a.H2img = H2img;
     if ((size_t)a.n_groups * 2 * 2 * LF_MAX_KB * sizeof(unsigned) > 8192) { set_error("lstm_fused: too many groups"); return MDF_EUNSUPPORTED; }
@@ -587,7 +598,7 @@ int launch_lstm_fused(mdf_ctx *ctx, int H, int n, const __half *W, int phases, c
     memset(&a.tmW, 0, sizeof(a.tmW));
     memset(&a.tmH, 0, sizeof(a.tmH));
     if (pair) {
-        MDF_TRY(make_tile_map(&a.tmW, a.W, (size_t)3 * phases * 4 * H * H * 2));
+        MDF_TRY(make_tile_map(&a.tmW, a.W, (size_t)3 * (phases + 2) * 4 * H * H * 2));
         MDF_TRY(make_tile_map(&a.tmH, a.hbuf, (size_t)a.n_groups * 2 * 4 * LF_M * H * 2));
     }
     a.trace = nullptr; a.trace_items = 0;

@@ -224,11 +224,12 @@ int tc_model_init(mdf_model *m, const mdf_model_desc *d)
     if (lstm_fused_supported(H, m->n_lstm)) {
         // fused kernel: slice s owns units [64s, 64s+64) of both layers; rows ordered (slice, gate, unit) so that
         // TMEM column = gate*64 + unit: image row s*256 + gate*64 + u <- ONNX row gate*H + s*64 + u.
-        // One image per matrix and dither phase, contiguous: [R1, W2, R2][phase][4H x H].
+        // Per matrix, contiguous: P time-dither roundings, then the exact split (hi, lo) that long proteins use:
+        // [R1, W2, R2][P + 2][4H x H].
         const float *src[3] = {d->lstm_R[0], d->lstm_W[1], d->lstm_R[1]};
         const int P = t->lstm_phases;
         const size_t img_elems = (size_t)H4 * H;
-        std::vector<__half> all(3 * (size_t)P * img_elems);
+        std::vector<__half> all(3 * (size_t)(P + 2) * img_elems);
         std::vector<float> Wp(img_elems);
         for (int mi = 0; mi < 3; ++mi) {
             for (int s = 0; s < H / 64; ++s)
@@ -236,7 +237,10 @@ int tc_model_init(mdf_model *m, const mdf_model_desc *d)
                     for (int u = 0; u < 64; ++u)
                         std::copy(src[mi] + (size_t)(gate * H + s * 64 + u) * H, src[mi] + (size_t)(gate * H + s * 64 + u + 1) * H,
                                   Wp.begin() + (size_t)(s * 256 + gate * 64 + u) * H);
-            build_dither_images_host(Wp.data(), H4, H, P, all.data() + (size_t)mi * P * img_elems);
+            build_dither_images_host(Wp.data(), H4, H, P, all.data() + (size_t)mi * (P + 2) * img_elems);
+            build_image_host(Wp.data(), H4, H, false, H, hi, lo);
+            std::copy(hi.begin(), hi.end(), all.begin() + ((size_t)mi * (P + 2) + P) * img_elems);
+            std::copy(lo.begin(), lo.end(), all.begin() + ((size_t)mi * (P + 2) + P + 1) * img_elems);
         }
         MDF_TRY(upload_half(m, &t->lstm_fused_W, all));
     }
