@@ -1,4 +1,6 @@
 // tcgen05 GEMM kernel (see gemm_tc.cuh).
+#include <algorithm>
+
 #include "gemm_tc.cuh"
 
 namespace mdf {
@@ -18,6 +20,83 @@ __device__ __forceinline__ float act_f(float v, int act, float alpha)
     return v;
 }
 
+// One 32-column chunk of an output row: fused scale / bias / activation / gather, then fp16 image or fp32 store.
+template <int EPI>
+__device__ __forceinline__ void gemm_epilogue_chunk(const GemmArgs &g, uint32_t (&r)[32], int64_t m, int n0, float rs,
+                                                    const float *grow, uint8_t *row_ptr)
+{
+    if (EPI == EPI_F32_BIAS) {
+        if (m < g.m_valid) {
+            float *dst = g.out_f32 + (size_t)m * g.ldc + n0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                if (n0 + 4 * q < g.n_valid) {
+                    float4 v;
+                    const float4 b = g.bias ? __ldg(reinterpret_cast<const float4 *>(g.bias + n0 + 4 * q)) : make_float4(0, 0, 0, 0);
+                    v.x = __uint_as_float(r[4 * q + 0]) + b.x; v.y = __uint_as_float(r[4 * q + 1]) + b.y;
+                    v.z = __uint_as_float(r[4 * q + 2]) + b.z; v.w = __uint_as_float(r[4 * q + 3]) + b.w;
+                    *reinterpret_cast<float4 *>(dst + 4 * q) = v;
+                }
+            }
+        }
+    } else {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (EPI == EPI_IMG_COLSCALE) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 cs = __ldg(reinterpret_cast<const float4 *>(g.colscale + n0 + 4 * q));
+                v[4 * q + 0] = cs.x != 0.0f ? v[4 * q + 0] * cs.x : 0.0f;
+                v[4 * q + 1] = cs.y != 0.0f ? v[4 * q + 1] * cs.y : 0.0f;
+                v[4 * q + 2] = cs.z != 0.0f ? v[4 * q + 2] * cs.z : 0.0f;
+                v[4 * q + 3] = cs.w != 0.0f ? v[4 * q + 3] * cs.w : 0.0f;
+            }
+        } else if (EPI == EPI_IMG_ROWSCALE) {
+            if (g.bias) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float4 b = __ldg(reinterpret_cast<const float4 *>(g.bias + n0 + 4 * q));
+                    v[4 * q + 0] = fmaf(v[4 * q + 0], rs, b.x); v[4 * q + 1] = fmaf(v[4 * q + 1], rs, b.y);
+                    v[4 * q + 2] = fmaf(v[4 * q + 2], rs, b.z); v[4 * q + 3] = fmaf(v[4 * q + 3], rs, b.w);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] *= rs;
+            }
+            if (g.act == 1) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+            } else if (g.act == 2) {
+                const float alpha = g.alpha;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float e = alpha * (__expf(fminf(v[j], 0.0f)) - 1.0f);   // branch-free ELU
+                    v[j] = v[j] > 0.0f ? v[j] : e;
+                }
+            }
+        } else if (EPI == EPI_IMG_EMBED) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 b = __ldg(reinterpret_cast<const float4 *>(g.bias + n0 + 4 * q));
+                const float4 a = __ldg(reinterpret_cast<const float4 *>(grow + n0 + 4 * q));
+                v[4 * q + 0] = fmaxf(v[4 * q + 0] + b.x + a.x, 0.0f);
+                v[4 * q + 1] = fmaxf(v[4 * q + 1] + b.y + a.y, 0.0f);
+                v[4 * q + 2] = fmaxf(v[4 * q + 2] + b.z + a.z, 0.0f);
+                v[4 * q + 3] = fmaxf(v[4 * q + 3] + b.w + a.w, 0.0f);
+            }
+        }
+        uint8_t *dst = row_ptr + (size_t)(n0 >> 6) * TILE_BYTES + (((n0 & 63) >> 3) * 2048);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint4 pk;
+            pk.x = pack_half2(v[8 * q + 0], v[8 * q + 1]); pk.y = pack_half2(v[8 * q + 2], v[8 * q + 3]);
+            pk.z = pack_half2(v[8 * q + 4], v[8 * q + 5]); pk.w = pack_half2(v[8 * q + 6], v[8 * q + 7]);
+            *reinterpret_cast<uint4 *>(dst + q * 2048) = pk;
+        }
+    }
+}
+
 template <int EPI, int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(GemmArgs g, int a_terms, int b_terms, int stages)
@@ -30,7 +109,10 @@ gemm_tc_kernel(GemmArgs g, int a_terms, int b_terms, int stages)
     const int a_bytes = (a_per_sub ? NSUB : a_terms) * TILE_BYTES;
     const int stage_bytes = a_bytes + b_terms * NSUB * TILE_BYTES;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int total_tiles = g.m_tiles * g.n_tiles;
+    // One CTA walks a whole group of tiles that share an operand panel back to back (all feature tiles of one
+    // residue block when m_fastest, all column tiles of one row block otherwise), so the shared panel is re-read
+    // from L2 by the CTA that just touched it instead of by neighbours that may have drifted out of phase.
+    const int inner = g.m_fastest ? g.m_tiles : g.n_tiles, outer = g.m_fastest ? g.n_tiles : g.m_tiles;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) { mbar_init(&bars.full[s], 1); mbar_init(&bars.empty[s], 1); }
@@ -47,8 +129,9 @@ gemm_tc_kernel(GemmArgs g, int a_terms, int b_terms, int stages)
         // ===================== producer: bulk-TMA tile images into the stage ring
         if (lane == 0) {
             int st = 0; uint32_t ph = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const int mt = g.m_fastest ? t % g.m_tiles : t / g.n_tiles, nt = g.m_fastest ? t / g.m_tiles : t % g.n_tiles;
+            for (int grp = blockIdx.x; grp < outer; grp += gridDim.x)
+            for (int in = 0; in < inner; ++in) {
+                const int mt = g.m_fastest ? in : grp, nt = g.m_fastest ? grp : in;
                 int a_tile0, b_kb0, nkb;
                 if (g.tile_info) { const int4 ti = g.tile_info[mt]; a_tile0 = ti.x; b_kb0 = ti.y; nkb = ti.z; }
                 else { a_tile0 = mt * g.KB_A; b_kb0 = 0; nkb = g.nkb; }
@@ -85,8 +168,9 @@ gemm_tc_kernel(GemmArgs g, int a_terms, int b_terms, int stages)
             constexpr uint32_t idesc = umma_idesc_f16(128, 128);
             int st = 0; uint32_t ph = 0;
             int acc = 0; uint32_t acc_ph = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const int mt = g.m_fastest ? t % g.m_tiles : t / g.n_tiles;
+            for (int grp = blockIdx.x; grp < outer; grp += gridDim.x)
+            for (int in = 0; in < inner; ++in) {
+                const int mt = g.m_fastest ? in : grp;
                 const int nkb = g.tile_info ? g.tile_info[mt].z : g.nkb;
                 mbar_wait(&bars.tmem_empty[acc], acc_ph ^ 1);
                 tcgen05_fence_after();
@@ -132,8 +216,9 @@ gemm_tc_kernel(GemmArgs g, int a_terms, int b_terms, int stages)
         const int lb = (warp & 3) * 32;          // this warp's TMEM lane block = output rows
         const int ch = (warp - 2) >> 2;          // column half handled by this warp
         int acc = 0; uint32_t acc_ph = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-            const int mt = g.m_fastest ? t % g.m_tiles : t / g.n_tiles, nt = g.m_fastest ? t / g.m_tiles : t % g.n_tiles;
+        for (int grp = blockIdx.x; grp < outer; grp += gridDim.x)
+        for (int in = 0; in < inner; ++in) {
+            const int mt = g.m_fastest ? in : grp, nt = g.m_fastest ? grp : in;
             const int nkb = g.tile_info ? g.tile_info[mt].z : g.nkb;
             mbar_wait(&bars.tmem_full[acc], acc_ph);
             tcgen05_fence_after();
@@ -156,77 +241,7 @@ gemm_tc_kernel(GemmArgs g, int a_terms, int b_terms, int stages)
 #pragma unroll
                     for (int j = 0; j < 32; ++j) r[j] = 0u;
                 }
-                const int n0 = nt * BN + c0;
-                if (EPI == EPI_F32_BIAS) {
-                    if (m < g.m_valid) {
-                        float *dst = g.out_f32 + (size_t)m * g.ldc + n0;
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            if (n0 + 4 * q < g.n_valid) {
-                                float4 v;
-                                const float4 b = g.bias ? __ldg(reinterpret_cast<const float4 *>(g.bias + n0 + 4 * q)) : make_float4(0, 0, 0, 0);
-                                v.x = __uint_as_float(r[4 * q + 0]) + b.x; v.y = __uint_as_float(r[4 * q + 1]) + b.y;
-                                v.z = __uint_as_float(r[4 * q + 2]) + b.z; v.w = __uint_as_float(r[4 * q + 3]) + b.w;
-                                *reinterpret_cast<float4 *>(dst + 4 * q) = v;
-                            }
-                        }
-                    }
-                } else {
-                    float v[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                    if (EPI == EPI_IMG_COLSCALE) {
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const float4 cs = __ldg(reinterpret_cast<const float4 *>(g.colscale + n0 + 4 * q));
-                            v[4 * q + 0] = cs.x != 0.0f ? v[4 * q + 0] * cs.x : 0.0f;
-                            v[4 * q + 1] = cs.y != 0.0f ? v[4 * q + 1] * cs.y : 0.0f;
-                            v[4 * q + 2] = cs.z != 0.0f ? v[4 * q + 2] * cs.z : 0.0f;
-                            v[4 * q + 3] = cs.w != 0.0f ? v[4 * q + 3] * cs.w : 0.0f;
-                        }
-                    } else if (EPI == EPI_IMG_ROWSCALE) {
-                        if (g.bias) {
-#pragma unroll
-                            for (int q = 0; q < 8; ++q) {
-                                const float4 b = __ldg(reinterpret_cast<const float4 *>(g.bias + n0 + 4 * q));
-                                v[4 * q + 0] = fmaf(v[4 * q + 0], rs, b.x); v[4 * q + 1] = fmaf(v[4 * q + 1], rs, b.y);
-                                v[4 * q + 2] = fmaf(v[4 * q + 2], rs, b.z); v[4 * q + 3] = fmaf(v[4 * q + 3], rs, b.w);
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] *= rs;
-                        }
-                        if (g.act == 1) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
-                        } else if (g.act == 2) {
-                            const float alpha = g.alpha;
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                const float e = alpha * (__expf(fminf(v[j], 0.0f)) - 1.0f);   // branch-free ELU
-                                v[j] = v[j] > 0.0f ? v[j] : e;
-                            }
-                        }
-                    } else if (EPI == EPI_IMG_EMBED) {
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const float4 b = __ldg(reinterpret_cast<const float4 *>(g.bias + n0 + 4 * q));
-                            const float4 a = __ldg(reinterpret_cast<const float4 *>(grow + n0 + 4 * q));
-                            v[4 * q + 0] = fmaxf(v[4 * q + 0] + b.x + a.x, 0.0f);
-                            v[4 * q + 1] = fmaxf(v[4 * q + 1] + b.y + a.y, 0.0f);
-                            v[4 * q + 2] = fmaxf(v[4 * q + 2] + b.z + a.z, 0.0f);
-                            v[4 * q + 3] = fmaxf(v[4 * q + 3] + b.w + a.w, 0.0f);
-                        }
-                    }
-                    uint8_t *dst = row_ptr + (size_t)(n0 >> 6) * TILE_BYTES + (((n0 & 63) >> 3) * 2048);
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        uint4 pk;
-                        pk.x = pack_half2(v[8 * q + 0], v[8 * q + 1]); pk.y = pack_half2(v[8 * q + 2], v[8 * q + 3]);
-                        pk.z = pack_half2(v[8 * q + 4], v[8 * q + 5]); pk.w = pack_half2(v[8 * q + 6], v[8 * q + 7]);
-                        *reinterpret_cast<uint4 *>(dst + q * 2048) = pk;
-                    }
-                }
+                gemm_epilogue_chunk<EPI>(g, r, m, nt * BN + c0, rs, grow, row_ptr);
             }
             tcgen05_fence_before();
             __syncwarp();
@@ -237,6 +252,211 @@ gemm_tc_kernel(GemmArgs g, int a_terms, int b_terms, int stages)
     tcgen05_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc<2 * BN>(tmem_base);
+}
+
+
+// ------------------------------------------------------------------------------------------- CTA-pair GEMM (cta_group::2)
+// 256 x 256 output tiles on two SMs: each CTA stages its own 128 rows of A and its own 128 rows of B (per term),
+// the leader issues M = 256, N = 256 MMAs that read both CTAs' shared memory, and each CTA's TMEM receives its
+// 128 rows x 256 columns.  Per SM that is half the L2 -> SM operand traffic per FLOP of the 128 x 128/256 single-CTA
+// tiles - the weight GEMMs (K = 512 / 1024, two fp16 terms on the weight side) are bound by that traffic, not by
+// the tensor pipe.  Operand tiles arrive by tensor-map TMA (cta_group::2 form) so that both CTAs' copies complete
+// on the leader's barrier.
+struct PairGemmArgs {
+    GemmArgs g;                        // m_tiles / n_tiles count 256-row / 256-column tiles here
+    alignas(64) CUtensorMap tmA[2];    // flat [bytes/512][256] u16 maps over the A / B term images
+    alignas(64) CUtensorMap tmB[2];
+    int a_terms, b_terms, stages;
+};
+
+template <int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_pair_kernel(const __grid_constant__ PairGemmArgs pa)
+{
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    constexpr int BN = 256;
+    __shared__ GemmBarriers bars;
+    const GemmArgs &g = pa.g;
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int a_terms = pa.a_terms, b_terms = pa.b_terms, stages = pa.stages;
+    const int a_bytes = a_terms * TILE_BYTES;
+    const int stage_bytes = a_bytes + b_terms * TILE_BYTES;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = (int)cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const int inner = g.m_fastest ? g.m_tiles : g.n_tiles, outer = g.m_fastest ? g.n_tiles : g.m_tiles;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) { mbar_init(&bars.full[s], 1); mbar_init(&bars.empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&bars.tmem_full[s], 1); mbar_init(&bars.tmem_empty[s], 16); }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc_pair<2 * BN>(&bars.tmem_base);
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = bars.tmem_base;
+
+    if (warp == 0) {
+        // ===================== producer (both CTAs): my 128 rows of every A / B term tile; bytes land on the leader's barrier.
+        // (Measured alternative: the leader issuing the peer's copies too is 10-20 % slower - one SM's TMA engine then
+        // carries the traffic of two.)
+        if (lane == 0) {
+            int st = 0; uint32_t ph = 0;
+            for (int grp = pair; grp < outer; grp += n_pairs)
+            for (int in = 0; in < inner; ++in) {
+                const int mt = g.m_fastest ? in : grp, nt = g.m_fastest ? grp : in;
+                for (int kb = 0; kb < g.nkb; ++kb) {
+                    mbar_wait(&bars.empty[st], ph ^ 1);
+                    if (leader) mbar_arrive_expect_tx(&bars.full[st], (uint32_t)(2 * stage_bytes));
+                    uint8_t *dst = smem + (size_t)st * stage_bytes;
+                    for (int ta = 0; ta < a_terms; ++ta)
+                        tma_tile_g2s_pair(dst + ta * TILE_BYTES, &pa.tmA[ta], ((mt * 2 + rank) * g.KB_A + kb) * (TILE_BYTES / 512), &bars.full[st]);
+                    for (int tb = 0; tb < b_terms; ++tb)
+                        tma_tile_g2s_pair(dst + a_bytes + tb * TILE_BYTES, &pa.tmB[tb], ((nt * 2 + rank) * g.KB_B + kb) * (TILE_BYTES / 512),
+                                          &bars.full[st]);
+                    if (++st == stages) { st = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA)
+        if (lane == 0 && leader) {
+            constexpr uint32_t idesc = umma_idesc_f16(256, 256);
+            int st = 0; uint32_t ph = 0;
+            int acc = 0; uint32_t acc_ph = 0;
+            for (int grp = pair; grp < outer; grp += n_pairs)
+            for (int in = 0; in < inner; ++in) {
+                mbar_wait(&bars.tmem_empty[acc], acc_ph ^ 1);
+                tcgen05_fence_after();
+                const uint32_t d0 = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < g.nkb; ++kb) {
+                    mbar_wait(&bars.full[st], ph);
+                    tcgen05_fence_after();
+                    const uint32_t sa = smem_u32(smem + (size_t)st * stage_bytes);
+                    const uint32_t sb = sa + a_bytes;
+                    for (int ta = 0; ta < a_terms; ++ta)
+                        for (int tb = 0; tb < b_terms; ++tb)
+#pragma unroll
+                            for (int ks = 0; ks < TILE_K / 16; ++ks) {
+                                const uint64_t ad = umma_smem_desc(sa + ta * TILE_BYTES + ks * 2 * TILE_LBO, TILE_LBO, TILE_SBO);
+                                const uint64_t bd = umma_smem_desc(sb + tb * TILE_BYTES + ks * 2 * TILE_LBO, TILE_LBO, TILE_SBO);
+                                umma_f16_pair(d0, ad, bd, idesc, (kb | ks | ta | tb) != 0);
+                            }
+                    umma_commit_pair(&bars.empty[st], 3);          // frees the stage in both CTAs when the MMAs retire
+                    if (kb == g.nkb - 1) umma_commit_pair(&bars.tmem_full[acc], 3);
+                    if (++st == stages) { st = 0; ph ^= 1; }
+                }
+                if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue (both CTAs): my 128 rows x 256 columns
+        const int lb = (warp & 3) * 32;
+        const int ch = (warp - 2) >> 2;
+        int acc = 0; uint32_t acc_ph = 0;
+        for (int grp = pair; grp < outer; grp += n_pairs)
+        for (int in = 0; in < inner; ++in) {
+            const int mt = g.m_fastest ? in : grp, nt = g.m_fastest ? grp : in;
+            mbar_wait(&bars.tmem_full[acc], acc_ph);
+            tcgen05_fence_after();
+            const int64_t m = ((int64_t)mt * 2 + rank) * 128 + lb + lane;
+            const uint32_t trow = tmem_base + ((uint32_t)lb << 16) + (uint32_t)(acc * BN);
+            float rs = 1.0f;
+            const float *grow = nullptr;
+            if (EPI == EPI_IMG_ROWSCALE) rs = g.rowscale[m];
+            if (EPI == EPI_IMG_EMBED) grow = g.gtab + (size_t)g.gidx[m] * g.ldg;
+            uint8_t *row_ptr = reinterpret_cast<uint8_t *>(g.out_img) + (size_t)(m >> 7) * g.KB_out * TILE_BYTES +
+                               (size_t)((((int)m & 127) >> 3) * 128 + ((int)m & 7) * 16);
+#pragma unroll 1
+            for (int c0 = ch * (BN / 2); c0 < (ch + 1) * (BN / 2); c0 += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(trow + c0, r);
+                tmem_ld_wait();
+                gemm_epilogue_chunk<EPI>(g, r, m, nt * BN + c0, rs, grow, row_ptr);
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (leader) mbar_arrive(&bars.tmem_empty[acc]); else mbar_arrive_remote(&bars.tmem_empty[acc], 0);
+            }
+            if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) tmem_dealloc_pair<2 * BN>(tmem_base);
+}
+
+int make_tile_map(CUtensorMap *map, const void *base, size_t bytes)
+{
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        MDF_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        if (!fn || q != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled is unavailable"); return MDF_ECUDA; }
+        encode = reinterpret_cast<EncodeFn>(fn);
+    }
+    const cuuint64_t dims[2] = {256, (cuuint64_t)(bytes / 512)};
+    const cuuint64_t strides[1] = {512};
+    const cuuint32_t box[2] = {256, 32};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return MDF_ECUDA; }
+    return MDF_OK;
+}
+
+template <int EPI>
+static int launch_pair(mdf_ctx *ctx, int a_terms, int b_terms, const GemmArgs &args, const size_t a_bytes[2], const size_t b_bytes[2])
+{
+    PairGemmArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    pa.g = args;
+    pa.a_terms = a_terms; pa.b_terms = b_terms;
+    const int stage_bytes = (a_terms + b_terms) * TILE_BYTES;
+    pa.stages = std::min(8, (int)((200 * 1024) / stage_bytes));
+    for (int t = 0; t < a_terms; ++t) MDF_TRY(make_tile_map(&pa.tmA[t], args.A[t], a_bytes[t]));
+    for (int t = 0; t < b_terms; ++t) MDF_TRY(make_tile_map(&pa.tmB[t], args.B[t], b_bytes[t]));
+    const size_t smem = (size_t)pa.stages * stage_bytes + 1024;
+    auto kern = gemm_pair_kernel<EPI>;
+    MDF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int outer = args.m_fastest ? args.n_tiles : args.m_tiles;
+    if (outer <= 0 || args.m_tiles * args.n_tiles <= 0) return MDF_OK;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * std::min(outer, ctx->sm_count / 2));
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    MDF_CUDA(cudaLaunchKernelEx(&cfg, kern, pa));
+    ctx->launches++;
+    return MDF_OK;
+}
+
+// m_tiles / n_tiles in `args` count 256-row / 256-column tiles; a_bytes / b_bytes = sizes of the term images
+int launch_gemm_pair(mdf_ctx *ctx, int epi, int a_terms, int b_terms, const GemmArgs &args, const size_t a_bytes[2], const size_t b_bytes[2])
+{
+    if (a_terms < 1 || a_terms > 2 || b_terms < 1 || b_terms > 2 || (a_terms == 2 && b_terms == 2) || args.tile_info || args.a_phases ||
+        args.b_phases) {
+        set_error("gemm_pair: unsupported configuration");
+        return MDF_EUNSUPPORTED;
+    }
+    if (epi == EPI_IMG_EMBED) return launch_pair<EPI_IMG_EMBED>(ctx, a_terms, b_terms, args, a_bytes, b_bytes);
+    if (epi == EPI_IMG_COLSCALE) return launch_pair<EPI_IMG_COLSCALE>(ctx, a_terms, b_terms, args, a_bytes, b_bytes);
+    set_error("gemm_pair: no kernel for epilogue %d", epi);
+    return MDF_EUNSUPPORTED;
 }
 
 template <int EPI, int BN>
@@ -251,7 +471,8 @@ static int launch_one(mdf_ctx *ctx, int a_terms, int b_terms, const GemmArgs &ar
     MDF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int total = args.m_tiles * args.n_tiles;
     if (total <= 0) return MDF_OK;
-    const int grid = total < ctx->sm_count ? total : ctx->sm_count;
+    const int outer = args.m_fastest ? args.n_tiles : args.m_tiles;
+    const int grid = outer < ctx->sm_count ? outer : ctx->sm_count;
     kern<<<grid, GEMM_THREADS, smem, ctx->stream>>>(args, a_terms, b_terms, stages);
     MDF_LAUNCH_CHECK(ctx);
     return MDF_OK;

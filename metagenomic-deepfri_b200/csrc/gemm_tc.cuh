@@ -4,6 +4,8 @@
 // warps 2..5 = epilogue (TMEM -> registers -> global).  Accumulators are double-buffered in TMEM so
 // the epilogue of tile i overlaps the MMAs of tile i+1.
 #pragma once
+#include <cuda.h>
+
 #include "mdf_common.cuh"
 #include "tc_ptx.cuh"
 
@@ -52,6 +54,13 @@ struct GemmArgs {
 };
 
 int launch_gemm_tc(mdf_ctx *ctx, int epi, int bn, int a_terms, int b_terms, const GemmArgs &args);
+
+// CTA-pair (cta_group::2) variant for the regular weight GEMMs: 256 x 256 tiles, m_tiles / n_tiles in `args` count
+// 256-row / 256-column tiles, a_bytes / b_bytes are the byte sizes of the term images (for the tensor maps).
+int launch_gemm_pair(mdf_ctx *ctx, int epi, int a_terms, int b_terms, const GemmArgs &args, const size_t a_bytes[2], const size_t b_bytes[2]);
+
+// flat [bytes/512][256] u16 tensor map whose [32 x 256] boxes are the 16 KiB operand tiles of an image
+int make_tile_map(CUtensorMap *map, const void *base, size_t bytes);
 
 }  // namespace tc
 }  // namespace mdf

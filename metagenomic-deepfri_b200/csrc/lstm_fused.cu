@@ -518,31 +518,6 @@ size_t lstm_fused_scratch_bytes(const mdf_ctx *ctx, int H)
     return (size_t)covers * 4 * LF_M * H * 2 + 8192;
 }
 
-// flat u16 tensor map whose [32 x 256] boxes are the 16 KiB operand tiles of an image
-static int make_tile_map(CUtensorMap *map, const void *base, size_t bytes)
-{
-    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    static EncodeFn encode = nullptr;
-    if (!encode) {
-        void *fn = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        MDF_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
-        if (!fn || q != cudaDriverEntryPointSuccess) { set_error("lstm_fused: cuTensorMapEncodeTiled is unavailable"); return MDF_ECUDA; }
-        encode = reinterpret_cast<EncodeFn>(fn);
-    }
-    const cuuint64_t dims[2] = {256, (cuuint64_t)(bytes / 512)};
-    const cuuint64_t strides[1] = {512};
-    const cuuint32_t box[2] = {256, 32};
-    const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void *>(base), dims, strides, box, estr,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("lstm_fused: cuTensorMapEncodeTiled failed (%d)", (int)r); return MDF_ECUDA; }
-    return MDF_OK;
-}
-
 template <bool PAIR, int MODE>
 static int launch_variant(mdf_ctx *ctx, LstmFusedArgs &a, size_t smem)
 {

@@ -29,6 +29,7 @@ using namespace tc;
 struct TcModel {
     __half *lm_W[2] = {nullptr, nullptr};                  // [E rows x H k]  (B operand of the embed GEMM), hi / lo terms
     __half *gc_W[MDF_MAX_GC][2] = {{nullptr}};             // [g rows x k_in] (A operand of X.W, transposed), hi / lo terms
+    int gemm_pair = 1;                                     // CTA-pair (cta_group::2) kernels for the embedding and X.W GEMMs
     int gemm_phases = 0;                                   // > 0 (MDF_GEMM_PHASES, experiment): single-term dithered weights, phase = residue tile
                                                            // % phases.  Measured and rejected as default: a short protein spans 1-3 tiles, so
                                                            // the rounding error does not cancel (6.7e-4 at L~128) and scores depend on the batch
@@ -120,6 +121,7 @@ int tc_model_init(mdf_model *m, const mdf_model_desc *d)
     if (const char *e = getenv("MDF_LSTM_STREAM_MIN")) t->lstm_stream_min = atoi(e);
     if (const char *e = getenv("MDF_LSTM_FUSED")) t->lstm_fused = atoi(e);
     if (const char *e = getenv("MDF_LSTM_PHASES")) t->lstm_phases = std::min(64, std::max(1, atoi(e)));
+    if (const char *e = getenv("MDF_GEMM_PAIR")) t->gemm_pair = atoi(e);
     if (const char *e = getenv("MDF_GEMM_PHASES")) t->gemm_phases = std::min(64, std::max(0, atoi(e)));   // 0: hi+lo split on every tile
     // shape constraints of the tile-image GEMMs
     bool ok = m->H % 64 == 0 && m->E % 128 == 0;
@@ -551,6 +553,10 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto)
             g.B[0] = tm->lm_Wd; g.B[1] = nullptr;
             g.b_phases = tm->gemm_phases; g.b_phase_stride = (size_t)m->E * m->H * 2;
             MDF_TRY(launch_gemm_tc(ctx, EPI_IMG_EMBED, 128, 1, 1, g));
+        } else if (tm->gemm_pair && Tp % 256 == 0 && m->E % 256 == 0) {   // CTA pairs: 256 x 256 tiles
+            g.m_tiles = (int)(Tp / 256); g.n_tiles = m->E / 256;
+            const size_t ab[2] = {(size_t)Tp * m->H * 2, 0}, bb[2] = {(size_t)m->E * m->H * 2, (size_t)m->E * m->H * 2};
+            MDF_TRY(launch_gemm_pair(ctx, EPI_IMG_EMBED, 1, 2, g, ab, bb));
         } else {
             MDF_TRY(launch_gemm_tc(ctx, EPI_IMG_EMBED, 128, 1, 2, g));
         }
@@ -592,6 +598,10 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto)
                 g.A[0] = tm->gc_Wd[l]; g.A[1] = nullptr;
                 g.a_phases = tm->gemm_phases; g.a_phase_stride = (size_t)gd * kin * 2;
                 MDF_TRY(launch_gemm_tc(ctx, EPI_IMG_COLSCALE, 256, 1, 1, g));
+            } else if (tm->gemm_pair && gd % 256 == 0 && Tp % 256 == 0) {   // CTA pairs: 256 features x 256 residues
+                g.m_tiles = gd / 256; g.n_tiles = (int)(Tp / 256);
+                const size_t ab[2] = {(size_t)gd * kin * 2, (size_t)gd * kin * 2}, bb[2] = {(size_t)Tp * kin * 2, 0};
+                MDF_TRY(launch_gemm_pair(ctx, EPI_IMG_COLSCALE, 2, 1, g, ab, bb));
             } else {
                 MDF_TRY(launch_gemm_tc(ctx, EPI_IMG_COLSCALE, 256, 2, 1, g));
             }

@@ -204,6 +204,18 @@ __device__ __forceinline__ void tma_tile_g2s_pair(void *dst_smem, const void *tm
                  ::"r"(smem_u32(dst_smem)), "l"(tmap), "r"(0), "r"(row512), "r"(mbar) : "memory");
 }
 
+// Same copy issued by the LEADER on behalf of CTA `dst_cta` of its pair: the tile lands at the same offset of that CTA's
+// shared memory and the bytes are credited to the leader's own barrier - the peer needs no producer thread and its
+// stage is refilled without waiting for a commit to cross the pair.
+__device__ __forceinline__ void tma_tile_g2s_pair_to(void *dst_smem, uint32_t dst_cta, const void *tmap, int32_t row512, uint64_t *bar)
+{
+    uint32_t dst;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(dst) : "r"(smem_u32(dst_smem)), "r"(dst_cta));
+    const uint32_t mbar = smem_u32(bar) & 0xFEFFFFFFu;
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(tmap), "r"(0), "r"(row512), "r"(mbar) : "memory");
+}
+
 // ---------------------------------------------------------------- fast transcendental primitives (MUFU, flush-to-zero)
 __device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
