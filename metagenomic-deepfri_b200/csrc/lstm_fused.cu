@@ -49,9 +49,12 @@ constexpr int LF_UPT = LF_U / (LF_EW / 4);           // units per epilogue threa
 constexpr int LF_THREADS = (3 + LF_EW) * 32;         // warp 0: weight producer, 1: operand loader, 2: MMA issuer, 3..: epilogue
 constexpr int LF_TAB_STRIDE = 260;   // floats per residue row of the layer-1 table slice (64 units x 4 gates + pad)
 constexpr int LF_MAX_KB = 8;
+constexpr size_t LF_SCRATCH_HEAD = 1 << 20;   // flags (8 KiB) + schedule, ahead of the exchange buffers
 
 struct LstmFusedArgs {
     int H, n, n_groups, cpg, n_sub;
+    const int *sched;         // [n_groups][sched_stride] sub-batches of each group in execution order, -1 terminated
+    int sched_stride;
     int cell_mode;            // 0: exp/rcp cell (fp32-accurate), 1: tanh.approx cell
     const __half *W;          // [R1, W2, R2][phases + 2][4H rows (slice, gate, unit) x H] operand images: `phases` time-dither
     int phases;               //   roundings, then the exact split (hi, lo)
@@ -128,15 +131,17 @@ __device__ __forceinline__ void lf_cell(float xi, float xo, float xf, float xg, 
 struct LfSub {
     int sb, Lmax;
 };
+// next sub-batch of group g (the host balances the groups' total step counts, see launch_lstm_fused)
 template <bool PAIR>
-__device__ __forceinline__ LfSub lf_next(int &cursor, const LstmFusedArgs &a)
+__device__ __forceinline__ LfSub lf_next(int &cursor, int g, const LstmFusedArgs &a)
 {
     LfSub r{-1, 0};
-    if (cursor < a.n_sub) {
-        const int p0 = a.order[cursor * (PAIR ? 2 * LF_M : LF_M)];   // longest protein of the sub-batch
+    const int sb = cursor < a.sched_stride ? a.sched[g * a.sched_stride + cursor] : -1;
+    if (sb >= 0) {
+        const int p0 = a.order[sb * (PAIR ? 2 * LF_M : LF_M)];       // longest protein of the sub-batch
         r.Lmax = (int)(a.seq_off[p0 + 1] - a.seq_off[p0]);
-        if (r.Lmax > 0) r.sb = cursor;                               // sorted descending: zero length = nothing left
-        cursor += a.n_groups;
+        r.sb = sb;
+        ++cursor;
     }
     return r;
 }
@@ -256,8 +261,8 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
                     }
                   }
             };
-            int cursor = g;
-            for (LfSub sbt = lf_next<PAIR>(cursor, a); sbt.sb >= 0; sbt = lf_next<PAIR>(cursor, a)) {
+            int cursor = 0;
+            for (LfSub sbt = lf_next<PAIR>(cursor, g, a); sbt.sb >= 0; sbt = lf_next<PAIR>(cursor, g, a)) {
                 precise = sbt.Lmax > a.precise_len;
                 for (int tau = 0; tau <= sbt.Lmax; ++tau) {
                     if (tau >= 1 && tau < sbt.Lmax) stream(0, tau);                   // P1: layer-1 step tau
@@ -300,8 +305,8 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
                 }
                 hph ^= 1;
             };
-            int cursor = g;
-            for (LfSub sbt = lf_next<PAIR>(cursor, a); sbt.sb >= 0; sbt = lf_next<PAIR>(cursor, a)) {
+            int cursor = 0;
+            for (LfSub sbt = lf_next<PAIR>(cursor, g, a); sbt.sb >= 0; sbt = lf_next<PAIR>(cursor, g, a)) {
                 for (int tau = 1; tau <= sbt.Lmax; ++tau, ++item) {
                     load(0, tau - 1, done + (unsigned)tau);                        // h1_{tau-1}: published at tick tau-1
                     if (tau >= 2) load(1, tau - 2, done + (unsigned)(tau - 1));    // h2_{tau-2}: published at tick tau-1
@@ -369,8 +374,8 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
                 if (PAIR) umma_commit_pair(&bar_gfull[acc], 3); else umma_commit(&bar_gfull[acc]);
                 ++rounds[acc];
             };
-            int cursor = g;
-            for (LfSub sbt = lf_next<PAIR>(cursor, a); sbt.sb >= 0; sbt = lf_next<PAIR>(cursor, a)) {
+            int cursor = 0;
+            for (LfSub sbt = lf_next<PAIR>(cursor, g, a); sbt.sb >= 0; sbt = lf_next<PAIR>(cursor, g, a)) {
                 nterms = sbt.Lmax > a.precise_len ? 2 : 1;
                 for (int tau = 1; tau <= sbt.Lmax; ++tau, ++item) {
                     const bool tr = a.trace && blockIdx.x == 0 && item < a.trace_items;
@@ -411,9 +416,9 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
         float c1[LF_UPT], c2[LF_UPT];
         unsigned done = 0;
         uint32_t rounds[2] = {0, 0};
-        int cursor = g;
+        int cursor = 0;
         int item = 0;
-        for (LfSub sbt = lf_next<PAIR>(cursor, a); sbt.sb >= 0; sbt = lf_next<PAIR>(cursor, a)) {
+        for (LfSub sbt = lf_next<PAIR>(cursor, g, a); sbt.sb >= 0; sbt = lf_next<PAIR>(cursor, g, a)) {
             // The exchange buffers are reused: every CTA of this half-group must have finished the previous
             // sub-batch (its last operand loads precede its last layer-2 publish) before tick 0 writes them.
             if (et < KB) {
@@ -515,7 +520,7 @@ size_t lstm_fused_scratch_bytes(const mdf_ctx *ctx, int H)
 {
     const int ctas_per_unit_cover = std::max(1, H / LF_U);             // CTAs (of 128 proteins each) covering all units once
     const int covers = std::max(1, ctx->sm_count / ctas_per_unit_cover);
-    return (size_t)covers * 4 * LF_M * H * 2 + 8192;
+    return (size_t)covers * 4 * LF_M * H * 2 + LF_SCRATCH_HEAD;
 }
 
 template <bool PAIR, int MODE>
@@ -530,9 +535,15 @@ static int launch_variant(mdf_ctx *ctx, LstmFusedArgs &a, size_t smem)
     cfg.stream = ctx->stream;
     cudaLaunchAttribute attrs[2];
     int na = 0;
-    attrs[na].id = cudaLaunchAttributeCooperative;      // co-residency: the CTAs spin on each other's release counters
-    attrs[na].val.cooperative = 1;
-    ++na;
+    // Co-residency: the CTAs spin on each other's release counters.  The grid never exceeds one CTA per SM, so a plain
+    // launch is co-resident too whenever the stream owns the GPU; MDF_LSTM_COOP=0 drops the attribute because Nsight
+    // Compute cannot profile a cooperative launch that also carries a cluster dimension.
+    static const int coop_env = getenv("MDF_LSTM_COOP") ? atoi(getenv("MDF_LSTM_COOP")) : 1;
+    if (coop_env) {
+        attrs[na].id = cudaLaunchAttributeCooperative;
+        attrs[na].val.cooperative = 1;
+        ++na;
+    }
     if (PAIR) {
         attrs[na].id = cudaLaunchAttributeClusterDimension;
         attrs[na].val.clusterDim.x = 2; attrs[na].val.clusterDim.y = 1; attrs[na].val.clusterDim.z = 1;
@@ -547,7 +558,7 @@ static int launch_variant(mdf_ctx *ctx, LstmFusedArgs &a, size_t smem)
 
 int launch_lstm_fused(mdf_ctx *ctx, int H, int n, const __half *W, int phases, const float *tab, const float *b2,
                       const uint8_t *idx_pad, const int *order, const int64_t *seq_off, const int64_t *seg_off,
-                      __half *H1img, __half *H2img, void *scratch)
+                      __half *H1img, __half *H2img, void *scratch, const int *h_order, const int64_t *h_seq_off)
 {
     if (n <= 0) return MDF_OK;
     static const int pair_env = getenv("MDF_LSTM_PAIR") ? atoi(getenv("MDF_LSTM_PAIR")) : 1;
@@ -568,8 +579,34 @@ int launch_lstm_fused(mdf_ctx *ctx, int H, int n, const __half *W, int phases, c
     a.seq_off = seq_off; a.seg_off = seg_off; a.H1img = H1img; a.H2img = H2img;
     if ((size_t)a.n_groups * 2 * 2 * LF_MAX_KB * sizeof(unsigned) > 8192) { set_error("lstm_fused: too many groups"); return MDF_EUNSUPPORTED; }
     a.flags = reinterpret_cast<unsigned *>(scratch);
-    a.hbuf = reinterpret_cast<__half *>(reinterpret_cast<uint8_t *>(scratch) + 8192);
+    a.hbuf = reinterpret_cast<__half *>(reinterpret_cast<uint8_t *>(scratch) + LF_SCRATCH_HEAD);
     MDF_CUDA(cudaMemsetAsync(scratch, 0, 8192, ctx->stream));
+    {
+        // Schedule: sub-batch j = proteins order[j*sub_n ..] (length-descending) costs Lmax_j + 1 ticks whatever its other
+        // members' lengths; longest-processing-time-first over the groups keeps them within one sub-batch of each other
+        // (round-robin leaves the first group ~20 % more ticks than the last on a metagenomic length distribution).
+        int used = 0;
+        std::vector<long long> load(a.n_groups, 0);
+        std::vector<std::vector<int>> lists(a.n_groups);
+        for (int j = 0; j < a.n_sub; ++j) {
+            const int p0 = h_order[(size_t)j * sub_n];
+            const long long L = h_seq_off[p0 + 1] - h_seq_off[p0];
+            if (L <= 0) break;                                 // sorted descending: nothing left
+            const int gmin = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+            lists[gmin].push_back(j);
+            load[gmin] += L + 1 + 8;                           // + sub-batch switch overhead
+            ++used;
+        }
+        size_t stride = 1;
+        for (auto &l : lists) stride = std::max(stride, l.size() + 1);
+        if ((size_t)a.n_groups * stride * sizeof(int) > LF_SCRATCH_HEAD - 8192) { set_error("lstm_fused: schedule does not fit"); return MDF_EUNSUPPORTED; }
+        std::vector<int> sched((size_t)a.n_groups * stride, -1);
+        for (int gi = 0; gi < a.n_groups; ++gi) std::copy(lists[gi].begin(), lists[gi].end(), sched.begin() + (size_t)gi * stride);
+        int *d_sched = reinterpret_cast<int *>(reinterpret_cast<uint8_t *>(scratch) + 8192);
+        MDF_CUDA(cudaMemcpyAsync(d_sched, sched.data(), sched.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        a.sched = d_sched; a.sched_stride = (int)stride;
+        (void)used;
+    }
     memset(&a.tmW, 0, sizeof(a.tmW));
     memset(&a.tmH, 0, sizeof(a.tmH));
     if (pair) {

@@ -502,7 +502,8 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto)
         // both layers + the layer-2 input projection in one persistent wavefront kernel (lstm_fused.cu)
         ProfScope ps(ctx, "lstm_fused", 3.0 * 2.0 * T * 4 * m->H * m->H);
         MDF_TRY(launch_lstm_fused(ctx, m->H, n, tm->lstm_fused_W, tm->lstm_phases, tm->lstm_tab_full, tm->lstm_bperm[1], idx_pad, b->d_order,
-                                  b->d_seq_off, meta->seg_off, ctx->debug_taps ? Hlimg[0] : nullptr, Hlimg[1], scratch));
+                                  b->d_seq_off, meta->seg_off, ctx->debug_taps ? Hlimg[0] : nullptr, Hlimg[1], scratch, b->h_order.data(),
+                                  b->h_seq_off.data()));
         b->tap_h[0] = b->tap_h[1] = nullptr;
     }
     // fallback: persistent tcgen05 recurrence per layer, input GEMM between layers
