@@ -7,6 +7,15 @@ namespace mdf {
 namespace tc {
 
 constexpr int GEMM_THREADS = 320;   // warp 0 producer, warp 1 MMA, warps 2-9 epilogue
+// Adjacency instance (EPI_IMG_ROWSCALE, BN = 256): its K is one protein long (a handful of k-blocks), so the ELU
+// epilogue, not the tensor pipe, sets the pace - it gets 16 epilogue warps (4 per scheduler, better latency hiding) and
+// four more warps that expand the A tiles from the bit-packed contact map.
+__host__ __device__ constexpr int gemm_epi_warps(int epi, int bn) { return (epi == EPI_IMG_ROWSCALE && bn == 256) ? 16 : 8; }
+__host__ __device__ constexpr int gemm_threads(int epi, int bn, bool expand) { return (2 + gemm_epi_warps(epi, bn) + (expand ? 4 : 0)) * 32; }
+// Warp roles, lowest warp id first: epilogue warps, (expander warps), producer, MMA issuer.  The SM's warp arbiter prefers
+// the highest warp id among the eligible warps of a scheduler, so the single-thread roles that feed the tensor pipe sit
+// at the top: with the issuer as warp 1 it starved behind the epilogue warps of its scheduler and the tensor pipe idled
+// 70 % of the adjacency GEMM.
 
 struct __align__(8) GemmBarriers {
     uint64_t full[8], empty[8], tmem_full[2], tmem_empty[2];
@@ -70,8 +79,8 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmArgs &g, uint32_t 
             } else if (g.act == 2) {
                 const float alpha = g.alpha;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float e = alpha * (__expf(fminf(v[j], 0.0f)) - 1.0f);   // branch-free ELU
+                for (int j = 0; j < 32; ++j) {                                   // branch-free ELU, one MUFU + 5 ALU ops
+                    const float e = fmaf(alpha, ex2_ftz(fminf(v[j], 0.0f) * 1.4426950408889634f), -alpha);
                     v[j] = v[j] > 0.0f ? v[j] : e;
                 }
             }
@@ -98,9 +107,10 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmArgs &g, uint32_t 
 }
 
 template <int EPI, int BN>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(gemm_threads(EPI, BN, true), 1)
 gemm_tc_kernel(GemmArgs g, int a_terms, int b_terms, int stages)
 {
+    constexpr int EW = gemm_epi_warps(EPI, BN);    // epilogue warps: 4 TMEM lane quarters x EW/4 column ranges
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     constexpr int NSUB = BN / 128;                 // B sub-tiles (one 128x128x16 MMA each)
     __shared__ GemmBarriers bars;
@@ -109,23 +119,26 @@ gemm_tc_kernel(GemmArgs g, int a_terms, int b_terms, int stages)
     const int a_bytes = (a_per_sub ? NSUB : a_terms) * TILE_BYTES;
     const int stage_bytes = a_bytes + b_terms * NSUB * TILE_BYTES;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_warps = blockDim.x >> 5;
+    const int w_prod = n_warps - 2, w_mma = n_warps - 1;
     // One CTA walks a whole group of tiles that share an operand panel back to back (all feature tiles of one
     // residue block when m_fastest, all column tiles of one row block otherwise), so the shared panel is re-read
     // from L2 by the CTA that just touched it instead of by neighbours that may have drifted out of phase.
     const int inner = g.m_fastest ? g.m_tiles : g.n_tiles, outer = g.m_fastest ? g.n_tiles : g.m_tiles;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < stages; ++s) { mbar_init(&bars.full[s], 1); mbar_init(&bars.empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&bars.tmem_full[s], 1); mbar_init(&bars.tmem_empty[s], 8); }
+        // adjacency mode: a stage is full when the B copies landed AND the four expander warps finished the A tile
+        for (int s = 0; s < stages; ++s) { mbar_init(&bars.full[s], g.adj_packed ? 5 : 1); mbar_init(&bars.empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&bars.tmem_full[s], 1); mbar_init(&bars.tmem_empty[s], EW); }
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc<2 * BN>(&bars.tmem_base);
+    if (warp == w_mma) tmem_alloc<2 * BN>(&bars.tmem_base);
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = bars.tmem_base;
 
-    if (warp == 0) {
+    if (warp == w_prod) {
         // ===================== producer: bulk-TMA tile images into the stage ring
         if (lane == 0) {
             int st = 0; uint32_t ph = 0;
@@ -137,9 +150,11 @@ gemm_tc_kernel(GemmArgs g, int a_terms, int b_terms, int stages)
                 else { a_tile0 = mt * g.KB_A; b_kb0 = 0; nkb = g.nkb; }
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(&bars.empty[st], ph ^ 1);
-                    mbar_arrive_expect_tx(&bars.full[st], (uint32_t)stage_bytes);
+                    mbar_arrive_expect_tx(&bars.full[st], (uint32_t)(g.adj_packed ? stage_bytes - a_bytes : stage_bytes));
                     uint8_t *dst = smem + (size_t)st * stage_bytes;
-                    if (a_per_sub) {
+                    if (g.adj_packed) {
+                        // A tile comes from the expander warps
+                    } else if (a_per_sub) {
                         for (int j = 0; j < NSUB; ++j)
                             bulk_g2s(dst + j * TILE_BYTES,
                                      reinterpret_cast<const uint8_t *>(g.A[0]) + (size_t)((nt * NSUB + j) % g.a_phases) * g.a_phase_stride +
@@ -162,21 +177,29 @@ gemm_tc_kernel(GemmArgs g, int a_terms, int b_terms, int stages)
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer
-        if (lane == 0) {
+    } else if (warp == w_mma) {
+        // ===================== MMA issuer: the whole warp walks the loop converged, one elected lane issues
+        {
             constexpr uint32_t idesc = umma_idesc_f16(128, 128);
             int st = 0; uint32_t ph = 0;
             int acc = 0; uint32_t acc_ph = 0;
+            const bool tr = g.trace && blockIdx.x == 0;
+            long long t_info = 0, t_acc = 0, t_full = 0, n_tiles_done = 0;
+            const long long t_begin = tr ? clock64() : 0;
             for (int grp = blockIdx.x; grp < outer; grp += gridDim.x)
             for (int in = 0; in < inner; ++in) {
                 const int mt = g.m_fastest ? in : grp;
+                long long c0 = tr ? clock64() : 0;
                 const int nkb = g.tile_info ? g.tile_info[mt].z : g.nkb;
+                if (tr) { const long long c1 = clock64() + (nkb & 0); t_info += c1 - c0; c0 = c1; }
                 mbar_wait(&bars.tmem_empty[acc], acc_ph ^ 1);
+                if (tr) { const long long c1 = clock64(); t_acc += c1 - c0; ++n_tiles_done; }
                 tcgen05_fence_after();
                 const uint32_t d0 = tmem_base + (uint32_t)(acc * BN);
                 for (int kb = 0; kb < nkb; ++kb) {
+                    c0 = tr ? clock64() : 0;
                     mbar_wait(&bars.full[st], ph);
+                    if (tr) t_full += clock64() - c0;
                     tcgen05_fence_after();
                     const uint32_t sa = smem_u32(smem + (size_t)st * stage_bytes);
                     const uint32_t sb = sa + a_bytes;
@@ -187,34 +210,81 @@ gemm_tc_kernel(GemmArgs g, int a_terms, int b_terms, int stages)
                             for (int j = 0; j < NSUB; ++j) {
                                 const uint64_t ad = umma_smem_desc(sa + j * TILE_BYTES + ks * 2 * TILE_LBO, TILE_LBO, TILE_SBO);
                                 const uint64_t bd = umma_smem_desc(sb + j * TILE_BYTES + ks * 2 * TILE_LBO, TILE_LBO, TILE_SBO);
-                                umma_f16(d0 + j * 128, ad, bd, idesc, (kb | ks) != 0);
+                                umma_f16_elect(d0 + j * 128, ad, bd, idesc, (kb | ks) != 0);
                             }
-                    } else
-                    // every (A term, B term) pair contributes; at most one side has two terms
-                    for (int ta = 0; ta < a_terms; ++ta)
-                        for (int tb = 0; tb < b_terms; ++tb)
+                    } else {
+                        // every (A term, B term) pair contributes; at most one side has two terms
+                        for (int ta = 0; ta < a_terms; ++ta)
+                            for (int tb = 0; tb < b_terms; ++tb)
 #pragma unroll
-                            for (int ks = 0; ks < TILE_K / 16; ++ks) {
-                                const uint64_t ad = umma_smem_desc(sa + ta * TILE_BYTES + ks * 2 * TILE_LBO, TILE_LBO, TILE_SBO);
+                                for (int ks = 0; ks < TILE_K / 16; ++ks) {
+                                    const uint64_t ad = umma_smem_desc(sa + ta * TILE_BYTES + ks * 2 * TILE_LBO, TILE_LBO, TILE_SBO);
 #pragma unroll
-                                for (int j = 0; j < NSUB; ++j) {
-                                    const uint64_t bd = umma_smem_desc(sb + (tb * NSUB + j) * TILE_BYTES + ks * 2 * TILE_LBO,
-                                                                       TILE_LBO, TILE_SBO);
-                                    umma_f16(d0 + j * 128, ad, bd, idesc, (kb | ks | ta | tb) != 0);
+                                    for (int j = 0; j < NSUB; ++j) {
+                                        const uint64_t bd = umma_smem_desc(sb + (tb * NSUB + j) * TILE_BYTES + ks * 2 * TILE_LBO,
+                                                                           TILE_LBO, TILE_SBO);
+                                        umma_f16_elect(d0 + j * 128, ad, bd, idesc, (kb | ks | ta | tb) != 0);
+                                    }
                                 }
-                            }
-                    umma_commit(&bars.empty[st]);                 // frees the smem stage when the MMAs retire
-                    if (kb == nkb - 1) umma_commit(&bars.tmem_full[acc]);
+                    }
+                    umma_commit_elect(&bars.empty[st]);               // frees the smem stage when the MMAs retire
+                    if (kb == nkb - 1) umma_commit_elect(&bars.tmem_full[acc]);
+                    __syncwarp();
                     if (++st == stages) { st = 0; ph ^= 1; }
                 }
-                if (nkb == 0) umma_commit(&bars.tmem_full[acc]);
+                if (nkb == 0) umma_commit_elect(&bars.tmem_full[acc]);
+                __syncwarp();
                 if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+            }
+            if (tr && lane == 0) { g.trace[0] = clock64() - t_begin; g.trace[1] = t_info; g.trace[2] = t_acc; g.trace[3] = t_full; g.trace[4] = n_tiles_done; }
+        }
+    } else if (warp >= EW) {
+        // ===================== A-tile expanders (adjacency mode, 128 threads): thread = one row of the 128 x 64 tile
+        // (measured: a second group of four warps alternating stages is slower - the kernel is issue-bound, not
+        // expander-bound)
+        const int et = threadIdx.x - EW * 32;
+        int st = 0; uint32_t ph = 0;
+        for (int grp = blockIdx.x; grp < outer; grp += gridDim.x)
+        for (int in = 0; in < inner; ++in) {
+            const int mt = g.m_fastest ? in : grp;
+            const int4 ti = g.tile_info[mt];
+            const int nkb = ti.z, p = ti.w;
+            const int L = (int)(g.adj_seq_off[p + 1] - g.adj_seq_off[p]);
+            const int rw = packed_row_words(L);
+            const int i = (mt - (int)(g.adj_seg_off[p] >> 7)) * 128 + et;                 // row of the protein's map
+            const uint32_t *row = g.adj_packed + g.adj_packed_off[p] + (size_t)i * rw;
+            for (int kb = 0; kb < nkb; ++kb) {
+                {
+                    uint32_t w[2] = {0u, 0u};
+                    if (i < L) {
+                        if (2 * kb < rw) w[0] = __ldg(row + 2 * kb);
+                        if (2 * kb + 1 < rw) w[1] = __ldg(row + 2 * kb + 1);
+                    }
+                    if (lane == 0) mbar_wait(&bars.empty[st], ph ^ 1);
+                    __syncwarp();
+                    uint8_t *dst = smem + (size_t)st * stage_bytes + (et >> 3) * 128 + (et & 7) * 16;
+                    const uint32_t one = 0x3C00u;                                            // fp16 1.0
+#pragma unroll
+                    for (int k8 = 0; k8 < 8; ++k8) {
+                        const uint32_t b8 = (w[k8 >> 2] >> (8 * (k8 & 3))) & 0xFFu;
+                        uint4 pk;
+                        pk.x = ((b8 & 1u) ? one : 0u) | ((b8 & 2u) ? one << 16 : 0u);
+                        pk.y = ((b8 & 4u) ? one : 0u) | ((b8 & 8u) ? one << 16 : 0u);
+                        pk.z = ((b8 & 16u) ? one : 0u) | ((b8 & 32u) ? one << 16 : 0u);
+                        pk.w = ((b8 & 64u) ? one : 0u) | ((b8 & 128u) ? one << 16 : 0u);
+                        *reinterpret_cast<uint4 *>(dst + k8 * 2048) = pk;
+                    }
+                    fence_proxy_async_smem();                    // generic-proxy tile -> tensor-core (async proxy) reads
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars.full[st]);
+                }
+                if (++st == stages) { st = 0; ph ^= 1; }
             }
         }
     } else {
         // ===================== epilogue: TMEM -> registers -> global (8 warps: 4 lane blocks x 2 column halves)
         const int lb = (warp & 3) * 32;          // this warp's TMEM lane block = output rows
-        const int ch = (warp - 2) >> 2;          // column half handled by this warp
+        const int ch = warp >> 2;                // column range handled by this warp
         int acc = 0; uint32_t acc_ph = 0;
         for (int grp = blockIdx.x; grp < outer; grp += gridDim.x)
         for (int in = 0; in < inner; ++in) {
@@ -232,7 +302,7 @@ gemm_tc_kernel(GemmArgs g, int a_terms, int b_terms, int stages)
             uint8_t *row_ptr = reinterpret_cast<uint8_t *>(g.out_img) + (size_t)(m >> 7) * g.KB_out * TILE_BYTES +
                                (size_t)((((int)m & 127) >> 3) * 128 + ((int)m & 7) * 16);
 #pragma unroll 1
-            for (int c0 = ch * (BN / 2); c0 < (ch + 1) * (BN / 2); c0 += 32) {
+            for (int c0 = ch * (BN * 4 / EW); c0 < (ch + 1) * (BN * 4 / EW); c0 += 32) {
                 uint32_t r[32];
                 if (nkb > 0) {
                     tmem_ld_32x32b_x32(trow + c0, r);
@@ -251,7 +321,7 @@ gemm_tc_kernel(GemmArgs g, int a_terms, int b_terms, int stages)
     }
     tcgen05_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc<2 * BN>(tmem_base);
+    if (warp == w_mma) tmem_dealloc<2 * BN>(tmem_base);
 }
 
 
@@ -282,6 +352,7 @@ gemm_pair_kernel(const __grid_constant__ PairGemmArgs pa)
     const int a_bytes = a_terms * TILE_BYTES;
     const int stage_bytes = a_bytes + b_terms * TILE_BYTES;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int w_prod = GEMM_THREADS / 32 - 2, w_mma = GEMM_THREADS / 32 - 1;     // warps 0-7 epilogue, 8 producer, 9 MMA issuer
     const int rank = (int)cluster_ctarank();
     const bool leader = rank == 0;
     const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
@@ -292,14 +363,14 @@ gemm_pair_kernel(const __grid_constant__ PairGemmArgs pa)
         for (int s = 0; s < 2; ++s) { mbar_init(&bars.tmem_full[s], 1); mbar_init(&bars.tmem_empty[s], 16); }
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc_pair<2 * BN>(&bars.tmem_base);
+    if (warp == w_mma) tmem_alloc_pair<2 * BN>(&bars.tmem_base);
     tcgen05_fence_before();
     __syncthreads();
     cluster_sync_all();
     tcgen05_fence_after();
     const uint32_t tmem_base = bars.tmem_base;
 
-    if (warp == 0) {
+    if (warp == w_prod) {
         // ===================== producer (both CTAs): my 128 rows of every A / B term tile; bytes land on the leader's barrier.
         // (Measured alternative: the leader issuing the peer's copies too is 10-20 % slower - one SM's TMA engine then
         // carries the traffic of two.)
@@ -321,7 +392,7 @@ gemm_pair_kernel(const __grid_constant__ PairGemmArgs pa)
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == w_mma) {
         // ===================== MMA issuer (leader CTA)
         if (lane == 0 && leader) {
             constexpr uint32_t idesc = umma_idesc_f16(256, 256);
@@ -355,7 +426,7 @@ gemm_pair_kernel(const __grid_constant__ PairGemmArgs pa)
     } else {
         // ===================== epilogue (both CTAs): my 128 rows x 256 columns
         const int lb = (warp & 3) * 32;
-        const int ch = (warp - 2) >> 2;
+        const int ch = warp >> 2;
         int acc = 0; uint32_t acc_ph = 0;
         for (int grp = pair; grp < outer; grp += n_pairs)
         for (int in = 0; in < inner; ++in) {
@@ -388,7 +459,7 @@ gemm_pair_kernel(const __grid_constant__ PairGemmArgs pa)
     tcgen05_fence_before();
     __syncthreads();
     cluster_sync_all();
-    if (warp == 1) tmem_dealloc_pair<2 * BN>(tmem_base);
+    if (warp == w_mma) tmem_dealloc_pair<2 * BN>(tmem_base);
 }
 
 int make_tile_map(CUtensorMap *map, const void *base, size_t bytes)
@@ -473,7 +544,7 @@ static int launch_one(mdf_ctx *ctx, int a_terms, int b_terms, const GemmArgs &ar
     if (total <= 0) return MDF_OK;
     const int outer = args.m_fastest ? args.n_tiles : args.m_tiles;
     const int grid = outer < ctx->sm_count ? outer : ctx->sm_count;
-    kern<<<grid, GEMM_THREADS, smem, ctx->stream>>>(args, a_terms, b_terms, stages);
+    kern<<<grid, gemm_threads(EPI, BN, args.adj_packed != nullptr), smem, ctx->stream>>>(args, a_terms, b_terms, stages);
     MDF_LAUNCH_CHECK(ctx);
     return MDF_OK;
 }

@@ -37,6 +37,12 @@ struct GemmArgs {
     // grouped case (adjacency product): per m-tile {A tile index of its first k-block, first k-block
     // on the B side, number of k-blocks, unused}
     const int4 *tile_info = nullptr;
+    // grouped case with on-the-fly A tiles: instead of reading an expanded fp16 A_hat image (2 B per matrix entry, read
+    // once per column tile) four extra warps build every 128 x 64 A tile in shared memory from the bit-packed contact
+    // map (1 bit per entry).  adj_packed != nullptr selects it; A[] is then unused.
+    long long *trace = nullptr;      // optional [8] cycle counters of CTA 0 (MDF_GEMM_TRACE=1, adjacency GEMM)
+    const uint32_t *adj_packed = nullptr;
+    const int64_t *adj_packed_off = nullptr, *adj_seq_off = nullptr, *adj_seg_off = nullptr;
     // epilogue
     float *out_f32 = nullptr;
     int ldc = 0;

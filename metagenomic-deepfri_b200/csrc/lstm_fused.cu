@@ -46,7 +46,9 @@ constexpr int LF_STAGES = 4;         // weight ring (16 KiB tiles: 128 gate rows
 #endif
 constexpr int LF_EW = LF_EPI_WARPS;                  // epilogue warps (8 or 16): 4 TMEM lane quarters x LF_EW/4 unit ranges
 constexpr int LF_UPT = LF_U / (LF_EW / 4);           // units per epilogue thread (per layer)
-constexpr int LF_THREADS = (3 + LF_EW) * 32;         // warp 0: weight producer, 1: operand loader, 2: MMA issuer, 3..: epilogue
+constexpr int LF_THREADS = (3 + LF_EW) * 32;         // warps 0..LF_EW-1: epilogue, then weight producer, operand loader, MMA issuer
+constexpr int LF_W_PROD = LF_EW, LF_W_LOAD = LF_EW + 1, LF_W_MMA = LF_EW + 2;   // single-thread roles on the highest warp ids: the
+                                                     // arbiter prefers them over the epilogue warps of their scheduler
 constexpr int LF_TAB_STRIDE = 260;   // floats per residue row of the layer-1 table slice (64 units x 4 gates + pad)
 constexpr int LF_MAX_KB = 8;
 constexpr size_t LF_SCRATCH_HEAD = 1 << 20;   // flags (8 KiB) + schedule, ahead of the exchange buffers
@@ -223,7 +225,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
         for (int i = 0; i < 2; ++i) { mbar_init(&bar_gfull[i], 1); mbar_init(&bar_gfree[i], LF_EW * HALVES); }
         fence_mbar_init();
     }
-    if (warp == 2) {
+    if (warp == LF_W_MMA) {
         if (PAIR) tmem_alloc_pair<512>(&tmem_slot); else tmem_alloc<512>(&tmem_slot);
     }
     tcgen05_fence_before();
@@ -234,7 +236,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
     unsigned *flags = a.flags + (size_t)(g * HALVES + r) * 2 * LF_MAX_KB;
     uint8_t *hb = reinterpret_cast<uint8_t *>(a.hbuf) + (size_t)(g * HALVES + r) * 4 * h_bytes;    // [layer][parity][h_bytes]
 
-    if (warp == 0) {
+    if (warp == LF_W_PROD) {
         // =========================================================== weight producer
         if (lane == 0) {
             int st = 0; uint32_t ph = 0;
@@ -271,7 +273,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == LF_W_LOAD) {
         // =========================================================== operand loader (h1_{tau-1}, then h2_{tau-2})
         if (lane == 0) {
             uint32_t hph = 0;
@@ -314,7 +316,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
                 done += (unsigned)sbt.Lmax;
             }
         }
-    } else if (warp == 2) {
+    } else if (warp == LF_W_MMA) {
         // =========================================================== MMA issuer (PAIR: leader CTA only)
         if (lane == 0 && leader) {
             constexpr uint32_t idesc = PAIR ? umma_idesc_f16(256, 256) : umma_idesc_f16(128, 128);
@@ -403,9 +405,9 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
         }
     } else {
         // =========================================================== epilogue: thread = one protein x LF_UPT units x both layers
-        const int et = tid - 96;
+        const int et = tid;
         const int q = warp & 3;                                // TMEM lane quarter this warp may access
-        const int part = (warp - 3) >> 2;                      // units [LF_UPT*part, LF_UPT*(part+1)) of this slice
+        const int part = warp >> 2;                      // units [LF_UPT*part, LF_UPT*(part+1)) of this slice
         const int p = q * 32 + lane;                           // protein inside this CTA's 128 = TMEM lane
         const int ub = part * LF_UPT;                          // first unit (within the slice) of this thread
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)ub;
@@ -501,7 +503,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
     tcgen05_fence_before();
     __syncthreads();
     if (PAIR) cluster_sync_all();          // no MMA, commit or remote arrive of the pair is still in flight
-    if (warp == 2) {
+    if (warp == LF_W_MMA) {
         if (PAIR) tmem_dealloc_pair<512>(tmem_base); else tmem_dealloc<512>(tmem_base);
     }
 }

@@ -29,6 +29,7 @@ using namespace tc;
 struct TcModel {
     __half *lm_W[2] = {nullptr, nullptr};                  // [E rows x H k]  (B operand of the embed GEMM), hi / lo terms
     __half *gc_W[MDF_MAX_GC][2] = {{nullptr}};             // [g rows x k_in] (A operand of X.W, transposed), hi / lo terms
+    int adj_expand = 1;                                    // adjacency GEMM expands its A tiles from the bit-packed map on the fly
     int gemm_pair = 1;                                     // CTA-pair (cta_group::2) kernels for the embedding and X.W GEMMs
     int gemm_phases = 0;                                   // > 0 (MDF_GEMM_PHASES, experiment): single-term dithered weights, phase = residue tile
                                                            // % phases.  Measured and rejected as default: a short protein spans 1-3 tiles, so
@@ -122,6 +123,7 @@ int tc_model_init(mdf_model *m, const mdf_model_desc *d)
     if (const char *e = getenv("MDF_LSTM_FUSED")) t->lstm_fused = atoi(e);
     if (const char *e = getenv("MDF_LSTM_PHASES")) t->lstm_phases = std::min(64, std::max(1, atoi(e)));
     if (const char *e = getenv("MDF_GEMM_PAIR")) t->gemm_pair = atoi(e);
+    if (const char *e = getenv("MDF_ADJ_EXPAND")) t->adj_expand = atoi(e);
     if (const char *e = getenv("MDF_GEMM_PHASES")) t->gemm_phases = std::min(64, std::max(0, atoi(e)));   // 0: hi+lo split on every tile
     // shape constraints of the tile-image GEMMs
     bool ok = m->H % 64 == 0 && m->E % 128 == 0;
@@ -445,7 +447,7 @@ size_t tc_workspace_bytes(const mdf_model *m, int n, const int64_t *seq_off)
     add((size_t)Tp * 4); add((size_t)Tp);             // deg_pad, idx_pad
     add((size_t)Tp * m->E * 2);                       // X0 image
     add((size_t)Tp * gmax * 2); add((size_t)Tp * gmax * 2); add((size_t)Tp * gmax * 2);   // Y^T, X_a, X_b images
-    add((size_t)tiles * TILE_BYTES + 256);            // A_hat images
+    if (!(m->tc && static_cast<const TcModel *>(m->tc)->adj_expand)) add((size_t)tiles * TILE_BYTES + 256);   // A_hat images
     add((size_t)T * gmax * 4); add((size_t)T * m->E * 4);   // fp32 taps of the last GraphConv layer and of X0
     return b + 8192;
 }
@@ -493,7 +495,7 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto)
     MDF_TRY(ctx->alloc_n(&Yt, (size_t)Tp * gmax));
     MDF_TRY(ctx->alloc_n(&Xa, (size_t)Tp * gmax));
     MDF_TRY(ctx->alloc_n(&Xb, (size_t)Tp * gmax));
-    MDF_TRY(ctx->alloc((void **)&Aimg, (size_t)meta->n_adj_tiles * TILE_BYTES + 256));
+    MDF_TRY(ctx->alloc((void **)&Aimg, tm->adj_expand ? 256 : (size_t)meta->n_adj_tiles * TILE_BYTES + 256));
     pad_vectors_kernel<<<(unsigned)cdiv64(Tp, 256), 256, 0, s>>>(Tp, meta->rowmap, b->d_deg, b->d_idx, deg_pad, idx_pad);
     MDF_LAUNCH_CHECK(ctx);
 
@@ -572,7 +574,7 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto)
     }
     if (upto < 3) return MDF_OK;
     // ---- adjacency operand tiles
-    if (meta->n_adj_tiles > 0) {
+    if (meta->n_adj_tiles > 0 && !tm->adj_expand) {
         ProfScope ps(ctx, "expand_adjacency", 0.0);
         expand_adjacency_kernel<<<meta->n_adj_tiles, 256, 0, s>>>(meta->exp_tiles, b->d_seq_off, b->d_packed,
                                                                   b->d_packed_off, Aimg);
@@ -613,11 +615,30 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto)
             GemmArgs g;                                   // X_l[Tp x gd] = act(d_i * A_hat . Y + b), grouped per protein
             g.A[0] = Aimg; g.B[0] = Yt; g.KB_B = (int)(Tp / TILE_K);
             g.tile_info = meta->tile_info;
+            if (tm->adj_expand) {                         // A tiles built in shared memory from the bit-packed map
+                g.adj_packed = b->d_packed; g.adj_packed_off = b->d_packed_off; g.adj_seq_off = b->d_seq_off; g.adj_seg_off = meta->seg_off;
+            }
             const int bn = gd % 256 == 0 ? 256 : 128;
             g.m_tiles = meta->m_tiles; g.n_tiles = gd / bn;
             g.out_img = Xout; g.KB_out = gd / TILE_K;
             g.rowscale = deg_pad; g.bias = m->gc_b[l]; g.act = m->act; g.alpha = m->alpha;
+            static const bool want_trace = getenv("MDF_GEMM_TRACE") != nullptr;
+            long long *d_trace = nullptr;
+            if (want_trace) {
+                MDF_CUDA(cudaMalloc((void **)&d_trace, 64));
+                MDF_CUDA(cudaMemsetAsync(d_trace, 0, 64, s));
+                g.trace = d_trace;
+            }
             MDF_TRY(launch_gemm_tc(ctx, EPI_IMG_ROWSCALE, bn, 1, 1, g));
+            if (want_trace) {
+                long long h[8];
+                MDF_CUDA(cudaStreamSynchronize(s));
+                MDF_CUDA(cudaMemcpy(h, d_trace, 64, cudaMemcpyDeviceToHost));
+                cudaFree(d_trace);
+                fprintf(stderr, "[adj gemm trace] CTA 0 issuer: %lld tiles, %.0f cyc/tile | tile_info load %.0f, accumulator wait %.0f, operand wait %.0f (per tile)\n",
+                        h[4], h[4] ? (double)h[0] / h[4] : 0.0, h[4] ? (double)h[1] / h[4] : 0.0, h[4] ? (double)h[2] / h[4] : 0.0,
+                        h[4] ? (double)h[3] / h[4] : 0.0);
+            }
         }
         {
             ProfScope ps(ctx, "pool", 0.0);

@@ -11,6 +11,21 @@ namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a fully converged warp (CUTLASS cute::elect_one_sync).  The single-thread tcgen05 / TMA instructions take
+// their operands from uniform registers: issued under `if (lane == 0)` the compiler cannot prove uniformity and wraps
+// every one of them in a per-lane "waterfall" loop (ELECT / BRA.U.ANY, ~200 cycles per MMA measured); issued by the
+// elected lane of a warp that runs the surrounding loop converged, they are a single predicated instruction.
+__device__ __forceinline__ bool elect_one_sync()
+{
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, 0xffffffff;\n\t"
+        "@px mov.s32 %0, 1;\n\t}"
+        : "+r"(pred));
+    return pred != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {
@@ -134,6 +149,26 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t a_desc, uint6
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
+}
+
+// Converged-warp forms: executed by ALL 32 lanes with identical operands, the instruction itself predicated on the
+// elected lane inside the asm block - no C++ branch, so the operands stay in uniform registers (no waterfall loop).
+__device__ __forceinline__ void umma_f16_elect(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint64_t *bar)
+{
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        ::"r"(smem_u32(bar)) : "memory");
 }
 
 // all previously issued MMAs of this thread arrive on the mbarrier when they complete
