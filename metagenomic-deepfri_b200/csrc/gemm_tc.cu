@@ -32,7 +32,7 @@ __device__ __forceinline__ float act_f(float v, int act, float alpha)
 // One 32-column chunk of an output row: fused scale / bias / activation / gather, then fp16 image or fp32 store.
 template <int EPI>
 __device__ __forceinline__ void gemm_epilogue_chunk(const GemmArgs &g, uint32_t (&r)[32], int64_t m, int n0, float rs,
-                                                    const float *grow, uint8_t *row_ptr)
+                                                    const float *grow, uint8_t *row_ptr, float *pool_row = nullptr)
 {
     if (EPI == EPI_F32_BIAS) {
         if (m < g.m_valid) {
@@ -94,6 +94,25 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmArgs &g, uint32_t 
                 v[4 * q + 2] = fmaxf(v[4 * q + 2] + b.z + a.z, 0.0f);
                 v[4 * q + 3] = fmaxf(v[4 * q + 3] + b.w + a.w, 0.0f);
             }
+        }
+        if (EPI == EPI_IMG_ROWSCALE && pool_row) {
+            // fused sum-pool: column sums over the 32 rows of this warp (pad rows masked), butterfly transpose-reduce so
+            // that lane l ends with the total of column n0 + l (31 shuffles), then one fp32 atomic per lane
+            float c[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) c[j] = rs != 0.0f ? v[j] : 0.0f;
+            const int lane = threadIdx.x & 31;
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+                const bool upper = (lane & off) != 0;
+#pragma unroll
+                for (int j = 0; j < off; ++j) {
+                    const float send = upper ? c[j] : c[j + off];
+                    const float keep = upper ? c[j + off] : c[j];
+                    c[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                }
+            }
+            atomicAdd(pool_row + n0 + lane, c[0]);
         }
         uint8_t *dst = row_ptr + (size_t)(n0 >> 6) * TILE_BYTES + (((n0 & 63) >> 3) * 2048);
 #pragma unroll
@@ -298,6 +317,8 @@ gemm_tc_kernel(GemmArgs g, int a_terms, int b_terms, int stages)
             const float *grow = nullptr;
             if (EPI == EPI_IMG_ROWSCALE) rs = g.rowscale[m];
             if (EPI == EPI_IMG_EMBED) grow = g.gtab + (size_t)g.gidx[m] * g.ldg;
+            float *pool_row = nullptr;
+            if (EPI == EPI_IMG_ROWSCALE && g.pool && g.tile_info) pool_row = g.pool + (size_t)g.tile_info[mt].w * g.pool_ld + g.pool_off;
             // byte address of (row m, k = 0) in the output image; a 32-column chunk stays inside one k-block
             uint8_t *row_ptr = reinterpret_cast<uint8_t *>(g.out_img) + (size_t)(m >> 7) * g.KB_out * TILE_BYTES +
                                (size_t)((((int)m & 127) >> 3) * 128 + ((int)m & 7) * 16);
@@ -311,7 +332,7 @@ gemm_tc_kernel(GemmArgs g, int a_terms, int b_terms, int stages)
 #pragma unroll
                     for (int j = 0; j < 32; ++j) r[j] = 0u;
                 }
-                gemm_epilogue_chunk<EPI>(g, r, m, nt * BN + c0, rs, grow, row_ptr);
+                gemm_epilogue_chunk<EPI>(g, r, m, nt * BN + c0, rs, grow, row_ptr, pool_row);
             }
             tcgen05_fence_before();
             __syncwarp();
@@ -393,8 +414,8 @@ gemm_pair_kernel(const __grid_constant__ PairGemmArgs pa)
             }
         }
     } else if (warp == w_mma) {
-        // ===================== MMA issuer (leader CTA)
-        if (lane == 0 && leader) {
+        // ===================== MMA issuer (leader CTA): converged warp, elected lane issues
+        if (leader) {
             constexpr uint32_t idesc = umma_idesc_f16(256, 256);
             int st = 0; uint32_t ph = 0;
             int acc = 0; uint32_t acc_ph = 0;
@@ -414,10 +435,10 @@ gemm_pair_kernel(const __grid_constant__ PairGemmArgs pa)
                             for (int ks = 0; ks < TILE_K / 16; ++ks) {
                                 const uint64_t ad = umma_smem_desc(sa + ta * TILE_BYTES + ks * 2 * TILE_LBO, TILE_LBO, TILE_SBO);
                                 const uint64_t bd = umma_smem_desc(sb + tb * TILE_BYTES + ks * 2 * TILE_LBO, TILE_LBO, TILE_SBO);
-                                umma_f16_pair(d0, ad, bd, idesc, (kb | ks | ta | tb) != 0);
+                                umma_f16_pair_elect(d0, ad, bd, idesc, (kb | ks | ta | tb) != 0);
                             }
-                    umma_commit_pair(&bars.empty[st], 3);          // frees the stage in both CTAs when the MMAs retire
-                    if (kb == g.nkb - 1) umma_commit_pair(&bars.tmem_full[acc], 3);
+                    umma_commit_pair_elect(&bars.empty[st], 3);    // frees the stage in both CTAs when the MMAs retire
+                    if (kb == g.nkb - 1) umma_commit_pair_elect(&bars.tmem_full[acc], 3);
                     if (++st == stages) { st = 0; ph ^= 1; }
                 }
                 if (++acc == 2) { acc = 0; acc_ph ^= 1; }

@@ -40,6 +40,10 @@ struct GemmArgs {
     // grouped case with on-the-fly A tiles: instead of reading an expanded fp16 A_hat image (2 B per matrix entry, read
     // once per column tile) four extra warps build every 128 x 64 A tile in shared memory from the bit-packed contact
     // map (1 bit per entry).  adj_packed != nullptr selects it; A[] is then unused.
+    // sum-pool readout fused into the EPI_IMG_ROWSCALE epilogue (grouped case): pool[protein * pool_ld + pool_off + n] +=
+    // fp32 activations of the valid rows (rowscale != 0) of the tile; protein = tile_info[mt].w
+    float *pool = nullptr;
+    int pool_ld = 0, pool_off = 0;
     long long *trace = nullptr;      // optional [8] cycle counters of CTA 0 (MDF_GEMM_TRACE=1, adjacency GEMM)
     const uint32_t *adj_packed = nullptr;
     const int64_t *adj_packed_off = nullptr, *adj_seq_off = nullptr, *adj_seg_off = nullptr;

@@ -47,10 +47,18 @@ constexpr int LF_STAGES = 4;         // weight ring (16 KiB tiles: 128 gate rows
 constexpr int LF_EW = LF_EPI_WARPS;                  // epilogue warps (8 or 16): 4 TMEM lane quarters x LF_EW/4 unit ranges
 constexpr int LF_UPT = LF_U / (LF_EW / 4);           // units per epilogue thread (per layer)
 constexpr int LF_THREADS = (3 + LF_EW) * 32;         // warps 0..LF_EW-1: epilogue, then weight producer, operand loader, MMA issuer
+#ifndef LF_ROLES_LOW
 constexpr int LF_W_PROD = LF_EW, LF_W_LOAD = LF_EW + 1, LF_W_MMA = LF_EW + 2;   // single-thread roles on the highest warp ids: the
                                                      // arbiter prefers them over the epilogue warps of their scheduler
+constexpr int LF_W_EPI0 = 0;
+#else
+constexpr int LF_W_PROD = 0, LF_W_LOAD = 1, LF_W_MMA = 2, LF_W_EPI0 = 3;
+#endif
 constexpr int LF_TAB_STRIDE = 260;   // floats per residue row of the layer-1 table slice (64 units x 4 gates + pad)
 constexpr int LF_MAX_KB = 8;
+#ifndef LF_EPI_SLEEP_NS
+#define LF_EPI_SLEEP_NS 200
+#endif
 constexpr size_t LF_SCRATCH_HEAD = 1 << 20;   // flags (8 KiB) + schedule, ahead of the exchange buffers
 
 struct LstmFusedArgs {
@@ -60,6 +68,8 @@ struct LstmFusedArgs {
     int cell_mode;            // 0: exp/rcp cell (fp32-accurate), 1: tanh.approx cell
     const __half *W;          // [R1, W2, R2][phases + 2][4H rows (slice, gate, unit) x H] operand images: `phases` time-dither
     int phases;               //   roundings, then the exact split (hi, lo)
+    int spc;                  // PAIR: unit slices per cluster (cluster = spc CTA pairs; 1 or 4).  The h operand of a protein half is
+                              //   multicast to the spc same-rank CTAs of a cluster: 1/spc of the L2 reads
     int precise_len;          // sub-batches whose longest protein exceeds this run both split terms on every step
     const float *tab;         // [26][H][4] layer-1 pre-activation table ([unit][gate] order, bias folded)
     const float *b2;          // [H][4] layer-2 bias ([unit][gate] order)
@@ -200,8 +210,14 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
     const int cta_in_group = blockIdx.x % (a.cpg * HALVES);
     const int g = blockIdx.x / (a.cpg * HALVES);
     const int s = PAIR ? cta_in_group >> 1 : cta_in_group;             // unit slice
-    const int r = PAIR ? (int)cluster_ctarank() : 0;                   // protein half = rank in the CTA pair
+    const int crank = PAIR ? (int)cluster_ctarank() : 0;               // rank in the cluster (spc consecutive slices x 2)
+    const int r = crank & 1;                                           // protein half = rank in the CTA pair
+    const int si = crank >> 1;                                         // slice index inside the cluster
+    const int spc = PAIR ? a.spc : 1;
     const bool leader = r == 0;
+    const uint16_t pair_mask = (uint16_t)(3u << (2 * si));             // both CTAs of my pair
+    uint16_t rank_mask = 0;                                            // the spc CTAs of the cluster holding my protein half
+    for (int j = 0; j < spc; ++j) rank_mask |= (uint16_t)(1u << (2 * j + r));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *sH = smem;                                               // [KB][16 KiB] operand, rows = proteins
@@ -221,9 +237,13 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
     if (tid == 0) {
         // PAIR: only the leader's full barriers are used; they collect the bytes of both CTAs' TMA loads
         for (int i = 0; i < LF_STAGES; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
-        for (int i = 0; i < LF_MAX_KB; ++i) { mbar_init(&bar_hfull[i], 1); mbar_init(&bar_hfree[i], 1); }
+        // PAIR: chunk kb is fetched by slice kb % spc of the cluster for all its pairs: that CTA's hfree collects one commit
+        // per pair, and every leader arms its own hfull (bytes of both halves) itself
+        for (int i = 0; i < LF_MAX_KB; ++i) { mbar_init(&bar_hfull[i], 1); mbar_init(&bar_hfree[i], spc); }
         for (int i = 0; i < 2; ++i) { mbar_init(&bar_gfull[i], 1); mbar_init(&bar_gfree[i], LF_EW * HALVES); }
         fence_mbar_init();
+        if (PAIR && leader)
+            for (int i = 0; i < KB; ++i) mbar_arrive_expect_tx(&bar_hfull[i], 2 * TILE_BYTES);
     }
     if (warp == LF_W_MMA) {
         if (PAIR) tmem_alloc_pair<512>(&tmem_slot); else tmem_alloc<512>(&tmem_slot);
@@ -283,23 +303,23 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
             auto load = [&](int layer, int step, unsigned target) {
                 const uint8_t *src = hb + (size_t)(layer * 2 + (step & 1)) * h_bytes;
                 const bool trh = a.trace && blockIdx.x < 2 && layer == 0 && item < a.trace_items;
-                // every slice of the group has published its tile of this operand ...
-                for (int kb = 0; kb < KB; ++kb) {
+                // the slices that produce my chunks have published them (PAIR: I fetch chunks kb = si, si + spc, ... for the
+                // whole cluster; otherwise all of them for myself) ...
+                for (int kb = si; kb < KB; kb += spc) {
                     const unsigned *f = flags + layer * LF_MAX_KB + kb;
-                    while (lf_ld_acquire(f) < target) { }
+                    while (lf_ld_acquire(f) < target) __nanosleep(100);
                 }
                 if (trh) th[item * 16 + blockIdx.x * 8 + 1] = lf_gtime();
                 // ... and ONE proxy fence orders those generic-proxy stores before the async-proxy reads below (a fence
                 // per chunk serialises the chunk loads: it waits for this thread's TMA copies already in flight)
                 asm volatile("fence.proxy.async.global;" ::: "memory");
-                for (int kb = 0; kb < KB; ++kb) {
-                    mbar_wait(&bar_hfree[kb], hph ^ 1);                  // the MMAs reading the previous operand retired
+                for (int kb = si; kb < KB; kb += spc) {
+                    mbar_wait(&bar_hfree[kb], hph ^ 1);                  // the MMAs reading the previous operand retired (all pairs)
                     if (trh && (kb == 0 || kb == KB - 1)) th[item * 16 + blockIdx.x * 8 + (kb ? 4 : 0) + 0] = lf_gtime();
                     if (PAIR) {
-                        if (leader) mbar_arrive_expect_tx(&bar_hfull[kb], 2 * TILE_BYTES);       // my proteins + the peer's
-                        tma_tile_g2s_pair(sH + (size_t)kb * TILE_BYTES, &a.tmH,
-                                          (int32_t)((size_t)(src - reinterpret_cast<const uint8_t *>(a.hbuf)) / 512) + kb * (TILE_BYTES / 512),
-                                          &bar_hfull[kb]);
+                        tma_tile_g2s_pair_mc(sH + (size_t)kb * TILE_BYTES, &a.tmH,
+                                             (int32_t)((size_t)(src - reinterpret_cast<const uint8_t *>(a.hbuf)) / 512) + kb * (TILE_BYTES / 512),
+                                             &bar_hfull[kb], rank_mask);
                     } else {
                         mbar_arrive_expect_tx(&bar_hfull[kb], TILE_BYTES);
                         bulk_g2s(sH + (size_t)kb * TILE_BYTES, src + (size_t)kb * TILE_BYTES, TILE_BYTES, &bar_hfull[kb]);
@@ -317,14 +337,16 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
             }
         }
     } else if (warp == LF_W_MMA) {
-        // =========================================================== MMA issuer (PAIR: leader CTA only)
-        if (lane == 0 && leader) {
+        // =========================================================== MMA issuer (PAIR: leader CTA only).  The whole warp walks the
+        // loops converged and the single-thread instructions are predicated on elect.sync inside their asm blocks: under
+        // `if (lane == 0)` the compiler wraps each tcgen05.mma / commit in a per-lane waterfall loop.
+        if (leader) {
             constexpr uint32_t idesc = PAIR ? umma_idesc_f16(256, 256) : umma_idesc_f16(128, 128);
             int st = 0; uint32_t ph = 0, hph = 0;
             uint32_t rounds[2] = {0, 0};
             const uint32_t sh_addr = smem_u32(sH);
             int item = 0;
-            const bool trw = a.trace && blockIdx.x == 0;
+            const bool trw = a.trace && blockIdx.x == 0 && lane == 0;
             long long *tw = a.trace + (size_t)a.trace_items * 8;     // [item][4]: per tick cycles waiting on operand chunks, weights, g1/g2 drain
             long long acc_h = 0, acc_w = 0, acc_g = 0;
             // one pass over the operand in shared memory: gates[acc] (+)= W_slice . operand
@@ -334,6 +356,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
                     if (wait_h) {
                         const long long c0 = trw ? clock64() : 0;
                         mbar_wait(&bar_hfull[kb], hph);
+                        if (PAIR) mbar_arrive_expect_tx_elect(&bar_hfull[kb], 2 * TILE_BYTES);     // arm the next operand's phase
                         if (trw) acc_h += clock64() - c0;
                         if (trw && d0 == 0u && item < a.trace_items && (kb == 0 || kb == KB - 1))
                             a.trace[(size_t)a.trace_items * 12 + item * 16 + (kb ? 4 : 0) + 2] = lf_gtime();
@@ -352,17 +375,17 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
 #pragma unroll
                         for (int ks = 0; ks < TILE_K / 16; ++ks) {
                             if (PAIR)
-                                umma_f16_pair(tmem_base + d0, hd + (uint64_t)(ks * 256), wd + (uint64_t)(ks * 256), idesc,
-                                              accumulate || (kb | ks | term) != 0);
+                                umma_f16_pair_elect(tmem_base + d0, hd + (uint64_t)(ks * 256), wd + (uint64_t)(ks * 256), idesc,
+                                                    accumulate || (kb | ks | term) != 0);
                             else
-                                umma_f16(tmem_base + d0 + (uint32_t)(jj * 128), hd + (uint64_t)(ks * 256), wd + (uint64_t)(ks * 256), idesc,
-                                         accumulate || (kb | ks | term) != 0);
+                                umma_f16_elect(tmem_base + d0 + (uint32_t)(jj * 128), hd + (uint64_t)(ks * 256), wd + (uint64_t)(ks * 256), idesc,
+                                               accumulate || (kb | ks | term) != 0);
                         }
-                        if (PAIR) umma_commit_pair(&bar_empty[st], 3); else umma_commit(&bar_empty[st]);
+                        if (PAIR) umma_commit_pair_elect(&bar_empty[st], pair_mask); else umma_commit_elect(&bar_empty[st]);
                         if (++st == LF_STAGES) { st = 0; ph ^= 1; }
                     }
                     if (release_chunks) {
-                        if (PAIR) umma_commit_pair(&bar_hfree[kb], 3); else umma_commit(&bar_hfree[kb]);
+                        if (PAIR) umma_commit_pair_elect(&bar_hfree[kb], (uint16_t)(3u << (2 * (kb % spc)))); else umma_commit_elect(&bar_hfree[kb]);
                     }
                 }
             };
@@ -373,14 +396,14 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
                 tcgen05_fence_after();
             };
             auto commit_gfull = [&](int acc) {
-                if (PAIR) umma_commit_pair(&bar_gfull[acc], 3); else umma_commit(&bar_gfull[acc]);
+                if (PAIR) umma_commit_pair_elect(&bar_gfull[acc], pair_mask); else umma_commit_elect(&bar_gfull[acc]);
                 ++rounds[acc];
             };
             int cursor = 0;
             for (LfSub sbt = lf_next<PAIR>(cursor, g, a); sbt.sb >= 0; sbt = lf_next<PAIR>(cursor, g, a)) {
                 nterms = sbt.Lmax > a.precise_len ? 2 : 1;
                 for (int tau = 1; tau <= sbt.Lmax; ++tau, ++item) {
-                    const bool tr = a.trace && blockIdx.x == 0 && item < a.trace_items;
+                    const bool tr = a.trace && blockIdx.x == 0 && lane == 0 && item < a.trace_items;
                     if (tr) { a.trace[item * 8 + 0] = clock64(); a.trace[(size_t)a.trace_items * 12 + item * 16 + 3] = lf_gtime(); }
                     const bool p1 = tau < sbt.Lmax;
                     if (p1) {                                             // P1
@@ -405,9 +428,9 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
         }
     } else {
         // =========================================================== epilogue: thread = one protein x LF_UPT units x both layers
-        const int et = tid;
+        const int et = tid - LF_W_EPI0 * 32;
         const int q = warp & 3;                                // TMEM lane quarter this warp may access
-        const int part = warp >> 2;                      // units [LF_UPT*part, LF_UPT*(part+1)) of this slice
+        const int part = (warp - LF_W_EPI0) >> 2;                      // units [LF_UPT*part, LF_UPT*(part+1)) of this slice
         const int p = q * 32 + lane;                           // protein inside this CTA's 128 = TMEM lane
         const int ub = part * LF_UPT;                          // first unit (within the slice) of this thread
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)ub;
@@ -450,7 +473,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
                     if (tau + 1 < len) aa_next = (int)a.idx_pad[row0 + tau + 1];
                     const float4 *pre4 = reinterpret_cast<const float4 *>(tabS + aa * LF_TAB_STRIDE + ub * 4);
                     if (tau >= 1) {
-                        mbar_wait(&bar_gfull[0], rounds[0] & 1);
+                        mbar_wait_sleep(&bar_gfull[0], rounds[0] & 1, LF_EPI_SLEEP_NS);
                         ++rounds[0];
                         tcgen05_fence_after();
                     }
@@ -467,7 +490,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
                         tcgen05_fence_before();
                         __syncwarp();
                         if (lane == 0) {                                  // g1 drained by this warp
-                            if (PAIR && !leader) mbar_arrive_remote(&bar_gfree[0], 0); else mbar_arrive(&bar_gfree[0]);
+                            if (PAIR && !leader) mbar_arrive_remote(&bar_gfree[0], (uint32_t)(crank & ~1)); else mbar_arrive(&bar_gfree[0]);
                         }
                     }
                     lf_bar_sync(1, LF_EW * 32);                                  // all h1_tau stores of this CTA issued
@@ -479,7 +502,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
                 if (tau >= 1) {
                     const int t2 = tau - 1;
                     const bool active = t2 < len;
-                    mbar_wait(&bar_gfull[1], rounds[1] & 1);
+                    mbar_wait_sleep(&bar_gfull[1], rounds[1] & 1, LF_EPI_SLEEP_NS);
                     ++rounds[1];
                     tcgen05_fence_after();
                     const long long row = row0 + t2;
@@ -490,7 +513,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
                     tcgen05_fence_before();
                     __syncwarp();
                     if (lane == 0) {                                      // g2 drained by this warp
-                        if (PAIR && !leader) mbar_arrive_remote(&bar_gfree[1], 0); else mbar_arrive(&bar_gfree[1]);
+                        if (PAIR && !leader) mbar_arrive_remote(&bar_gfree[1], (uint32_t)(crank & ~1)); else mbar_arrive(&bar_gfree[1]);
                     }
                     lf_bar_sync(1, LF_EW * 32);                                  // all h2 stores of this CTA issued
                     if (et == 0) lf_red_release(flags + LF_MAX_KB + s, 1u);
@@ -548,7 +571,7 @@ static int launch_variant(mdf_ctx *ctx, LstmFusedArgs &a, size_t smem)
     }
     if (PAIR) {
         attrs[na].id = cudaLaunchAttributeClusterDimension;
-        attrs[na].val.clusterDim.x = 2; attrs[na].val.clusterDim.y = 1; attrs[na].val.clusterDim.z = 1;
+        attrs[na].val.clusterDim.x = 2 * a.spc; attrs[na].val.clusterDim.y = 1; attrs[na].val.clusterDim.z = 1;
         ++na;
     }
     cfg.attrs = attrs;
@@ -572,7 +595,29 @@ int launch_lstm_fused(mdf_ctx *ctx, int H, int n, const __half *W, int phases, c
     a.cpg = H / LF_U;
     const int sub_n = pair ? 2 * LF_M : LF_M;
     a.n_sub = cdiv(n, sub_n);
-    const int max_groups = std::max(1, ctx->sm_count / (a.cpg * (pair ? 2 : 1)));
+    // cluster of 8 (h operand multicast to 4 slices) measured: same tick, but only 8 groups fit (GPC granularity) -> 2 is the default
+    static const int cluster_env = getenv("MDF_LSTM_CLUSTER") ? atoi(getenv("MDF_LSTM_CLUSTER")) : 2;
+    a.spc = (pair && cluster_env >= 8 && a.cpg % 4 == 0) ? 4 : 1;
+    int max_groups = std::max(1, ctx->sm_count / (a.cpg * (pair ? 2 : 1)));
+    if (pair && a.spc > 1) {
+        // clusters of 2*spc CTAs must fit inside a GPC: ask the driver how many can be co-resident
+        static int max_clusters = -1;
+        if (max_clusters < 0) {
+            cudaLaunchConfig_t q = {};
+            q.gridDim = dim3(2 * a.spc * 64); q.blockDim = dim3(LF_THREADS); q.dynamicSmemBytes = lstm_fused_smem_bytes(H);
+            cudaLaunchAttribute qa[1];
+            qa[0].id = cudaLaunchAttributeClusterDimension;
+            qa[0].val.clusterDim.x = 2 * a.spc; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+            q.attrs = qa; q.numAttrs = 1;
+            auto kern = lstm_fused_kernel<true, 0>;
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lstm_fused_smem_bytes(H));
+            int nc = 0;
+            if (cudaOccupancyMaxActiveClusters(&nc, kern, &q) != cudaSuccess || nc <= 0) { cudaGetLastError(); nc = 0; }
+            max_clusters = nc;
+        }
+        const int by_clusters = max_clusters * a.spc / a.cpg;             // groups = clusters * spc / slices per group
+        if (by_clusters >= 1) max_groups = std::min(max_groups, by_clusters); else a.spc = 1;
+    }
     a.n_groups = std::min(max_groups, a.n_sub);
     a.W = W; a.phases = phases;
     static const int precise_env = getenv("MDF_LSTM_PRECISE_LEN") ? atoi(getenv("MDF_LSTM_PRECISE_LEN")) : 1000;
@@ -674,6 +719,16 @@ int launch_lstm_fused(mdf_ctx *ctx, int H, int n, const __half *W, int phases, c
                 v[7] += t[8] - t0; v[8] += t[9] - t0;                             // cta1 chunk0: free, flag
                 v[9] += t[12] - t0; v[10] += t[13] - t0;                          // cta1 chunk7
                 ++k;
+            }
+            {
+                double ns = 0; int kk = 0;
+                for (int i = 40; i < a.trace_items - 1; ++i) {
+                    const long long t1 = th[(size_t)i * 16 + 3], t0 = th[(size_t)(i - 1) * 16 + 3];
+                    if (!t1 || !t0 || t1 - t0 > 1000000) continue;
+                    ns += (double)(t1 - t0); ++kk;
+                }
+                if (kk && cnt) fprintf(stderr, "[lstm fused trace] tick %.0f ns (globaltimer) = %.0f cycles (clock64) -> SM clock %.0f MHz during the kernel\n",
+                                      ns / kk, sum[0] / cnt, 1e3 * (sum[0] / cnt) / (ns / kk));
             }
             if (k) fprintf(stderr, "[lstm fused trace] h1 operand vs tick start (ns): E1 publish %.0f | cta0 chunk0 free %.0f all-flags %.0f seen %.0f | chunk7 free %.0f (-) %.0f seen %.0f | "
                            "cta1 chunk0 free %.0f all-flags %.0f | chunk7 free %.0f (-) %.0f\n", v[0] / k, v[1] / k, v[2] / k, v[3] / k, v[4] / k, v[5] / k, v[6] / k,

@@ -29,6 +29,7 @@ using namespace tc;
 struct TcModel {
     __half *lm_W[2] = {nullptr, nullptr};                  // [E rows x H k]  (B operand of the embed GEMM), hi / lo terms
     __half *gc_W[MDF_MAX_GC][2] = {{nullptr}};             // [g rows x k_in] (A operand of X.W, transposed), hi / lo terms
+    int pool_fused = 1;                                    // sum-pool readout inside the adjacency GEMM epilogue (fp32, no X re-read)
     int adj_expand = 1;                                    // adjacency GEMM expands its A tiles from the bit-packed map on the fly
     int gemm_pair = 1;                                     // CTA-pair (cta_group::2) kernels for the embedding and X.W GEMMs
     int gemm_phases = 0;                                   // > 0 (MDF_GEMM_PHASES, experiment): single-term dithered weights, phase = residue tile
@@ -124,6 +125,7 @@ int tc_model_init(mdf_model *m, const mdf_model_desc *d)
     if (const char *e = getenv("MDF_LSTM_PHASES")) t->lstm_phases = std::min(64, std::max(1, atoi(e)));
     if (const char *e = getenv("MDF_GEMM_PAIR")) t->gemm_pair = atoi(e);
     if (const char *e = getenv("MDF_ADJ_EXPAND")) t->adj_expand = atoi(e);
+    if (const char *e = getenv("MDF_POOL_FUSED")) t->pool_fused = atoi(e);
     if (const char *e = getenv("MDF_GEMM_PHASES")) t->gemm_phases = std::min(64, std::max(0, atoi(e)));   // 0: hi+lo split on every tile
     // shape constraints of the tile-image GEMMs
     bool ok = m->H % 64 == 0 && m->E % 128 == 0;
@@ -622,6 +624,7 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto)
             g.m_tiles = meta->m_tiles; g.n_tiles = gd / bn;
             g.out_img = Xout; g.KB_out = gd / TILE_K;
             g.rowscale = deg_pad; g.bias = m->gc_b[l]; g.act = m->act; g.alpha = m->alpha;
+            if (tm->pool_fused) { g.pool = b->d_pooled; g.pool_ld = m->G; g.pool_off = goff; }   // readout from the fp32 accumulators
             static const bool want_trace = getenv("MDF_GEMM_TRACE") != nullptr;
             long long *d_trace = nullptr;
             if (want_trace) {
@@ -640,7 +643,7 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto)
                         h[4] ? (double)h[3] / h[4] : 0.0);
             }
         }
-        {
+        if (!tm->pool_fused) {
             ProfScope ps(ctx, "pool", 0.0);
             dim3 grid(meta->m_tiles, gd / TILE_K);
             pool_image_kernel<<<grid, 256, 0, s>>>(Xout, gd, meta->rowmap, b->d_res_prot, b->d_pooled, m->G, goff);

@@ -58,6 +58,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
     while (!mbar_try_wait(bar, parity)) { }
 }
 
+// Wait that backs off with nanosleep between polls: the B200 runs these kernels at its power cap, and a warp spinning on
+// try_wait burns issue energy for the whole time its producer needs - use for waits that are expected to be long.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity, uint32_t ns)
+{
+    while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
+}
+
 // ---------------------------------------------------------------- bulk TMA (1-D, no tensor map)
 // global -> shared, completion signalled on an mbarrier through complete_tx::bytes
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
@@ -171,6 +178,33 @@ __device__ __forceinline__ void umma_commit_elect(uint64_t *bar)
         ::"r"(smem_u32(bar)) : "memory");
 }
 
+__device__ __forceinline__ void umma_f16_pair_elect(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair_elect(uint64_t *bar, uint16_t cta_mask)
+{
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+        ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+// arrive + expect_tx by the elected lane of a converged warp
+__device__ __forceinline__ void mbar_arrive_expect_tx_elect(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}"
+        ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
 // all previously issued MMAs of this thread arrive on the mbarrier when they complete
 __device__ __forceinline__ void umma_commit(uint64_t *bar)
 {
@@ -237,6 +271,17 @@ __device__ __forceinline__ void tma_tile_g2s_pair(void *dst_smem, const void *tm
     const uint32_t mbar = smem_u32(bar) & 0xFEFFFFFFu;
     asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  ::"r"(smem_u32(dst_smem)), "l"(tmap), "r"(0), "r"(row512), "r"(mbar) : "memory");
+}
+
+// Multicast form: the tile lands at the same shared-memory offset in every CTA of `cta_mask` (cluster ranks) and its bytes
+// are credited to the barrier at this offset in the leader of each destination CTA's pair (CUTLASS
+// SM100_TMA_2SM_LOAD_MULTICAST) - one L2 read feeds all the CTAs that need the same operand tile.
+__device__ __forceinline__ void tma_tile_g2s_pair_mc(void *dst_smem, const void *tmap, int32_t row512, uint64_t *bar, uint16_t cta_mask)
+{
+    const uint32_t mbar = smem_u32(bar) & 0xFEFFFFFFu;
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+                 " [%0], [%1, {%2, %3}], [%4], %5;"
+                 ::"r"(smem_u32(dst_smem)), "l"(tmap), "r"(0), "r"(row512), "r"(mbar), "h"(cta_mask) : "memory");
 }
 
 // Same copy issued by the LEADER on behalf of CTA `dst_cta` of its pair: the tile lands at the same offset of that CTA's
