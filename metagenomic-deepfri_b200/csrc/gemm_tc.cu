@@ -44,6 +44,7 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmArgs &g, uint32_t 
                     const float4 b = g.bias ? __ldg(reinterpret_cast<const float4 *>(g.bias + n0 + 4 * q)) : make_float4(0, 0, 0, 0);
                     v.x = __uint_as_float(r[4 * q + 0]) + b.x; v.y = __uint_as_float(r[4 * q + 1]) + b.y;
                     v.z = __uint_as_float(r[4 * q + 2]) + b.z; v.w = __uint_as_float(r[4 * q + 3]) + b.w;
+                    if (g.act == 1) { v.x = fmaxf(v.x, 0.0f); v.y = fmaxf(v.y, 0.0f); v.z = fmaxf(v.z, 0.0f); v.w = fmaxf(v.w, 0.0f); }
                     *reinterpret_cast<float4 *>(dst + 4 * q) = v;
                 }
             }
@@ -234,7 +235,7 @@ gemm_tc_kernel(GemmArgs g, int a_terms, int b_terms, int stages)
                     } else {
                         // every (A term, B term) pair contributes; at most one side has two terms
                         for (int ta = 0; ta < a_terms; ++ta)
-                            for (int tb = 0; tb < b_terms; ++tb)
+                            for (int tb = 0; tb < b_terms - (ta == 1 && b_terms == 2 ? 1 : 0); ++tb)     // both split: skip lo x lo
 #pragma unroll
                                 for (int ks = 0; ks < TILE_K / 16; ++ks) {
                                     const uint64_t ad = umma_smem_desc(sa + ta * TILE_BYTES + ks * 2 * TILE_LBO, TILE_LBO, TILE_SBO);
@@ -572,7 +573,7 @@ static int launch_one(mdf_ctx *ctx, int a_terms, int b_terms, const GemmArgs &ar
 
 int launch_gemm_tc(mdf_ctx *ctx, int epi, int bn, int a_terms, int b_terms, const GemmArgs &args)
 {
-    if (a_terms < 1 || a_terms > 2 || b_terms < 1 || b_terms > 2 || (a_terms == 2 && b_terms == 2)) {
+    if (a_terms < 1 || a_terms > 2 || b_terms < 1 || b_terms > 2) {
         set_error("gemm_tc: unsupported term split %d x %d", a_terms, b_terms);
         return MDF_EUNSUPPORTED;
     }

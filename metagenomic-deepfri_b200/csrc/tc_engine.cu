@@ -22,6 +22,7 @@
 namespace mdf {
 
 int head_forward(mdf_model *m, int n, const float *pooled, float *fc, float *logits, float *scores);
+int launch_softmax0(mdf_ctx *ctx, int64_t total, const float *logits, float *scores);
 int simt_lstm_stack(mdf_model *m, mdf_batch *b, float **Hl, float *pre, float *Cst, unsigned *barrier);
 
 using namespace tc;
@@ -29,6 +30,10 @@ using namespace tc;
 struct TcModel {
     __half *lm_W[2] = {nullptr, nullptr};                  // [E rows x H k]  (B operand of the embed GEMM), hi / lo terms
     __half *gc_W[MDF_MAX_GC][2] = {{nullptr}};             // [g rows x k_in] (A operand of X.W, transposed), hi / lo terms
+    __half *fc_W[2] = {nullptr, nullptr};                  // head: [F rows x G k] hi / lo (B operand)
+    __half *out_W[2] = {nullptr, nullptr};                 // head: [2C rows x F k] hi / lo
+    float *out_b_pad = nullptr;                            // head: output bias padded to a multiple of 4 entries
+    int head_tc = 1;                                       // head GEMMs on tensor cores (activations and weights both split hi + lo)
     int pool_fused = 1;                                    // sum-pool readout inside the adjacency GEMM epilogue (fp32, no X re-read)
     int adj_expand = 1;                                    // adjacency GEMM expands its A tiles from the bit-packed map on the fly
     int gemm_pair = 1;                                     // CTA-pair (cta_group::2) kernels for the embedding and X.W GEMMs
@@ -126,6 +131,7 @@ int tc_model_init(mdf_model *m, const mdf_model_desc *d)
     if (const char *e = getenv("MDF_GEMM_PAIR")) t->gemm_pair = atoi(e);
     if (const char *e = getenv("MDF_ADJ_EXPAND")) t->adj_expand = atoi(e);
     if (const char *e = getenv("MDF_POOL_FUSED")) t->pool_fused = atoi(e);
+    if (const char *e = getenv("MDF_HEAD_TC")) t->head_tc = atoi(e);
     if (const char *e = getenv("MDF_GEMM_PHASES")) t->gemm_phases = std::min(64, std::max(0, atoi(e)));   // 0: hi+lo split on every tile
     // shape constraints of the tile-image GEMMs
     bool ok = m->H % 64 == 0 && m->E % 128 == 0;
@@ -135,6 +141,19 @@ int tc_model_init(mdf_model *m, const mdf_model_desc *d)
     build_image_host(d->lm_W, m->E, m->H, true, m->E, hi, lo);       // rows = E (n), k = H : lm_W[k][n]
     MDF_TRY(upload_half(m, &t->lm_W[0], hi));
     MDF_TRY(upload_half(m, &t->lm_W[1], lo));
+    if (m->G % TILE_K == 0 && m->F % TILE_K == 0) {
+        build_image_host(d->fc_W, m->F, m->G, true, m->F, hi, lo);            // rows = F, k = G : fc_W[k][f]
+        MDF_TRY(upload_half(m, &t->fc_W[0], hi));
+        MDF_TRY(upload_half(m, &t->fc_W[1], lo));
+        build_image_host(d->out_W, 2 * m->C, m->F, true, 2 * m->C, hi, lo);   // rows = 2C, k = F : out_W[k][c]
+        MDF_TRY(upload_half(m, &t->out_W[0], hi));
+        MDF_TRY(upload_half(m, &t->out_W[1], lo));
+        std::vector<float> bp((size_t)(2 * m->C + 3) / 4 * 4, 0.0f);
+        if (d->out_b) std::copy(d->out_b, d->out_b + 2 * m->C, bp.begin());
+        MDF_CUDA(cudaMalloc((void **)&t->out_b_pad, bp.size() * sizeof(float)));
+        m->owned.push_back(t->out_b_pad);
+        MDF_CUDA(cudaMemcpy(t->out_b_pad, bp.data(), bp.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
     auto upload_dithered = [&](const float *src_kn, int rows, int K, __half **dst) -> int {   // src[k][row] -> [phases][rows x K] images
         std::vector<float> tr((size_t)rows * K);
         for (int r = 0; r < rows; ++r)
@@ -376,6 +395,78 @@ pool_image_kernel(const __half *__restrict__ img, int K, const int *__restrict__
     }
 }
 
+// fp32 row-major [n, K] -> hi / lo fp16 images over rows padded to a multiple of 128 (pad rows zero)
+__global__ void f32_rows_to_split_images_kernel(const float *__restrict__ src, int n, int K, int rows_pad, __half *__restrict__ hi,
+                                                __half *__restrict__ lo)
+{
+    const int KB = K / TILE_K;
+    const int64_t chunk = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;    // one 16-byte chunk (8 k) per thread
+    if (chunk >= (int64_t)rows_pad * (K / 8)) return;
+    const int r = (int)(chunk / (K / 8));
+    const int k = (int)(chunk % (K / 8)) * 8;
+    uint4 ph = make_uint4(0, 0, 0, 0), pl = make_uint4(0, 0, 0, 0);
+    if (r < n) {
+        float v[8], h[8];
+        *reinterpret_cast<float4 *>(v) = *reinterpret_cast<const float4 *>(src + (size_t)r * K + k);
+        *reinterpret_cast<float4 *>(v + 4) = *reinterpret_cast<const float4 *>(src + (size_t)r * K + k + 4);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) h[j] = __half2float(__float2half_rn(v[j]));
+        ph.x = pack_half2(h[0], h[1]); ph.y = pack_half2(h[2], h[3]); ph.z = pack_half2(h[4], h[5]); ph.w = pack_half2(h[6], h[7]);
+        pl.x = pack_half2(v[0] - h[0], v[1] - h[1]); pl.y = pack_half2(v[2] - h[2], v[3] - h[3]);
+        pl.z = pack_half2(v[4] - h[4], v[5] - h[5]); pl.w = pack_half2(v[6] - h[6], v[7] - h[7]);
+    }
+    const size_t off = image_offset_bytes(r, k, KB);
+    *reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(hi) + off) = ph;
+    *reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(lo) + off) = pl;
+}
+
+// score[p, c] = softmax(logits[p, 2c : 2c+2])[0] with a row stride (the fp32 GEMM epilogue wants 16-byte aligned rows)
+__global__ void softmax0_strided_kernel(int n, int C, int ld, const float *__restrict__ logits, float *__restrict__ scores)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= (int64_t)n * C) return;
+    const int p = (int)(i / C), c = (int)(i % C);
+    const float2 v = *reinterpret_cast<const float2 *>(logits + (size_t)p * ld + 2 * c);
+    const float mx = fmaxf(v.x, v.y);
+    const float ea = expf(v.x - mx), eb = expf(v.y - mx);
+    scores[i] = ea / (ea + eb);
+}
+
+// Head on tensor cores: fc = relu(pooled W_fc + b), logits = fc W_out + b, softmax channel 0.  This is after the sum-pool,
+// so activation rounding no longer averages out: activations AND weights are split hi + lo (three MMAs per k-step,
+// lo x lo dropped: ~2^-21 relative).
+static int head_forward_tc(mdf_model *m, TcModel *tm, int n, const float *pooled, float *fc, float *logits, float *scores)
+{
+    mdf_ctx *ctx = m->ctx;
+    cudaStream_t s = ctx->stream;
+    const int rows_pad = cdiv(n, 128) * 128;
+    __half *ah = nullptr, *al = nullptr;
+    const int kmax = std::max(m->G, m->F);
+    MDF_TRY(ctx->alloc_n(&ah, (size_t)rows_pad * kmax));
+    MDF_TRY(ctx->alloc_n(&al, (size_t)rows_pad * kmax));
+    const int ld_logits = (2 * m->C + 3) / 4 * 4;
+    float *logits_pad = nullptr;
+    MDF_TRY(ctx->alloc_n(&logits_pad, (size_t)n * ld_logits));
+    (void)logits;
+    auto gemm = [&](const float *src, int K, __half *const W[2], int N, int ldc, const float *bias, int act, float *out) -> int {
+        const int64_t chunks = (int64_t)rows_pad * (K / 8);
+        f32_rows_to_split_images_kernel<<<(unsigned)cdiv64(chunks, 256), 256, 0, s>>>(src, n, K, rows_pad, ah, al);
+        MDF_LAUNCH_CHECK(ctx);
+        GemmArgs g;
+        g.A[0] = ah; g.A[1] = al; g.KB_A = K / TILE_K;
+        g.B[0] = W[0]; g.B[1] = W[1]; g.KB_B = K / TILE_K;
+        g.m_tiles = rows_pad / 128; g.n_tiles = cdiv(N, 128); g.nkb = K / TILE_K;
+        g.out_f32 = out; g.ldc = ldc; g.bias = bias; g.act = act;
+        g.m_valid = n; g.n_valid = N;
+        return launch_gemm_tc(ctx, EPI_F32_BIAS, 128, 2, 2, g);
+    };
+    MDF_TRY(gemm(pooled, m->G, tm->fc_W, m->F, m->F, m->fc_b, 1, fc));
+    MDF_TRY(gemm(fc, m->F, tm->out_W, 2 * m->C, ld_logits, tm->out_b_pad, 0, logits_pad));
+    softmax0_strided_kernel<<<(unsigned)cdiv64((int64_t)n * m->C, 256), 256, 0, s>>>(n, m->C, ld_logits, logits_pad, scores);
+    MDF_LAUNCH_CHECK(ctx);
+    return MDF_OK;
+}
+
 // ------------------------------------------------------------------------------------------- batch metadata
 static int build_meta(mdf_ctx *ctx, mdf_batch *b, TcBatchMeta &meta)
 {
@@ -451,6 +542,8 @@ size_t tc_workspace_bytes(const mdf_model *m, int n, const int64_t *seq_off)
     add((size_t)Tp * gmax * 2); add((size_t)Tp * gmax * 2); add((size_t)Tp * gmax * 2);   // Y^T, X_a, X_b images
     if (!(m->tc && static_cast<const TcModel *>(m->tc)->adj_expand)) add((size_t)tiles * TILE_BYTES + 256);   // A_hat images
     add((size_t)T * gmax * 4); add((size_t)T * m->E * 4);   // fp32 taps of the last GraphConv layer and of X0
+    add((size_t)(cdiv(n, 128) * 128) * std::max(m->G, m->F) * 2); add((size_t)(cdiv(n, 128) * 128) * std::max(m->G, m->F) * 2);   // head operand images
+    add((size_t)n * m->F * 4); add((size_t)n * 2 * m->C * 4); add((size_t)n * (2 * m->C + 4) * 4);
     return b + 8192;
 }
 
@@ -666,6 +759,8 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto)
     ProfScope ps(ctx, "head", 2.0 * n * ((double)m->G * m->F + (double)m->F * 2 * m->C));
     MDF_TRY(ctx->alloc_n(&fc, (size_t)n * m->F));
     MDF_TRY(ctx->alloc_n(&logits, (size_t)n * 2 * m->C));
+    if (tm->head_tc && tm->fc_W[0] && m->F % 4 == 0)
+        return head_forward_tc(m, tm, n, b->d_pooled, fc, logits, b->d_scores);
     return head_forward(m, n, b->d_pooled, fc, logits, b->d_scores);
 }
 
