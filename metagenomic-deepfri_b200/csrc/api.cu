@@ -349,6 +349,14 @@ static void carve_batch(mdf_batch *b, Carver &c, size_t seq_bytes, size_t ncoord
 }
 
 // Builds host metadata, allocates (cudaMalloc when `persistent`, arena otherwise) and uploads.
+__global__ void fill_res_prot_kernel(int n, const int64_t *__restrict__ seq_off, int *__restrict__ res_prot)
+{
+    for (int p = blockIdx.x; p < n; p += gridDim.x) {
+        const int64_t s0 = seq_off[p], s1 = seq_off[p + 1];
+        for (int64_t i = s0 + threadIdx.x; i < s1; i += blockDim.x) res_prot[i] = p;
+    }
+}
+
 static int batch_build(mdf_ctx *ctx, mdf_batch *b, bool persistent, int n, const char *seq, const int64_t *seq_off,
                        const float *coords, const int64_t *coord_off, const char *q_aln, const char *t_aln,
                        const int64_t *aln_off, const uint32_t *packed_host, int G, int C, size_t extra_reserve)
@@ -376,9 +384,6 @@ static int batch_build(mdf_ctx *ctx, mdf_batch *b, bool persistent, int n, const
     std::stable_sort(b->h_order.begin(), b->h_order.end(), [&](int x, int y) {
         return (b->h_seq_off[x + 1] - b->h_seq_off[x]) > (b->h_seq_off[y + 1] - b->h_seq_off[y]);
     });
-    std::vector<int> res_prot((size_t)b->T);
-    for (int p = 0; p < n; ++p)
-        std::fill(res_prot.begin() + b->h_seq_off[p], res_prot.begin() + b->h_seq_off[p + 1], p);
     b->has_structure = coords != nullptr;
     size_t ncoord = 0, alnb = 0;
     b->n_coord_rows = coords ? coord_off[n] : 0;
@@ -412,7 +417,10 @@ static int batch_build(mdf_ctx *ctx, mdf_batch *b, bool persistent, int n, const
     MDF_CUDA(cudaMemcpyAsync(b->d_packed_off, b->h_packed_off.data(), (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
     if (b->nwork) MDF_CUDA(cudaMemcpyAsync(b->d_work, work.data(), work.size() * sizeof(int2), cudaMemcpyHostToDevice, s));
     if (n) MDF_CUDA(cudaMemcpyAsync(b->d_order, b->h_order.data(), n * sizeof(int), cudaMemcpyHostToDevice, s));
-    if (b->T) MDF_CUDA(cudaMemcpyAsync(b->d_res_prot, res_prot.data(), (size_t)b->T * sizeof(int), cudaMemcpyHostToDevice, s));
+    if (b->T) {                                     // [T] protein of each residue: filled on the device (20 MB for 16k proteins)
+        fill_res_prot_kernel<<<std::min(n, 8 * ctx->sm_count), 128, 0, s>>>(n, b->d_seq_off, b->d_res_prot);
+        MDF_LAUNCH_CHECK(ctx);
+    }
     if (b->has_structure) {
         if (ncoord) MDF_CUDA(cudaMemcpyAsync(b->d_coords, coords, ncoord * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
         MDF_CUDA(cudaMemcpyAsync(b->d_coord_off, coord_off, (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));

@@ -468,7 +468,17 @@ static int head_forward_tc(mdf_model *m, TcModel *tm, int n, const float *pooled
 }
 
 // ------------------------------------------------------------------------------------------- batch metadata
-static int build_meta(mdf_ctx *ctx, mdf_batch *b, TcBatchMeta &meta)
+// rowmap[seg_off[p] + i] = seq_off[p] + i for the residues of protein p (pad rows were preset to -1)
+__global__ void fill_rowmap_kernel(int n, const int64_t *__restrict__ seq_off, const int64_t *__restrict__ seg_off, int *__restrict__ rowmap)
+{
+    for (int p = blockIdx.x; p < n; p += gridDim.x) {
+        const int64_t s0 = seq_off[p], r0 = seg_off[p];
+        const int L = (int)(seq_off[p + 1] - s0);
+        for (int i = threadIdx.x; i < L; i += blockDim.x) rowmap[r0 + i] = (int)(s0 + i);
+    }
+}
+
+static int build_meta(mdf_ctx *ctx, mdf_batch *b, TcBatchMeta &meta, bool want_exp_tiles)
 {
     const int n = b->n;
     std::vector<int64_t> seg_off(n + 1, 0);
@@ -477,17 +487,16 @@ static int build_meta(mdf_ctx *ctx, mdf_batch *b, TcBatchMeta &meta)
         seg_off[p + 1] = seg_off[p] + (L + 127) / 128 * 128;
     }
     const int64_t Tp = (seg_off[n] + 255) / 256 * 256;
-    std::vector<int> rowmap((size_t)Tp, -1);
     std::vector<int4> tile_info((size_t)(Tp / 128), make_int4(0, 0, 0, 0));
     std::vector<int4> exp_tiles;
     int tile_base = 0;
     for (int p = 0; p < n; ++p) {
         const int L = (int)(b->h_seq_off[p + 1] - b->h_seq_off[p]);
-        for (int i = 0; i < L; ++i) rowmap[(size_t)seg_off[p] + i] = (int)(b->h_seq_off[p] + i);
         const int KBp = (L + TILE_K - 1) / TILE_K, MT = (L + 127) / 128;
         for (int mt = 0; mt < MT; ++mt) {
             tile_info[(size_t)(seg_off[p] / 128) + mt] = make_int4(tile_base + mt * KBp, (int)(seg_off[p] / TILE_K), KBp, p);
-            for (int kb = 0; kb < KBp; ++kb) exp_tiles.push_back(make_int4(p, mt, kb, tile_base));
+            if (want_exp_tiles)
+                for (int kb = 0; kb < KBp; ++kb) exp_tiles.push_back(make_int4(p, mt, kb, tile_base));
         }
         tile_base += MT * KBp;
     }
@@ -509,11 +518,16 @@ static int build_meta(mdf_ctx *ctx, mdf_batch *b, TcBatchMeta &meta)
     meta.exp_tiles = (int4 *)base; base += align_up(exp_tiles.size() * 16 + 16, 256);
     meta.seg_off = (int64_t *)base;
     cudaStream_t s = ctx->stream;
-    MDF_CUDA(cudaMemcpyAsync(meta.rowmap, rowmap.data(), (size_t)Tp * 4, cudaMemcpyHostToDevice, s));
+    // the [Tp] row map (24 MB for a 16k-protein batch) is filled on the device; only the per-tile / per-protein arrays travel
+    MDF_CUDA(cudaMemcpyAsync(meta.seg_off, seg_off.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, s));
+    MDF_CUDA(cudaMemsetAsync(meta.rowmap, 0xFF, (size_t)Tp * 4, s));
+    if (n > 0) {
+        fill_rowmap_kernel<<<std::min(n, 8 * ctx->sm_count), 128, 0, s>>>(n, b->d_seq_off, meta.seg_off, meta.rowmap);
+        MDF_LAUNCH_CHECK(ctx);
+    }
     MDF_CUDA(cudaMemcpyAsync(meta.tile_info, tile_info.data(), tile_info.size() * 16, cudaMemcpyHostToDevice, s));
     if (!exp_tiles.empty())
         MDF_CUDA(cudaMemcpyAsync(meta.exp_tiles, exp_tiles.data(), exp_tiles.size() * 16, cudaMemcpyHostToDevice, s));
-    MDF_CUDA(cudaMemcpyAsync(meta.seg_off, seg_off.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, s));
     MDF_CUDA(cudaStreamSynchronize(s));      // host vectors are pageable
     return MDF_OK;
 }
@@ -532,16 +546,20 @@ size_t tc_workspace_bytes(const mdf_model *m, int n, const int64_t *seq_off)
     for (int l = 0; l < m->n_gc; ++l) gmax = std::max(gmax, m->gc[l]);
     size_t b = 0;
     auto add = [&](size_t x) { b += align_up(x, 256) + 256; };
-    for (int l = 0; l < m->n_lstm; ++l) add((size_t)Tp * m->H * 2);   // H_l images
-    add((size_t)Tp * 4 * m->H * 4);                   // input pre-activations of the upper LSTM layers
+    const TcModel *tm = static_cast<const TcModel *>(m->tc);
+    const bool fused = tm && tm->lstm_fused && tm->lstm_fused_W;
+    const bool taps = m->ctx->debug_taps;
+    for (int l = 0; l < m->n_lstm; ++l)
+        if (!fused || l == m->n_lstm - 1 || taps) add((size_t)Tp * m->H * 2);   // H_l images
+    if (!fused) add((size_t)Tp * 4 * m->H * 4);       // input pre-activations of the upper LSTM layers
     add(std::max({lstm_tc_scratch_bytes(m->ctx, m->H), lstm_stream_scratch_bytes(m->ctx, m->H), lstm_fused_scratch_bytes(m->ctx, m->H)}));
-    for (int l = 0; l < m->n_lstm; ++l) add((size_t)T * m->H * 4);    // optional fp32 taps
+    if (taps) for (int l = 0; l < m->n_lstm; ++l) add((size_t)T * m->H * 4);    // optional fp32 taps
     add((size_t)Tp * 4 + (size_t)Tp / 128 * 16 + (size_t)(tiles + 1) * 16 + (size_t)(n + 1) * 8 + 1024);   // metadata
     add((size_t)Tp * 4); add((size_t)Tp);             // deg_pad, idx_pad
     add((size_t)Tp * m->E * 2);                       // X0 image
     add((size_t)Tp * gmax * 2); add((size_t)Tp * gmax * 2); add((size_t)Tp * gmax * 2);   // Y^T, X_a, X_b images
     if (!(m->tc && static_cast<const TcModel *>(m->tc)->adj_expand)) add((size_t)tiles * TILE_BYTES + 256);   // A_hat images
-    add((size_t)T * gmax * 4); add((size_t)T * m->E * 4);   // fp32 taps of the last GraphConv layer and of X0
+    if (taps) { add((size_t)T * gmax * 4); add((size_t)T * m->E * 4); }   // fp32 taps of the last GraphConv layer and of X0
     add((size_t)(cdiv(n, 128) * 128) * std::max(m->G, m->F) * 2); add((size_t)(cdiv(n, 128) * 128) * std::max(m->G, m->F) * 2);   // head operand images
     add((size_t)n * m->F * 4); add((size_t)n * 2 * m->C * 4); add((size_t)n * (2 * m->C + 4) * 4);
     return b + 8192;
@@ -563,13 +581,13 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto)
     if (b->owns_memory) {
         if (!b->tc_meta) {
             TcBatchMeta *pm = new TcBatchMeta();
-            int r = build_meta(ctx, b, *pm);
+            int r = build_meta(ctx, b, *pm, !tm->adj_expand);
             if (r != MDF_OK) { delete pm; return r; }
             b->tc_meta = pm;
         }
         meta = static_cast<TcBatchMeta *>(b->tc_meta);
     } else {
-        MDF_TRY(build_meta(ctx, b, local_meta));
+        MDF_TRY(build_meta(ctx, b, local_meta, !tm->adj_expand));
     }
     const int64_t Tp = meta->Tp;
     int gmax = 0;
@@ -581,7 +599,9 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto)
     void *scratch = nullptr;
     MDF_TRY(ctx->alloc_n(&deg_pad, (size_t)Tp));
     MDF_TRY(ctx->alloc_n(&idx_pad, (size_t)Tp));
-    for (int l = 0; l < m->n_lstm; ++l) MDF_TRY(ctx->alloc_n(&Hlimg[l], (size_t)Tp * m->H));
+    const bool fused_lstm = tm->lstm_fused && tm->lstm_fused_W != nullptr;
+    for (int l = 0; l < m->n_lstm; ++l)      // the fused LSTM keeps layer 1 on chip: its image only exists for the debug taps
+        if (!fused_lstm || l == m->n_lstm - 1 || ctx->debug_taps) MDF_TRY(ctx->alloc_n(&Hlimg[l], (size_t)Tp * m->H));
     if (m->n_lstm > 1 && !(tm->lstm_fused && tm->lstm_fused_W)) MDF_TRY(ctx->alloc_n(&pre, (size_t)Tp * 4 * m->H));
     const bool fused = tm->lstm_fused && tm->lstm_fused_W != nullptr;
     MDF_TRY(ctx->alloc(&scratch, std::max({lstm_tc_scratch_bytes(ctx, m->H), lstm_stream_scratch_bytes(ctx, m->H),
