@@ -223,7 +223,7 @@ static int contact_map_packed(mdf_ctx *ctx, const float *coords, int n, float th
     MDF_CUDA(cudaMemcpyAsync(dwork, work.data(), work.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
     MDF_CUDA(cudaMemcpyAsync(doff, offs, sizeof offs, cudaMemcpyHostToDevice, ctx->stream));
     MDF_TRY(launch_coords_to_frame(ctx, n, dC, qc));
-    MDF_TRY(launch_cmap_pair(ctx, (int)work.size(), dwork, qc, doff, thr2, 0, 0.0f < thr2 ? 1 : 0, packed, doff + 2));
+    MDF_TRY(launch_cmap_pair(ctx, 1, (int)work.size(), dwork, qc, doff, thr2, 0, 0.0f < thr2 ? 1 : 0, packed, doff + 2));
     *packed_out = packed; *work_out = dwork; *off_out = doff; *nwork_out = (int)work.size();
     return MDF_OK;
 }
@@ -453,7 +453,7 @@ static int run_cmap(mdf_ctx *ctx, mdf_batch *b, float thr2, int gen)
     ProfScope ps(ctx, "cmap_build_transfer", ctx->profiling ? cmap_algorithmic_bytes(b, b->n_coord_rows, b->n_aln_cols) : 0.0);
     MDF_TRY(launch_aln_transfer(ctx, b->n, b->d_qaln, b->d_taln, b->d_aln_off, b->d_seq_off, b->d_coords,
                                 b->d_coord_off, b->d_qc));
-    return launch_cmap_pair(ctx, b->nwork, b->d_work, b->d_qc, b->d_seq_off, thr2, gen, 1, b->d_packed, b->d_packed_off);
+    return launch_cmap_pair(ctx, b->n, b->nwork, b->d_work, b->d_qc, b->d_seq_off, thr2, gen, 1, b->d_packed, b->d_packed_off);
 }
 
 static size_t engine_workspace(const mdf_model *m, int n, const int64_t *seq_off)

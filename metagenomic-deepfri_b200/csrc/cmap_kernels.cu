@@ -154,30 +154,51 @@ cmap_pair_kernel(const int2 *__restrict__ work, const float4 *__restrict__ qc,
             float4 v = j < L ? q[j] : make_float4(qnan, qnan, qnan, 0.f);
             cx[k] = v.x; cy[k] = v.y; cz[k] = v.z;
         }
-#pragma unroll 2
-        for (int r = 0; r < 8; ++r) {
-            const int i = rb * 32 + rs * 8 + r;
-            if (i >= L) break;
-            const float4 a = rows[rs * 8 + r];
-            uint32_t w[4];
+        // 8 rows x 128 columns per item.  The ballots give every lane the four words of a row; lane r keeps row r and
+        // lanes 0..7 store their rows together afterwards (the diagonal / generated-contact band is OR-ed in by
+        // cmap_band_kernel: handled here it cost a divergent lane-0 path on every row, more warp instructions than the
+        // distance arithmetic itself)
+        const int i0 = rb * 32 + rs * 8;
+        uint32_t keep[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                w[k] = __ballot_sync(0xffffffffu, sqdist3(a.x, a.y, a.z, cx[k], cy[k], cz[k]) < thr2);
-            if (lane == 0) {
-                if (i + gen >= jlo && i - gen < jlo + 128) {   // tile touches the diagonal band
-                    const int gi = __float_as_int(a.w) & 1;
-                    for (int dj = -gen; dj <= gen; ++dj) {
-                        const int j = i + dj;
-                        if (j < 0 || j >= L || j < jlo || j >= jlo + 128) continue;
-                        bool set = dj == 0 ? (diag_val != 0) : (gi || (__float_as_int(q[j].w) & 1));
-                        if (set) w[(j - jlo) >> 5] |= 1u << (j & 31);
-                    }
-                }
-                *reinterpret_cast<uint4 *>(out + (size_t)i * rw + tile * 4) = make_uint4(w[0], w[1], w[2], w[3]);
+        for (int r = 0; r < 8; ++r) {
+            const float4 a = rows[rs * 8 + r];                     // rows past L hold NaN -> all-zero words, never stored
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t w = __ballot_sync(0xffffffffu, sqdist3(a.x, a.y, a.z, cx[k], cy[k], cz[k]) < thr2);
+                if (lane == r) keep[k] = w;
+            }
+        }
+        if (lane < 8 && i0 + lane < L)
+            *reinterpret_cast<uint4 *>(out + (size_t)(i0 + lane) * rw + tile * 4) = make_uint4(keep[0], keep[1], keep[2], keep[3]);
+    }
+}
+
+// Diagonal and generated contacts (contact_map_utils.pyx:82-97): out[i][i] = diag_val ? 1 : computed; out[i][i +- d] = 1 for
+// d = 1..gen when residue i or residue i +- d was generated (a query residue facing a target gap).  One thread per row, at
+// most 2 gen + 1 bits: OR-ed into the words cmap_pair_kernel wrote.
+__global__ void cmap_band_kernel(int n, const float4 *__restrict__ qc, const int64_t *__restrict__ seq_off, int gen, int diag_val,
+                                 uint32_t *__restrict__ packed, const int64_t *__restrict__ packed_off)
+{
+    for (int p = blockIdx.x; p < n; p += gridDim.x) {
+        const int64_t s0 = seq_off[p];
+        const int L = (int)(seq_off[p + 1] - s0);
+        const int rw = packed_row_words(L);
+        const float4 *__restrict__ q = qc + s0;
+        uint32_t *__restrict__ out = packed + packed_off[p];
+        for (int i = threadIdx.x; i < L; i += blockDim.x) {
+            const int gi = __float_as_int(q[i].w) & 1;
+            uint32_t *row = out + (size_t)i * rw;
+            for (int dj = -gen; dj <= gen; ++dj) {
+                const int j = i + dj;
+                if (j < 0 || j >= L) continue;
+                const bool set = dj == 0 ? (diag_val != 0) : (gi || (__float_as_int(q[j].w) & 1));
+                if (set) row[j >> 5] |= 1u << (j & 31);
             }
         }
     }
 }
+
 
 // packed -> dense int32 [L, L] (the reference's layout; bio_utils.py:220 / contact_map_utils.pyx:82)
 __global__ void unpack_dense_kernel(const int2 *__restrict__ work, const int64_t *__restrict__ seq_off,
@@ -366,13 +387,17 @@ int launch_coords_to_frame(mdf_ctx *ctx, int64_t total, const float *coords, flo
     return MDF_OK;
 }
 
-int launch_cmap_pair(mdf_ctx *ctx, int nwork, const int2 *work, const float4 *qc, const int64_t *seq_off,
+int launch_cmap_pair(mdf_ctx *ctx, int n, int nwork, const int2 *work, const float4 *qc, const int64_t *seq_off,
                      float thr2, int gen, int diag_val, uint32_t *packed, const int64_t *packed_off)
 {
     if (nwork <= 0) return MDF_OK;
     cmap_pair_kernel<<<nwork, PAIR_WARPS * 32, 0, ctx->stream>>>(work, qc, seq_off, thr2, gen < 0 ? 0 : gen,
                                                                  diag_val, packed, packed_off);
     MDF_LAUNCH_CHECK(ctx);
+    if (n > 0 && (diag_val || gen > 0)) {
+        cmap_band_kernel<<<std::min(n, 16 * ctx->sm_count), 128, 0, ctx->stream>>>(n, qc, seq_off, gen < 0 ? 0 : gen, diag_val, packed, packed_off);
+        MDF_LAUNCH_CHECK(ctx);
+    }
     return MDF_OK;
 }
 

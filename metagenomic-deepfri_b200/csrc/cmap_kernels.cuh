@@ -7,7 +7,7 @@ namespace mdf {
 int launch_aln_transfer(mdf_ctx *ctx, int n, const char *q_aln, const char *t_aln, const int64_t *aln_off,
                         const int64_t *seq_off, const float *coords, const int64_t *coord_off, float4 *qc);
 int launch_coords_to_frame(mdf_ctx *ctx, int64_t total, const float *coords, float4 *qc);
-int launch_cmap_pair(mdf_ctx *ctx, int nwork, const int2 *work, const float4 *qc, const int64_t *seq_off,
+int launch_cmap_pair(mdf_ctx *ctx, int n, int nwork, const int2 *work, const float4 *qc, const int64_t *seq_off,
                      float thr2, int gen, int diag_val, uint32_t *packed, const int64_t *packed_off);
 int launch_unpack_dense(mdf_ctx *ctx, int nwork, const int2 *work, const int64_t *seq_off, const uint32_t *packed,
                         const int64_t *packed_off, int32_t *dense, const int64_t *dense_off);
