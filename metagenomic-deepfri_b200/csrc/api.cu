@@ -467,10 +467,19 @@ static int run_path(mdf_model *m, mdf_batch *b, float thr2, int gen, int upto, b
 {
     mdf_ctx *ctx = m->ctx;
     MDF_CUDA(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
-    if (with_cmap) MDF_TRY(run_cmap(ctx, b, thr2, gen));
+    // a persistent batch that already holds the maps for this (threshold, generated contacts) keeps them for the next head
+    const bool maps_cached = with_cmap && b->owns_memory && b->cmap_valid && b->cmap_thr2 == thr2 && b->cmap_gen == gen &&
+                             b->cmap_eps == m->eps && upto >= 2;
+    if (with_cmap && !maps_cached) {
+        MDF_TRY(run_cmap(ctx, b, thr2, gen));
+        b->cmap_valid = false;
+    }
     if (upto < 2) return MDF_OK;
     MDF_TRY(launch_seq_to_idx(ctx, b->T, b->d_seq, b->d_idx));
-    MDF_TRY(launch_prep_adjacency(ctx, b, m->eps));
+    if (!maps_cached) {
+        MDF_TRY(launch_prep_adjacency(ctx, b, m->eps));
+        if (with_cmap && b->owns_memory) { b->cmap_valid = true; b->cmap_thr2 = thr2; b->cmap_gen = gen; b->cmap_eps = m->eps; }
+    }
     if (m->engine == 1) return tc_forward(m, b, upto);
     return simt_forward(m, b, upto);
 }
@@ -511,6 +520,7 @@ extern "C" int mdf_batch_destroy(mdf_batch *b)
         cudaStreamSynchronize(b->ctx->stream);
         cudaFree(b->block);
         if (b->out_block) cudaFree(b->out_block);
+        if (b->lm_cache) cudaFree(b->lm_cache);
     }
     tc_batch_free(b);
     delete b;

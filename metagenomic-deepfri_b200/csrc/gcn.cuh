@@ -59,6 +59,14 @@ struct mdf_batch {
     float *tap_h[MDF_MAX_LSTM] = {nullptr};
     float *tap_x0 = nullptr, *tap_gc_last = nullptr;
     void *tc_meta = nullptr;     // tensor-core engine metadata of persistent batches (tc_engine.cu)
+    // persistent batches keep what several heads (MF / BP / CC / EC models) share, so that running the next head on the same
+    // uploaded batch skips it: the contact maps + degrees for (thr2, gen), and the LSTM-LM output image for a given LM
+    bool cmap_valid = false;
+    float cmap_thr2 = 0.f, cmap_eps = 0.f;
+    int cmap_gen = 0;
+    void *lm_cache = nullptr;    // [Tp x H] fp16 operand image of the last LSTM layer
+    size_t lm_cache_bytes = 0;
+    unsigned long long lm_hash = 0;
 };
 
 namespace mdf {

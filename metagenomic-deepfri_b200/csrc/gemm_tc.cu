@@ -282,7 +282,7 @@ gemm_tc_kernel(GemmArgs g, int a_terms, int b_terms, int stages)
                     }
                     if (lane == 0) mbar_wait(&bars.empty[st], ph ^ 1);
                     __syncwarp();
-                    uint8_t *dst = smem + (size_t)st * stage_bytes + (et >> 3) * 128 + (et & 7) * 16;
+                    const uint32_t dst = smem_u32(smem + (size_t)st * stage_bytes) + (uint32_t)((et >> 3) * 128 + (et & 7) * 16);
                     const uint32_t one = 0x3C00u;                                            // fp16 1.0
 #pragma unroll
                     for (int k8 = 0; k8 < 8; ++k8) {
@@ -292,7 +292,7 @@ gemm_tc_kernel(GemmArgs g, int a_terms, int b_terms, int stages)
                         pk.y = ((b8 & 4u) ? one : 0u) | ((b8 & 8u) ? one << 16 : 0u);
                         pk.z = ((b8 & 16u) ? one : 0u) | ((b8 & 32u) ? one << 16 : 0u);
                         pk.w = ((b8 & 64u) ? one : 0u) | ((b8 & 128u) ? one << 16 : 0u);
-                        *reinterpret_cast<uint4 *>(dst + k8 * 2048) = pk;
+                        st_shared_v4(dst + k8 * 2048, pk);
                     }
                     fence_proxy_async_smem();                    // generic-proxy tile -> tensor-core (async proxy) reads
                     __syncwarp();

@@ -33,6 +33,7 @@ struct TcModel {
     __half *fc_W[2] = {nullptr, nullptr};                  // head: [F rows x G k] hi / lo (B operand)
     __half *out_W[2] = {nullptr, nullptr};                 // head: [2C rows x F k] hi / lo
     float *out_b_pad = nullptr;                            // head: output bias padded to a multiple of 4 entries
+    unsigned long long lm_hash = 0;                        // FNV-1a of the LSTM weights: heads that share the LM share its output
     int head_tc = 1;                                       // head GEMMs on tensor cores (activations and weights both split hi + lo)
     int pool_fused = 1;                                    // sum-pool readout inside the adjacency GEMM epilogue (fp32, no X re-read)
     int adj_expand = 1;                                    // adjacency GEMM expands its A tiles from the bit-packed map on the fly
@@ -170,6 +171,18 @@ int tc_model_init(mdf_model *m, const mdf_model_desc *d)
         MDF_TRY(upload_half(m, &t->gc_W[l][1], lo));
         if (t->gemm_phases > 0) MDF_TRY(upload_dithered(d->gc_W[l], m->gc[l], prev, &t->gc_Wd[l]));
         prev = m->gc[l];
+    }
+    {
+        unsigned long long hsh = 1469598103934665603ull;
+        auto mix = [&](const float *p, size_t count) {
+            const unsigned char *c = reinterpret_cast<const unsigned char *>(p);
+            for (size_t i = 0; p && i < count * sizeof(float); ++i) { hsh ^= c[i]; hsh *= 1099511628211ull; }
+        };
+        for (int l = 0; l < m->n_lstm; ++l) {
+            const int in = l == 0 ? m->I : m->H;
+            mix(d->lstm_W[l], (size_t)4 * m->H * in); mix(d->lstm_R[l], (size_t)4 * m->H * m->H); mix(d->lstm_B[l], (size_t)8 * m->H);
+        }
+        t->lm_hash = hsh ? hsh : 1;
     }
     // ---- LSTM: resident recurrent slices, layer-1 table, input-GEMM weights of the upper layers
     const int H = m->H, H4 = 4 * H, cpg = H / 16;
@@ -614,8 +627,24 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto)
     pad_vectors_kernel<<<(unsigned)cdiv64(Tp, 256), 256, 0, s>>>(Tp, meta->rowmap, b->d_deg, b->d_idx, deg_pad, idx_pad);
     MDF_LAUNCH_CHECK(ctx);
 
-    // ---- LSTM language model
-    if (fused) {
+    // ---- LSTM language model.  A persistent batch keeps the last layer's output image: another head with the same LM
+    // (the MF / BP / CC / EC models share it) skips the recurrence altogether.
+    bool lm_cached = false;
+    if (b->owns_memory && !ctx->debug_taps) {
+        const size_t need = (size_t)Tp * m->H * sizeof(__half);
+        if (b->lm_cache && b->lm_cache_bytes == need && b->lm_hash == tm->lm_hash) {
+            lm_cached = true;
+        } else {
+            if (b->lm_cache) { MDF_CUDA(cudaStreamSynchronize(s)); cudaFree(b->lm_cache); b->lm_cache = nullptr; }
+            MDF_CUDA(cudaMalloc(&b->lm_cache, need));
+            b->lm_cache_bytes = need;
+            b->lm_hash = 0;
+        }
+        Hlimg[m->n_lstm - 1] = static_cast<__half *>(b->lm_cache);
+    }
+    if (lm_cached) {
+        b->tap_h[0] = b->tap_h[1] = nullptr;
+    } else if (fused) {
         // both layers + the layer-2 input projection in one persistent wavefront kernel (lstm_fused.cu)
         ProfScope ps(ctx, "lstm_fused", 3.0 * 2.0 * T * 4 * m->H * m->H);
         MDF_TRY(launch_lstm_fused(ctx, m->H, n, tm->lstm_fused_W, tm->lstm_phases, tm->lstm_tab_full, tm->lstm_bperm[1], idx_pad, b->d_order,
@@ -624,7 +653,7 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto)
         b->tap_h[0] = b->tap_h[1] = nullptr;
     }
     // fallback: persistent tcgen05 recurrence per layer, input GEMM between layers
-    for (int l = 0; l < (fused ? 0 : m->n_lstm); ++l) {
+    for (int l = 0; l < ((fused || lm_cached) ? 0 : m->n_lstm); ++l) {
         if (l > 0) {
             ProfScope ps(ctx, "lstm_input_gemm", 2.0 * T * 4 * m->H * m->H);
             GemmArgs g;                                   // pre[Tp x 4H] = H_{l-1} . W_in^T + b   ([unit][gate] columns)
@@ -648,6 +677,7 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto)
         }
         b->tap_h[l] = nullptr;
     }
+    if (b->owns_memory && !ctx->debug_taps) b->lm_hash = tm->lm_hash;
     if (ctx->debug_taps) {                                // fp32 copies of the LSTM outputs over packed residues
         for (int l = 0; l < m->n_lstm; ++l) {
             float *tap = nullptr;

@@ -26,6 +26,13 @@ __device__ __forceinline__ bool elect_one_sync()
     return pred != 0;
 }
 
+// 16-byte store to shared memory by shared-window address (a generic pointer rebuilt from uintptr arithmetic makes the
+// compiler emit generic ST.E instead of STS)
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v)
+{
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {

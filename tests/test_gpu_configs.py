@@ -108,3 +108,43 @@ def test_tc_engine_batch_invariance_and_order(tmp_path):
     one = pred.forward_structures(*take(wl, [7]), threshold=10.0, generated_contacts=2)
     assert np.abs(one[0] - full[7]).max() < 2e-5
     pred.close()
+
+
+def test_pipeline_adapter_shares_maps_and_lm_across_heads(tmp_path):
+    """`pipeline.predict_structures`: one upload, one contact-map build and one LSTM-LM run serve all four heads; the
+    scores equal what each head computes on its own, rows come out like pipeline.py:318-319 writes them."""
+    import csv
+    import io
+    from conftest import Aln
+    from metagenomic_deepfri_b200 import pipeline
+    preds, paths = {}, {}
+    for head, C in HEADS.items():
+        paths[head] = str(tmp_path / f"{head}.onnx")
+        synth.write_gcn_model(paths[head], synth.GCNConfig(n_terms=C), seed=77 + C)      # same LM (lm_seed), own heads
+        preds[head] = predict.Predictor(paths[head])
+        preds[head].set_engine("tc")
+    wl = synth.config_workload(2, 0.004)           # 40 proteins, LogNormal lengths
+    alns = [Aln(wl.gapped_query[i], wl.gapped_target[i], wl.coords[i], i) for i in range(len(wl))]
+    alns[5].coords = None                          # no structure: reported back, not predicted
+    sinks = {h: io.StringIO() for h in HEADS}
+    writers = {h: csv.writer(sinks[h], delimiter="\t") for h in HEADS}
+    scores, kept, skipped = pipeline.predict_structures(preds, alns, wl.threshold, wl.generated_contacts, max_residues=4000,
+                                                        writers=writers)
+    assert skipped == [5] and kept == [i for i in range(len(wl)) if i != 5]
+    for head, pred in preds.items():
+        alone = pred.forward_structures(*take(wl, kept), threshold=wl.threshold, generated_contacts=wl.generated_contacts)
+        assert scores[head].shape == (len(kept), HEADS[head])
+        assert np.abs(scores[head] - alone).max() < 2e-5
+        rows = list(csv.reader(io.StringIO(sinks[head].getvalue()), delimiter="\t"))
+        assert [r[0] for r in rows] == [alns[i].query_name for i in kept] and all(r[1] == "gcn" for r in rows)
+        assert np.allclose(np.array(rows[3][2:], np.float64), scores[head][3], atol=1e-7)
+    assert_scores(scores["mf"][:4], oracle_scores(paths["mf"], wl, kept[:4]))
+    # the reference helper's signature on precomputed maps
+    pairs = [(alns[i], co.build_align_contact_map(wl.gapped_query[i], wl.gapped_target[i], wl.coords[i], wl.threshold,
+                                                  wl.generated_contacts)) for i in kept[:6]]
+    sink = io.StringIO()
+    pipeline.run_prediction_loop(preds["cc"], pairs, len(pairs), "gcn", csv.writer(sink, delimiter="\t"), "cc")
+    rows = list(csv.reader(io.StringIO(sink.getvalue()), delimiter="\t"))
+    assert len(rows) == 6 and np.abs(np.array([r[2:] for r in rows], np.float64) - scores["cc"][:6]).max() < 2e-5
+    for p in preds.values():
+        p.close()

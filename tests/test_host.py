@@ -70,3 +70,10 @@ def test_config_workloads_shapes():
         assert len(wl) >= 1 and all(len(q) == len(t) for q, t in zip(wl.gapped_query, wl.gapped_target))
     lens = [len(s) for s in synth.config_workload(3, 0.005).query_seqs]
     assert min(lens) >= 1000 and max(lens) <= 2500
+
+
+def test_pipeline_chunks_by_residue_budget():
+    from metagenomic_deepfri_b200 import pipeline
+    assert pipeline._chunks([], 100) == []
+    assert pipeline._chunks([50, 60, 10, 200, 5], 100) == [(0, 1), (1, 3), (3, 4), (4, 5)]
+    assert pipeline._chunks([10, 10, 10], 1000) == [(0, 3)]
