@@ -150,6 +150,10 @@ int mdf_batch_upload(mdf_ctx *ctx, int n,
                      mdf_batch **out);
 int mdf_batch_destroy(mdf_batch *batch);
 int mdf_path_run(mdf_model *model, mdf_batch *batch, float thr2, int generated_contacts);
+/* mdf_path_run that keeps what an earlier run on this batch computed and this head shares: the contact maps and degrees
+ * (same thr2 / generated_contacts / eps) and the LSTM-LM output (same LM weights).  pipeline.py:546-655 runs the MF / BP /
+ * CC / EC heads one after the other over the same proteins; mdf_path_run itself always recomputes everything. */
+int mdf_path_run_shared(mdf_model *model, mdf_batch *batch, float thr2, int generated_contacts);
 /* stage selector for profiling / unit parity: 1 = cmap only, 2 = + LSTM-LM, 3 = + GraphConv, 4 = all */
 int mdf_path_run_stages(mdf_model *model, mdf_batch *batch, float thr2, int generated_contacts, int upto);
 int mdf_batch_fetch_scores(mdf_model *model, mdf_batch *batch, float *scores /* host [n,C] */);

@@ -83,6 +83,7 @@ def lib() -> C.CDLL:
         L.mdf_batch_destroy.argtypes = [vp]
         L.mdf_path_run.argtypes = [vp, vp, C.c_float, C.c_int]
         L.mdf_path_run_stages.argtypes = [vp, vp, C.c_float, C.c_int, C.c_int]
+        L.mdf_path_run_shared.argtypes = [vp, vp, C.c_float, C.c_int]
         L.mdf_batch_fetch_scores.argtypes = [vp, vp, vp]
         L.mdf_batch_fetch.argtypes = [vp, vp, C.c_int, vp, C.c_size_t]
         L.mdf_batch_scores_device.argtypes = [vp]
@@ -91,8 +92,8 @@ def lib() -> C.CDLL:
                      "mdf_contact_map_dense", "mdf_contact_map_sparse", "mdf_align_contact_map",
                      "mdf_cmap_build_transfer", "mdf_model_create", "mdf_model_destroy", "mdf_model_set_engine",
                      "mdf_gcn_forward_dense", "mdf_gcn_forward_packed", "mdf_path_forward", "mdf_batch_upload",
-                     "mdf_batch_destroy", "mdf_path_run", "mdf_path_run_stages", "mdf_batch_fetch_scores",
-                     "mdf_batch_fetch"):
+                     "mdf_batch_destroy", "mdf_path_run", "mdf_path_run_stages", "mdf_path_run_shared",
+                     "mdf_batch_fetch_scores", "mdf_batch_fetch"):
             getattr(L, name).restype = C.c_int
         _lib = L
         return _lib
@@ -103,8 +104,8 @@ EXPORTED_SYMBOLS = [
     "mdf_ctx_launch_count", "mdf_ctx_profile", "mdf_ctx_profile_report", "mdf_ctx_set_debug_taps", "mdf_pairwise_sqeuclidean", "mdf_contact_map_dense", "mdf_contact_map_sparse",
     "mdf_align_contact_map", "mdf_cmap_build_transfer", "mdf_model_create", "mdf_model_destroy",
     "mdf_model_set_engine", "mdf_model_get_engine", "mdf_gcn_forward_dense", "mdf_gcn_forward_packed", "mdf_path_forward",
-    "mdf_batch_upload", "mdf_batch_destroy", "mdf_path_run", "mdf_path_run_stages", "mdf_batch_fetch_scores",
-    "mdf_batch_fetch", "mdf_batch_scores_device",
+    "mdf_batch_upload", "mdf_batch_destroy", "mdf_path_run", "mdf_path_run_stages", "mdf_path_run_shared",
+    "mdf_batch_fetch_scores", "mdf_batch_fetch", "mdf_batch_scores_device",
 ]
 
 

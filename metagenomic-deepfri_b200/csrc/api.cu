@@ -468,7 +468,7 @@ static int run_path(mdf_model *m, mdf_batch *b, float thr2, int gen, int upto, b
     mdf_ctx *ctx = m->ctx;
     MDF_CUDA(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
     // a persistent batch that already holds the maps for this (threshold, generated contacts) keeps them for the next head
-    const bool maps_cached = with_cmap && b->owns_memory && b->cmap_valid && b->cmap_thr2 == thr2 && b->cmap_gen == gen &&
+    const bool maps_cached = with_cmap && b->owns_memory && b->reuse && b->cmap_valid && b->cmap_thr2 == thr2 && b->cmap_gen == gen &&
                              b->cmap_eps == m->eps && upto >= 2;
     if (with_cmap && !maps_cached) {
         MDF_TRY(run_cmap(ctx, b, thr2, gen));
@@ -551,6 +551,18 @@ extern "C" int mdf_path_run_stages(mdf_model *m, mdf_batch *b, float thr2, int g
 extern "C" int mdf_path_run(mdf_model *m, mdf_batch *b, float thr2, int gen)
 {
     return mdf_path_run_stages(m, b, thr2, gen, 4);
+}
+
+// Same as mdf_path_run, but results of an earlier run on this batch that do not depend on the head are kept: the contact
+// maps + degrees (same threshold / generated contacts / eps) and the LSTM-LM output (same LM weights).  This is how the
+// MF / BP / CC / EC heads of one prediction job share their common front end (pipeline.py:546-655 runs them in sequence).
+extern "C" int mdf_path_run_shared(mdf_model *m, mdf_batch *b, float thr2, int gen)
+{
+    MDF_REQUIRE(m && b, "mdf_path_run_shared: bad arguments");
+    b->reuse = true;
+    const int r = mdf_path_run_stages(m, b, thr2, gen, 4);
+    b->reuse = false;
+    return r;
 }
 
 extern "C" int mdf_batch_fetch_scores(mdf_model *m, mdf_batch *b, float *scores)

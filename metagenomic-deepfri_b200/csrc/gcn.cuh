@@ -61,6 +61,7 @@ struct mdf_batch {
     void *tc_meta = nullptr;     // tensor-core engine metadata of persistent batches (tc_engine.cu)
     // persistent batches keep what several heads (MF / BP / CC / EC models) share, so that running the next head on the same
     // uploaded batch skips it: the contact maps + degrees for (thr2, gen), and the LSTM-LM output image for a given LM
+    bool reuse = false;          // set per call: mdf_path_run_shared allows reuse, mdf_path_run / _stages recompute everything
     bool cmap_valid = false;
     float cmap_thr2 = 0.f, cmap_eps = 0.f;
     int cmap_gen = 0;

@@ -361,8 +361,14 @@ struct PairGemmArgs {
     int a_terms, b_terms, stages;
 };
 
+#ifndef MDF_PAIR_EPI_WARPS
+#define MDF_PAIR_EPI_WARPS 8
+#endif
+constexpr int PAIR_EW = MDF_PAIR_EPI_WARPS;               // epilogue warps per CTA (8 or 16)
+constexpr int PAIR_THREADS = (PAIR_EW + 2) * 32;
+
 template <int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(PAIR_THREADS, 1)
 gemm_pair_kernel(const __grid_constant__ PairGemmArgs pa)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -374,7 +380,7 @@ gemm_pair_kernel(const __grid_constant__ PairGemmArgs pa)
     const int a_bytes = a_terms * TILE_BYTES;
     const int stage_bytes = a_bytes + b_terms * TILE_BYTES;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int w_prod = GEMM_THREADS / 32 - 2, w_mma = GEMM_THREADS / 32 - 1;     // warps 0-7 epilogue, 8 producer, 9 MMA issuer
+    constexpr int w_prod = PAIR_EW, w_mma = PAIR_EW + 1;     // warps 0..PAIR_EW-1 epilogue, then producer, MMA issuer
     const int rank = (int)cluster_ctarank();
     const bool leader = rank == 0;
     const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
@@ -382,7 +388,7 @@ gemm_pair_kernel(const __grid_constant__ PairGemmArgs pa)
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) { mbar_init(&bars.full[s], 1); mbar_init(&bars.empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&bars.tmem_full[s], 1); mbar_init(&bars.tmem_empty[s], 16); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&bars.tmem_full[s], 1); mbar_init(&bars.tmem_empty[s], 2 * PAIR_EW); }
         fence_mbar_init();
     }
     if (warp == w_mma) tmem_alloc_pair<2 * BN>(&bars.tmem_base);
@@ -464,7 +470,7 @@ gemm_pair_kernel(const __grid_constant__ PairGemmArgs pa)
             uint8_t *row_ptr = reinterpret_cast<uint8_t *>(g.out_img) + (size_t)(m >> 7) * g.KB_out * TILE_BYTES +
                                (size_t)((((int)m & 127) >> 3) * 128 + ((int)m & 7) * 16);
 #pragma unroll 1
-            for (int c0 = ch * (BN / 2); c0 < (ch + 1) * (BN / 2); c0 += 32) {
+            for (int c0 = ch * (BN * 4 / PAIR_EW); c0 < (ch + 1) * (BN * 4 / PAIR_EW); c0 += 32) {
                 uint32_t r[32];
                 tmem_ld_32x32b_x32(trow + c0, r);
                 tmem_ld_wait();
@@ -526,7 +532,7 @@ static int launch_pair(mdf_ctx *ctx, int a_terms, int b_terms, const GemmArgs &a
     if (outer <= 0 || args.m_tiles * args.n_tiles <= 0) return MDF_OK;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * std::min(outer, ctx->sm_count / 2));
-    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.blockDim = dim3(PAIR_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = ctx->stream;
     cudaLaunchAttribute attr[1];

@@ -630,7 +630,7 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto)
     // ---- LSTM language model.  A persistent batch keeps the last layer's output image: another head with the same LM
     // (the MF / BP / CC / EC models share it) skips the recurrence altogether.
     bool lm_cached = false;
-    if (b->owns_memory && !ctx->debug_taps) {
+    if (b->owns_memory && b->reuse && !ctx->debug_taps) {
         const size_t need = (size_t)Tp * m->H * sizeof(__half);
         if (b->lm_cache && b->lm_cache_bytes == need && b->lm_hash == tm->lm_hash) {
             lm_cached = true;
@@ -677,7 +677,7 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto)
         }
         b->tap_h[l] = nullptr;
     }
-    if (b->owns_memory && !ctx->debug_taps) b->lm_hash = tm->lm_hash;
+    if (b->owns_memory && b->reuse && !ctx->debug_taps) b->lm_hash = tm->lm_hash;
     if (ctx->debug_taps) {                                // fp32 copies of the LSTM outputs over packed residues
         for (int l = 0; l < m->n_lstm; ++l) {
             float *tap = nullptr;

@@ -78,7 +78,7 @@ def predict_structures(predictors: Dict[str, Predictor], alignments: Sequence, t
                              [a.gapped_target for a in part], [np.ascontiguousarray(a.coords, np.float32) for a in part])
         try:
             for mode, pred in predictors.items():
-                pred.run(batch, threshold, generated_contacts)      # maps and LM output are reused from the first head
+                pred.run(batch, threshold, generated_contacts, share=True)   # maps and LM output come from the first head
                 pred.fetch_scores(batch, out[mode][lo:hi])
         finally:
             batch.close()

@@ -260,8 +260,17 @@ class Predictor:
     def upload(self, seqs, gapped_query, gapped_target, coords) -> PathBatch:
         return PathBatch(self._ctx, seqs, gapped_query, gapped_target, coords)
 
-    def run(self, batch: PathBatch, threshold: float = 6, generated_contacts: int = 2, upto: int = 4) -> None:
+    def run(self, batch: PathBatch, threshold: float = 6, generated_contacts: int = 2, upto: int = 4,
+            share: bool = False) -> None:
+        """Run the path on an uploaded batch.  `share=True` keeps what an earlier run of ANOTHER head on this batch
+        already computed and this head shares (contact maps, LSTM-LM output); the default recomputes everything."""
         from .bio_utils import threshold_sq
+        if share:
+            if upto != 4:
+                raise ValueError("run(share=True) runs the whole path")
+            _lib.check(_lib.lib().mdf_path_run_shared(self._handle, batch.handle, float(threshold_sq(threshold)),
+                                                      int(generated_contacts)))
+            return
         _lib.check(_lib.lib().mdf_path_run_stages(self._handle, batch.handle, float(threshold_sq(threshold)),
                                                   int(generated_contacts), upto))
 

@@ -53,7 +53,7 @@ def main():
             per = {}
             for h, p in preds.items():
                 ta = time.perf_counter()
-                p.run(batch, wl.threshold, wl.generated_contacts)
+                p.run(batch, wl.threshold, wl.generated_contacts, share=True)
                 ctx.synchronize()
                 per[h] = (time.perf_counter() - ta) * 1e3
             dt = time.perf_counter() - t0
