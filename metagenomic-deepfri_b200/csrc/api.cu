@@ -544,7 +544,7 @@ extern "C" int mdf_path_run_stages(mdf_model *m, mdf_batch *b, float thr2, int g
         b->out_G = m->G; b->out_C = m->C;
     }
     ArenaScope scope(ctx);
-    MDF_TRY(ctx->reserve(engine_workspace(m, b->n, b->h_seq_off.data())));
+    MDF_TRY(ctx->reserve(upto >= 2 ? engine_workspace(m, b->n, b->h_seq_off.data()) : 4096));   // stage 1 works in the batch's own memory
     return run_path(m, b, thr2, gen, upto, b->has_structure);
 }
 

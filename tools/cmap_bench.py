@@ -1,0 +1,71 @@
+"""BASELINE configs[1]: contact-map build + alignment transfer only, on synthetic query/target pairs with
+MMseqs2-style gapped alignments (thr 6 A, generated contacts 2).  Reports pairs/s with the inputs resident in HBM,
+the algorithmic HBM rate (12 Lt + 2 La + Lq^2/8 bytes per pair) against the measured HBM peak, and the
+non-fusable FP32 rate (9 ops per residue pair) against the 37 Top/s issue peak - the kernel emits bit-packed maps, so
+the second is the roofline that binds.  A bounded sample is checked bit for bit against the oracle.
+
+  python tools/cmap_bench.py [--pairs 100000] [--reps 5]
+"""
+import argparse
+import json
+import os
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import mdf_pkg  # noqa: E402
+
+mdf_pkg.load()
+from metagenomic_deepfri_b200 import synth, predict, batching, _lib  # noqa: E402
+import cmap_oracle as co  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--pairs", type=int, default=100_000)
+    ap.add_argument("--reps", type=int, default=5)
+    args = ap.parse_args()
+    t0 = time.perf_counter()
+    wl = synth.config_workload(1, args.pairs / 100_000)
+    lq = np.array([len(s) for s in wl.query_seqs], np.float64)
+    lt = np.array([len(c) for c in wl.coords], np.float64)
+    la = np.array([len(a) for a in wl.gapped_query], np.float64)
+    print(f"config 1: {len(wl)} pairs, Lq mean {lq.mean():.0f}, thr {wl.threshold} A, gen {wl.generated_contacts} "
+          f"(generated in {time.perf_counter() - t0:.1f} s)", flush=True)
+    path = os.path.join(tempfile.mkdtemp(), "m.onnx")
+    synth.write_gcn_model(path, synth.GCNConfig())
+    pred = predict.Predictor(path)
+    ctx = _lib.default_context()
+    batch = pred.upload(wl.query_seqs, wl.gapped_query, wl.gapped_target, wl.coords)
+    times = []
+    for _ in range(args.reps + 2):
+        ctx.synchronize()
+        t0 = time.perf_counter()
+        pred.run(batch, wl.threshold, wl.generated_contacts, upto=1)       # K2 transfer + K1 distance/threshold/pack (+ band)
+        ctx.synchronize()
+        times.append(time.perf_counter() - t0)
+    dt = float(np.median(times[2:]))
+    alg_bytes = float((12 * lt + 2 * la + lq * lq / 8).sum())
+    flops = float((9 * lq * lq).sum())                   # the kernel evaluates the full Lq x Lq square of the transferred frame
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0}
+    print(json.dumps({"pairs_per_s": len(wl) / dt, "ms": dt * 1e3, "algorithmic_GBps": alg_bytes / dt / 1e9,
+                      "hbm_frac": alg_bytes / dt / 1e9 / peaks["hbm_gbs"], "fp32_Tops": flops / dt / 1e12,
+                      "fp32_issue_frac_of_37Tops": flops / dt / 1e12 / 37.0}))
+    # bit-exact check of a bounded sample through the same resident batch
+    packed = pred.fetch(batch, "packed")
+    idx = np.linspace(0, len(wl) - 1, 64).astype(int)
+    for i in idx:
+        want = co.build_align_contact_map(wl.gapped_query[i], wl.gapped_target[i], wl.coords[i], wl.threshold, wl.generated_contacts)
+        L = want.shape[0]
+        rows = packed[batch.packed_off[i]:batch.packed_off[i + 1]].reshape(L, -1)
+        assert np.array_equal(batching.unpack_bits(rows, L), want), i
+    print(f"bit-exact against the oracle on {len(idx)} sampled pairs")
+
+
+if __name__ == "__main__":
+    main()
