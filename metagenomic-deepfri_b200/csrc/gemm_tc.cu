@@ -558,6 +558,220 @@ int launch_gemm_pair(mdf_ctx *ctx, int epi, int a_terms, int b_terms, const Gemm
     return MDF_EUNSUPPORTED;
 }
 
+
+// ------------------------------------------------------------------------------------------- CTA-pair adjacency GEMM
+// X_l = act(d_i * A_hat . Y + b) grouped per protein, two 128-row tiles of one protein per CTA pair (cta_group::2,
+// M = 256, N = 256).  The single-CTA form is bound by shared-memory bandwidth (tensor-core operand reads + TMA fills +
+// expander stores); here each CTA expands only its own A tile, stages only HALF of each Y^T k-block and the tensor core
+// reads 64 B/clk instead of 128.  A protein with an odd number of tiles leaves the peer of its last pair idle (its A
+// tile is all zeros, nothing is stored).
+struct AdjPairArgs {
+    GemmArgs g;                        // adj_* fields, B[0] = Y^T image, rowscale / bias / act / pool / out_img as in gemm_tc_kernel
+    const int4 *pairs;                 // [n_pairs] {m-tile of rank 0, m-tile of rank 1 or -1, first k-block on the B side, k-blocks}
+    int n_pairs;
+    alignas(64) CUtensorMap tmB;
+    int stages;
+};
+
+constexpr int ADJ_EW = 16;                                  // epilogue warps per CTA
+constexpr int ADJ_THREADS = (ADJ_EW + 4 + 2) * 32;          // + 4 expander warps, producer, MMA issuer
+
+__global__ void __launch_bounds__(ADJ_THREADS, 1)
+gemm_adj_pair_kernel(const __grid_constant__ AdjPairArgs pa)
+{
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    constexpr int BN = 256;
+    __shared__ GemmBarriers bars;
+    const GemmArgs &g = pa.g;
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    constexpr int stage_bytes = 2 * TILE_BYTES;             // my A tile + my half of the B k-block
+    const int stages = pa.stages;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int w_prod = ADJ_EW + 4, w_mma = ADJ_EW + 5;
+    const int rank = (int)cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair0 = blockIdx.x >> 1, pair_stride = gridDim.x >> 1;
+    const int n_tiles = g.n_tiles;                           // 256-column tiles of the output
+
+    if (threadIdx.x == 0) {
+        // leader: a stage is full when both halves of B landed (tx bytes) and both CTAs' expander warps finished their A tiles
+        for (int s = 0; s < stages; ++s) { mbar_init(&bars.full[s], 1 + 8); mbar_init(&bars.empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&bars.tmem_full[s], 1); mbar_init(&bars.tmem_empty[s], 2 * ADJ_EW); }
+        fence_mbar_init();
+    }
+    if (warp == w_mma) tmem_alloc_pair<2 * BN>(&bars.tmem_base);
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = bars.tmem_base;
+
+    if (warp == w_prod) {
+        // ===================== B producer (both CTAs): my 128 feature rows of every Y^T k-block
+        if (lane == 0) {
+            int st = 0; uint32_t ph = 0;
+            for (int pi = pair0; pi < pa.n_pairs; pi += pair_stride) {
+                const int4 pr = pa.pairs[pi];
+                for (int nt = 0; nt < n_tiles; ++nt)
+                    for (int kb = 0; kb < pr.w; ++kb) {
+                        mbar_wait(&bars.empty[st], ph ^ 1);
+                        if (leader) mbar_arrive_expect_tx(&bars.full[st], (uint32_t)(2 * TILE_BYTES));
+                        tma_tile_g2s_pair(smem + (size_t)st * stage_bytes + TILE_BYTES, &pa.tmB,
+                                          ((nt * 2 + rank) * g.KB_B + pr.z + kb) * (TILE_BYTES / 512), &bars.full[st]);
+                        if (++st == stages) { st = 0; ph ^= 1; }
+                    }
+            }
+        }
+    } else if (warp == w_mma) {
+        // ===================== MMA issuer (leader CTA): converged warp, elected lane issues
+        if (leader) {
+            constexpr uint32_t idesc = umma_idesc_f16(256, 256);
+            int st = 0; uint32_t ph = 0;
+            int acc = 0; uint32_t acc_ph = 0;
+            for (int pi = pair0; pi < pa.n_pairs; pi += pair_stride) {
+                const int nkb = pa.pairs[pi].w;
+                for (int nt = 0; nt < n_tiles; ++nt) {
+                    mbar_wait(&bars.tmem_empty[acc], acc_ph ^ 1);
+                    tcgen05_fence_after();
+                    const uint32_t d0 = tmem_base + (uint32_t)(acc * BN);
+                    for (int kb = 0; kb < nkb; ++kb) {
+                        mbar_wait(&bars.full[st], ph);
+                        tcgen05_fence_after();
+                        const uint32_t sa = smem_u32(smem + (size_t)st * stage_bytes);
+                        const uint32_t sb = sa + TILE_BYTES;
+#pragma unroll
+                        for (int ks = 0; ks < TILE_K / 16; ++ks) {
+                            const uint64_t ad = umma_smem_desc(sa + ks * 2 * TILE_LBO, TILE_LBO, TILE_SBO);
+                            const uint64_t bd = umma_smem_desc(sb + ks * 2 * TILE_LBO, TILE_LBO, TILE_SBO);
+                            umma_f16_pair_elect(d0, ad, bd, idesc, (kb | ks) != 0);
+                        }
+                        umma_commit_pair_elect(&bars.empty[st], 3);
+                        if (kb == nkb - 1) umma_commit_pair_elect(&bars.tmem_full[acc], 3);
+                        if (++st == stages) { st = 0; ph ^= 1; }
+                    }
+                    if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp >= ADJ_EW) {
+        // ===================== A-tile expanders (both CTAs, 128 threads): thread = one row of my 128 x 64 tile
+        const int et = threadIdx.x - ADJ_EW * 32;
+        int st = 0; uint32_t ph = 0;
+        for (int pi = pair0; pi < pa.n_pairs; pi += pair_stride) {
+            const int4 pr = pa.pairs[pi];
+            const int mt = rank == 0 ? pr.x : pr.y;
+            int L = 0, rw = 0, i = 0;
+            const uint32_t *row = nullptr;
+            if (mt >= 0) {
+                const int p = g.tile_info[mt].w;
+                L = (int)(g.adj_seq_off[p + 1] - g.adj_seq_off[p]);
+                rw = packed_row_words(L);
+                i = (mt - (int)(g.adj_seg_off[p] >> 7)) * 128 + et;
+                row = g.adj_packed + g.adj_packed_off[p] + (size_t)i * rw;
+            }
+            for (int nt = 0; nt < n_tiles; ++nt)
+                for (int kb = 0; kb < pr.w; ++kb) {
+                    uint32_t w[2] = {0u, 0u};
+                    if (mt >= 0 && i < L) {
+                        if (2 * kb < rw) w[0] = __ldg(row + 2 * kb);
+                        if (2 * kb + 1 < rw) w[1] = __ldg(row + 2 * kb + 1);
+                    }
+                    if (lane == 0) mbar_wait(&bars.empty[st], ph ^ 1);
+                    __syncwarp();
+                    const uint32_t dst = smem_u32(smem + (size_t)st * stage_bytes) + (uint32_t)((et >> 3) * 128 + (et & 7) * 16);
+                    const uint32_t one = 0x3C00u;                                            // fp16 1.0
+#pragma unroll
+                    for (int k8 = 0; k8 < 8; ++k8) {
+                        const uint32_t b8 = (w[k8 >> 2] >> (8 * (k8 & 3))) & 0xFFu;
+                        uint4 pk;
+                        pk.x = ((b8 & 1u) ? one : 0u) | ((b8 & 2u) ? one << 16 : 0u);
+                        pk.y = ((b8 & 4u) ? one : 0u) | ((b8 & 8u) ? one << 16 : 0u);
+                        pk.z = ((b8 & 16u) ? one : 0u) | ((b8 & 32u) ? one << 16 : 0u);
+                        pk.w = ((b8 & 64u) ? one : 0u) | ((b8 & 128u) ? one << 16 : 0u);
+                        st_shared_v4(dst + k8 * 2048, pk);
+                    }
+                    fence_proxy_async_smem();                    // generic-proxy tile -> tensor-core (async proxy) reads
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (leader) mbar_arrive(&bars.full[st]); else mbar_arrive_remote(&bars.full[st], 0);
+                    }
+                    if (++st == stages) { st = 0; ph ^= 1; }
+                }
+        }
+    } else {
+        // ===================== epilogue (both CTAs): my 128 rows x 256 columns, 16 warps
+        const int lb = (warp & 3) * 32;
+        const int ch = warp >> 2;
+        int acc = 0; uint32_t acc_ph = 0;
+        for (int pi = pair0; pi < pa.n_pairs; pi += pair_stride) {
+            const int4 pr = pa.pairs[pi];
+            const int mt = rank == 0 ? pr.x : pr.y;
+            for (int nt = 0; nt < n_tiles; ++nt) {
+                mbar_wait(&bars.tmem_full[acc], acc_ph);
+                tcgen05_fence_after();
+                if (mt >= 0) {
+                    const int64_t m = (int64_t)mt * 128 + lb + lane;
+                    const uint32_t trow = tmem_base + ((uint32_t)lb << 16) + (uint32_t)(acc * BN);
+                    const float rs = g.rowscale[m];
+                    float *pool_row = g.pool ? g.pool + (size_t)g.tile_info[mt].w * g.pool_ld + g.pool_off : nullptr;
+                    uint8_t *row_ptr = reinterpret_cast<uint8_t *>(g.out_img) + (size_t)(m >> 7) * g.KB_out * TILE_BYTES +
+                                       (size_t)((((int)m & 127) >> 3) * 128 + ((int)m & 7) * 16);
+#pragma unroll 1
+                    for (int c0 = ch * (BN * 4 / ADJ_EW); c0 < (ch + 1) * (BN * 4 / ADJ_EW); c0 += 32) {
+                        uint32_t r[32];
+                        if (pr.w > 0) {
+                            tmem_ld_32x32b_x32(trow + c0, r);
+                            tmem_ld_wait();
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) r[j] = 0u;
+                        }
+                        gemm_epilogue_chunk<EPI_IMG_ROWSCALE>(g, r, m, nt * BN + c0, rs, nullptr, row_ptr, pool_row);
+                    }
+                }
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (leader) mbar_arrive(&bars.tmem_empty[acc]); else mbar_arrive_remote(&bars.tmem_empty[acc], 0);
+                }
+                if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == w_mma) tmem_dealloc_pair<2 * BN>(tmem_base);
+}
+
+// pairs: device array of n_pairs int4 {m-tile 0, m-tile 1 or -1, first B k-block, k-blocks}; args as for the grouped
+// gemm_tc case with adj_packed set; y_bytes = size of the Y^T image (for the tensor map)
+int launch_gemm_adj_pair(mdf_ctx *ctx, const GemmArgs &args, const int4 *pairs, int n_pairs, size_t y_bytes)
+{
+    if (n_pairs <= 0) return MDF_OK;
+    if (!args.adj_packed || !args.tile_info || args.n_tiles <= 0) { set_error("gemm_adj_pair: bad arguments"); return MDF_EINVAL; }
+    AdjPairArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    pa.g = args;
+    pa.pairs = pairs; pa.n_pairs = n_pairs;
+    pa.stages = 6;
+    MDF_TRY(make_tile_map(&pa.tmB, args.B[0], y_bytes));
+    const size_t smem = (size_t)pa.stages * 2 * TILE_BYTES + 1024;
+    MDF_CUDA(cudaFuncSetAttribute(gemm_adj_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * std::min(n_pairs, ctx->sm_count / 2));
+    cfg.blockDim = dim3(ADJ_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    MDF_CUDA(cudaLaunchKernelEx(&cfg, gemm_adj_pair_kernel, pa));
+    ctx->launches++;
+    return MDF_OK;
+}
+
 template <int EPI, int BN>
 static int launch_one(mdf_ctx *ctx, int a_terms, int b_terms, const GemmArgs &args)
 {

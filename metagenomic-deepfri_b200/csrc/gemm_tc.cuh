@@ -69,6 +69,10 @@ int launch_gemm_tc(mdf_ctx *ctx, int epi, int bn, int a_terms, int b_terms, cons
 // 256-row / 256-column tiles, a_bytes / b_bytes are the byte sizes of the term images (for the tensor maps).
 int launch_gemm_pair(mdf_ctx *ctx, int epi, int a_terms, int b_terms, const GemmArgs &args, const size_t a_bytes[2], const size_t b_bytes[2]);
 
+// CTA-pair form of the grouped adjacency GEMM (bit-packed A): pairs = device [n_pairs] int4 {m-tile of rank 0, m-tile of
+// rank 1 or -1, first k-block on the B side, k-blocks}; n_tiles in `args` counts 256-column tiles; y_bytes = size of Y^T
+int launch_gemm_adj_pair(mdf_ctx *ctx, const GemmArgs &args, const int4 *pairs, int n_pairs, size_t y_bytes);
+
 // flat [bytes/512][256] u16 tensor map whose [32 x 256] boxes are the 16 KiB operand tiles of an image
 int make_tile_map(CUtensorMap *map, const void *base, size_t bytes);
 

@@ -35,6 +35,9 @@ struct TcModel {
     float *out_b_pad = nullptr;                            // head: output bias padded to a multiple of 4 entries
     unsigned long long lm_hash = 0;                        // FNV-1a of the LSTM weights: heads that share the LM share its output
     int head_tc = 1;                                       // head GEMMs on tensor cores (activations and weights both split hi + lo)
+    int adj_pair = 0;                                      // MDF_ADJ_PAIR=1: CTA-pair (cta_group::2) form of the adjacency GEMM.  Measured
+                                                           // 4.7-5.0 ms vs 4.5 ms per layer: halving the shared-memory operand traffic does
+                                                           // not help, the kernel is paced by draining its short-K accumulators
     int pool_fused = 1;                                    // sum-pool readout inside the adjacency GEMM epilogue (fp32, no X re-read)
     int adj_expand = 1;                                    // adjacency GEMM expands its A tiles from the bit-packed map on the fly
     int gemm_pair = 1;                                     // CTA-pair (cta_group::2) kernels for the embedding and X.W GEMMs
@@ -65,6 +68,8 @@ struct TcBatchMeta {
     int *rowmap = nullptr;      // [Tp] padded row -> packed residue index, -1 on pads
     int4 *tile_info = nullptr;  // [m_tiles] grouped-GEMM info per 128-row tile
     int4 *exp_tiles = nullptr;  // [n_adj_tiles] {protein, local m-tile, k-block, first tile of protein}
+    int4 *pairs = nullptr;      // [n_pairs] CTA-pair work list of the adjacency GEMM {m-tile 0, m-tile 1 or -1, first B k-block, k-blocks}
+    int n_pairs = 0;
     int64_t *seg_off = nullptr; // [n+1] padded row offsets
     void *block = nullptr;
     bool persistent = false;
@@ -132,6 +137,7 @@ int tc_model_init(mdf_model *m, const mdf_model_desc *d)
     if (const char *e = getenv("MDF_GEMM_PAIR")) t->gemm_pair = atoi(e);
     if (const char *e = getenv("MDF_ADJ_EXPAND")) t->adj_expand = atoi(e);
     if (const char *e = getenv("MDF_POOL_FUSED")) t->pool_fused = atoi(e);
+    if (const char *e = getenv("MDF_ADJ_PAIR")) t->adj_pair = atoi(e);
     if (const char *e = getenv("MDF_HEAD_TC")) t->head_tc = atoi(e);
     if (const char *e = getenv("MDF_GEMM_PHASES")) t->gemm_phases = std::min(64, std::max(0, atoi(e)));   // 0: hi+lo split on every tile
     // shape constraints of the tile-image GEMMs
@@ -501,23 +507,29 @@ static int build_meta(mdf_ctx *ctx, mdf_batch *b, TcBatchMeta &meta, bool want_e
     }
     const int64_t Tp = (seg_off[n] + 255) / 256 * 256;
     std::vector<int4> tile_info((size_t)(Tp / 128), make_int4(0, 0, 0, 0));
-    std::vector<int4> exp_tiles;
+    std::vector<int4> exp_tiles, pairs;
     int tile_base = 0;
     for (int p = 0; p < n; ++p) {
         const int L = (int)(b->h_seq_off[p + 1] - b->h_seq_off[p]);
         const int KBp = (L + TILE_K - 1) / TILE_K, MT = (L + 127) / 128;
+        const int mt0 = (int)(seg_off[p] / 128);
         for (int mt = 0; mt < MT; ++mt) {
-            tile_info[(size_t)(seg_off[p] / 128) + mt] = make_int4(tile_base + mt * KBp, (int)(seg_off[p] / TILE_K), KBp, p);
+            tile_info[(size_t)mt0 + mt] = make_int4(tile_base + mt * KBp, (int)(seg_off[p] / TILE_K), KBp, p);
             if (want_exp_tiles)
                 for (int kb = 0; kb < KBp; ++kb) exp_tiles.push_back(make_int4(p, mt, kb, tile_base));
+            if ((mt & 1) == 0) pairs.push_back(make_int4(mt0 + mt, mt + 1 < MT ? mt0 + mt + 1 : -1, (int)(seg_off[p] / TILE_K), KBp));
         }
         tile_base += MT * KBp;
     }
+    // longest k-range first: the pairs are dealt round-robin to the CTA pairs, and the big ones should not end the kernel
+    std::stable_sort(pairs.begin(), pairs.end(), [](const int4 &x, const int4 &y) { return x.w > y.w; });
     meta.Tp = Tp;
     meta.m_tiles = (int)(Tp / 128);
     meta.n_adj_tiles = tile_base;
+    meta.n_pairs = (int)pairs.size();
     const size_t bytes = align_up((size_t)Tp * 4, 256) + align_up(tile_info.size() * 16, 256) +
-                         align_up(exp_tiles.size() * 16 + 16, 256) + align_up((size_t)(n + 1) * 8, 256);
+                         align_up(exp_tiles.size() * 16 + 16, 256) + align_up((size_t)(n + 1) * 8, 256) +
+                         align_up(pairs.size() * 16 + 16, 256);
     char *base = nullptr;
     if (b->owns_memory) {
         MDF_CUDA(cudaMalloc((void **)&base, bytes));
@@ -529,7 +541,8 @@ static int build_meta(mdf_ctx *ctx, mdf_batch *b, TcBatchMeta &meta, bool want_e
     meta.rowmap = (int *)base; base += align_up((size_t)Tp * 4, 256);
     meta.tile_info = (int4 *)base; base += align_up(tile_info.size() * 16, 256);
     meta.exp_tiles = (int4 *)base; base += align_up(exp_tiles.size() * 16 + 16, 256);
-    meta.seg_off = (int64_t *)base;
+    meta.seg_off = (int64_t *)base; base += align_up((size_t)(n + 1) * 8, 256);
+    meta.pairs = (int4 *)base;
     cudaStream_t s = ctx->stream;
     // the [Tp] row map (24 MB for a 16k-protein batch) is filled on the device; only the per-tile / per-protein arrays travel
     MDF_CUDA(cudaMemcpyAsync(meta.seg_off, seg_off.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, s));
@@ -541,6 +554,7 @@ static int build_meta(mdf_ctx *ctx, mdf_batch *b, TcBatchMeta &meta, bool want_e
     MDF_CUDA(cudaMemcpyAsync(meta.tile_info, tile_info.data(), tile_info.size() * 16, cudaMemcpyHostToDevice, s));
     if (!exp_tiles.empty())
         MDF_CUDA(cudaMemcpyAsync(meta.exp_tiles, exp_tiles.data(), exp_tiles.size() * 16, cudaMemcpyHostToDevice, s));
+    if (!pairs.empty()) MDF_CUDA(cudaMemcpyAsync(meta.pairs, pairs.data(), pairs.size() * 16, cudaMemcpyHostToDevice, s));
     MDF_CUDA(cudaStreamSynchronize(s));      // host vectors are pageable
     return MDF_OK;
 }
@@ -567,7 +581,7 @@ size_t tc_workspace_bytes(const mdf_model *m, int n, const int64_t *seq_off)
     if (!fused) add((size_t)Tp * 4 * m->H * 4);       // input pre-activations of the upper LSTM layers
     add(std::max({lstm_tc_scratch_bytes(m->ctx, m->H), lstm_stream_scratch_bytes(m->ctx, m->H), lstm_fused_scratch_bytes(m->ctx, m->H)}));
     if (taps) for (int l = 0; l < m->n_lstm; ++l) add((size_t)T * m->H * 4);    // optional fp32 taps
-    add((size_t)Tp * 4 + (size_t)Tp / 128 * 16 + (size_t)(tiles + 1) * 16 + (size_t)(n + 1) * 8 + 1024);   // metadata
+    add((size_t)Tp * 4 + (size_t)Tp / 128 * 32 + (size_t)(tiles + 1) * 16 + (size_t)(n + 1) * 8 + 2048);   // metadata
     add((size_t)Tp * 4); add((size_t)Tp);             // deg_pad, idx_pad
     add((size_t)Tp * m->E * 2);                       // X0 image
     add((size_t)Tp * gmax * 2); add((size_t)Tp * gmax * 2); add((size_t)Tp * gmax * 2);   // Y^T, X_a, X_b images
@@ -775,7 +789,12 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto)
                 MDF_CUDA(cudaMemsetAsync(d_trace, 0, 64, s));
                 g.trace = d_trace;
             }
-            MDF_TRY(launch_gemm_tc(ctx, EPI_IMG_ROWSCALE, bn, 1, 1, g));
+            if (tm->adj_pair && tm->adj_expand && gd % 256 == 0 && !want_trace) {
+                g.n_tiles = gd / 256;
+                MDF_TRY(launch_gemm_adj_pair(ctx, g, meta->pairs, meta->n_pairs, (size_t)Tp * gd * sizeof(__half)));
+            } else {
+                MDF_TRY(launch_gemm_tc(ctx, EPI_IMG_ROWSCALE, bn, 1, 1, g));
+            }
             if (want_trace) {
                 long long h[8];
                 MDF_CUDA(cudaStreamSynchronize(s));
