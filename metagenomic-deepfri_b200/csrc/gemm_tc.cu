@@ -273,13 +273,19 @@ gemm_tc_kernel(GemmArgs g, int a_terms, int b_terms, int stages)
             const int rw = packed_row_words(L);
             const int i = (mt - (int)(g.adj_seg_off[p] >> 7)) * 128 + et;                 // row of the protein's map
             const uint32_t *row = g.adj_packed + g.adj_packed_off[p] + (size_t)i * rw;
+            // the packed row is read four words (two k-blocks) at a time, one load AHEAD of the stage that consumes it: a
+            // load issued right before its stage put ~1 k cycles of L2 latency on every stage and paced the whole kernel
+            uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
+            if (i < L && 0 < rw) nxt = __ldg(reinterpret_cast<const uint4 *>(row));
+            uint4 cur = nxt;
             for (int kb = 0; kb < nkb; ++kb) {
                 {
-                    uint32_t w[2] = {0u, 0u};
-                    if (i < L) {
-                        if (2 * kb < rw) w[0] = __ldg(row + 2 * kb);
-                        if (2 * kb + 1 < rw) w[1] = __ldg(row + 2 * kb + 1);
+                    if ((kb & 1) == 0) {
+                        cur = nxt;
+                        nxt = make_uint4(0u, 0u, 0u, 0u);
+                        if (i < L && 2 * (kb + 2) < rw) nxt = __ldg(reinterpret_cast<const uint4 *>(row + 2 * (kb + 2)));
                     }
+                    const uint32_t w[2] = {(kb & 1) ? cur.z : cur.x, (kb & 1) ? cur.w : cur.y};
                     if (lane == 0) mbar_wait(&bars.empty[st], ph ^ 1);
                     __syncwarp();
                     const uint32_t dst = smem_u32(smem + (size_t)st * stage_bytes) + (uint32_t)((et >> 3) * 128 + (et & 7) * 16);
@@ -669,13 +675,18 @@ gemm_adj_pair_kernel(const __grid_constant__ AdjPairArgs pa)
                 i = (mt - (int)(g.adj_seg_off[p] >> 7)) * 128 + et;
                 row = g.adj_packed + g.adj_packed_off[p] + (size_t)i * rw;
             }
-            for (int nt = 0; nt < n_tiles; ++nt)
+            const bool live = mt >= 0 && i < L;
+            for (int nt = 0; nt < n_tiles; ++nt) {
+                uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
+                if (live && 0 < rw) nxt = __ldg(reinterpret_cast<const uint4 *>(row));
+                uint4 cur = nxt;
                 for (int kb = 0; kb < pr.w; ++kb) {
-                    uint32_t w[2] = {0u, 0u};
-                    if (mt >= 0 && i < L) {
-                        if (2 * kb < rw) w[0] = __ldg(row + 2 * kb);
-                        if (2 * kb + 1 < rw) w[1] = __ldg(row + 2 * kb + 1);
+                    if ((kb & 1) == 0) {                         // four words = two k-blocks per load, one load ahead
+                        cur = nxt;
+                        nxt = make_uint4(0u, 0u, 0u, 0u);
+                        if (live && 2 * (kb + 2) < rw) nxt = __ldg(reinterpret_cast<const uint4 *>(row + 2 * (kb + 2)));
                     }
+                    const uint32_t w[2] = {(kb & 1) ? cur.z : cur.x, (kb & 1) ? cur.w : cur.y};
                     if (lane == 0) mbar_wait(&bars.empty[st], ph ^ 1);
                     __syncwarp();
                     const uint32_t dst = smem_u32(smem + (size_t)st * stage_bytes) + (uint32_t)((et >> 3) * 128 + (et & 7) * 16);
@@ -697,6 +708,7 @@ gemm_adj_pair_kernel(const __grid_constant__ AdjPairArgs pa)
                     }
                     if (++st == stages) { st = 0; ph ^= 1; }
                 }
+            }
         }
     } else {
         // ===================== epilogue (both CTAs): my 128 rows x 256 columns, 16 warps
