@@ -235,7 +235,9 @@ gemm_tc_kernel(GemmArgs g, int a_terms, int b_terms, int stages)
                     } else {
                         // every (A term, B term) pair contributes; at most one side has two terms
                         for (int ta = 0; ta < a_terms; ++ta)
-                            for (int tb = 0; tb < b_terms - (ta == 1 && b_terms == 2 ? 1 : 0); ++tb)     // both split: skip lo x lo
+                            for (int tb = (a_terms == 3 && ta == 2) ? 1 : 0;
+                                 tb < ((a_terms == 3) ? (ta == 2 ? 2 : 1) : b_terms - (ta == 1 && b_terms == 2 ? 1 : 0)); ++tb)
+                            // a_terms 2 x b_terms 2: hi.hi, hi.lo, lo.hi (lo.lo skipped); a_terms 3: (hi, hi), (lo, hi), (hi*2^-11, lo*2^11)
 #pragma unroll
                                 for (int ks = 0; ks < TILE_K / 16; ++ks) {
                                     const uint64_t ad = umma_smem_desc(sa + ta * TILE_BYTES + ks * 2 * TILE_LBO, TILE_LBO, TILE_SBO);
@@ -805,7 +807,7 @@ static int launch_one(mdf_ctx *ctx, int a_terms, int b_terms, const GemmArgs &ar
 
 int launch_gemm_tc(mdf_ctx *ctx, int epi, int bn, int a_terms, int b_terms, const GemmArgs &args)
 {
-    if (a_terms < 1 || a_terms > 2 || b_terms < 1 || b_terms > 2) {
+    if (a_terms < 1 || a_terms > 3 || b_terms < 1 || b_terms > 2 || (a_terms == 3 && b_terms != 2)) {
         set_error("gemm_tc: unsupported term split %d x %d", a_terms, b_terms);
         return MDF_EUNSUPPORTED;
     }

@@ -20,7 +20,7 @@ enum Epi : int {
 };
 
 struct GemmArgs {
-    const __half *A[2] = {nullptr, nullptr};
+    const __half *A[3] = {nullptr, nullptr, nullptr};
     const __half *B[2] = {nullptr, nullptr};
     int KB_A = 0, KB_B = 0;          // k-blocks per row tile of the A / B images
     int m_tiles = 0, n_tiles = 0;    // output tiles (128 rows x BN columns)

@@ -35,6 +35,7 @@ struct TcModel {
     float *out_b_pad = nullptr;                            // head: output bias padded to a multiple of 4 entries
     unsigned long long lm_hash = 0;                        // FNV-1a of the LSTM weights: heads that share the LM share its output
     int head_tc = 1;                                       // head GEMMs on tensor cores (activations and weights both split hi + lo)
+    int single_term_mask = 0;                              // MDF_SINGLE_TERM (experiment): bit 0 embedding, bit 1+l GraphConv layer l use the hi weight term only
     int adj_pair = 0;                                      // MDF_ADJ_PAIR=1: CTA-pair (cta_group::2) form of the adjacency GEMM.  Measured
                                                            // 4.7-5.0 ms vs 4.5 ms per layer: halving the shared-memory operand traffic does
                                                            // not help, the kernel is paced by draining its short-K accumulators
@@ -77,7 +78,7 @@ struct TcBatchMeta {
 
 // ------------------------------------------------------------------------------------------- weight images
 static void build_image_host(const float *src, int rows, int K, bool transposed_src, int ld,
-                             std::vector<__half> &hi, std::vector<__half> &lo, bool dither = false)
+                             std::vector<__half> &hi, std::vector<__half> &lo, bool dither = false, float lo_scale = 1.0f)
 {
     // dither = false: (hi, lo) with hi + lo ~ v;  dither = true: (a, b) with a + b ~ 2v (time-dithered pair)
     // element (r, k) = transposed_src ? src[k * ld + r] : src[r * ld + k]
@@ -89,7 +90,7 @@ static void build_image_host(const float *src, int rows, int K, bool transposed_
         for (int k = 0; k < K; ++k) {
             const float v = transposed_src ? src[(size_t)k * ld + r] : src[(size_t)r * ld + k];
             const __half h = __float2half_rn(v);
-            const __half l = dither ? __float2half_rn(2.0f * v - __half2float(h)) : __float2half_rn(v - __half2float(h));
+            const __half l = dither ? __float2half_rn(2.0f * v - __half2float(h)) : __float2half_rn((v - __half2float(h)) * lo_scale);
             const size_t off = image_offset_bytes(r, k, KB) / 2;
             hi[off] = h;
             lo[off] = l;
@@ -138,6 +139,7 @@ int tc_model_init(mdf_model *m, const mdf_model_desc *d)
     if (const char *e = getenv("MDF_ADJ_EXPAND")) t->adj_expand = atoi(e);
     if (const char *e = getenv("MDF_POOL_FUSED")) t->pool_fused = atoi(e);
     if (const char *e = getenv("MDF_ADJ_PAIR")) t->adj_pair = atoi(e);
+    if (const char *e = getenv("MDF_SINGLE_TERM")) t->single_term_mask = atoi(e);
     if (const char *e = getenv("MDF_HEAD_TC")) t->head_tc = atoi(e);
     if (const char *e = getenv("MDF_GEMM_PHASES")) t->gemm_phases = std::min(64, std::max(0, atoi(e)));   // 0: hi+lo split on every tile
     // shape constraints of the tile-image GEMMs
@@ -149,10 +151,12 @@ int tc_model_init(mdf_model *m, const mdf_model_desc *d)
     MDF_TRY(upload_half(m, &t->lm_W[0], hi));
     MDF_TRY(upload_half(m, &t->lm_W[1], lo));
     if (m->G % TILE_K == 0 && m->F % TILE_K == 0) {
-        build_image_host(d->fc_W, m->F, m->G, true, m->F, hi, lo);            // rows = F, k = G : fc_W[k][f]
+        // head weights: hi and the residual scaled by 2^11 (HEAD_LO_SHIFT): unscaled, the residual of a 0.03-sized weight
+        // is an fp16 denormal with ~8 significant bits, and after the sum-pool that is visible in the scores
+        build_image_host(d->fc_W, m->F, m->G, true, m->F, hi, lo, false, 2048.0f);            // rows = F, k = G : fc_W[k][f]
         MDF_TRY(upload_half(m, &t->fc_W[0], hi));
         MDF_TRY(upload_half(m, &t->fc_W[1], lo));
-        build_image_host(d->out_W, 2 * m->C, m->F, true, 2 * m->C, hi, lo);   // rows = 2C, k = F : out_W[k][c]
+        build_image_host(d->out_W, 2 * m->C, m->F, true, 2 * m->C, hi, lo, false, 2048.0f);   // rows = 2C, k = F : out_W[k][c]
         MDF_TRY(upload_half(m, &t->out_W[0], hi));
         MDF_TRY(upload_half(m, &t->out_W[1], lo));
         std::vector<float> bp((size_t)(2 * m->C + 3) / 4 * 4, 0.0f);
@@ -416,14 +420,14 @@ pool_image_kernel(const __half *__restrict__ img, int K, const int *__restrict__
 
 // fp32 row-major [n, K] -> hi / lo fp16 images over rows padded to a multiple of 128 (pad rows zero)
 __global__ void f32_rows_to_split_images_kernel(const float *__restrict__ src, int n, int K, int rows_pad, __half *__restrict__ hi,
-                                                __half *__restrict__ lo)
+                                                __half *__restrict__ lo, __half *__restrict__ hs)
 {
     const int KB = K / TILE_K;
     const int64_t chunk = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;    // one 16-byte chunk (8 k) per thread
     if (chunk >= (int64_t)rows_pad * (K / 8)) return;
     const int r = (int)(chunk / (K / 8));
     const int k = (int)(chunk % (K / 8)) * 8;
-    uint4 ph = make_uint4(0, 0, 0, 0), pl = make_uint4(0, 0, 0, 0);
+    uint4 ph = make_uint4(0, 0, 0, 0), pl = make_uint4(0, 0, 0, 0), ps = make_uint4(0, 0, 0, 0);
     if (r < n) {
         float v[8], h[8];
         *reinterpret_cast<float4 *>(v) = *reinterpret_cast<const float4 *>(src + (size_t)r * K + k);
@@ -433,10 +437,14 @@ __global__ void f32_rows_to_split_images_kernel(const float *__restrict__ src, i
         ph.x = pack_half2(h[0], h[1]); ph.y = pack_half2(h[2], h[3]); ph.z = pack_half2(h[4], h[5]); ph.w = pack_half2(h[6], h[7]);
         pl.x = pack_half2(v[0] - h[0], v[1] - h[1]); pl.y = pack_half2(v[2] - h[2], v[3] - h[3]);
         pl.z = pack_half2(v[4] - h[4], v[5] - h[5]); pl.w = pack_half2(v[6] - h[6], v[7] - h[7]);
+        const float sc = 1.0f / 2048.0f;                     // pairs with the weight residual scaled by 2^11
+        ps.x = pack_half2(h[0] * sc, h[1] * sc); ps.y = pack_half2(h[2] * sc, h[3] * sc);
+        ps.z = pack_half2(h[4] * sc, h[5] * sc); ps.w = pack_half2(h[6] * sc, h[7] * sc);
     }
     const size_t off = image_offset_bytes(r, k, KB);
     *reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(hi) + off) = ph;
     *reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(lo) + off) = pl;
+    *reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(hs) + off) = ps;
 }
 
 // score[p, c] = softmax(logits[p, 2c : 2c+2])[0] with a row stride (the fp32 GEMM epilogue wants 16-byte aligned rows)
@@ -452,32 +460,33 @@ __global__ void softmax0_strided_kernel(int n, int C, int ld, const float *__res
 }
 
 // Head on tensor cores: fc = relu(pooled W_fc + b), logits = fc W_out + b, softmax channel 0.  This is after the sum-pool,
-// so activation rounding no longer averages out: activations AND weights are split hi + lo (three MMAs per k-step,
-// lo x lo dropped: ~2^-21 relative).
+// so activation rounding no longer averages out: activations AND weights are split (three MMAs per k-step: hi.hi, lo.hi and
+// hi.residual with the weight residual scaled by 2^11 and the activation by 2^-11 so that neither is an fp16 denormal).
 static int head_forward_tc(mdf_model *m, TcModel *tm, int n, const float *pooled, float *fc, float *logits, float *scores)
 {
     mdf_ctx *ctx = m->ctx;
     cudaStream_t s = ctx->stream;
     const int rows_pad = cdiv(n, 128) * 128;
-    __half *ah = nullptr, *al = nullptr;
+    __half *ah = nullptr, *al = nullptr, *as = nullptr;
     const int kmax = std::max(m->G, m->F);
     MDF_TRY(ctx->alloc_n(&ah, (size_t)rows_pad * kmax));
     MDF_TRY(ctx->alloc_n(&al, (size_t)rows_pad * kmax));
+    MDF_TRY(ctx->alloc_n(&as, (size_t)rows_pad * kmax));
     const int ld_logits = (2 * m->C + 3) / 4 * 4;
     float *logits_pad = nullptr;
     MDF_TRY(ctx->alloc_n(&logits_pad, (size_t)n * ld_logits));
     (void)logits;
     auto gemm = [&](const float *src, int K, __half *const W[2], int N, int ldc, const float *bias, int act, float *out) -> int {
         const int64_t chunks = (int64_t)rows_pad * (K / 8);
-        f32_rows_to_split_images_kernel<<<(unsigned)cdiv64(chunks, 256), 256, 0, s>>>(src, n, K, rows_pad, ah, al);
+        f32_rows_to_split_images_kernel<<<(unsigned)cdiv64(chunks, 256), 256, 0, s>>>(src, n, K, rows_pad, ah, al, as);
         MDF_LAUNCH_CHECK(ctx);
         GemmArgs g;
-        g.A[0] = ah; g.A[1] = al; g.KB_A = K / TILE_K;
+        g.A[0] = ah; g.A[1] = al; g.A[2] = as; g.KB_A = K / TILE_K;      // (hi, hi) + (lo, hi) + (hi * 2^-11, residual * 2^11)
         g.B[0] = W[0]; g.B[1] = W[1]; g.KB_B = K / TILE_K;
         g.m_tiles = rows_pad / 128; g.n_tiles = cdiv(N, 128); g.nkb = K / TILE_K;
         g.out_f32 = out; g.ldc = ldc; g.bias = bias; g.act = act;
         g.m_valid = n; g.n_valid = N;
-        return launch_gemm_tc(ctx, EPI_F32_BIAS, 128, 2, 2, g);
+        return launch_gemm_tc(ctx, EPI_F32_BIAS, 128, 3, 2, g);
     };
     MDF_TRY(gemm(pooled, m->G, tm->fc_W, m->F, m->F, m->fc_b, 1, fc));
     MDF_TRY(gemm(fc, m->F, tm->out_W, 2 * m->C, ld_logits, tm->out_b_pad, 0, logits_pad));
@@ -587,7 +596,7 @@ size_t tc_workspace_bytes(const mdf_model *m, int n, const int64_t *seq_off)
     add((size_t)Tp * gmax * 2); add((size_t)Tp * gmax * 2); add((size_t)Tp * gmax * 2);   // Y^T, X_a, X_b images
     if (!(m->tc && static_cast<const TcModel *>(m->tc)->adj_expand)) add((size_t)tiles * TILE_BYTES + 256);   // A_hat images
     if (taps) { add((size_t)T * gmax * 4); add((size_t)T * m->E * 4); }   // fp32 taps of the last GraphConv layer and of X0
-    add((size_t)(cdiv(n, 128) * 128) * std::max(m->G, m->F) * 2); add((size_t)(cdiv(n, 128) * 128) * std::max(m->G, m->F) * 2);   // head operand images
+    for (int q = 0; q < 3; ++q) add((size_t)(cdiv(n, 128) * 128) * std::max(m->G, m->F) * 2);   // head operand images
     add((size_t)n * m->F * 4); add((size_t)n * 2 * m->C * 4); add((size_t)n * (2 * m->C + 4) * 4);
     return b + 8192;
 }
@@ -718,7 +727,7 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto)
         } else if (tm->gemm_pair && Tp % 256 == 0 && m->E % 256 == 0) {   // CTA pairs: 256 x 256 tiles
             g.m_tiles = (int)(Tp / 256); g.n_tiles = m->E / 256;
             const size_t ab[2] = {(size_t)Tp * m->H * 2, 0}, bb[2] = {(size_t)m->E * m->H * 2, (size_t)m->E * m->H * 2};
-            MDF_TRY(launch_gemm_pair(ctx, EPI_IMG_EMBED, 1, 2, g, ab, bb));
+            MDF_TRY(launch_gemm_pair(ctx, EPI_IMG_EMBED, 1, (tm->single_term_mask & 1) ? 1 : 2, g, ab, bb));
         } else {
             MDF_TRY(launch_gemm_tc(ctx, EPI_IMG_EMBED, 128, 1, 2, g));
         }
@@ -763,7 +772,7 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto)
             } else if (tm->gemm_pair && gd % 256 == 0 && Tp % 256 == 0) {   // CTA pairs: 256 features x 256 residues
                 g.m_tiles = gd / 256; g.n_tiles = (int)(Tp / 256);
                 const size_t ab[2] = {(size_t)gd * kin * 2, (size_t)gd * kin * 2}, bb[2] = {(size_t)Tp * kin * 2, 0};
-                MDF_TRY(launch_gemm_pair(ctx, EPI_IMG_COLSCALE, 2, 1, g, ab, bb));
+                MDF_TRY(launch_gemm_pair(ctx, EPI_IMG_COLSCALE, (tm->single_term_mask & (2 << l)) ? 1 : 2, 1, g, ab, bb));
             } else {
                 MDF_TRY(launch_gemm_tc(ctx, EPI_IMG_COLSCALE, 256, 2, 1, g));
             }
