@@ -166,6 +166,36 @@ int mdf_batch_fetch(mdf_model *model, mdf_batch *batch, int what, void *dst, siz
 /* device pointer of the scores of the last mdf_path_run ([n, C] float32) */
 const float *mdf_batch_scores_device(const mdf_batch *batch);
 
+/* ---- predict.pyx:91-95  Predictor.forward_pass(seqres, cmap=None): the sequence-only DeepCNN branch ----
+ * (models `DeepCNN-MERGED_*.onnx`, mDeepFRI/__init__.py:68; used for every query without a structure hit,
+ * pipeline.py:600-620 / :638-648).  Graph: parallel Conv1D layers over the one-hot sequence ('same' padding) ->
+ * concat -> BatchNormalization -> ReLU -> global max-pool over residues -> FuncPredictor dense -> softmax.
+ * The host side folds conv bias + BatchNormalization into one scale / shift per channel. */
+#define MDF_MAX_CONV 32
+typedef struct mdf_cnn_desc {
+    int n_channels;                     /* 26 */
+    int n_conv;                         /* parallel Conv1D layers (<= MDF_MAX_CONV) */
+    int conv_width[MDF_MAX_CONV];       /* kernel sizes (<= 128) */
+    int conv_filters[MDF_MAX_CONV];     /* filters per layer (multiples of 128) */
+    int conv_pad_left[MDF_MAX_CONV];    /* zero residues before position 0 (TF 'same': (w - 1) / 2) */
+    const float *conv_W[MDF_MAX_CONV];  /* ONNX Conv layout [filters, 26, width] */
+    const float *scale;                 /* [sum filters] y = conv * scale + shift, then ReLU */
+    const float *shift;                 /* [sum filters] */
+    int n_terms;                        /* C */
+    const float *out_W;                 /* [sum filters, 2C] */
+    const float *out_b;                 /* [2C] or NULL */
+} mdf_cnn_desc;
+typedef struct mdf_cnn_model mdf_cnn_model;
+
+int mdf_cnn_model_create(mdf_ctx *ctx, const mdf_cnn_desc *desc, mdf_cnn_model **out);
+int mdf_cnn_model_destroy(mdf_cnn_model *model);
+/* n sequences (ASCII residues, CSR offsets; every sequence needs >= 1 residue) -> scores host float32 [n, C] */
+int mdf_cnn_forward(mdf_cnn_model *model, int n, const char *seq, const int64_t *seq_off, float *scores);
+/* same with the sequences already resident: upload once, run many times (bench `value`), fetch */
+int mdf_cnn_upload(mdf_cnn_model *model, int n, const char *seq, const int64_t *seq_off);
+int mdf_cnn_run(mdf_cnn_model *model);
+int mdf_cnn_fetch(mdf_cnn_model *model, float *scores /* host [n, C] */, float *pooled /* host [n, sum filters] or NULL */);
+
 #ifdef __cplusplus
 }
 #endif

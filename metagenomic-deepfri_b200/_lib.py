@@ -35,6 +35,18 @@ class ModelDesc(C.Structure):
     ]
 
 
+MAX_CONV = 32
+
+
+class CnnDesc(C.Structure):
+    _fields_ = [
+        ("n_channels", C.c_int), ("n_conv", C.c_int),
+        ("conv_width", C.c_int * MAX_CONV), ("conv_filters", C.c_int * MAX_CONV), ("conv_pad_left", C.c_int * MAX_CONV),
+        ("conv_W", c_f32p * MAX_CONV), ("scale", c_f32p), ("shift", c_f32p),
+        ("n_terms", C.c_int), ("out_W", c_f32p), ("out_b", c_f32p),
+    ]
+
+
 _lib = None
 _lib_lock = threading.Lock()
 
@@ -88,6 +100,15 @@ def lib() -> C.CDLL:
         L.mdf_batch_fetch.argtypes = [vp, vp, C.c_int, vp, C.c_size_t]
         L.mdf_batch_scores_device.argtypes = [vp]
         L.mdf_batch_scores_device.restype = vp
+        L.mdf_cnn_model_create.argtypes = [vp, C.POINTER(CnnDesc), C.POINTER(vp)]
+        L.mdf_cnn_model_destroy.argtypes = [vp]
+        L.mdf_cnn_forward.argtypes = [vp, C.c_int, vp, c_i64p, vp]
+        L.mdf_cnn_upload.argtypes = [vp, C.c_int, vp, c_i64p]
+        L.mdf_cnn_run.argtypes = [vp]
+        L.mdf_cnn_fetch.argtypes = [vp, vp, vp]
+        for name in ("mdf_cnn_model_create", "mdf_cnn_model_destroy", "mdf_cnn_forward", "mdf_cnn_upload", "mdf_cnn_run",
+                     "mdf_cnn_fetch"):
+            getattr(L, name).restype = C.c_int
         for name in ("mdf_ctx_create", "mdf_ctx_destroy", "mdf_ctx_synchronize", "mdf_pairwise_sqeuclidean",
                      "mdf_contact_map_dense", "mdf_contact_map_sparse", "mdf_align_contact_map",
                      "mdf_cmap_build_transfer", "mdf_model_create", "mdf_model_destroy", "mdf_model_set_engine",
@@ -106,6 +127,7 @@ EXPORTED_SYMBOLS = [
     "mdf_model_set_engine", "mdf_model_get_engine", "mdf_gcn_forward_dense", "mdf_gcn_forward_packed", "mdf_path_forward",
     "mdf_batch_upload", "mdf_batch_destroy", "mdf_path_run", "mdf_path_run_stages", "mdf_path_run_shared",
     "mdf_batch_fetch_scores", "mdf_batch_fetch", "mdf_batch_scores_device",
+    "mdf_cnn_model_create", "mdf_cnn_model_destroy", "mdf_cnn_forward", "mdf_cnn_upload", "mdf_cnn_run", "mdf_cnn_fetch",
 ]
 
 

@@ -495,6 +495,42 @@ static int head_forward_tc(mdf_model *m, TcModel *tm, int n, const float *pooled
     return MDF_OK;
 }
 
+// Exported pieces of the head for the sequence-only CNN branch (cnn_tc.cu): same exact-split dense layer and softmax.
+int tc_dense_split(mdf_ctx *ctx, int n, const float *src, int K, const __half *const W[2], int N, int ldc, const float *bias,
+                   int act, float *out)
+{
+    if (K % TILE_K != 0 || ldc % 4 != 0) { set_error("tc_dense_split: K = %d / ldc = %d unsupported", K, ldc); return MDF_EUNSUPPORTED; }
+    const int rows_pad = cdiv(n, 128) * 128;
+    __half *ah = nullptr, *al = nullptr, *as = nullptr;
+    MDF_TRY(ctx->alloc_n(&ah, (size_t)rows_pad * K));
+    MDF_TRY(ctx->alloc_n(&al, (size_t)rows_pad * K));
+    MDF_TRY(ctx->alloc_n(&as, (size_t)rows_pad * K));
+    const int64_t chunks = (int64_t)rows_pad * (K / 8);
+    f32_rows_to_split_images_kernel<<<(unsigned)cdiv64(chunks, 256), 256, 0, ctx->stream>>>(src, n, K, rows_pad, ah, al, as);
+    MDF_LAUNCH_CHECK(ctx);
+    GemmArgs g;
+    g.A[0] = ah; g.A[1] = al; g.A[2] = as; g.KB_A = K / TILE_K;
+    g.B[0] = W[0]; g.B[1] = W[1]; g.KB_B = K / TILE_K;
+    g.m_tiles = rows_pad / 128; g.n_tiles = cdiv(N, 128); g.nkb = K / TILE_K;
+    g.out_f32 = out; g.ldc = ldc; g.bias = bias; g.act = act;
+    g.m_valid = n; g.n_valid = N;
+    return launch_gemm_tc(ctx, EPI_F32_BIAS, 128, 3, 2, g);
+}
+
+int tc_softmax0_strided(mdf_ctx *ctx, int n, int C, int ld, const float *logits, float *scores)
+{
+    if (n <= 0) return MDF_OK;
+    softmax0_strided_kernel<<<(unsigned)cdiv64((int64_t)n * C, 256), 256, 0, ctx->stream>>>(n, C, ld, logits, scores);
+    MDF_LAUNCH_CHECK(ctx);
+    return MDF_OK;
+}
+
+// host: W[k][row] (ONNX MatMul layout [K, rows]) -> hi image and residual image scaled by 2^11, rows x K
+void tc_build_split_weight_images(const float *src_kn, int rows, int K, std::vector<__half> &hi, std::vector<__half> &lo)
+{
+    build_image_host(src_kn, rows, K, true, rows, hi, lo, false, 2048.0f);
+}
+
 // ------------------------------------------------------------------------------------------- batch metadata
 // rowmap[seg_off[p] + i] = seq_off[p] + i for the residues of protein p (pad rows were preset to -1)
 __global__ void fill_rowmap_kernel(int n, const int64_t *__restrict__ seq_off, const int64_t *__restrict__ seg_off, int *__restrict__ rowmap)

@@ -11,4 +11,10 @@ size_t tc_workspace_bytes(const mdf_model *m, int n, const int64_t *seq_off);
 void tc_batch_free(mdf_batch *b);
 int tc_forward(mdf_model *m, mdf_batch *b, int upto);
 
+// pieces of the head shared with the CNN branch (cnn_tc.cu)
+int tc_dense_split(mdf_ctx *ctx, int n, const float *src, int K, const __half *const W[2], int N, int ldc, const float *bias,
+                   int act, float *out);
+int tc_softmax0_strided(mdf_ctx *ctx, int n, int C, int ld, const float *logits, float *scores);
+void tc_build_split_weight_images(const float *src_kn, int rows, int K, std::vector<__half> &hi, std::vector<__half> &lo);
+
 }  // namespace mdf

@@ -1,4 +1,4 @@
-"""Pattern-matches a DeepFRI GCN `.onnx` graph into the fused pipeline's weight set.
+"""Pattern-matches a DeepFRI GCN (or sequence-only DeepCNN) `.onnx` graph into the fused pipeline's weight set.
 
 The reference never looks inside the model file: it hands it to onnxruntime
 (`mDeepFRI/predict.pyx:62-73`).  The B200 path runs a fixed fused pipeline (LSTM-LM ->
@@ -60,7 +60,7 @@ def plan_from_model(model: ox.Model) -> GCNPlan:
     g = model.graph
     init = g.initializers
     if len(g.inputs) == 1:
-        _fail("single-input model (the sequence-only CNN branch, predict.pyx:91-95) is out of scope")
+        _fail("single-input model: this is a sequence-only DeepCNN head, see cnn_plan_from_model")
     if len(g.inputs) != 2:
         _fail(f"expected 2 inputs (cmap, seq), found {len(g.inputs)}")
     in_names = [vi.name for vi in g.inputs]
@@ -303,5 +303,188 @@ def _after_add(a: str, b: str, consumers) -> str:
     _fail("LM_embedding and AA_embedding are not summed")
 
 
-def load_plan(path: str) -> GCNPlan:
-    return plan_from_model(ox.load(path))
+@dataclass
+class CNNPlan:
+    """Sequence-only DeepCNN head (`predict.pyx:91-95`): parallel Conv1D -> concat -> BatchNormalization -> ReLU ->
+    max over residues -> dense -> softmax.  Conv bias and BatchNormalization are folded into `scale` / `shift`."""
+    input_names: List[str]
+    n_channels: int
+    conv_W: List[np.ndarray]          # [F, 26, width] each, concat order
+    conv_pad_left: List[int]
+    scale: np.ndarray                 # [sum F]
+    shift: np.ndarray                 # [sum F]
+    out_W: np.ndarray                 # [sum F, 2C]
+    out_b: Optional[np.ndarray]
+    n_terms: int
+    notes: List[str] = field(default_factory=list)
+
+
+def _cnn_fail(msg: str):
+    raise UnsupportedModelError(f"ONNX graph is not a supported DeepCNN head: {msg}")
+
+
+def cnn_plan_from_model(model: ox.Model) -> CNNPlan:
+    g = model.graph
+    if len(g.inputs) != 1:
+        _cnn_fail(f"expected the one-hot sequence as the single input, found {len(g.inputs)} inputs")
+    vi = g.inputs[0]
+    if len(vi.shape) != 3 or vi.shape[-1] != 26:
+        _cnn_fail(f"input {vi.name!r} is not [batch, L, 26]")
+    seq_name = vi.name
+    const: Dict[str, np.ndarray] = dict(g.initializers)
+    producer: Dict[str, ox.Node] = {}
+    consumers: Dict[str, List[ox.Node]] = {}
+    for n in g.nodes:
+        if n.op_type == "Constant" and "value" in n.attrs:
+            const[n.outputs[0]] = np.asarray(n.attrs["value"])
+        for o in n.outputs:
+            producer[o] = n
+        for i in n.inputs:
+            consumers.setdefault(i, []).append(n)
+
+    def back(t: str) -> str:
+        while t in producer and producer[t].op_type in _SHAPE_OPS:
+            t = producer[t].inputs[0]
+        return t
+
+    def fwd(t: str) -> List[ox.Node]:
+        out = []
+        for n in consumers.get(t, []):
+            out += fwd(n.outputs[0]) if n.op_type in _SHAPE_OPS else [n]
+        return out
+
+    def only(nodes: List[ox.Node], what: str) -> ox.Node:
+        if len(nodes) != 1:
+            _cnn_fail(f"expected exactly one consumer {what}, found {[n.op_type for n in nodes]}")
+        return nodes[0]
+
+    allowed = {"Conv", "Concat", "BatchNormalization", "Relu", "ReduceMax", "GlobalMaxPool", "MatMul", "Gemm", "Add", "Softmax",
+               "Constant"} | _SHAPE_OPS
+    for n in g.nodes:
+        if n.op_type not in allowed:
+            _cnn_fail(f"unexpected operator {n.op_type} ({n.name!r}); a language-model DeepCNN variant is not supported")
+
+    convs = [n for n in g.nodes if n.op_type == "Conv"]
+    if not convs:
+        _cnn_fail("no Conv layers found")
+    info = {}
+    for n in convs:
+        if back(n.inputs[0]) != seq_name:
+            _cnn_fail(f"Conv {n.name!r} is not fed by the sequence input")
+        W = const.get(n.inputs[1])
+        if W is None:
+            _cnn_fail(f"Conv {n.name!r}: weights are not constant")
+        W = np.asarray(W, np.float32)
+        if W.ndim == 4 and W.shape[2] == 1:
+            W3, two_d = W[:, :, 0, :], True
+        elif W.ndim == 3:
+            W3, two_d = W, False
+        else:
+            _cnn_fail(f"Conv {n.name!r}: weight shape {W.shape} is not [F, 26, 1, w] / [F, 26, w]")
+        F, Cin, k = W3.shape
+        if Cin != 26:
+            _cnn_fail(f"Conv {n.name!r}: {Cin} input channels")
+        a = n.attrs
+        if a.get("group", 1) != 1 or any(int(v) != 1 for v in a.get("strides", [1])) or any(int(v) != 1 for v in a.get("dilations", [1])):
+            _cnn_fail(f"Conv {n.name!r}: only group 1 / stride 1 / dilation 1")
+        auto = a.get("auto_pad", "NOTSET")
+        if auto == "SAME_UPPER":
+            pl, pr = (k - 1) // 2, k - 1 - (k - 1) // 2
+        elif auto == "SAME_LOWER":
+            pl, pr = k - 1 - (k - 1) // 2, (k - 1) // 2
+        elif auto == "NOTSET":
+            pads = [int(v) for v in a.get("pads", [0, 0, 0, 0] if two_d else [0, 0])]
+            if two_d:
+                if len(pads) != 4 or pads[0] or pads[2]:
+                    _cnn_fail(f"Conv {n.name!r}: pads {pads}")
+                pl, pr = pads[1], pads[3]
+            else:
+                if len(pads) != 2:
+                    _cnn_fail(f"Conv {n.name!r}: pads {pads}")
+                pl, pr = pads
+        else:
+            _cnn_fail(f"Conv {n.name!r}: auto_pad {auto}")
+        if pl + pr != k - 1:
+            _cnn_fail(f"Conv {n.name!r}: padding ({pl}, {pr}) does not keep the sequence length for width {k} ('same' expected)")
+        b = np.zeros(F, np.float32)
+        if len(n.inputs) > 2 and n.inputs[2]:
+            if n.inputs[2] not in const:
+                _cnn_fail(f"Conv {n.name!r}: bias is not constant")
+            b = np.asarray(const[n.inputs[2]], np.float32).reshape(-1)
+        info[n.outputs[0]] = (np.ascontiguousarray(W3), int(pl), b)
+
+    # concat order = channel order
+    nxt = {id(c): c for n in convs for c in fwd(n.outputs[0])}
+    if len(convs) > 1:
+        cat = only(list(nxt.values()), "of the Conv outputs (Concat)")
+        if cat.op_type != "Concat" or cat.attrs.get("axis") not in (1, -2):
+            _cnn_fail("Conv outputs are not concatenated over the channel axis (axis 1 of [b, F, L])")
+        order = [back(i) for i in cat.inputs]
+        if sorted(order) != sorted(info):
+            _cnn_fail("Concat inputs are not exactly the Conv outputs")
+        cur = cat.outputs[0]
+    else:
+        order = [convs[0].outputs[0]]
+        cur = convs[0].outputs[0]
+    conv_W = [info[o][0] for o in order]
+    pad_left = [info[o][1] for o in order]
+    bias = np.concatenate([info[o][2] for o in order])
+    tot = int(bias.size)
+    scale, shift = np.ones(tot, np.float32), bias.copy()
+    n = only(fwd(cur), "after the concatenation")
+    if n.op_type == "BatchNormalization":
+        try:
+            gam, bet, mean, var = (np.asarray(const[i], np.float64).reshape(-1) for i in n.inputs[1:5])
+        except KeyError:
+            _cnn_fail("BatchNormalization parameters are not constant")
+        if any(v.size != tot for v in (gam, bet, mean, var)):
+            _cnn_fail("BatchNormalization width does not match the concatenated filters")
+        s64 = gam / np.sqrt(var + float(n.attrs.get("epsilon", 1e-5)))
+        scale = s64.astype(np.float32)
+        shift = ((bias.astype(np.float64) - mean) * s64 + bet).astype(np.float32)
+        n = only(fwd(n.outputs[0]), "after BatchNormalization")
+    if n.op_type != "Relu":
+        _cnn_fail(f"expected ReLU before the pooling, found {n.op_type}")
+    n = only(fwd(n.outputs[0]), "after ReLU")
+    if n.op_type == "ReduceMax":
+        if [int(v) for v in n.attrs.get("axes", [])] not in ([2], [-1]):
+            _cnn_fail("ReduceMax is not over the residue axis of [b, F, L]")
+    elif n.op_type != "GlobalMaxPool":
+        _cnn_fail(f"expected a global max-pool over residues, found {n.op_type}")
+    n = only(fwd(n.outputs[0]), "after the max-pool")
+    if n.op_type not in ("MatMul", "Gemm") or n.inputs[1] not in const:
+        _cnn_fail(f"expected the FuncPredictor dense layer after the max-pool, found {n.op_type}")
+    out_W = np.asarray(const[n.inputs[1]], np.float32)
+    if n.op_type == "Gemm":
+        if n.attrs.get("transA", 0) or float(n.attrs.get("alpha", 1.0)) != 1.0 or float(n.attrs.get("beta", 1.0)) != 1.0:
+            _cnn_fail("Gemm with transA / alpha / beta is not supported")
+        if n.attrs.get("transB", 0):
+            out_W = out_W.T
+    if out_W.ndim != 2 or out_W.shape[0] != tot or out_W.shape[1] % 2:
+        _cnn_fail(f"output layer weight {out_W.shape} does not follow {tot} pooled channels")
+    out_b = None
+    if n.op_type == "Gemm" and len(n.inputs) > 2 and n.inputs[2]:
+        out_b = np.asarray(const[n.inputs[2]], np.float32).reshape(-1)
+        t = n.outputs[0]
+    else:
+        t = n.outputs[0]
+        for c in fwd(t):
+            if c.op_type == "Add":
+                other = [i for i in c.inputs if i in const]
+                if len(other) == 1:
+                    out_b, t = np.asarray(const[other[0]], np.float32).reshape(-1), c.outputs[0]
+    if out_b is not None and out_b.size != out_W.shape[1]:
+        _cnn_fail("output bias width mismatch")
+    sm = only(fwd(t), "after the output layer")
+    if sm.op_type != "Softmax" or sm.outputs[0] != g.outputs[0].name or sm.attrs.get("axis", -1) not in (-1, 2):
+        _cnn_fail("graph does not end in a Softmax over the last axis")
+    return CNNPlan(input_names=[seq_name], n_channels=26, conv_W=conv_W, conv_pad_left=pad_left, scale=scale, shift=shift,
+                   out_W=np.ascontiguousarray(out_W), out_b=out_b, n_terms=int(out_W.shape[1] // 2))
+
+
+def load_plan(path: str):
+    """`GCNPlan` for a two-input (cmap, seq) model, `CNNPlan` for a single-input sequence model."""
+    model = ox.load(path)
+    if len(model.graph.inputs) == 1:
+        return cnn_plan_from_model(model)
+    return plan_from_model(model)

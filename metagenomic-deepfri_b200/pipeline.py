@@ -11,7 +11,8 @@ row per call.  Here the same rows come out of a few batched launches:
   four heads - runs once, and every further head only runs its embedding, GraphConv stack and classifier.
 
 Nothing here falls back to the CPU; sequences without structure (`alignment.coords is None`,
-`bio_utils.py:381-383`) are reported back so the caller can route them to the sequence-only branch.
+`bio_utils.py:381-383`) are reported back so the caller can route them to the sequence-only branch
+(`run_prediction_loop(..., net_type="cnn")` over a `DeepCNN-MERGED_*` Predictor).
 """
 from __future__ import annotations
 
@@ -44,9 +45,17 @@ def run_prediction_loop(predictor: Predictor, data_iterable: Iterable, data_len:
     """`pipeline._run_prediction_loop` (`pipeline.py:292-319`): one `[query_id, net_type] + scores` row per
     item, in input order.  `net_type == "gcn"` items are `(alignment, aligned_cmap)` pairs; the maps are
     bit-packed on the host and pushed through `Predictor.forward_batch` chunk by chunk."""
-    if net_type != "gcn":
-        raise NotImplementedError("run_prediction_loop: only the structure branch (net_type='gcn') runs on the B200 path")
     items = list(data_iterable)
+    if net_type == "cnn":
+        # items are (query_id, sequence) pairs (`pipeline.py:313-316`): the sequence-only DeepCNN branch
+        lengths = [len(s) for _, s in items]
+        for lo, hi in _chunks(lengths, max_residues):
+            scores = predictor.forward_sequences([s for _, s in items[lo:hi]])
+            for (query_id, _), vec in zip(items[lo:hi], scores):
+                tsv_writer.writerow([query_id, net_type] + vec.tolist())
+        return
+    if net_type != "gcn":
+        raise ValueError(f"run_prediction_loop: unknown net_type {net_type!r}")
     lengths = [len(a.query_sequence) for a, _ in items]
     for lo, hi in _chunks(lengths, max_residues):
         seqs = [a.query_sequence for a, _ in items[lo:hi]]

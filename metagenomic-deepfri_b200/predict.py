@@ -8,8 +8,10 @@ session, the `.onnx` file is recognised by `onnx_plan` and executed by the fused
 behind the C ABI.  Batched entry points (`forward_batch`, `forward_structures`) run the same
 kernels over many proteins per launch; `forward_pass` is a batch of one.
 
-`cmap=None` selects the reference's sequence-only CNN branch, which is out of scope here and
-raises `NotImplementedError` (there is no CPU or library fallback).
+A single-input `.onnx` file (the `DeepCNN-MERGED_*` models) is the reference's sequence-only CNN
+branch: `forward_pass(seqres)` with `cmap=None` (`predict.pyx:91-95`) and the batched
+`forward_sequences` run it through the tcgen05 convolution kernel (`csrc/cnn_tc.cu`).  There is no
+CPU or library fallback on either branch.
 """
 from __future__ import annotations
 
@@ -20,7 +22,7 @@ import numpy as np
 
 from . import _lib
 from .batching import pack_sequences, pack_structures, packed_offsets
-from .onnx_plan import GCNPlan, load_plan
+from .onnx_plan import CNNPlan, GCNPlan, load_plan
 
 _ALPHABET = b"-DGULNTKHYWCPVSOIEFXQABZRM"          # predict.pyx:26
 _LUT = np.full(256, -1, np.int16)
@@ -152,6 +154,9 @@ class Predictor:
     # -- predict.pyx:62-73
     def _load_model(self):
         plan = load_plan(self.model_path)        # FileNotFoundError / RuntimeError on bad files
+        self.is_cnn = isinstance(plan, CNNPlan)
+        if self.is_cnn:
+            return self._load_cnn(plan)
         d = _lib.ModelDesc()
         keep = []
 
@@ -182,6 +187,64 @@ class Predictor:
         self.session = _Session(plan, h, self._ctx)
         self.input_names = list(plan.input_names)
 
+    def _load_cnn(self, plan: CNNPlan):
+        d = _lib.CnnDesc()
+        keep = []
+
+        def ptr(a):
+            if a is None:
+                return None
+            a = np.ascontiguousarray(a, np.float32)
+            keep.append(a)
+            return _lib.fp(a)
+
+        if len(plan.conv_W) > _lib.MAX_CONV:
+            raise NotImplementedError("DeepCNN model has more parallel Conv layers than the kernel supports")
+        d.n_channels, d.n_conv = plan.n_channels, len(plan.conv_W)
+        for l, (w, pl) in enumerate(zip(plan.conv_W, plan.conv_pad_left)):
+            d.conv_filters[l], d.conv_width[l], d.conv_pad_left[l], d.conv_W[l] = w.shape[0], w.shape[2], pl, ptr(w)
+        d.scale, d.shift = ptr(plan.scale), ptr(plan.shift)
+        d.n_terms, d.out_W, d.out_b = plan.n_terms, ptr(plan.out_W), ptr(plan.out_b)
+        h = C.c_void_p()
+        _lib.check(_lib.lib().mdf_cnn_model_create(self._ctx.handle, C.byref(d), C.byref(h)))
+        self._handle = h
+        self.n_terms = plan.n_terms
+        self.n_pooled = int(plan.scale.size)
+        self.plan = plan
+        self.session = _Session(plan, h, self._ctx)
+        self.input_names = list(plan.input_names)
+
+    # -- predict.pyx:91-95, batched: the sequence-only branch for n sequences
+    def forward_sequences(self, seqs: Sequence[str], out: Optional[np.ndarray] = None) -> np.ndarray:
+        if not self.is_cnn:
+            raise ValueError("forward_sequences needs a sequence-only DeepCNN model; this Predictor holds a GCN head")
+        n = len(seqs)
+        seq_bytes, seq_off = pack_sequences([_encode(s).decode() for s in seqs])
+        if out is None:
+            out = np.empty((n, self.n_terms), np.float32)
+        if n == 0:
+            return out
+        _lib.check(_lib.lib().mdf_cnn_forward(self._handle, n, seq_bytes, _lib.lp(seq_off), out.ctypes.data))
+        return out
+
+    def upload_sequences(self, seqs: Sequence[str]) -> int:
+        """Keep n sequences resident in HBM for `run_sequences` / `fetch_sequences` (bench); returns the bytes copied."""
+        if not self.is_cnn:
+            raise ValueError("upload_sequences needs a sequence-only DeepCNN model")
+        seq_bytes, seq_off = pack_sequences([_encode(s).decode() for s in seqs])
+        _lib.check(_lib.lib().mdf_cnn_upload(self._handle, len(seqs), seq_bytes, _lib.lp(seq_off)))
+        self._n_resident = len(seqs)
+        return len(seq_bytes) + seq_off.nbytes
+
+    def run_sequences(self) -> None:
+        _lib.check(_lib.lib().mdf_cnn_run(self._handle))
+
+    def fetch_sequences(self, pooled: bool = False):
+        out = np.empty((self._n_resident, self.n_terms), np.float32)
+        pl = np.empty((self._n_resident, self.n_pooled), np.float32) if pooled else None
+        _lib.check(_lib.lib().mdf_cnn_fetch(self._handle, out.ctypes.data, pl.ctypes.data if pooled else None))
+        return (out, pl) if pooled else out
+
     def set_engine(self, engine: str) -> None:
         """'simt' = exact-fp32 CUDA-core engine, 'tc' = tcgen05 tensor-core engine."""
         _lib.check(_lib.lib().mdf_model_set_engine(self._handle, {"simt": 0, "tc": 1}[engine]))
@@ -194,9 +257,16 @@ class Predictor:
     def forward_pass(self, seqres: str, cmap=None) -> np.ndarray:
         seq = _encode(seqres)
         if cmap is None:
-            raise NotImplementedError(
-                "Predictor.forward_pass(seqres, cmap=None) selects the sequence-only CNN branch "
-                "(predict.pyx:91-95), which the B200 structure-branch path does not implement")
+            if not self.is_cnn:
+                # the reference would feed one input to a two-input graph and onnxruntime would reject it
+                raise ValueError("forward_pass(seqres) without a contact map needs a sequence-only DeepCNN model; "
+                                 "this Predictor holds a GCN head (inputs: %s)" % ", ".join(self.input_names))
+            if len(seq) == 0:
+                raise ValueError("forward_pass: empty sequence (the max-pool over residues needs at least one)")
+            return self.forward_sequences([seqres])[0]
+        if self.is_cnn:
+            # predict.pyx:87-90 would index input_names[1] of a single-input model
+            raise ValueError("forward_pass(seqres, cmap): this Predictor holds a sequence-only DeepCNN model (one input)")
         A = cmap.reshape(cmap.shape[0], cmap.shape[1])
         L = len(seq)
         if A.shape != (L, L):
@@ -296,7 +366,10 @@ class Predictor:
 
     def close(self):
         if getattr(self, "_handle", None):
-            _lib.lib().mdf_model_destroy(self._handle)
+            if getattr(self, "is_cnn", False):
+                _lib.lib().mdf_cnn_model_destroy(self._handle)
+            else:
+                _lib.lib().mdf_model_destroy(self._handle)
             self._handle = None
 
     def __del__(self):

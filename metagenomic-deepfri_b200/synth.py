@@ -162,6 +162,80 @@ def write_gcn_model(path: str, cfg: GCNConfig, seed: int = 1234) -> None:
     ox.save(build_gcn_model(cfg, seed=seed), path)
 
 
+# ----------------------------------------------------------------------------- sequence-only DeepCNN heads
+@dataclass
+class CNNConfig:
+    """Upstream DeepFRI `DeepCNN` (the `DeepCNN-MERGED_*` models, `mDeepFRI/__init__.py:68`): parallel Conv1D layers over
+    the one-hot sequence, concatenated, BatchNormalization, ReLU, global max-pool, FuncPredictor.  Defaults = the trained
+    models' 16 x 512 filters of widths 8..128."""
+    n_channels: int = 26
+    filter_lens: Tuple[int, ...] = tuple(range(8, 129, 8))
+    num_filters: Tuple[int, ...] = (512,) * 16
+    n_terms: int = 489
+    bn_epsilon: float = 1e-3          # Keras BatchNormalization default
+    logit_scale: float = 0.15
+
+
+def make_cnn_weights(cfg: CNNConfig, seed: int = 4321) -> Dict[str, np.ndarray]:
+    rng = np.random.default_rng(seed)
+    w: Dict[str, np.ndarray] = {}
+    for l, (k, f) in enumerate(zip(cfg.filter_lens, cfg.num_filters), 1):
+        # ONNX Conv weight [F, C, 1, k] (tf2onnx lowers Keras Conv1D to a Conv over [N, C, 1, L]); one-hot input: a window sums
+        # k weights, so a gain of ~1/sqrt(k) keeps the pre-activations O(1)
+        w[f"conv1d_{l}_W"] = _uniform(rng, np.sqrt(3.0 / k), (f, cfg.n_channels, 1, k))
+        w[f"conv1d_{l}_b"] = _uniform(rng, 0.1, (f,))
+    tot = int(sum(cfg.num_filters))
+    w["bn_gamma"] = rng.uniform(0.5, 1.5, tot).astype(np.float32)
+    w["bn_beta"] = _uniform(rng, 0.3, (tot,))
+    w["bn_mean"] = _uniform(rng, 0.3, (tot,))
+    w["bn_var"] = rng.uniform(0.5, 1.5, tot).astype(np.float32)
+    w["labels_W"] = _uniform(rng, np.sqrt(6.0 / (tot + 2 * cfg.n_terms)) * cfg.logit_scale, (tot, 2 * cfg.n_terms))
+    w["labels_b"] = _uniform(rng, 1.0, (2 * cfg.n_terms,))
+    return w
+
+
+def build_cnn_model(cfg: CNNConfig, weights: Optional[Dict[str, np.ndarray]] = None, seed: int = 4321) -> ox.Model:
+    """DeepCNN head as an ONNX graph in tf2onnx style: one input `seq` [b, L, 26] (the reference feeds it alone,
+    `predict.pyx:91-95`), channels-first Conv nodes with explicit TF 'same' pads ((k-1)//2 before, the rest after),
+    Concat, BatchNormalization, Relu, ReduceMax over residues, MatMul/Add, Reshape, Softmax -> [1, C, 2]."""
+    w = dict(weights) if weights is not None else make_cnn_weights(cfg, seed)
+    g = ox.Graph(name="DeepCNN")
+    g.inputs = [ox.ValueInfo("seq", ox.FLOAT, ("unk__b", "unk__l", cfg.n_channels))]
+    g.outputs = [ox.ValueInfo("labels", ox.FLOAT, ("unk__b", cfg.n_terms, 2))]
+    init, N = g.initializers, g.nodes
+    for k, v in w.items():
+        init[k] = v
+    init["const_axes_2"] = np.array([2], np.int64)
+    init["const_out_shape"] = np.array([-1, cfg.n_terms, 2], np.int64)
+
+    def add(op, ins, outs, **attrs):
+        N.append(ox.Node(op, list(ins), list(outs), name=f"{op}__{len(N)}", attrs=attrs))
+        return outs[0]
+
+    x = add("Transpose", ["seq"], ["seq_cf"], perm=[0, 2, 1])                 # [b, 26, L]
+    x = add("Unsqueeze", [x, "const_axes_2"], ["seq_cf4"])                    # [b, 26, 1, L]
+    outs = []
+    for l, k in enumerate(cfg.filter_lens, 1):
+        pl = (k - 1) // 2
+        y = add("Conv", [x, f"conv1d_{l}_W", f"conv1d_{l}_b"], [f"conv1d_{l}/Conv2D"], kernel_shape=[1, k], strides=[1, 1],
+                dilations=[1, 1], group=1, pads=[0, pl, 0, k - 1 - pl])
+        outs.append(add("Squeeze", [y, "const_axes_2"], [f"conv1d_{l}/Squeeze"]))   # [b, F, L]
+    cat = add("Concat", outs, ["concatenate/concat"], axis=1) if len(outs) > 1 else outs[0]
+    bn = add("BatchNormalization", [cat, "bn_gamma", "bn_beta", "bn_mean", "bn_var"], ["batch_normalization/bn"],
+             epsilon=float(cfg.bn_epsilon), momentum=0.99)
+    r = add("Relu", [bn], ["CAM_layer/Relu"])
+    p = add("ReduceMax", [r], ["global_max_pooling1d/Max"], axes=[2], keepdims=0)   # [b, sum F]
+    o = add("MatMul", [p, "labels_W"], ["labels/dense/MatMul"])
+    o = add("Add", [o, "labels_b"], ["labels/dense/BiasAdd"])
+    o = add("Reshape", [o, "const_out_shape"], ["labels/reshape"])
+    add("Softmax", [o], ["labels"], axis=-1)
+    return ox.Model(g, ir_version=8, opset=15, producer_name="mdf-b200-synth", producer_version="1")
+
+
+def write_cnn_model(path: str, cfg: CNNConfig, seed: int = 4321) -> None:
+    ox.save(build_cnn_model(cfg, seed=seed), path)
+
+
 # ----------------------------------------------------------------------------- workloads
 def random_sequences(rng: np.random.Generator, lengths: Sequence[int]) -> List[str]:
     """Uniform over the 20 standard residues."""

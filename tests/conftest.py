@@ -41,6 +41,25 @@ def model_dir(tmp_path_factory):
     return paths
 
 
+@pytest.fixture(scope="session")
+def cnn_golden():
+    return np.load(os.path.join(ROOT, "tests", "golden", "cnn_golden.npz"))
+
+
+@pytest.fixture(scope="session")
+def cnn_model_dir(tmp_path_factory):
+    """Seeded random-init DeepCNN heads of tests/golden/spec.py (sequence-only branch)."""
+    import spec
+    from metagenomic_deepfri_b200 import synth
+    d = tmp_path_factory.mktemp("cnn_models")
+    paths = {}
+    for tag, (kw, seed, n, lo, hi) in spec.CNN_CASES.items():
+        p = str(d / f"{tag}.onnx")
+        synth.write_cnn_model(p, synth.CNNConfig(**kw), seed=seed)
+        paths[tag] = p
+    return paths
+
+
 def golden_workload(tag):
     import spec
     from metagenomic_deepfri_b200 import synth

@@ -129,8 +129,8 @@ def test_forward_pass_contract_and_errors(engines):
         pred.forward_pass("ACD", cm)                                                # shape mismatch
     with pytest.raises(ValueError):
         pred.forward_pass("ACDE", 3 * cm)
-    with pytest.raises(NotImplementedError):
-        pred.forward_pass("ACDE")                                                   # CNN branch: out of scope, loud
+    with pytest.raises(ValueError, match="DeepCNN"):
+        pred.forward_pass("ACDE")                                                   # a GCN head has no sequence-only branch
     with pytest.raises(ValueError):
         pred.forward_structures(["ACDE"], ["ACD-"], ["ACDE"], [np.zeros((4, 3), np.float32)])
     with pytest.raises(FileNotFoundError):

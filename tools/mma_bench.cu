@@ -10,7 +10,7 @@ __global__ void bench(long long *out, int reps, uint32_t lbo_a, uint32_t lbo_b)
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bar;
     __shared__ uint32_t slot;
-    for (int i = threadIdx.x; i < 160 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem)[i] = 0;
+    for (int i = threadIdx.x; i < 192 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem)[i] = 0;
     if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
     if (threadIdx.x < 32) tmem_alloc<512>(&slot);
     fence_proxy_async_smem();
@@ -24,7 +24,7 @@ __global__ void bench(long long *out, int reps, uint32_t lbo_a, uint32_t lbo_b)
         long long t0 = clock64();
         for (int r = 0; r < reps; ++r) {
 #pragma unroll 8
-            for (int ks = 0; ks < 32; ++ks)
+            for (int ks = 0; ks < 16; ++ks)
                 umma_f16(slot, ad + (uint64_t)(ks * (2 * lbo_a >> 4)), bd + (uint64_t)(ks * (2 * lbo_b >> 4)), idesc, ks != 0);
         }
         long long t1 = clock64();
@@ -43,13 +43,13 @@ void run(long long *d)
 {
     const int reps = 16;
     cudaFuncSetAttribute(bench<M, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    // A: M rows x 512 K -> lbo = (M/8)*128 ; B: N rows x 512 K -> lbo = (N/8)*128
+    // A: M rows x 256 K -> lbo = (M/8)*128 ; B: N rows x 256 K -> lbo = (N/8)*128
     bench<M, N><<<1, 128, 200 * 1024>>>(d, reps, (M / 8) * 128, (N / 8) * 128);
     long long h[2];
     cudaMemcpy(h, d, sizeof h, cudaMemcpyDeviceToHost);
     cudaError_t e = cudaGetLastError();
-    printf("M=%3d N=%3d: issue %.1f cyc/MMA, complete %.1f cyc/MMA  (%.0f MAC/cyc) %s\n", M, N, h[0] / (32.0 * reps), h[1] / (32.0 * reps),
-           (double)M * N * 16 * 32 * reps / h[1], e == cudaSuccess ? "" : cudaGetErrorString(e));
+    printf("M=%3d N=%3d: issue %.1f cyc/MMA, complete %.1f cyc/MMA  (%.0f MAC/cyc) %s\n", M, N, h[0] / (16.0 * reps), h[1] / (16.0 * reps),
+           (double)M * N * 16 * 16 * reps / h[1], e == cudaSuccess ? "" : cudaGetErrorString(e));
 }
 
 int main()
