@@ -377,7 +377,7 @@ extern "C" int mdf_cnn_upload(mdf_cnn_model *m, int n, const char *seq, const in
     mdf_ctx *ctx = m->ctx;
     MDF_CUDA(cudaSetDevice(ctx->device));
     MDF_CUDA(cudaStreamSynchronize(ctx->stream));
-    cnn_free_batch(m);
+    m->n = 0; m->T = 0; m->n_tiles = 0;
     if (n == 0) return MDF_OK;
     MDF_REQUIRE(seq_off[0] == 0, "mdf_cnn_upload: seq_off[0] must be 0");
     const int64_t T = seq_off[n];
@@ -391,9 +391,14 @@ extern "C" int mdf_cnn_upload(mdf_cnn_model *m, int n, const char *seq, const in
     }
     const size_t b_seq = align_up((size_t)T, 256), b_idx = align_up((size_t)T, 256), b_tiles = align_up(tiles.size() * sizeof(int4), 256),
                  b_pool = align_up((size_t)n * m->Ctot * 4, 256), b_sc = align_up((size_t)n * m->C * 4, 256);
-    m->block_bytes = b_seq + b_idx + b_tiles + b_pool + b_sc;
-    cudaError_t e = cudaMalloc(&m->block, m->block_bytes);
-    if (e != cudaSuccess) { cudaGetLastError(); m->block = nullptr; set_error("mdf_cnn_upload: cudaMalloc(%zu) failed: %s", m->block_bytes, cudaGetErrorString(e)); return MDF_ENOMEM; }
+    const size_t need = b_seq + b_idx + b_tiles + b_pool + b_sc;
+    if (need > m->block_bytes) {            // the resident block only grows: back-to-back batches reuse it
+        cnn_free_batch(m);
+        const size_t want = need + need / 8;
+        cudaError_t e = cudaMalloc(&m->block, want);
+        if (e != cudaSuccess) { cudaGetLastError(); m->block = nullptr; set_error("mdf_cnn_upload: cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e)); return MDF_ENOMEM; }
+        m->block_bytes = want;
+    }
     char *p = static_cast<char *>(m->block);
     m->d_seq = p; p += b_seq;
     m->d_idx = reinterpret_cast<uint8_t *>(p); p += b_idx;

@@ -21,7 +21,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 from . import _lib
-from .batching import pack_sequences, pack_structures, packed_offsets
+from .batching import pack_structures, packed_offsets
 from .onnx_plan import CNNPlan, GCNPlan, load_plan
 
 _ALPHABET = b"-DGULNTKHYWCPVSOIEFXQABZRM"          # predict.pyx:26
@@ -36,6 +36,22 @@ def _encode(seq: str) -> bytes:
     if bad.size:
         raise ValueError(f"Invalid character in sequence: {seq[int(bad[0])]}")
     return b
+
+
+def _pack_checked(seqs: Sequence[str]):
+    """n sequences -> (ASCII bytes of all residues, int64 CSR offsets), validated in one vectorised pass with the error
+    behaviour of `_encode` (per-sequence NumPy calls cost more than the GPU work for short proteins)."""
+    n = len(seqs)
+    joined = "".join(seqs)
+    b = joined.encode("ascii")                      # UnicodeEncodeError like predict.pyx:19
+    if b:
+        bad = np.flatnonzero(_LUT[np.frombuffer(b, np.uint8)] < 0)
+        if bad.size:
+            raise ValueError(f"Invalid character in sequence: {joined[int(bad[0])]}")
+    off = np.zeros(n + 1, np.int64)
+    if n:
+        np.cumsum(np.fromiter(map(len, seqs), np.int64, n), out=off[1:])
+    return b, off
 
 
 def seq2onehot(seq: str) -> np.ndarray:
@@ -73,7 +89,7 @@ class PathInputs:
     def __init__(self, seqs: Sequence[str], gapped_query: Sequence[str], gapped_target: Sequence[str],
                  coords: Sequence[np.ndarray], pin: bool = False):
         ps = pack_structures(gapped_query, gapped_target, coords)
-        seq_bytes, seq_off = pack_sequences([_encode(s).decode() for s in seqs])
+        seq_bytes, seq_off = _pack_checked(seqs)
         if not np.array_equal(seq_off, ps.seq_off):
             raise ValueError("query sequences do not match the gap-stripped query alignments")
         self.n = len(seqs)
@@ -113,7 +129,7 @@ class PathBatch:
     def __init__(self, ctx: _lib.Context, seqs: Sequence[str], gapped_query: Sequence[str],
                  gapped_target: Sequence[str], coords: Sequence[np.ndarray]):
         ps = pack_structures(gapped_query, gapped_target, coords)
-        seq_bytes, seq_off = pack_sequences([_encode(s).decode() for s in seqs])
+        seq_bytes, seq_off = _pack_checked(seqs)
         if not np.array_equal(seq_off, ps.seq_off):
             raise ValueError("query sequences do not match the gap-stripped query alignments")
         self.n = len(seqs)
@@ -219,7 +235,7 @@ class Predictor:
         if not self.is_cnn:
             raise ValueError("forward_sequences needs a sequence-only DeepCNN model; this Predictor holds a GCN head")
         n = len(seqs)
-        seq_bytes, seq_off = pack_sequences([_encode(s).decode() for s in seqs])
+        seq_bytes, seq_off = _pack_checked(seqs)
         if out is None:
             out = np.empty((n, self.n_terms), np.float32)
         if n == 0:
@@ -231,7 +247,7 @@ class Predictor:
         """Keep n sequences resident in HBM for `run_sequences` / `fetch_sequences` (bench); returns the bytes copied."""
         if not self.is_cnn:
             raise ValueError("upload_sequences needs a sequence-only DeepCNN model")
-        seq_bytes, seq_off = pack_sequences([_encode(s).decode() for s in seqs])
+        seq_bytes, seq_off = _pack_checked(seqs)
         _lib.check(_lib.lib().mdf_cnn_upload(self._handle, len(seqs), seq_bytes, _lib.lp(seq_off)))
         self._n_resident = len(seqs)
         return len(seq_bytes) + seq_off.nbytes
@@ -284,7 +300,7 @@ class Predictor:
     def forward_batch(self, seqs: Sequence[str], packed_cmaps: Sequence[np.ndarray]) -> np.ndarray:
         """GCN forward for n proteins with bit-packed maps (uint32 [L, row_words] each)."""
         n = len(seqs)
-        seq_bytes, seq_off = pack_sequences([_encode(s).decode() for s in seqs])
+        seq_bytes, seq_off = _pack_checked(seqs)
         poff = packed_offsets(np.diff(seq_off))
         flat = np.concatenate([np.ascontiguousarray(c, np.uint32).reshape(-1) for c in packed_cmaps]) \
             if n else np.zeros(0, np.uint32)
@@ -303,7 +319,7 @@ class Predictor:
         from .bio_utils import threshold_sq
         n = len(seqs)
         ps = pack_structures(gapped_query, gapped_target, coords)
-        seq_bytes, seq_off = pack_sequences([_encode(s).decode() for s in seqs])
+        seq_bytes, seq_off = _pack_checked(seqs)
         if not np.array_equal(seq_off, ps.seq_off):
             raise ValueError("query sequences do not match the gap-stripped query alignments")
         if out is None:
