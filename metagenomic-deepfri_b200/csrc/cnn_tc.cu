@@ -109,7 +109,7 @@ cnn_conv_kernel(const __grid_constant__ CnnArgs a)
                     const int c = a.item_conv[item], KB = a.kb[c];
                     const uint8_t *src = reinterpret_cast<const uint8_t *>(a.W[c]) + (size_t)a.item_fb[item] * KB * TILE_BYTES;
                     for (int kb = 0; kb < KB; ++kb) {
-                        mbar_wait(&bars.empty[st], ph ^ 1);
+                        mbar_wait_sleep(&bars.empty[st], ph ^ 1, 32);
                         mbar_arrive_expect_tx(&bars.full[st], TILE_BYTES);
                         bulk_g2s(stg + (size_t)st * TILE_BYTES, src + (size_t)kb * TILE_BYTES, TILE_BYTES, &bars.full[st]);
                         if (++st == CNN_STAGES) { st = 0; ph ^= 1; }
@@ -161,7 +161,7 @@ cnn_conv_kernel(const __grid_constant__ CnnArgs a)
         int it = 0;
         for (int g = blockIdx.x; g < a.n_groups; g += gridDim.x, ++it) {
             const int buf = it & 1;
-            if (lane == 0) mbar_wait(&bars.img_empty[buf], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+            if (lane == 0) mbar_wait_sleep(&bars.img_empty[buf], ((uint32_t)(it >> 1) & 1u) ^ 1u, 1000);
             __syncwarp();
             const int nt = min(CNN_TILES, a.n_tiles - g * CNN_TILES);
             for (int t = 0; t < nt; ++t) {
@@ -207,7 +207,7 @@ cnn_conv_kernel(const __grid_constant__ CnnArgs a)
             for (int item = 0; item < a.n_items; ++item) {
                 const int ch_item = a.choff[a.item_conv[item]] + a.item_fb[item] * 128;
                 const float *sc = a.scale + ch_item + cg * 32, *sh = a.shift + ch_item + cg * 32;
-                mbar_wait(&bars.tmem_full, item_ph);
+                mbar_wait_sleep(&bars.tmem_full, item_ph, 64);      // thousands of cycles per item: do not burn issue slots (power cap)
                 tcgen05_fence_after();
 #pragma unroll
                 for (int t = 0; t < CNN_TILES; ++t) {

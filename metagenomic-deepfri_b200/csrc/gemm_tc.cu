@@ -168,7 +168,9 @@ gemm_tc_kernel(GemmArgs g, int a_terms, int b_terms, int stages)
                 int a_tile0, b_kb0, nkb;
                 if (g.tile_info) { const int4 ti = g.tile_info[mt]; a_tile0 = ti.x; b_kb0 = ti.y; nkb = ti.z; }
                 else { a_tile0 = mt * g.KB_A; b_kb0 = 0; nkb = g.nkb; }
-                for (int kb = 0; kb < nkb; ++kb) {
+                if (g.adj_kb_cnt) nkb = g.adj_kb_cnt[mt];
+                for (int j = 0; j < nkb; ++j) {
+                    const int kb = g.adj_kb_idx ? (int)g.adj_kb_idx[a_tile0 + j] : j;
                     mbar_wait(&bars.empty[st], ph ^ 1);
                     mbar_arrive_expect_tx(&bars.full[st], (uint32_t)(g.adj_packed ? stage_bytes - a_bytes : stage_bytes));
                     uint8_t *dst = smem + (size_t)st * stage_bytes;
@@ -210,7 +212,7 @@ gemm_tc_kernel(GemmArgs g, int a_terms, int b_terms, int stages)
             for (int in = 0; in < inner; ++in) {
                 const int mt = g.m_fastest ? in : grp;
                 long long c0 = tr ? clock64() : 0;
-                const int nkb = g.tile_info ? g.tile_info[mt].z : g.nkb;
+                const int nkb = g.adj_kb_cnt ? g.adj_kb_cnt[mt] : g.tile_info ? g.tile_info[mt].z : g.nkb;
                 if (tr) { const long long c1 = clock64() + (nkb & 0); t_info += c1 - c0; c0 = c1; }
                 mbar_wait(&bars.tmem_empty[acc], acc_ph ^ 1);
                 if (tr) { const long long c1 = clock64(); t_acc += c1 - c0; ++n_tiles_done; }
@@ -270,11 +272,42 @@ gemm_tc_kernel(GemmArgs g, int a_terms, int b_terms, int stages)
         for (int in = 0; in < inner; ++in) {
             const int mt = g.m_fastest ? in : grp;
             const int4 ti = g.tile_info[mt];
-            const int nkb = ti.z, p = ti.w;
+            const int nkb = g.adj_kb_cnt ? g.adj_kb_cnt[mt] : ti.z, p = ti.w;
             const int L = (int)(g.adj_seq_off[p + 1] - g.adj_seq_off[p]);
             const int rw = packed_row_words(L);
             const int i = (mt - (int)(g.adj_seg_off[p] >> 7)) * 128 + et;                 // row of the protein's map
             const uint32_t *row = g.adj_packed + g.adj_packed_off[p] + (size_t)i * rw;
+            if (g.adj_kb_idx) {
+                // block-sparse walk: the two words of listed k-block j, loaded one list entry ahead of the stage that uses them
+                const unsigned short *list = g.adj_kb_idx + ti.x;
+                uint2 nx = make_uint2(0u, 0u);
+                if (nkb > 0 && i < L) nx = __ldg(reinterpret_cast<const uint2 *>(row + 2 * (int)list[0]));
+                for (int j = 0; j < nkb; ++j) {
+                    const uint2 cw = nx;
+                    nx = make_uint2(0u, 0u);
+                    if (j + 1 < nkb && i < L) nx = __ldg(reinterpret_cast<const uint2 *>(row + 2 * (int)list[j + 1]));
+                    const uint32_t w[2] = {cw.x, cw.y};
+                    if (lane == 0) mbar_wait(&bars.empty[st], ph ^ 1);
+                    __syncwarp();
+                    const uint32_t dst = smem_u32(smem + (size_t)st * stage_bytes) + (uint32_t)((et >> 3) * 128 + (et & 7) * 16);
+                    const uint32_t one = 0x3C00u;
+#pragma unroll
+                    for (int k8 = 0; k8 < 8; ++k8) {
+                        const uint32_t b8 = (w[k8 >> 2] >> (8 * (k8 & 3))) & 0xFFu;
+                        uint4 pk;
+                        pk.x = ((b8 & 1u) ? one : 0u) | ((b8 & 2u) ? one << 16 : 0u);
+                        pk.y = ((b8 & 4u) ? one : 0u) | ((b8 & 8u) ? one << 16 : 0u);
+                        pk.z = ((b8 & 16u) ? one : 0u) | ((b8 & 32u) ? one << 16 : 0u);
+                        pk.w = ((b8 & 64u) ? one : 0u) | ((b8 & 128u) ? one << 16 : 0u);
+                        st_shared_v4(dst + k8 * 2048, pk);
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars.full[st]);
+                    if (++st == stages) { st = 0; ph ^= 1; }
+                }
+                continue;
+            }
             // the packed row is read four words (two k-blocks) at a time, one load AHEAD of the stage that consumes it: a
             // load issued right before its stage put ~1 k cycles of L2 latency on every stage and paced the whole kernel
             uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
@@ -317,7 +350,7 @@ gemm_tc_kernel(GemmArgs g, int a_terms, int b_terms, int stages)
         for (int grp = blockIdx.x; grp < outer; grp += gridDim.x)
         for (int in = 0; in < inner; ++in) {
             const int mt = g.m_fastest ? in : grp, nt = g.m_fastest ? grp : in;
-            const int nkb = g.tile_info ? g.tile_info[mt].z : g.nkb;
+            const int nkb = g.adj_kb_cnt ? g.adj_kb_cnt[mt] : g.tile_info ? g.tile_info[mt].z : g.nkb;
             mbar_wait(&bars.tmem_full[acc], acc_ph);
             tcgen05_fence_after();
             const int64_t m = (int64_t)mt * 128 + lb + lane;

@@ -45,6 +45,11 @@ struct GemmArgs {
     float *pool = nullptr;
     int pool_ld = 0, pool_off = 0;
     long long *trace = nullptr;      // optional [8] cycle counters of CTA 0 (MDF_GEMM_TRACE=1, adjacency GEMM)
+    // block-sparse adjacency (tc_engine.cu adj_tile_scan_kernel): the k-blocks of an m-tile whose 128 x 64 A tile holds at
+    // least one contact, as a compact list adj_kb_idx[tile_info[mt].x + j], j < adj_kb_cnt[mt].  All-zero tiles contribute
+    // nothing to A_hat . Y, so the producer, the expanders and the MMA issuer walk this list instead of 0..nkb-1.
+    const unsigned short *adj_kb_idx = nullptr;
+    const int *adj_kb_cnt = nullptr;
     const uint32_t *adj_packed = nullptr;
     const int64_t *adj_packed_off = nullptr, *adj_seq_off = nullptr, *adj_seg_off = nullptr;
     // epilogue

@@ -40,6 +40,7 @@ struct TcModel {
                                                            // 4.7-5.0 ms vs 4.5 ms per layer: halving the shared-memory operand traffic does
                                                            // not help, the kernel is paced by draining its short-K accumulators
     int pool_fused = 1;                                    // sum-pool readout inside the adjacency GEMM epilogue (fp32, no X re-read)
+    int adj_sparse = 1;                                    // adjacency GEMM skips all-zero 128 x 64 A tiles (MDF_ADJ_SPARSE=0: dense walk)
     int adj_expand = 1;                                    // adjacency GEMM expands its A tiles from the bit-packed map on the fly
     int gemm_pair = 1;                                     // CTA-pair (cta_group::2) kernels for the embedding and X.W GEMMs
     int gemm_phases = 0;                                   // > 0 (MDF_GEMM_PHASES, experiment): single-term dithered weights, phase = residue tile
@@ -139,6 +140,7 @@ int tc_model_init(mdf_model *m, const mdf_model_desc *d)
     if (const char *e = getenv("MDF_ADJ_EXPAND")) t->adj_expand = atoi(e);
     if (const char *e = getenv("MDF_POOL_FUSED")) t->pool_fused = atoi(e);
     if (const char *e = getenv("MDF_ADJ_PAIR")) t->adj_pair = atoi(e);
+    if (const char *e = getenv("MDF_ADJ_SPARSE")) t->adj_sparse = atoi(e);
     if (const char *e = getenv("MDF_SINGLE_TERM")) t->single_term_mask = atoi(e);
     if (const char *e = getenv("MDF_HEAD_TC")) t->head_tc = atoi(e);
     if (const char *e = getenv("MDF_GEMM_PHASES")) t->gemm_phases = std::min(64, std::max(0, atoi(e)));   // 0: hi+lo split on every tile
@@ -495,6 +497,54 @@ static int head_forward_tc(mdf_model *m, TcModel *tm, int n, const float *pooled
     return MDF_OK;
 }
 
+// Block-sparse adjacency: for every 128-row m-tile, the compact list of k-blocks (64 columns) whose A_hat tile holds at least
+// one contact (the diagonal set by prep_adjacency_kernel included).  Contacts cluster around the diagonal and in a few
+// off-diagonal patches, so a large share of the 128 x 64 tiles of a long protein is all-zero (41 % over the configs[4]
+// length distribution, > 60 % above 750 residues); the adjacency GEMM skips them - exact, zeros contribute nothing.
+// One block of 128 threads per m-tile, thread = row; reads the packed maps once (L^2 / 8 bytes per protein).
+__global__ void __launch_bounds__(128)
+adj_tile_scan_kernel(int m_tiles, const int4 *__restrict__ tile_info, const uint32_t *__restrict__ packed,
+                     const int64_t *__restrict__ packed_off, const int64_t *__restrict__ seq_off, const int64_t *__restrict__ seg_off,
+                     unsigned short *__restrict__ kb_idx, int *__restrict__ kb_cnt)
+{
+    __shared__ uint32_t mask;
+    __shared__ int count;
+    const int mt = blockIdx.x;
+    const int4 ti = tile_info[mt];
+    const int nkb = ti.z, p = ti.w;
+    if (nkb == 0) { if (threadIdx.x == 0) kb_cnt[mt] = 0; return; }
+    const int L = (int)(seq_off[p + 1] - seq_off[p]);
+    const int rw = packed_row_words(L);
+    const int i = (mt - (int)(seg_off[p] >> 7)) * 128 + (int)threadIdx.x;
+    const uint32_t *row = packed + packed_off[p] + (size_t)i * rw;
+    if (threadIdx.x == 0) count = 0;
+    for (int c0 = 0; c0 < nkb; c0 += 32) {                    // 32 k-blocks (64 words of the row) per round
+        if (threadIdx.x == 0) mask = 0u;
+        __syncthreads();
+        uint32_t mine = 0u;
+        if (i < L) {
+            const int nk = min(32, nkb - c0);
+            for (int k = 0; k < nk; k += 2) {                 // rw is a multiple of 4 words: k-blocks come in aligned pairs
+                const uint4 w = __ldg(reinterpret_cast<const uint4 *>(row + 2 * (c0 + k)));
+                if (w.x | w.y) mine |= 1u << k;
+                if (w.z | w.w) mine |= 1u << (k + 1);
+            }
+        }
+        mine = __reduce_or_sync(0xffffffffu, mine);
+        if ((threadIdx.x & 31) == 0 && mine) atomicOr(&mask, mine);
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            const uint32_t mk = mask & (nkb - c0 >= 32 ? 0xffffffffu : (1u << (nkb - c0)) - 1u);
+            if ((mk >> threadIdx.x) & 1u)
+                kb_idx[ti.x + count + __popc(mk & ((1u << threadIdx.x) - 1u))] = (unsigned short)(c0 + threadIdx.x);
+            __syncwarp();
+            if (threadIdx.x == 0) count += __popc(mk);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) kb_cnt[mt] = count;
+}
+
 // Exported pieces of the head for the sequence-only CNN branch (cnn_tc.cu): same exact-split dense layer and softmax.
 int tc_dense_split(mdf_ctx *ctx, int n, const float *src, int K, const __half *const W[2], int N, int ldc, const float *bias,
                    int act, float *out)
@@ -628,6 +678,7 @@ size_t tc_workspace_bytes(const mdf_model *m, int n, const int64_t *seq_off)
     if (taps) for (int l = 0; l < m->n_lstm; ++l) add((size_t)T * m->H * 4);    // optional fp32 taps
     add((size_t)Tp * 4 + (size_t)Tp / 128 * 32 + (size_t)(tiles + 1) * 16 + (size_t)(n + 1) * 8 + 2048);   // metadata
     add((size_t)Tp * 4); add((size_t)Tp);             // deg_pad, idx_pad
+    add((size_t)(tiles + 8) * 2); add((size_t)Tp / 128 * 4);   // block-sparse walk lists of the adjacency GEMM
     add((size_t)Tp * m->E * 2);                       // X0 image
     add((size_t)Tp * gmax * 2); add((size_t)Tp * gmax * 2); add((size_t)Tp * gmax * 2);   // Y^T, X_a, X_b images
     if (!(m->tc && static_cast<const TcModel *>(m->tc)->adj_expand)) add((size_t)tiles * TILE_BYTES + 256);   // A_hat images
@@ -784,6 +835,17 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto)
                                                                   b->d_packed_off, Aimg);
         MDF_LAUNCH_CHECK(ctx);
     }
+    // ---- block-sparse walk lists of the adjacency GEMM (per run: they follow the contact maps of this threshold)
+    unsigned short *kb_idx = nullptr;
+    int *kb_cnt = nullptr;
+    if (tm->adj_expand && tm->adj_sparse && !tm->adj_pair && meta->n_adj_tiles > 0) {
+        ProfScope ps(ctx, "adj_tile_scan", 0.0);
+        MDF_TRY(ctx->alloc_n(&kb_idx, (size_t)meta->n_adj_tiles + 8));
+        MDF_TRY(ctx->alloc_n(&kb_cnt, (size_t)meta->m_tiles));
+        adj_tile_scan_kernel<<<meta->m_tiles, 128, 0, s>>>(meta->m_tiles, meta->tile_info, b->d_packed, b->d_packed_off, b->d_seq_off,
+                                                           meta->seg_off, kb_idx, kb_cnt);
+        MDF_LAUNCH_CHECK(ctx);
+    }
     MDF_CUDA(cudaMemsetAsync(b->d_pooled, 0, (size_t)n * m->G * sizeof(float), s));
     double l2 = 0.0;
     for (int p = 0; p < n; ++p) { const double L = (double)(b->h_seq_off[p + 1] - b->h_seq_off[p]); l2 += L * L; }
@@ -821,6 +883,7 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto)
             g.tile_info = meta->tile_info;
             if (tm->adj_expand) {                         // A tiles built in shared memory from the bit-packed map
                 g.adj_packed = b->d_packed; g.adj_packed_off = b->d_packed_off; g.adj_seq_off = b->d_seq_off; g.adj_seg_off = meta->seg_off;
+                g.adj_kb_idx = kb_idx; g.adj_kb_cnt = kb_cnt;
             }
             const int bn = gd % 256 == 0 ? 256 : 128;
             g.m_tiles = meta->m_tiles; g.n_tiles = gd / bn;
