@@ -10,7 +10,14 @@
 // residue per plane).  In the no-swizzle K-major UMMA layout a core matrix is 8 rows x 16 B with a fixed 16-byte row pitch, so
 // the A operand of position k is the SAME image with the descriptor start address advanced by k * 16 bytes (SBO = 128,
 // LBO = plane size): no im2col matrix is ever built, in HBM or in shared memory.  The only streamed operand is the weight
-// image (rows = filters, k = position * 32 + channel, channels 26..31 zero), one 16 KiB tile = 128 filters x 2 positions.
+// image, 16 KiB tiles of 128 filters x 64 k.
+//
+// K packing (26 channels do not fill four 8-channel planes): a K = 16 MMA step is ANY two 8-channel core-matrix columns of
+// the window image - the descriptor's LBO is simply the byte distance between them.  Planes 0-2 hold channels 0-23; the
+// fourth plane holds channels 24 and 25 of FOUR consecutive residues per row, so one of its columns serves four kernel
+// positions.  Steps: (plane 0, k)+(plane 1, k) for every position k; (plane 2, k)+(plane 2, k+1) for every other k
+// (LBO = one row = 16 bytes); (plane 3, 4q)+(plane 3, 4q+4).  That is 13 steps per 8 positions instead of 16 with channels
+// padded to 32: 19 % fewer MMAs.  The host writes the weight image in the same k order and a table of {start, LBO} per step.
 //
 // Work: a *group* of four residue tiles (four 128-column TMEM accumulators, 512 columns) x all (conv, 128-filter block)
 // items; every weight tile fetched from L2 feeds 16 MMAs (4 tiles x 4 k-steps): 16 B/clk/SM of L2 traffic at tensor peak.
@@ -29,6 +36,9 @@ struct mdf_cnn_model {
     int Ctot = 0, C = 0, pl_max = 0, n_items = 0;
     double macs_per_residue = 0.0;            // algorithmic: 26 * sum(w_c * F_c)
     __half *W[MDF_MAX_CONV] = {nullptr};      // weight images [F_c rows x kb_c * 64]
+    uint4 *ktab = nullptr;                    // per conv kb_c entries: the four K steps of a k-block as {start / 16 | LBO / 16 << 16}
+    int ktab_off[MDF_MAX_CONV] = {0};
+    double issued_macs_per_row = 0.0;         // 16 * K steps * F summed over the convs (what the kernel issues per padded row)
     float *scale = nullptr, *shift = nullptr;
     __half *out_W[2] = {nullptr, nullptr};    // [2C rows x Ctot k] hi / residual * 2^11
     float *out_b_pad = nullptr;
@@ -64,7 +74,9 @@ struct CnnArgs {
     const float *scale, *shift;      // [Ctot]
     int *pooled;                     // [n, Ctot] fp32 bit patterns (>= 0)
     const __half *W[MDF_MAX_CONV];
-    short kb[MDF_MAX_CONV], pl[MDF_MAX_CONV];
+    const uint4 *ktab;
+    short kb[MDF_MAX_CONV];
+    int ktab_off[MDF_MAX_CONV];
     int choff[MDF_MAX_CONV];
     unsigned char item_conv[CNN_MAX_ITEMS], item_fb[CNN_MAX_ITEMS];
 };
@@ -121,6 +133,9 @@ cnn_conv_kernel(const __grid_constant__ CnnArgs a)
         constexpr uint32_t idesc = umma_idesc_f16(128, 128);
         int st = 0; uint32_t ph = 0, item_ph = 0;
         int it = 0;
+        // K-step table entries are fetched one k-block ahead (the (item, k-block) sequence is the same for every group): a
+        // load issued right before its use stalls the issue loop for an L2 round trip per k-block
+        uint4 nxt = __ldg(a.ktab + a.ktab_off[a.item_conv[0]]);
         for (int g = blockIdx.x; g < a.n_groups; g += gridDim.x, ++it) {
             const int buf = it & 1;
             mbar_wait(&bars.img_full[buf], (uint32_t)(it >> 1) & 1u);
@@ -129,8 +144,12 @@ cnn_conv_kernel(const __grid_constant__ CnnArgs a)
             const uint32_t ia0 = smem_u32(img + (size_t)buf * CNN_TILES * CNN_IMG);
             for (int item = 0; item < a.n_items; ++item) {
                 const int c = a.item_conv[item], KB = a.kb[c];
-                const int shift0 = a.pl_max - a.pl[c];         // window row of (local row 0, position 0)
+                const uint4 *kt = a.ktab + a.ktab_off[c];
+                const uint4 *kt_next_item = a.ktab + a.ktab_off[a.item_conv[item + 1 < a.n_items ? item + 1 : 0]];
                 for (int kb = 0; kb < KB; ++kb) {
+                    const uint4 e4 = nxt;                       // the four K steps of this k-block: {start, LBO} in 16-byte units
+                    nxt = __ldg(kb + 1 < KB ? kt + kb + 1 : kt_next_item);
+                    const uint32_t ent[4] = {e4.x, e4.y, e4.z, e4.w};
                     mbar_wait(&bars.full[st], ph);
                     tcgen05_fence_after();
                     const uint32_t sb = smem_u32(stg + (size_t)st * TILE_BYTES);
@@ -138,9 +157,8 @@ cnn_conv_kernel(const __grid_constant__ CnnArgs a)
                         if (kb == 0) { mbar_wait(&bars.tmem_empty[t], item_ph ^ 1); tcgen05_fence_after(); }
                         const uint32_t ia = ia0 + (uint32_t)(t * CNN_IMG);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {           // k-step j: position 2 kb + j / 2, channels 16 (j % 2) ..+15
-                            const int pos = 2 * kb + (j >> 1);
-                            const uint64_t ad = umma_smem_desc(ia + (uint32_t)((j & 1) * 2 * CNN_PLANE + (pos + shift0) * 16), CNN_PLANE, 128);
+                        for (int j = 0; j < 4; ++j) {           // K step j: two 8-channel columns of the window image
+                            const uint64_t ad = umma_smem_desc(ia + ((ent[j] & 0xFFFFu) << 4), (ent[j] >> 16) << 4, 128);
                             const uint64_t bd = umma_smem_desc(sb + (uint32_t)(j * 2 * TILE_LBO), TILE_LBO, TILE_SBO);
                             umma_f16_elect(tmem_base + (uint32_t)(t * 128), ad, bd, idesc, (kb | j) != 0);
                         }
@@ -169,17 +187,26 @@ cnn_conv_kernel(const __grid_constant__ CnnArgs a)
                 const uint32_t base = smem_u32(img + (size_t)(buf * CNN_TILES + t) * CNN_IMG);
                 for (int w = bt; w < CNN_WIN; w += CNN_BW * 32) {
                     const int r = ti.y - a.pl_max + w;
-                    const int aa = (r >= 0 && r < ti.z) ? (int)__ldg(a.idx + (size_t)ti.w + r) : 255;
+                    int an[4];                                             // channels of residues r .. r + 3 (255 outside the protein)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) an[q] = (r + q >= 0 && r + q < ti.z) ? (int)__ldg(a.idx + (size_t)ti.w + r + q) : 255;
+                    const int aa = an[0];
                     const uint32_t val = 0x3C00u << ((aa & 1) * 16);      // fp16 1.0 in the low or high half
                     const int ws = (aa & 7) >> 1;
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
+                    for (int c = 0; c < 3; ++c) {                          // planes 0-2: channels 8c .. 8c+7 of residue r
                         const bool hit = (aa >> 3) == c;
                         uint4 v;
                         v.x = (hit && ws == 0) ? val : 0u; v.y = (hit && ws == 1) ? val : 0u;
                         v.z = (hit && ws == 2) ? val : 0u; v.w = (hit && ws == 3) ? val : 0u;
                         st_shared_v4(base + (uint32_t)(c * CNN_PLANE + w * 16), v);
                     }
+                    uint4 lv;                                              // plane 3: channels 24, 25 of residues r .. r + 3
+                    lv.x = (an[0] == 24 ? 0x3C00u : 0u) | (an[0] == 25 ? 0x3C000000u : 0u);
+                    lv.y = (an[1] == 24 ? 0x3C00u : 0u) | (an[1] == 25 ? 0x3C000000u : 0u);
+                    lv.z = (an[2] == 24 ? 0x3C00u : 0u) | (an[2] == 25 ? 0x3C000000u : 0u);
+                    lv.w = (an[3] == 24 ? 0x3C00u : 0u) | (an[3] == 25 ? 0x3C000000u : 0u);
+                    st_shared_v4(base + (uint32_t)(3 * CNN_PLANE + w * 16), lv);
                 }
             }
             fence_proxy_async_smem();
@@ -336,28 +363,59 @@ extern "C" int mdf_cnn_model_create(mdf_ctx *ctx, const mdf_cnn_desc *d, mdf_cnn
             set_error("cnn model: conv layer %d (width %d, %d filters, pad %d) unsupported: width <= 128, filters a multiple of 128", c, w, F, pl);
             return fail(MDF_EUNSUPPORTED);
         }
-        m->width[c] = w; m->filters[c] = F; m->pl[c] = pl; m->kb[c] = (w + 1) / 2; m->choff[c] = m->Ctot;
+        const int steps = w + (w + 1) / 2 + ((w + 3) / 4 + 1) / 2;      // K = 16 steps (see the header): 13 per 8 positions
+        m->width[c] = w; m->filters[c] = F; m->pl[c] = pl; m->kb[c] = (steps + 3) / 4; m->choff[c] = m->Ctot;
         m->Ctot += F;
         m->n_items += F / 128;
         m->pl_max = std::max(m->pl_max, pl);
-        pr_max = std::max(pr_max, 2 * m->kb[c] - 1 - pl);
+        pr_max = std::max(pr_max, (w + 3) / 4 * 4 - 1 - pl);               // the shared plane reaches up to 3 positions past the kernel
         m->macs_per_residue += 26.0 * w * F;
+        m->issued_macs_per_row += 16.0 * 4 * m->kb[c] * F;
     }
-    if (m->n_items > CNN_MAX_ITEMS || 128 + m->pl_max + pr_max > CNN_WIN) {
+    if (m->n_items > CNN_MAX_ITEMS || 128 + m->pl_max + pr_max + 1 > CNN_WIN) {      // + 1: the partner row of a zero column
         set_error("cnn model: %d filter blocks / window of %d residues exceed the kernel's limits", m->n_items, 128 + m->pl_max + pr_max);
         return fail(MDF_EUNSUPPORTED);
     }
     int r;
+    std::vector<uint32_t> ktab;
     for (int c = 0; c < d->n_conv; ++c) {
-        // weight image: rows = filters, k = position * 32 + channel (ONNX Conv weight [F, 26, w]); pad channels / positions stay 0
-        const int w = m->width[c], F = m->filters[c], KB = m->kb[c];
+        // K steps of this conv: pairs of window-image columns {plane, position}; plane 3 = channels 24/25 of positions pos..pos+3;
+        // plane -1 = a zero column (weights 0, the A side reads the row after its partner: finite values)
+        const int w = m->width[c], F = m->filters[c], KB = m->kb[c], pl = m->pl[c];
+        struct Col { int plane, pos; };
+        std::vector<std::pair<Col, Col>> steps;
+        const Col zero{-1, 0};
+        for (int k = 0; k < w; ++k) steps.push_back({Col{0, k}, Col{1, k}});
+        for (int k = 0; k < w; k += 2) steps.push_back({Col{2, k}, k + 1 < w ? Col{2, k + 1} : zero});
+        for (int q = 0; q < (w + 3) / 4; q += 2) steps.push_back({Col{3, 4 * q}, q + 1 < (w + 3) / 4 ? Col{3, 4 * (q + 1)} : zero});
+        while ((int)steps.size() < 4 * KB) steps.push_back({zero, zero});
+        auto off16 = [&](const Col &col) { return col.plane * (CNN_PLANE / 16) + (col.pos - pl + m->pl_max); };
+        m->ktab_off[c] = (int)(ktab.size() / 4);
         std::vector<__half> imgv((size_t)(F / 128) * KB * (TILE_BYTES / 2), __float2half(0.0f));
-        for (int f = 0; f < F; ++f)
-            for (int ch = 0; ch < 26; ++ch)
-                for (int k = 0; k < w; ++k)
-                    imgv[image_offset_bytes(f, k * 32 + ch, KB) / 2] = __float2half_rn(d->conv_W[c][((size_t)f * 26 + ch) * w + k]);
+        for (size_t sidx = 0; sidx < steps.size(); ++sidx) {
+            const Col ca = steps[sidx].first, cb = steps[sidx].second;
+            const int a_off = ca.plane >= 0 ? off16(ca) : 0;
+            const int lbo = cb.plane >= 0 ? off16(cb) - a_off : 1;
+            if (a_off < 0 || a_off > 0xFFFF || lbo <= 0 || lbo > 0x3FFF) { set_error("cnn model: internal K-step table overflow"); return fail(MDF_EUNSUPPORTED); }
+            ktab.push_back((uint32_t)a_off | ((uint32_t)lbo << 16));
+            for (int half = 0; half < 2; ++half) {
+                const Col col = half ? cb : ca;
+                if (col.plane < 0) continue;
+                for (int e = 0; e < 8; ++e) {
+                    const int ch = col.plane < 3 ? col.plane * 8 + e : 24 + (e & 1);
+                    const int pos = col.plane < 3 ? col.pos : col.pos + (e >> 1);
+                    if (pos >= w) continue;
+                    for (int f = 0; f < F; ++f)
+                        imgv[image_offset_bytes(f, (int)sidx * 16 + half * 8 + e, KB) / 2] =
+                            __float2half_rn(d->conv_W[c][((size_t)f * 26 + ch) * w + pos]);
+                }
+            }
+        }
         if ((r = cnn_upload_half(m, &m->W[c], imgv)) != MDF_OK) return fail(r);
     }
+    MDF_CUDA(cudaMalloc((void **)&m->ktab, ktab.size() * sizeof(uint32_t)));
+    m->owned.push_back(m->ktab);
+    MDF_CUDA(cudaMemcpy(m->ktab, ktab.data(), ktab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     if ((r = cnn_upload_f32(m, &m->scale, d->scale, m->Ctot)) != MDF_OK) return fail(r);
     if ((r = cnn_upload_f32(m, &m->shift, d->shift, m->Ctot)) != MDF_OK) return fail(r);
     std::vector<__half> hi, lo;
@@ -431,11 +489,11 @@ extern "C" int mdf_cnn_run(mdf_cnn_model *m)
         CnnArgs a;
         memset(&a, 0, sizeof a);
         a.n_tiles = m->n_tiles; a.n_groups = cdiv(m->n_tiles, CNN_TILES); a.n_items = m->n_items; a.pl_max = m->pl_max; a.Ctot = m->Ctot;
-        a.tile_info = m->d_tile_info; a.idx = m->d_idx; a.scale = m->scale; a.shift = m->shift;
+        a.tile_info = m->d_tile_info; a.idx = m->d_idx; a.scale = m->scale; a.shift = m->shift; a.ktab = m->ktab;
         a.pooled = reinterpret_cast<int *>(m->d_pooled);
         int item = 0;
         for (int c = 0; c < m->n_conv; ++c) {
-            a.W[c] = m->W[c]; a.kb[c] = (short)m->kb[c]; a.pl[c] = (short)m->pl[c]; a.choff[c] = m->choff[c];
+            a.W[c] = m->W[c]; a.kb[c] = (short)m->kb[c]; a.ktab_off[c] = m->ktab_off[c]; a.choff[c] = m->choff[c];
             for (int fb = 0; fb < m->filters[c] / 128; ++fb, ++item) { a.item_conv[item] = (unsigned char)c; a.item_fb[item] = (unsigned char)fb; }
         }
         MDF_CUDA(cudaFuncSetAttribute(cnn_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CNN_SMEM));

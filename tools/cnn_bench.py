@@ -3,8 +3,8 @@ the metagenomic length distribution of BASELINE configs[4] (L ~ LogNormal(250, 0
 models' shape (16 x 512 filters of widths 8..128, MF head C = 489, random-init weights in the reference's ONNX layout).
 
 Reports: resident throughput (CUDA-event stage times from mdf_ctx_profile), the convolution kernel's tensor-pipe fraction
-(algorithmic FLOPs = 2 * 26 * sum(w * F) per residue; the kernel issues 32 / 26 of that because channels are padded to 32,
-plus the padded rows of partly filled 128-residue tiles), end-to-end throughput through forward_sequences (host strings in,
+(algorithmic FLOPs = 2 * 26 * sum(w * F) per residue; the kernel issues 13 K-steps of 16 per 8 positions = 26 columns
+per position, plus the padded rows of partly filled 128-residue tiles), end-to-end throughput through forward_sequences (host strings in,
 host scores out), a parity check against the oracle on a bounded sample, and the oracle's own CPU rate.
 
   python tools/cnn_bench.py [--proteins 16384] [--reps 5] [--cpu-sample 8]
@@ -44,7 +44,9 @@ def main():
     ctx = _lib.default_context()
     T = int(lengths.sum())
     flops = 2.0 * 26 * sum(w * f for w, f in zip(cfg.filter_lens, cfg.num_filters)) * T
-    issued = 2.0 * 32 * sum((w + 1) // 2 * 2 * f for w, f in zip(cfg.filter_lens, cfg.num_filters)) * float(((lengths + 127) // 128 * 128).sum())
+    def k_blocks(w):      # K = 16 steps of a conv (csrc/cnn_tc.cu: 13 per 8 positions), four per 16 KiB weight tile
+        return -(-(w + (w + 1) // 2 + ((w + 3) // 4 + 1) // 2) // 4)
+    issued = 2.0 * sum(64 * k_blocks(w) * f for w, f in zip(cfg.filter_lens, cfg.num_filters)) * float(((lengths + 127) // 128 * 128).sum())
     pred.upload_sequences(seqs)
     for _ in range(2):
         pred.run_sequences()
