@@ -189,6 +189,16 @@ gemm_tc_kernel(GemmArgs g, int a_terms, int b_terms, int stages)
                                      TILE_BYTES, &bars.full[st]);
                     }
                     const size_t b_phase_off = g.b_phases > 0 ? (size_t)(mt % g.b_phases) * g.b_phase_stride : 0;
+                    if (g.wide_b && NSUB == 2) {
+                        // [k-group][256 rows]: k-group kg of sub-tile j (2 KiB = 16 row groups) lands at kg * 4096 + j * 2048
+                        for (int j = 0; j < NSUB; ++j) {
+                            const uint8_t *src = reinterpret_cast<const uint8_t *>(g.B[0]) + b_phase_off +
+                                                 ((size_t)(nt * NSUB + j) * g.KB_B + b_kb0 + kb) * TILE_BYTES;
+#pragma unroll
+                            for (int kg = 0; kg < 8; ++kg)
+                                bulk_g2s(dst + a_bytes + kg * 4096 + j * 2048, src + kg * 2048, 2048, &bars.full[st]);
+                        }
+                    } else
                     for (int tb = 0; tb < b_terms; ++tb)
                         for (int j = 0; j < NSUB; ++j)
                             bulk_g2s(dst + a_bytes + (tb * NSUB + j) * TILE_BYTES,
@@ -225,7 +235,15 @@ gemm_tc_kernel(GemmArgs g, int a_terms, int b_terms, int stages)
                     tcgen05_fence_after();
                     const uint32_t sa = smem_u32(smem + (size_t)st * stage_bytes);
                     const uint32_t sb = sa + a_bytes;
-                    if (a_per_sub) {
+                    if (g.wide_b && NSUB == 2) {
+                        constexpr uint32_t idesc_w = umma_idesc_f16(128, 256);
+#pragma unroll
+                        for (int ks = 0; ks < TILE_K / 16; ++ks) {
+                            const uint64_t ad = umma_smem_desc(sa + ks * 2 * TILE_LBO, TILE_LBO, TILE_SBO);
+                            const uint64_t bd = umma_smem_desc(sb + ks * 2 * 4096, 4096, TILE_SBO);
+                            umma_f16_elect(d0, ad, bd, idesc_w, (kb | ks) != 0);
+                        }
+                    } else if (a_per_sub) {
 #pragma unroll
                         for (int ks = 0; ks < TILE_K / 16; ++ks)
 #pragma unroll

@@ -48,6 +48,9 @@ struct GemmArgs {
     // block-sparse adjacency (tc_engine.cu adj_tile_scan_kernel): the k-blocks of an m-tile whose 128 x 64 A tile holds at
     // least one contact, as a compact list adj_kb_idx[tile_info[mt].x + j], j < adj_kb_cnt[mt].  All-zero tiles contribute
     // nothing to A_hat . Y, so the producer, the expanders and the MMA issuer walk this list instead of 0..nkb-1.
+    // BN = 256 only: land the two 128-row B sub-tiles of a stage interleaved by k-group ([k-group][256 rows], 16 copies of 2 KiB)
+    // so that ONE M128 x N256 MMA per k-step reads them (LBO = 4096) instead of two N = 128 MMAs that each re-read the A tile
+    int wide_b = 0;
     const unsigned short *adj_kb_idx = nullptr;
     const int *adj_kb_cnt = nullptr;
     const uint32_t *adj_packed = nullptr;

@@ -40,6 +40,7 @@ struct TcModel {
                                                            // 4.7-5.0 ms vs 4.5 ms per layer: halving the shared-memory operand traffic does
                                                            // not help, the kernel is paced by draining its short-K accumulators
     int pool_fused = 1;                                    // sum-pool readout inside the adjacency GEMM epilogue (fp32, no X re-read)
+    int adj_wide = 0;                                      // MDF_ADJ_WIDE=1 (measured, not default: stage 10.7 -> 11.1 ms): one N = 256 MMA per k-step, B sub-tiles interleaved by k-group
     int adj_sparse = 1;                                    // adjacency GEMM skips all-zero 128 x 64 A tiles (MDF_ADJ_SPARSE=0: dense walk)
     int adj_expand = 1;                                    // adjacency GEMM expands its A tiles from the bit-packed map on the fly
     int gemm_pair = 1;                                     // CTA-pair (cta_group::2) kernels for the embedding and X.W GEMMs
@@ -141,6 +142,7 @@ int tc_model_init(mdf_model *m, const mdf_model_desc *d)
     if (const char *e = getenv("MDF_POOL_FUSED")) t->pool_fused = atoi(e);
     if (const char *e = getenv("MDF_ADJ_PAIR")) t->adj_pair = atoi(e);
     if (const char *e = getenv("MDF_ADJ_SPARSE")) t->adj_sparse = atoi(e);
+    if (const char *e = getenv("MDF_ADJ_WIDE")) t->adj_wide = atoi(e);
     if (const char *e = getenv("MDF_SINGLE_TERM")) t->single_term_mask = atoi(e);
     if (const char *e = getenv("MDF_HEAD_TC")) t->head_tc = atoi(e);
     if (const char *e = getenv("MDF_GEMM_PHASES")) t->gemm_phases = std::min(64, std::max(0, atoi(e)));   // 0: hi+lo split on every tile
@@ -884,6 +886,7 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto)
             if (tm->adj_expand) {                         // A tiles built in shared memory from the bit-packed map
                 g.adj_packed = b->d_packed; g.adj_packed_off = b->d_packed_off; g.adj_seq_off = b->d_seq_off; g.adj_seg_off = meta->seg_off;
                 g.adj_kb_idx = kb_idx; g.adj_kb_cnt = kb_cnt;
+                g.wide_b = tm->adj_wide;
             }
             const int bn = gd % 256 == 0 ? 256 : 128;
             g.m_tiles = meta->m_tiles; g.n_tiles = gd / bn;
