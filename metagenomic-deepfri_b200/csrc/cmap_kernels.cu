@@ -12,6 +12,8 @@
 // is none) and the distance test is evaluated directly on query index pairs.  Because the
 // target->query map is injective on aligned residues, out[qi][qj] = 1 for a target contact
 // (ti,tj) <=> dist(coords[q2t[qi]], coords[q2t[qj]]) < thr2, which is what the gather computes.
+#include <stdlib.h>
+
 #include "mdf_common.cuh"
 #include "cmap_kernels.cuh"
 
@@ -171,6 +173,76 @@ cmap_pair_kernel(const int2 *__restrict__ work, const float4 *__restrict__ qc,
         }
         if (lane < 8 && i0 + lane < L)
             *reinterpret_cast<uint4 *>(out + (size_t)(i0 + lane) * rw + tile * 4) = make_uint4(keep[0], keep[1], keep[2], keep[3]);
+    }
+}
+
+// Symmetric form (the default).  The query-frame map is symmetric bit for bit - dist(a, b) and dist(b, a) square the same
+// differences with opposite signs, the reference mirrors D[i][j] = D[j][i] (contact_map_utils.pyx:30-35) and argwhere lists
+// both orientations - so a 32-row block only evaluates the 128-column tiles at or right of its own tile and writes every
+// strictly-right tile twice: as rows (words 4t..4t+3 of its 32 rows) and transposed (word rb of the tile's 128 rows).
+// Each lane accumulates the predicate of (row r, its column) into bit r of a register: after 32 rows that register IS the
+// transposed word (one predicated OR per pair, no ballot); the row words come from a 32 x 32 bit transpose across the
+// warp (5 shuffle stages per word).  Every word of the map is written exactly once: words of tiles >= tile(row) by the
+// row's own block, words of tiles < tile(row) by the transposed stores of block (word index).
+__device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, int lane)
+{
+#pragma unroll
+    for (int j = 16; j >= 1; j >>= 1) {
+        const uint32_t m = j == 16 ? 0x0000FFFFu : j == 8 ? 0x00FF00FFu : j == 4 ? 0x0F0F0F0Fu : j == 2 ? 0x33333333u : 0x55555555u;
+        const uint32_t o = __shfl_xor_sync(0xffffffffu, x, j);
+        x = (lane & j) ? (((o >> j) & m) | (x & ~m)) : ((x & m) | ((o & m) << j));
+    }
+    return x;
+}
+
+__global__ void __launch_bounds__(PAIR_WARPS * 32, 6)
+cmap_pair_sym_kernel(const int2 *__restrict__ work, const float4 *__restrict__ qc,
+                     const int64_t *__restrict__ seq_off, float thr2,
+                     uint32_t *__restrict__ packed, const int64_t *__restrict__ packed_off)
+{
+    __shared__ float4 rows[32];
+    const int p = work[blockIdx.x].x, rb = work[blockIdx.x].y;
+    const int64_t s0 = seq_off[p];
+    const int L = (int)(seq_off[p + 1] - s0);
+    const int rw = packed_row_words(L);
+    const float4 *__restrict__ q = qc + s0;
+    const float qnan = __int_as_float(0x7fc00000);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < 32) {
+        const int i = rb * 32 + threadIdx.x;
+        rows[threadIdx.x] = i < L ? q[i] : make_float4(qnan, qnan, qnan, 0.f);
+    }
+    __syncthreads();
+    uint32_t *__restrict__ out = packed + packed_off[p];
+    const int ntile = (L + 127) >> 7, dt = rb >> 2;              // dt = the tile that holds this block's own columns
+    for (int tile = dt + warp; tile < ntile; tile += PAIR_WARPS) {
+        const int jlo = tile << 7;
+        float cx[4], cy[4], cz[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int j = jlo + 32 * k + lane;
+            float4 v = j < L ? q[j] : make_float4(qnan, qnan, qnan, 0.f);
+            cx[k] = v.x; cy[k] = v.y; cz[k] = v.z;
+        }
+        uint32_t tw[4] = {0u, 0u, 0u, 0u};                       // bit r = contact(row rb*32 + r, column jlo + 32k + lane)
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+            const float4 a = rows[r];                            // rows past L hold NaN -> no contact
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (sqdist3(a.x, a.y, a.z, cx[k], cy[k], cz[k]) < thr2) tw[k] |= 1u << r;
+        }
+        if (tile > dt) {                                         // transposed copy: word rb of rows jlo .. jlo + 127
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int c = jlo + 32 * k + lane;
+                if (c < L) out[(size_t)c * rw + rb] = tw[k];
+            }
+        }
+        uint4 rowv;                                              // lane r: the four words of row rb*32 + r in this tile
+        rowv.x = warp_transpose32(tw[0], lane); rowv.y = warp_transpose32(tw[1], lane);
+        rowv.z = warp_transpose32(tw[2], lane); rowv.w = warp_transpose32(tw[3], lane);
+        if (rb * 32 + lane < L) *reinterpret_cast<uint4 *>(out + (size_t)(rb * 32 + lane) * rw + tile * 4) = rowv;
     }
 }
 
@@ -391,8 +463,12 @@ int launch_cmap_pair(mdf_ctx *ctx, int n, int nwork, const int2 *work, const flo
                      float thr2, int gen, int diag_val, uint32_t *packed, const int64_t *packed_off)
 {
     if (nwork <= 0) return MDF_OK;
-    cmap_pair_kernel<<<nwork, PAIR_WARPS * 32, 0, ctx->stream>>>(work, qc, seq_off, thr2, gen < 0 ? 0 : gen,
-                                                                 diag_val, packed, packed_off);
+    static const bool full_square = !(getenv("MDF_CMAP_SYM") && atoi(getenv("MDF_CMAP_SYM")) == 1);   // symmetric kernel: opt-in until verified on the GPU
+    if (full_square)
+        cmap_pair_kernel<<<nwork, PAIR_WARPS * 32, 0, ctx->stream>>>(work, qc, seq_off, thr2, gen < 0 ? 0 : gen,
+                                                                     diag_val, packed, packed_off);
+    else
+        cmap_pair_sym_kernel<<<nwork, PAIR_WARPS * 32, 0, ctx->stream>>>(work, qc, seq_off, thr2, packed, packed_off);
     MDF_LAUNCH_CHECK(ctx);
     if (n > 0 && (diag_val || gen > 0)) {
         cmap_band_kernel<<<std::min(n, 16 * ctx->sm_count), 128, 0, ctx->stream>>>(n, qc, seq_off, gen < 0 ? 0 : gen, diag_val, packed, packed_off);

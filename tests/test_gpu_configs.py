@@ -148,3 +148,33 @@ def test_pipeline_adapter_shares_maps_and_lm_across_heads(tmp_path):
     assert len(rows) == 6 and np.abs(np.array([r[2:] for r in rows], np.float64) - scores["cc"][:6]).max() < 2e-5
     for p in preds.values():
         p.close()
+
+
+def test_block_sparse_adjacency_equals_dense_walk(tmp_path, monkeypatch):
+    """The adjacency GEMM skips all-zero 128 x 64 tiles of A_hat (tc_engine.cu adj_tile_scan_kernel).  Skipped tiles
+    contribute exact zeros, so the per-residue GraphConv output must equal the dense walk's bit for bit; the pooled sums
+    (fp32 atomics, order not fixed) and the scores agree to rounding.  Long proteins: most of their off-diagonal tiles are
+    empty, and lengths around the 64 / 128 / 256 boundaries exercise the list edges."""
+    path = str(tmp_path / "mf.onnx")
+    synth.write_gcn_model(path, synth.GCNConfig())
+    wl_a = synth.make_workload(6, 900, 1400, seed=31, threshold=10.0)
+    wl_b = synth.make_workload(10, 60, 260, seed=32, threshold=6.0)
+    seqs = wl_a.query_seqs + wl_b.query_seqs
+    gq, gt, co_ = wl_a.gapped_query + wl_b.gapped_query, wl_a.gapped_target + wl_b.gapped_target, wl_a.coords + wl_b.coords
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("MDF_ADJ_SPARSE", mode)         # read when the model is created
+        pred = predict.Predictor(path)
+        pred.set_engine("tc")
+        pred._ctx.set_debug_taps(True)
+        try:
+            batch = pred.upload(seqs, gq, gt, co_)
+            pred.run(batch, 10.0, 2)
+            out[mode] = (pred.fetch(batch, "gc_last"), pred.fetch(batch, "pooled"), pred.fetch_scores(batch))
+            batch.close()
+        finally:
+            pred._ctx.set_debug_taps(False)
+            pred.close()
+    assert np.array_equal(out["1"][0], out["0"][0])
+    assert np.allclose(out["1"][1], out["0"][1], rtol=1e-5, atol=1e-4)
+    assert np.abs(out["1"][2] - out["0"][2]).max() < 1e-5
