@@ -463,7 +463,7 @@ int launch_cmap_pair(mdf_ctx *ctx, int n, int nwork, const int2 *work, const flo
                      float thr2, int gen, int diag_val, uint32_t *packed, const int64_t *packed_off)
 {
     if (nwork <= 0) return MDF_OK;
-    static const bool full_square = !(getenv("MDF_CMAP_SYM") && atoi(getenv("MDF_CMAP_SYM")) == 1);   // symmetric kernel: opt-in until verified on the GPU
+    static const bool full_square = getenv("MDF_CMAP_SYM") && atoi(getenv("MDF_CMAP_SYM")) == 0;   // A/B switch: evaluate both triangles
     if (full_square)
         cmap_pair_kernel<<<nwork, PAIR_WARPS * 32, 0, ctx->stream>>>(work, qc, seq_off, thr2, gen < 0 ? 0 : gen,
                                                                      diag_val, packed, packed_off);

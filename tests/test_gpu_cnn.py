@@ -98,3 +98,22 @@ def test_pipeline_loop_drop_in_cnn(cnn, tmp_path):
     rows = list(csv.reader(open(out), delimiter="\t"))
     assert [r[:2] for r in rows] == [r[:2] for r in ref_rows]
     assert np.array_equal(np.array([r[2:] for r in rows], np.float32), np.array([r[2:] for r in ref_rows], np.float32))
+
+
+def test_metagenomic_batch_properties(cnn, cnn_model_dir):
+    """A 2,048-sequence batch of the configs[4] length distribution through the trained models' shape (16 x 512 filters,
+    widths 8..128): a bounded sample against the oracle, and size-independent properties of the whole batch - every score in
+    (0, 1), identical sequences give identical scores wherever they sit in the batch, and a sequence scored alone equals its
+    score inside the batch (the max-pool is order-free, so this is exact)."""
+    pred = cnn["cnn_mf"]
+    rng = np.random.default_rng(77)
+    lengths = np.clip(np.exp(rng.normal(np.log(250.0), 0.6, size=2048)), 50, 1000).astype(np.int64)
+    seqs = synth.random_sequences(rng, lengths)
+    seqs[5] = seqs[1999]                                   # the same protein twice, far apart in the batch
+    got = pred.forward_sequences(seqs)
+    assert got.shape == (2048, 489) and np.isfinite(got).all() and (got > 0).all() and (got < 1).all()
+    assert np.array_equal(got[5], got[1999])
+    assert np.array_equal(pred.forward_sequences([seqs[1234]])[0], got[1234])
+    orc = go.Predictor(cnn_model_dir["cnn_mf"])
+    for i in (0, 777, 2047, int(np.argmax(lengths)), int(np.argmin(lengths))):
+        assert np.abs(orc.forward_pass(seqs[i]) - got[i]).max() <= TOL
