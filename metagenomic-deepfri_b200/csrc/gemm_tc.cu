@@ -115,6 +115,10 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmArgs &g, uint32_t 
             }
             atomicAdd(pool_row + n0 + lane, c[0]);
         }
+        // The adjacency product is bound by HBM bytes (Y^T in, X out), not by the tensor pipe: it never stores pad rows (nothing
+        // reads them as values: rows are independent in X.W and its column scale zeroes their Y^T columns), and stores no image
+        // at all when only the fused sum-pool consumes the layer (out_img == nullptr: the last GraphConv layer)
+        if (EPI == EPI_IMG_ROWSCALE && (g.out_img == nullptr || (rs == 0.0f && g.skip_pad_rows))) return;
         uint8_t *dst = row_ptr + (size_t)(n0 >> 6) * TILE_BYTES + (((n0 & 63) >> 3) * 2048);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {

@@ -58,7 +58,8 @@ struct GemmArgs {
     // epilogue
     float *out_f32 = nullptr;
     int ldc = 0;
-    __half *out_img = nullptr;
+    __half *out_img = nullptr;       // EPI_IMG_ROWSCALE: nullptr = no image (only the fused sum-pool consumes the tile)
+    int skip_pad_rows = 0;           // EPI_IMG_ROWSCALE: rows with rowscale == 0 (padding) are not stored
     int KB_out = 0;
     const float *bias = nullptr;
     const float *rowscale = nullptr;

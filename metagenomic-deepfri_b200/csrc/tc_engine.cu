@@ -41,6 +41,7 @@ struct TcModel {
                                                            // not help, the kernel is paced by draining its short-K accumulators
     int pool_fused = 1;                                    // sum-pool readout inside the adjacency GEMM epilogue (fp32, no X re-read)
     int adj_wide = 0;                                      // MDF_ADJ_WIDE=1 (measured, not default: stage 10.7 -> 11.1 ms): one N = 256 MMA per k-step, B sub-tiles interleaved by k-group
+    int adj_lean = 1;                                      // adjacency GEMM stores no pad rows and no image of the last layer (MDF_ADJ_LEAN=0: store all)
     int adj_sparse = 1;                                    // adjacency GEMM skips all-zero 128 x 64 A tiles (MDF_ADJ_SPARSE=0: dense walk)
     int adj_expand = 1;                                    // adjacency GEMM expands its A tiles from the bit-packed map on the fly
     int gemm_pair = 1;                                     // CTA-pair (cta_group::2) kernels for the embedding and X.W GEMMs
@@ -143,6 +144,7 @@ int tc_model_init(mdf_model *m, const mdf_model_desc *d)
     if (const char *e = getenv("MDF_ADJ_PAIR")) t->adj_pair = atoi(e);
     if (const char *e = getenv("MDF_ADJ_SPARSE")) t->adj_sparse = atoi(e);
     if (const char *e = getenv("MDF_ADJ_WIDE")) t->adj_wide = atoi(e);
+    if (const char *e = getenv("MDF_ADJ_LEAN")) t->adj_lean = atoi(e);
     if (const char *e = getenv("MDF_SINGLE_TERM")) t->single_term_mask = atoi(e);
     if (const char *e = getenv("MDF_HEAD_TC")) t->head_tc = atoi(e);
     if (const char *e = getenv("MDF_GEMM_PHASES")) t->gemm_phases = std::min(64, std::max(0, atoi(e)));   // 0: hi+lo split on every tile
@@ -891,6 +893,9 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto)
             const int bn = gd % 256 == 0 ? 256 : 128;
             g.m_tiles = meta->m_tiles; g.n_tiles = gd / bn;
             g.out_img = Xout; g.KB_out = gd / TILE_K;
+            // the last layer's activations are only summed (fused sum-pool): no image unless a tap or the separate pool kernel reads it
+            if (l == m->n_gc - 1 && tm->pool_fused && !ctx->debug_taps && tm->adj_lean) g.out_img = nullptr;
+            g.skip_pad_rows = tm->adj_lean;
             g.rowscale = deg_pad; g.bias = m->gc_b[l]; g.act = m->act; g.alpha = m->alpha;
             if (tm->pool_fused) { g.pool = b->d_pooled; g.pool_ld = m->G; g.pool_off = goff; }   // readout from the fp32 accumulators
             static const bool want_trace = getenv("MDF_GEMM_TRACE") != nullptr;
