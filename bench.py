@@ -253,13 +253,22 @@ def run_b200(args, rank, world, local_rank):
     for _ in range(args.warmup):
         pred.forward_inputs(inputs, THRESHOLD, GEN, out)
     barrier()
-    def gather_scores(host_scores):                             # the job's one collective: final result gather
-        sd = torch.from_numpy(host_scores).cuda()
+    # the job's one collective: the final result gather.  Source = the pinned score buffer of the last step, destination = a
+    # pinned [world, n, C] matrix on rank 0 allocated before the timed region (pageable staging of 8 x 32 MB cost more than a step)
+    gathered = torch.empty((world, n, C), dtype=torch.float32, pin_memory=True) if (world > 1 and rank == 0) else None
+
+    def gather_scores(host_scores):
+        sd = torch.from_numpy(host_scores).cuda(non_blocking=True)
         gl = [torch.empty_like(sd) for _ in range(world)] if rank == 0 else None
         dist.gather(sd, gl, dst=0)
-        return torch.stack(gl).cpu().numpy() if rank == 0 else None
+        if rank != 0:
+            return None
+        for r in range(world):
+            gathered[r].copy_(gl[r], non_blocking=True)
+        torch.cuda.synchronize()
+        return gathered.numpy()
     if world > 1:
-        gather_scores(out.copy())                               # warm-up: NCCL builds its gather channels lazily
+        gather_scores(out)                                      # warm-up: NCCL builds its gather channels lazily
     barrier()
     # Two lanes per GPU: a second context (own stream + workspace) and Predictor in a second host thread, so that one
     # batch's host-side packing, H2D and D2H overlap the other batch's kernels.  Every step still does the full
@@ -290,7 +299,7 @@ def run_b200(args, rank, world, local_rank):
     lane_worker(lanes[0], split[0])
     for th in threads:
         th.join()
-    local_scores = out.copy()
+    local_scores = out                                          # nothing writes the pinned buffer after the last step
     for _, _, o in lanes[1:]:
         assert np.abs(o - local_scores).max() < 1e-5, "the two end-to-end lanes disagree"
     if world > 1:

@@ -1,4 +1,5 @@
 // C-ABI entry points of libmdf_b200 (include/mdf_b200.h).
+#include <chrono>
 #include <stdarg.h>
 #include <algorithm>
 #include <numeric>
@@ -608,10 +609,21 @@ extern "C" int mdf_path_forward(mdf_model *m, int n, const char *seq, const int6
     MDF_CUDA(cudaSetDevice(ctx->device));
     ArenaScope scope(ctx);
     mdf_batch b;
+    static const bool timing = getenv("MDF_TIMING") != nullptr;       // host-side breakdown of one call on stderr
+    const auto t0 = std::chrono::steady_clock::now();
     MDF_TRY(batch_build(ctx, &b, false, n, seq, seq_off, coords, coord_off, q_aln, t_aln, aln_off, nullptr, m->G, m->C,
                         engine_workspace(m, n, seq_off)));
+    const auto t1 = std::chrono::steady_clock::now();
     MDF_TRY(run_path(m, &b, thr2, gen, 4, true));
-    return fetch_scores(m, &b, scores);
+    const auto t2 = std::chrono::steady_clock::now();
+    const int rc = fetch_scores(m, &b, scores);
+    if (timing) {
+        const auto t3 = std::chrono::steady_clock::now();
+        auto ms = [](auto a, auto b2) { return std::chrono::duration<double, std::milli>(b2 - a).count(); };
+        fprintf(stderr, "[mdf_path_forward] n=%d: batch build + H2D %.2f ms, enqueue (host) %.2f ms, wait + D2H %.2f ms\n", n, ms(t0, t1),
+                ms(t1, t2), ms(t2, t3));
+    }
+    return rc;
 }
 
 extern "C" int mdf_gcn_forward_packed(mdf_model *m, int n, const char *seq, const int64_t *seq_off,
