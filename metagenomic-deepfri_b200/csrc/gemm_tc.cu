@@ -86,6 +86,17 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmArgs &g, uint32_t 
                 }
             }
         } else if (EPI == EPI_IMG_EMBED) {
+            if (g.embed_staged) {
+                // pair kernel: `grow` points into the shared-memory slice of (W_aa + b) for this tile's columns (see there)
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float4 a = *reinterpret_cast<const float4 *>(grow + n0 + 4 * q);
+                    v[4 * q + 0] = fmaxf(v[4 * q + 0] + a.x, 0.0f);
+                    v[4 * q + 1] = fmaxf(v[4 * q + 1] + a.y, 0.0f);
+                    v[4 * q + 2] = fmaxf(v[4 * q + 2] + a.z, 0.0f);
+                    v[4 * q + 3] = fmaxf(v[4 * q + 3] + a.w, 0.0f);
+                }
+            } else
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const float4 b = __ldg(reinterpret_cast<const float4 *>(g.bias + n0 + 4 * q));
@@ -427,6 +438,7 @@ struct PairGemmArgs {
 #ifndef MDF_PAIR_EPI_WARPS
 #define MDF_PAIR_EPI_WARPS 8
 #endif
+constexpr int EMB_ROWS = 26, EMB_LD = 256 + 4;            // staged embedding-table slice: 26 residue types x 256 columns, rows padded by 16 B
 constexpr int PAIR_EW = MDF_PAIR_EPI_WARPS;               // epilogue warps per CTA (8 or 16)
 constexpr int PAIR_THREADS = (PAIR_EW + 2) * 32;
 
@@ -522,14 +534,36 @@ gemm_pair_kernel(const __grid_constant__ PairGemmArgs pa)
         for (int grp = pair; grp < outer; grp += n_pairs)
         for (int in = 0; in < inner; ++in) {
             const int mt = g.m_fastest ? in : grp, nt = g.m_fastest ? grp : in;
-            mbar_wait(&bars.tmem_full[acc], acc_ph);
-            tcgen05_fence_after();
             const int64_t m = ((int64_t)mt * 2 + rank) * 128 + lb + lane;
-            const uint32_t trow = tmem_base + ((uint32_t)lb << 16) + (uint32_t)(acc * BN);
             float rs = 1.0f;
             const float *grow = nullptr;
+            if (EPI == EPI_IMG_EMBED) {
+                if (g.embed_staged) {
+                    // The one-hot embedding is a gather of W_aa[idx[m]] per ROW, i.e. per lane: from global memory every LDG.128
+                    // touches 32 different lines and the LSU, not the tensor pipe, set the pace (tensor 74 % active).  The slice
+                    // of the 26-row table for this tile's 256 columns, bias folded in, is staged in shared memory instead (rows
+                    // padded by 16 B so that different residues hit different banks) while the tile's MMAs are still running.
+                    float *tab = reinterpret_cast<float *>(smem + (size_t)stages * stage_bytes);
+                    asm volatile("bar.sync 2, %0;" ::"n"(PAIR_EW * 32) : "memory");       // every warp is done with the previous slice
+                    for (int e = threadIdx.x; e < EMB_ROWS * (BN / 4); e += PAIR_EW * 32) {
+                        const int row = e / (BN / 4), c4 = (e % (BN / 4)) * 4;
+                        float4 w = __ldg(reinterpret_cast<const float4 *>(g.gtab + (size_t)row * g.ldg + nt * BN + c4));
+                        if (g.bias) {
+                            const float4 bb = __ldg(reinterpret_cast<const float4 *>(g.bias + nt * BN + c4));
+                            w.x += bb.x; w.y += bb.y; w.z += bb.z; w.w += bb.w;
+                        }
+                        *reinterpret_cast<float4 *>(tab + row * EMB_LD + c4) = w;
+                    }
+                    asm volatile("bar.sync 2, %0;" ::"n"(PAIR_EW * 32) : "memory");
+                    grow = tab + (size_t)g.gidx[m] * EMB_LD - nt * BN;                     // the chunk adds n0 = nt * BN + c0
+                } else {
+                    grow = g.gtab + (size_t)g.gidx[m] * g.ldg;
+                }
+            }
+            mbar_wait(&bars.tmem_full[acc], acc_ph);
+            tcgen05_fence_after();
+            const uint32_t trow = tmem_base + ((uint32_t)lb << 16) + (uint32_t)(acc * BN);
             if (EPI == EPI_IMG_ROWSCALE) rs = g.rowscale[m];
-            if (EPI == EPI_IMG_EMBED) grow = g.gtab + (size_t)g.gidx[m] * g.ldg;
             uint8_t *row_ptr = reinterpret_cast<uint8_t *>(g.out_img) + (size_t)(m >> 7) * g.KB_out * TILE_BYTES +
                                (size_t)((((int)m & 127) >> 3) * 128 + ((int)m & 7) * 16);
 #pragma unroll 1
@@ -588,7 +622,12 @@ static int launch_pair(mdf_ctx *ctx, int a_terms, int b_terms, const GemmArgs &a
     pa.stages = std::min(8, (int)((200 * 1024) / stage_bytes));
     for (int t = 0; t < a_terms; ++t) MDF_TRY(make_tile_map(&pa.tmA[t], args.A[t], a_bytes[t]));
     for (int t = 0; t < b_terms; ++t) MDF_TRY(make_tile_map(&pa.tmB[t], args.B[t], b_bytes[t]));
-    const size_t smem = (size_t)pa.stages * stage_bytes + 1024;
+    size_t smem = (size_t)pa.stages * stage_bytes + 1024;
+    if (EPI == EPI_IMG_EMBED && pa.g.embed_staged) {
+        const size_t tab = (size_t)EMB_ROWS * EMB_LD * sizeof(float);
+        while (pa.stages > 2 && smem + tab > 226 * 1024) { --pa.stages; smem -= stage_bytes; }
+        smem += tab;
+    }
     auto kern = gemm_pair_kernel<EPI>;
     MDF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int outer = args.m_fastest ? args.n_tiles : args.m_tiles;

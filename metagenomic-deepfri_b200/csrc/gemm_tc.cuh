@@ -67,6 +67,7 @@ struct GemmArgs {
     const float *gtab = nullptr;
     const uint8_t *gidx = nullptr;
     int ldg = 0;
+    int embed_staged = 0;            // pair kernel, EPI_IMG_EMBED: gather from a shared-memory slice of (gtab + bias) instead of global memory
     int act = 0;
     float alpha = 1.0f;
     int m_valid = 0, n_valid = 0;    // bounds for the fp32 epilogue

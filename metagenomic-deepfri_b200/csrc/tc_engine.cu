@@ -41,6 +41,7 @@ struct TcModel {
                                                            // not help, the kernel is paced by draining its short-K accumulators
     int pool_fused = 1;                                    // sum-pool readout inside the adjacency GEMM epilogue (fp32, no X re-read)
     int adj_wide = 0;                                      // MDF_ADJ_WIDE=1 (measured, not default: stage 10.7 -> 11.1 ms): one N = 256 MMA per k-step, B sub-tiles interleaved by k-group
+    int embed_staged = 1;                                  // embedding GEMM gathers W_aa + b from a per-tile shared-memory slice (MDF_EMBED_STAGED=0: from global memory)
     int adj_lean = 1;                                      // adjacency GEMM stores no pad rows and no image of the last layer (MDF_ADJ_LEAN=0: store all)
     int adj_sparse = 1;                                    // adjacency GEMM skips all-zero 128 x 64 A tiles (MDF_ADJ_SPARSE=0: dense walk)
     int adj_expand = 1;                                    // adjacency GEMM expands its A tiles from the bit-packed map on the fly
@@ -145,6 +146,7 @@ int tc_model_init(mdf_model *m, const mdf_model_desc *d)
     if (const char *e = getenv("MDF_ADJ_SPARSE")) t->adj_sparse = atoi(e);
     if (const char *e = getenv("MDF_ADJ_WIDE")) t->adj_wide = atoi(e);
     if (const char *e = getenv("MDF_ADJ_LEAN")) t->adj_lean = atoi(e);
+    if (const char *e = getenv("MDF_EMBED_STAGED")) t->embed_staged = atoi(e);
     if (const char *e = getenv("MDF_SINGLE_TERM")) t->single_term_mask = atoi(e);
     if (const char *e = getenv("MDF_HEAD_TC")) t->head_tc = atoi(e);
     if (const char *e = getenv("MDF_GEMM_PHASES")) t->gemm_phases = std::min(64, std::max(0, atoi(e)));   // 0: hi+lo split on every tile
@@ -817,6 +819,7 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto)
             MDF_TRY(launch_gemm_tc(ctx, EPI_IMG_EMBED, 128, 1, 1, g));
         } else if (tm->gemm_pair && Tp % 256 == 0 && m->E % 256 == 0) {   // CTA pairs: 256 x 256 tiles
             g.m_tiles = (int)(Tp / 256); g.n_tiles = m->E / 256;
+            g.embed_staged = tm->embed_staged;
             const size_t ab[2] = {(size_t)Tp * m->H * 2, 0}, bb[2] = {(size_t)m->E * m->H * 2, (size_t)m->E * m->H * 2};
             MDF_TRY(launch_gemm_pair(ctx, EPI_IMG_EMBED, 1, (tm->single_term_mask & 1) ? 1 : 2, g, ab, bb));
         } else {
