@@ -98,3 +98,47 @@ def test_cnn_golden_matches_oracle(cnn_golden, cnn_model_dir):
         assert want.shape == (len(seqs), kw["n_terms"])
         for i in spec.CNN_GOLDEN_CHECK[tag]:
             assert np.abs(orc.forward_pass(seqs[i]) - want[i]).max() < 1e-6
+
+
+def test_cnn_plan_accepts_equivalent_lowerings(tmp_path):
+    """tf2onnx versions lower the same Keras layers differently: `auto_pad=SAME_UPPER` instead of explicit pads, rank-3 Conv
+    weights, a Gemm instead of MatMul + Add, GlobalMaxPool instead of ReduceMax.  The recogniser must read the same plan and
+    the oracle must give the same scores for all of them."""
+    import copy
+    cfg = synth.CNNConfig(filter_lens=(4, 9), num_filters=(128, 128), n_terms=7, logit_scale=0.5)
+    base = synth.build_cnn_model(cfg, seed=8)
+    ref_plan = onnx_plan.cnn_plan_from_model(ox.loads(ox.dumps(base)))
+
+    def variant(edit):
+        m = ox.loads(ox.dumps(base))
+        edit(m.graph)
+        return m
+
+    def auto_pad(g):
+        for n in g.nodes:
+            if n.op_type == "Conv":
+                n.attrs.pop("pads")
+                n.attrs["auto_pad"] = "SAME_UPPER"
+
+    def gemm_head(g):
+        mm = next(n for n in g.nodes if n.op_type == "MatMul")
+        add = next(n for n in g.nodes if n.op_type == "Add" and mm.outputs[0] in n.inputs)
+        bias = [i for i in add.inputs if i != mm.outputs[0]][0]
+        g.nodes[g.nodes.index(mm)] = ox.Node("Gemm", [mm.inputs[0], mm.inputs[1], bias], [add.outputs[0]], name="Gemm__head", attrs={})
+        g.nodes.remove(add)
+
+    variants = {"auto_pad": variant(auto_pad), "gemm": variant(gemm_head)}
+    seqs = ["ACDEFGHIKLMNPQRSTVWY", "MK", "W" * 40 + "ACD"]
+    p0 = str(tmp_path / "base.onnx")
+    ox.save(base, p0)
+    want = [go.Predictor(p0).forward_pass(s) for s in seqs]
+    for tag, m in variants.items():
+        plan = onnx_plan.cnn_plan_from_model(m)
+        assert plan.conv_pad_left == ref_plan.conv_pad_left and plan.n_terms == ref_plan.n_terms, tag
+        assert np.array_equal(plan.scale, ref_plan.scale) and np.array_equal(plan.shift, ref_plan.shift), tag
+        assert np.array_equal(plan.out_W, ref_plan.out_W) and np.array_equal(plan.out_b, ref_plan.out_b), tag
+        pth = str(tmp_path / f"{tag}.onnx")
+        ox.save(m, pth)
+        orc = go.Predictor(pth)
+        for s, w in zip(seqs, want):
+            assert np.abs(orc.forward_pass(s) - w).max() < 1e-6, tag

@@ -77,3 +77,19 @@ def test_pipeline_chunks_by_residue_budget():
     assert pipeline._chunks([], 100) == []
     assert pipeline._chunks([50, 60, 10, 200, 5], 100) == [(0, 1), (1, 3), (3, 4), (4, 5)]
     assert pipeline._chunks([10, 10, 10], 1000) == [(0, 3)]
+
+
+def test_pack_checked_matches_per_sequence_encoding():
+    """predict._pack_checked validates a whole batch in one pass with the error behaviour of predict.pyx:17-48."""
+    from metagenomic_deepfri_b200 import predict
+    seqs = ["ACDE", "", "MKV-X", "W"]
+    b, off = predict._pack_checked(seqs)
+    assert b == b"ACDEMKV-XW" and off.tolist() == [0, 4, 4, 9, 10] and off.dtype == np.int64
+    b, off = predict._pack_checked([])
+    assert b == b"" and off.tolist() == [0]
+    with pytest.raises(ValueError, match="Invalid character in sequence: J"):
+        predict._pack_checked(["ACD", "AJC"])
+    with pytest.raises(ValueError, match="Invalid character in sequence: a"):
+        predict._pack_checked(["aCD"])
+    with pytest.raises(UnicodeEncodeError):
+        predict._pack_checked(["ACé"])
