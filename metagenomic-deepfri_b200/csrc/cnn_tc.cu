@@ -69,6 +69,7 @@ constexpr size_t CNN_SMEM = (size_t)2 * CNN_TILES * CNN_IMG + (size_t)CNN_STAGES
 
 struct CnnArgs {
     int n_tiles, n_groups, n_items, pl_max, Ctot;
+    int rounds;                      // ceil(n_groups / gridDim.x): with multicast every CTA of a cluster walks the same number of rounds
     const int4 *tile_info;           // per tile {protein, first row inside the protein, L, index of the protein's first residue}
     const uint8_t *idx;              // [T] residue channel (0..25)
     const float *scale, *shift;      // [Ctot]
@@ -86,6 +87,9 @@ struct __align__(8) CnnBarriers {
     uint32_t tmem_base;
 };
 
+// MC = CTAs per cluster that share the weight stream: every CTA fetches 1 / MC of each weight tile and multicasts it to the
+// shared-memory stage of all of them (a stage is free again when the MMAs of ALL of them that read it have retired).
+template <int MC>
 __global__ void __launch_bounds__(CNN_THREADS, 1)
 cnn_conv_kernel(const __grid_constant__ CnnArgs a)
 {
@@ -99,7 +103,7 @@ cnn_conv_kernel(const __grid_constant__ CnnArgs a)
     constexpr int w_prod = CNN_EW + CNN_BW, w_mma = CNN_EW + CNN_BW + 1;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < CNN_STAGES; ++s) { mbar_init(&bars.full[s], 1); mbar_init(&bars.empty[s], 1); }
+        for (int s = 0; s < CNN_STAGES; ++s) { mbar_init(&bars.full[s], 1); mbar_init(&bars.empty[s], MC); }
         for (int s = 0; s < 2; ++s) { mbar_init(&bars.img_full[s], CNN_BW); mbar_init(&bars.img_empty[s], 1); }
         mbar_init(&bars.tmem_full, 1);
         for (int t = 0; t < CNN_TILES; ++t) mbar_init(&bars.tmem_empty[t], CNN_EW);
@@ -109,24 +113,35 @@ cnn_conv_kernel(const __grid_constant__ CnnArgs a)
     if (warp == w_mma) tmem_alloc<512>(&bars.tmem_base);
     tcgen05_fence_before();
     __syncthreads();
+    if (MC > 1) cluster_sync_all();           // the peers' barriers exist before anything is multicast to them
     tcgen05_fence_after();
     const uint32_t tmem_base = bars.tmem_base;
+    const uint32_t crank = MC > 1 ? cluster_ctarank() : 0u;
+    constexpr uint16_t mc_mask = (uint16_t)((1u << MC) - 1u);
 
     if (warp == w_prod) {
-        // ===================== producer: weight tiles (128 filters x 2 positions x 32 channels) through the stage ring
+        // ===================== producer: weight tiles (128 filters x 64 k) through the stage ring
         if (lane == 0) {
             int st = 0; uint32_t ph = 0;
-            for (int g = blockIdx.x; g < a.n_groups; g += gridDim.x)
+            for (int round = 0; round < a.rounds; ++round) {
+                if (MC == 1 && round * (int)gridDim.x + (int)blockIdx.x >= a.n_groups) break;
                 for (int item = 0; item < a.n_items; ++item) {
                     const int c = a.item_conv[item], KB = a.kb[c];
                     const uint8_t *src = reinterpret_cast<const uint8_t *>(a.W[c]) + (size_t)a.item_fb[item] * KB * TILE_BYTES;
                     for (int kb = 0; kb < KB; ++kb) {
                         mbar_wait_sleep(&bars.empty[st], ph ^ 1, 32);
                         mbar_arrive_expect_tx(&bars.full[st], TILE_BYTES);
-                        bulk_g2s(stg + (size_t)st * TILE_BYTES, src + (size_t)kb * TILE_BYTES, TILE_BYTES, &bars.full[st]);
+                        if (MC == 1) {
+                            bulk_g2s(stg + (size_t)st * TILE_BYTES, src + (size_t)kb * TILE_BYTES, TILE_BYTES, &bars.full[st]);
+                        } else {
+                            constexpr uint32_t part = TILE_BYTES / MC;       // my share of the tile, delivered to every CTA of the cluster
+                            bulk_g2s_mc(stg + (size_t)st * TILE_BYTES + crank * part, src + (size_t)kb * TILE_BYTES + crank * part, part,
+                                        &bars.full[st], mc_mask);
+                        }
                         if (++st == CNN_STAGES) { st = 0; ph ^= 1; }
                     }
                 }
+            }
         }
     } else if (warp == w_mma) {
         // ===================== MMA issuer: converged warp, the elected lane issues (tc_ptx.cuh)
@@ -136,11 +151,15 @@ cnn_conv_kernel(const __grid_constant__ CnnArgs a)
         // K-step table entries are fetched one k-block ahead (the (item, k-block) sequence is the same for every group): a
         // load issued right before its use stalls the issue loop for an L2 round trip per k-block
         uint4 nxt = __ldg(a.ktab + a.ktab_off[a.item_conv[0]]);
-        for (int g = blockIdx.x; g < a.n_groups; g += gridDim.x, ++it) {
+        for (int round = 0; round < a.rounds; ++round) {
+            const int g = round * (int)gridDim.x + (int)blockIdx.x;
+            const int nt = max(0, min(CNN_TILES, a.n_tiles - g * CNN_TILES));   // 0: no group left for this CTA, but its cluster peers
+            if (MC == 1 && nt == 0) break;                                     // still need it to drain (and feed) the shared stages
             const int buf = it & 1;
-            mbar_wait(&bars.img_full[buf], (uint32_t)(it >> 1) & 1u);
-            tcgen05_fence_after();
-            const int nt = min(CNN_TILES, a.n_tiles - g * CNN_TILES);
+            if (nt > 0) {
+                mbar_wait(&bars.img_full[buf], (uint32_t)(it >> 1) & 1u);
+                tcgen05_fence_after();
+            }
             const uint32_t ia0 = smem_u32(img + (size_t)buf * CNN_TILES * CNN_IMG);
             for (int item = 0; item < a.n_items; ++item) {
                 const int c = a.item_conv[item], KB = a.kb[c];
@@ -163,25 +182,30 @@ cnn_conv_kernel(const __grid_constant__ CnnArgs a)
                             umma_f16_elect(tmem_base + (uint32_t)(t * 128), ad, bd, idesc, (kb | j) != 0);
                         }
                     }
-                    umma_commit_elect(&bars.empty[st]);
-                    if (kb == KB - 1) umma_commit_elect(&bars.tmem_full);
+                    if (MC == 1) umma_commit_elect(&bars.empty[st]); else umma_commit_mc_elect(&bars.empty[st], mc_mask);
+                    if (nt > 0 && kb == KB - 1) umma_commit_elect(&bars.tmem_full);
                     __syncwarp();
                     if (++st == CNN_STAGES) { st = 0; ph ^= 1; }
                 }
-                item_ph ^= 1;
+                if (nt > 0) item_ph ^= 1;
             }
-            umma_commit_elect(&bars.img_empty[buf]);            // the window images may be rebuilt once every MMA above retired
-            __syncwarp();
+            if (nt > 0) {
+                umma_commit_elect(&bars.img_empty[buf]);        // the window images may be rebuilt once every MMA above retired
+                __syncwarp();
+                ++it;
+            }
         }
     } else if (warp >= CNN_EW) {
         // ===================== window-image builders (128 threads): one-hot rows of the tile's residue window, 4 planes
         const int bt = threadIdx.x - CNN_EW * 32;
         int it = 0;
-        for (int g = blockIdx.x; g < a.n_groups; g += gridDim.x, ++it) {
+        for (int round = 0; round < a.rounds; ++round, ++it) {
+            const int g = round * (int)gridDim.x + (int)blockIdx.x;
+            const int nt = min(CNN_TILES, a.n_tiles - g * CNN_TILES);
+            if (nt <= 0) break;
             const int buf = it & 1;
             if (lane == 0) mbar_wait_sleep(&bars.img_empty[buf], ((uint32_t)(it >> 1) & 1u) ^ 1u, 1000);
             __syncwarp();
-            const int nt = min(CNN_TILES, a.n_tiles - g * CNN_TILES);
             for (int t = 0; t < nt; ++t) {
                 const int4 ti = __ldg(&a.tile_info[g * CNN_TILES + t]);
                 const uint32_t base = smem_u32(img + (size_t)(buf * CNN_TILES + t) * CNN_IMG);
@@ -218,8 +242,10 @@ cnn_conv_kernel(const __grid_constant__ CnnArgs a)
         const int lq = warp & 3, cg = warp >> 2;
         uint32_t item_ph = 0;
         int cm = 0;
-        for (int g = blockIdx.x; g < a.n_groups; g += gridDim.x) {
+        for (int round = 0; round < a.rounds; ++round) {
+            const int g = round * (int)gridDim.x + (int)blockIdx.x;
             const int nt = min(CNN_TILES, a.n_tiles - g * CNN_TILES);
+            if (nt <= 0) break;
             int prot[CNN_TILES];
             bool valid[CNN_TILES];
 #pragma unroll
@@ -298,6 +324,7 @@ cnn_conv_kernel(const __grid_constant__ CnnArgs a)
     }
     tcgen05_fence_before();
     __syncthreads();
+    if (MC > 1) cluster_sync_all();           // no CTA leaves while a peer may still multicast into its stages or arrive on its barriers
     if (warp == w_mma) tmem_dealloc<512>(tmem_base);
 }
 
@@ -496,10 +523,29 @@ extern "C" int mdf_cnn_run(mdf_cnn_model *m)
             a.W[c] = m->W[c]; a.kb[c] = (short)m->kb[c]; a.ktab_off[c] = m->ktab_off[c]; a.choff[c] = m->choff[c];
             for (int fb = 0; fb < m->filters[c] / 128; ++fb, ++item) { a.item_conv[item] = (unsigned char)c; a.item_fb[item] = (unsigned char)fb; }
         }
-        MDF_CUDA(cudaFuncSetAttribute(cnn_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CNN_SMEM));
-        const int grid = std::min(a.n_groups, ctx->sm_count);
-        cnn_conv_kernel<<<grid, CNN_THREADS, CNN_SMEM, ctx->stream>>>(a);
-        MDF_LAUNCH_CHECK(ctx);
+        static const int mc = getenv("MDF_CNN_MULTICAST") ? atoi(getenv("MDF_CNN_MULTICAST")) : 1;
+        if (mc == 2) {
+            // clusters of two CTAs share the weight stream (each fetches half of every tile and multicasts it)
+            auto kern = cnn_conv_kernel<2>;
+            MDF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CNN_SMEM));
+            const int grid = std::min((a.n_groups + 1) / 2 * 2, ctx->sm_count / 2 * 2);
+            a.rounds = cdiv(a.n_groups, grid);
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(grid); cfg.blockDim = dim3(CNN_THREADS); cfg.dynamicSmemBytes = CNN_SMEM; cfg.stream = ctx->stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            MDF_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
+            ctx->launches++;
+        } else {
+            auto kern = cnn_conv_kernel<1>;
+            MDF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CNN_SMEM));
+            const int grid = std::min(a.n_groups, ctx->sm_count);
+            a.rounds = cdiv(a.n_groups, grid);
+            kern<<<grid, CNN_THREADS, CNN_SMEM, ctx->stream>>>(a);
+            MDF_LAUNCH_CHECK(ctx);
+        }
     }
     {
         ProfScope ps(ctx, "cnn_head", 2.0 * n * (double)m->Ctot * 2 * m->C);

@@ -79,6 +79,13 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// multicast form: the bytes land at the same shared-memory offset in every CTA of `cta_mask` (cluster ranks) and complete_tx is
+// signalled on the barrier at the same offset in each of them - one L2 read feeds all the CTAs that stream the same operand
+__device__ __forceinline__ void bulk_g2s_mc(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar, uint16_t cta_mask)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
 // make generic-proxy shared-memory writes visible to the async proxy (tensor core / TMA)
 __device__ __forceinline__ void fence_proxy_async_smem()
 {
@@ -183,6 +190,16 @@ __device__ __forceinline__ void umma_commit_elect(uint64_t *bar)
         "elect.sync _|q, 0xffffffff;\n\t"
         "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
         ::"r"(smem_u32(bar)) : "memory");
+}
+
+// single-CTA MMAs, completion signalled on the barrier at this offset in every CTA of `cta_mask` (stages shared through multicast)
+__device__ __forceinline__ void umma_commit_mc_elect(uint64_t *bar, uint16_t cta_mask)
+{
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+        ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
 }
 
 __device__ __forceinline__ void umma_f16_pair_elect(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate)
