@@ -313,12 +313,18 @@ gemm_tc_kernel(GemmArgs g, int a_terms, int b_terms, int stages)
             if (g.adj_kb_idx) {
                 // block-sparse walk: the two words of listed k-block j, loaded one list entry ahead of the stage that uses them
                 const unsigned short *list = g.adj_kb_idx + ti.x;
+                // compact axis: listed block j = compact residues 64 (ti.y + j) .. + 63 = bits j0 .. j0 + 63 of this protein's row
+                const int jbase = g.adj_compact ? (int)(64ll * ti.y - g.adj_seq_off[p]) : 0;
+                auto window = [&](int j) -> uint2 {
+                    if (g.adj_compact) return adj_row_window(row, rw, jbase + 64 * j);
+                    return __ldg(reinterpret_cast<const uint2 *>(row + 2 * j));
+                };
                 uint2 nx = make_uint2(0u, 0u);
-                if (nkb > 0 && i < L) nx = __ldg(reinterpret_cast<const uint2 *>(row + 2 * (int)list[0]));
+                if (nkb > 0 && i < L) nx = window((int)list[0]);
                 for (int j = 0; j < nkb; ++j) {
                     const uint2 cw = nx;
                     nx = make_uint2(0u, 0u);
-                    if (j + 1 < nkb && i < L) nx = __ldg(reinterpret_cast<const uint2 *>(row + 2 * (int)list[j + 1]));
+                    if (j + 1 < nkb && i < L) nx = window((int)list[j + 1]);
                     const uint32_t w[2] = {cw.x, cw.y};
                     if (lane == 0) mbar_wait(&bars.empty[st], ph ^ 1);
                     __syncwarp();
@@ -386,11 +392,20 @@ gemm_tc_kernel(GemmArgs g, int a_terms, int b_terms, int stages)
             const int nkb = g.adj_kb_cnt ? g.adj_kb_cnt[mt] : g.tile_info ? g.tile_info[mt].z : g.nkb;
             mbar_wait(&bars.tmem_full[acc], acc_ph);
             tcgen05_fence_after();
-            const int64_t m = (int64_t)mt * 128 + lb + lane;
+            int64_t m = (int64_t)mt * 128 + lb + lane;
+            bool row_valid = true;
+            if (EPI == EPI_IMG_ROWSCALE && g.adj_compact) {
+                // row i of protein p lives at compact row seq_off[p] + i; rows past L are padding of the tile only
+                const int p = g.tile_info[mt].w;
+                const int64_t s0 = g.adj_seq_off[p];
+                const int i = (mt - (int)(g.adj_seg_off[p] >> 7)) * 128 + lb + lane;
+                row_valid = i < (int)(g.adj_seq_off[p + 1] - s0);
+                m = row_valid ? s0 + i : s0;
+            }
             const uint32_t trow = tmem_base + ((uint32_t)lb << 16) + (uint32_t)(acc * BN);
             float rs = 1.0f;
             const float *grow = nullptr;
-            if (EPI == EPI_IMG_ROWSCALE) rs = g.rowscale[m];
+            if (EPI == EPI_IMG_ROWSCALE) rs = row_valid ? g.rowscale[m] : 0.0f;
             if (EPI == EPI_IMG_EMBED) grow = g.gtab + (size_t)g.gidx[m] * g.ldg;
             float *pool_row = nullptr;
             if (EPI == EPI_IMG_ROWSCALE && g.pool && g.tile_info) pool_row = g.pool + (size_t)g.tile_info[mt].w * g.pool_ld + g.pool_off;

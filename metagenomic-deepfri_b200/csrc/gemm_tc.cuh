@@ -51,6 +51,7 @@ struct GemmArgs {
     // BN = 256 only: land the two 128-row B sub-tiles of a stage interleaved by k-group ([k-group][256 rows], 16 copies of 2 KiB)
     // so that ONE M128 x N256 MMA per k-step reads them (LBO = 4096) instead of two N = 128 MMAs that each re-read the A tile
     int wide_b = 0;
+    int adj_compact = 0;             // adjacency product on the compact residue axis (tc_engine.cu build_meta)
     const unsigned short *adj_kb_idx = nullptr;
     const int *adj_kb_cnt = nullptr;
     const uint32_t *adj_packed = nullptr;
@@ -72,6 +73,20 @@ struct GemmArgs {
     float alpha = 1.0f;
     int m_valid = 0, n_valid = 0;    // bounds for the fp32 epilogue
 };
+
+// bits j0 .. j0 + 63 of a bit-packed contact-map row (rw words, padding bits zero); j0 may be negative (> -64): the bits
+// before the row start read as zero.  Used by the compact-axis adjacency product, where a protein's columns start at an
+// arbitrary bit offset inside a 64-residue k-block.
+__device__ __forceinline__ uint2 adj_row_window(const uint32_t *__restrict__ row, int rw, int j0)
+{
+    if (j0 >= 0) {
+        const int wi = j0 >> 5, sh = j0 & 31;
+        const uint32_t a0 = wi < rw ? __ldg(row + wi) : 0u, a1 = wi + 1 < rw ? __ldg(row + wi + 1) : 0u, a2 = wi + 2 < rw ? __ldg(row + wi + 2) : 0u;
+        return make_uint2(__funnelshift_r(a0, a1, sh), __funnelshift_r(a1, a2, sh));
+    }
+    const unsigned long long v = (((unsigned long long)__ldg(row + 1) << 32) | (unsigned long long)__ldg(row)) << (-j0);
+    return make_uint2((uint32_t)v, (uint32_t)(v >> 32));
+}
 
 int launch_gemm_tc(mdf_ctx *ctx, int epi, int bn, int a_terms, int b_terms, const GemmArgs &args);
 

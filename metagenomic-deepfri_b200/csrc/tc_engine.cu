@@ -41,6 +41,7 @@ struct TcModel {
                                                            // not help, the kernel is paced by draining its short-K accumulators
     int pool_fused = 1;                                    // sum-pool readout inside the adjacency GEMM epilogue (fp32, no X re-read)
     int adj_wide = 0;                                      // MDF_ADJ_WIDE=1 (measured, not default: stage 10.7 -> 11.1 ms): one N = 256 MMA per k-step, B sub-tiles interleaved by k-group
+    int compact = 1;                                       // compact residue axis (MDF_COMPACT=0: per-protein segments padded to 128 rows)
     int embed_staged = 1;                                  // embedding GEMM gathers W_aa + b from a per-tile shared-memory slice (MDF_EMBED_STAGED=0: from global memory)
     int adj_lean = 1;                                      // adjacency GEMM stores no pad rows and no image of the last layer (MDF_ADJ_LEAN=0: store all)
     int adj_sparse = 1;                                    // adjacency GEMM skips all-zero 128 x 64 A tiles (MDF_ADJ_SPARSE=0: dense walk)
@@ -70,6 +71,8 @@ struct TcBatchMeta {
     int64_t Tp = 0;             // padded residue rows (multiple of 256)
     int n_adj_tiles = 0;        // tiles of all A_hat images
     int m_tiles = 0;            // Tp / 128
+    int adj_m_tiles = 0;        // 128-row tiles of the adjacency product: one protein each (== m_tiles on the padded axis)
+    bool compact = false;       // residue axis of every image = packed residue order (no per-protein padding), see build_meta
     int *rowmap = nullptr;      // [Tp] padded row -> packed residue index, -1 on pads
     int4 *tile_info = nullptr;  // [m_tiles] grouped-GEMM info per 128-row tile
     int4 *exp_tiles = nullptr;  // [n_adj_tiles] {protein, local m-tile, k-block, first tile of protein}
@@ -147,6 +150,7 @@ int tc_model_init(mdf_model *m, const mdf_model_desc *d)
     if (const char *e = getenv("MDF_ADJ_WIDE")) t->adj_wide = atoi(e);
     if (const char *e = getenv("MDF_ADJ_LEAN")) t->adj_lean = atoi(e);
     if (const char *e = getenv("MDF_EMBED_STAGED")) t->embed_staged = atoi(e);
+    if (const char *e = getenv("MDF_COMPACT")) t->compact = atoi(e);
     if (const char *e = getenv("MDF_SINGLE_TERM")) t->single_term_mask = atoi(e);
     if (const char *e = getenv("MDF_HEAD_TC")) t->head_tc = atoi(e);
     if (const char *e = getenv("MDF_GEMM_PHASES")) t->gemm_phases = std::min(64, std::max(0, atoi(e)));   // 0: hi+lo split on every tile
@@ -511,7 +515,7 @@ static int head_forward_tc(mdf_model *m, TcModel *tm, int n, const float *pooled
 __global__ void __launch_bounds__(128)
 adj_tile_scan_kernel(int m_tiles, const int4 *__restrict__ tile_info, const uint32_t *__restrict__ packed,
                      const int64_t *__restrict__ packed_off, const int64_t *__restrict__ seq_off, const int64_t *__restrict__ seg_off,
-                     unsigned short *__restrict__ kb_idx, int *__restrict__ kb_cnt)
+                     int compact, unsigned short *__restrict__ kb_idx, int *__restrict__ kb_cnt)
 {
     __shared__ uint32_t mask;
     __shared__ int count;
@@ -528,7 +532,15 @@ adj_tile_scan_kernel(int m_tiles, const int4 *__restrict__ tile_info, const uint
         if (threadIdx.x == 0) mask = 0u;
         __syncthreads();
         uint32_t mine = 0u;
-        if (i < L) {
+        if (i < L && compact) {
+            // compact K axis: listed block j covers compact residues 64 (ti.y + j) .. + 63 = bits j0 .. j0 + 63 of the row
+            const int nk = min(32, nkb - c0);
+            const int64_t s0 = seq_off[p];
+            for (int k = 0; k < nk; ++k) {
+                const uint2 w = adj_row_window(row, rw, (int)(64ll * (ti.y + c0 + k) - s0));
+                if (w.x | w.y) mine |= 1u << k;
+            }
+        } else if (i < L) {
             const int nk = min(32, nkb - c0);
             for (int k = 0; k < nk; k += 2) {                 // rw is a multiple of 4 words: k-blocks come in aligned pairs
                 const uint4 w = __ldg(reinterpret_cast<const uint4 *>(row + 2 * (c0 + k)));
@@ -598,7 +610,14 @@ __global__ void fill_rowmap_kernel(int n, const int64_t *__restrict__ seq_off, c
     }
 }
 
-static int build_meta(mdf_ctx *ctx, mdf_batch *b, TcBatchMeta &meta, bool want_exp_tiles)
+// Two layouts of the residue axis:
+//   padded  - per protein a segment of round_up(L, 128) rows: every 128-row tile and every 64-residue k-block belongs to one protein;
+//   compact - packed residue order (row = seq_off[p] + i), padded only at the very end.  The weight GEMMs (embedding, X.W) then spend
+//             no MMAs and no HBM bytes on per-protein padding (22 % of the rows of a configs[4] batch).  The adjacency product still
+//             walks one protein's 128-row tiles, but its K axis is the compact one: tile_info = {list offset, first compact k-block
+//             the protein touches, number of compact k-blocks it spans, protein}; the expanders cut each 64-column window out of the
+//             bit-packed row at the protein's own bit offset, and the epilogue stores row i of the protein at compact row seq_off + i.
+static int build_meta(mdf_ctx *ctx, mdf_batch *b, TcBatchMeta &meta, bool want_exp_tiles, bool compact)
 {
     const int n = b->n;
     std::vector<int64_t> seg_off(n + 1, 0);
@@ -606,16 +625,19 @@ static int build_meta(mdf_ctx *ctx, mdf_batch *b, TcBatchMeta &meta, bool want_e
         const int64_t L = b->h_seq_off[p + 1] - b->h_seq_off[p];
         seg_off[p + 1] = seg_off[p] + (L + 127) / 128 * 128;
     }
-    const int64_t Tp = (seg_off[n] + 255) / 256 * 256;
-    std::vector<int4> tile_info((size_t)(Tp / 128), make_int4(0, 0, 0, 0));
+    const int64_t Tp = ((compact ? b->h_seq_off[n] : seg_off[n]) + 255) / 256 * 256;
+    const int64_t adj_rows = (seg_off[n] + 255) / 256 * 256;
+    std::vector<int4> tile_info((size_t)(adj_rows / 128), make_int4(0, 0, 0, 0));
     std::vector<int4> exp_tiles, pairs;
     int tile_base = 0;
     for (int p = 0; p < n; ++p) {
         const int L = (int)(b->h_seq_off[p + 1] - b->h_seq_off[p]);
-        const int KBp = (L + TILE_K - 1) / TILE_K, MT = (L + 127) / 128;
+        const int64_t s0 = b->h_seq_off[p];
+        const int KBp = compact ? (L > 0 ? (int)((s0 + L - 1) / TILE_K - s0 / TILE_K + 1) : 0) : (L + TILE_K - 1) / TILE_K;
+        const int MT = (L + 127) / 128;
         const int mt0 = (int)(seg_off[p] / 128);
         for (int mt = 0; mt < MT; ++mt) {
-            tile_info[(size_t)mt0 + mt] = make_int4(tile_base + mt * KBp, (int)(seg_off[p] / TILE_K), KBp, p);
+            tile_info[(size_t)mt0 + mt] = make_int4(tile_base + mt * KBp, (int)((compact ? s0 : seg_off[p]) / TILE_K), KBp, p);
             if (want_exp_tiles)
                 for (int kb = 0; kb < KBp; ++kb) exp_tiles.push_back(make_int4(p, mt, kb, tile_base));
             if ((mt & 1) == 0) pairs.push_back(make_int4(mt0 + mt, mt + 1 < MT ? mt0 + mt + 1 : -1, (int)(seg_off[p] / TILE_K), KBp));
@@ -626,6 +648,8 @@ static int build_meta(mdf_ctx *ctx, mdf_batch *b, TcBatchMeta &meta, bool want_e
     std::stable_sort(pairs.begin(), pairs.end(), [](const int4 &x, const int4 &y) { return x.w > y.w; });
     meta.Tp = Tp;
     meta.m_tiles = (int)(Tp / 128);
+    meta.adj_m_tiles = (int)(adj_rows / 128);
+    meta.compact = compact;
     meta.n_adj_tiles = tile_base;
     meta.n_pairs = (int)pairs.size();
     const size_t bytes = align_up((size_t)Tp * 4, 256) + align_up(tile_info.size() * 16, 256) +
@@ -649,7 +673,8 @@ static int build_meta(mdf_ctx *ctx, mdf_batch *b, TcBatchMeta &meta, bool want_e
     MDF_CUDA(cudaMemcpyAsync(meta.seg_off, seg_off.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, s));
     MDF_CUDA(cudaMemsetAsync(meta.rowmap, 0xFF, (size_t)Tp * 4, s));
     if (n > 0) {
-        fill_rowmap_kernel<<<std::min(n, 8 * ctx->sm_count), 128, 0, s>>>(n, b->d_seq_off, meta.seg_off, meta.rowmap);
+        // compact axis: the row map is the identity on [0, T) (and -1 on the tail padding)
+        fill_rowmap_kernel<<<std::min(n, 8 * ctx->sm_count), 128, 0, s>>>(n, b->d_seq_off, compact ? b->d_seq_off : meta.seg_off, meta.rowmap);
         MDF_LAUNCH_CHECK(ctx);
     }
     MDF_CUDA(cudaMemcpyAsync(meta.tile_info, tile_info.data(), tile_info.size() * 16, cudaMemcpyHostToDevice, s));
@@ -666,7 +691,7 @@ size_t tc_workspace_bytes(const mdf_model *m, int n, const int64_t *seq_off)
     for (int p = 0; p < n; ++p) {
         const int64_t L = seq_off[p + 1] - seq_off[p];
         rows += (L + 127) / 128 * 128;
-        tiles += ((L + 127) / 128) * ((L + TILE_K - 1) / TILE_K);
+        tiles += ((L + 127) / 128) * ((L + TILE_K - 1) / TILE_K + 1);     // + 1: a protein may straddle one more compact k-block
     }
     const int64_t T = seq_off[n];
     const int64_t Tp = (rows + 255) / 256 * 256;
@@ -704,21 +729,24 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto)
     if (n == 0) return MDF_OK;
     cudaStream_t s = ctx->stream;
 
-    // ---- padded-axis metadata
+    // ---- residue-axis metadata (compact axis needs the list-walking adjacency GEMM)
+    const bool want_compact = tm->compact && tm->adj_expand && tm->adj_sparse && !tm->adj_pair;
     TcBatchMeta local_meta;
     TcBatchMeta *meta = &local_meta;
     if (b->owns_memory) {
         if (!b->tc_meta) {
             TcBatchMeta *pm = new TcBatchMeta();
-            int r = build_meta(ctx, b, *pm, !tm->adj_expand);
+            int r = build_meta(ctx, b, *pm, !tm->adj_expand, want_compact);
             if (r != MDF_OK) { delete pm; return r; }
             b->tc_meta = pm;
         }
         meta = static_cast<TcBatchMeta *>(b->tc_meta);
     } else {
-        MDF_TRY(build_meta(ctx, b, local_meta, !tm->adj_expand));
+        MDF_TRY(build_meta(ctx, b, local_meta, !tm->adj_expand, want_compact));
     }
     const int64_t Tp = meta->Tp;
+    const bool compact = meta->compact;
+    const int64_t *row_off = compact ? b->d_seq_off : meta->seg_off;      // first image row of every protein
     int gmax = 0;
     for (int l = 0; l < m->n_gc; ++l) gmax = std::max(gmax, m->gc[l]);
 
@@ -764,7 +792,7 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto)
         // both layers + the layer-2 input projection in one persistent wavefront kernel (lstm_fused.cu)
         ProfScope ps(ctx, "lstm_fused", 3.0 * 2.0 * T * 4 * m->H * m->H);
         MDF_TRY(launch_lstm_fused(ctx, m->H, n, tm->lstm_fused_W, tm->lstm_phases, tm->lstm_tab_full, tm->lstm_bperm[1], idx_pad, b->d_order,
-                                  b->d_seq_off, meta->seg_off, ctx->debug_taps ? Hlimg[0] : nullptr, Hlimg[1], scratch, b->h_order.data(),
+                                  b->d_seq_off, row_off, ctx->debug_taps ? Hlimg[0] : nullptr, Hlimg[1], scratch, b->h_order.data(),
                                   b->h_seq_off.data()));
         b->tap_h[0] = b->tap_h[1] = nullptr;
     }
@@ -785,11 +813,11 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto)
             if (tm->lstm_Rstream[l][0] && n >= tm->lstm_stream_min)      // large batch: streamed weights, N = 128
                 MDF_TRY(launch_lstm_stream(ctx, m->H, n, tm->lstm_Rstream[l][0], tm->lstm_Rstream[l][1],
                                            l == 0 ? tm->lstm_tab_full : nullptr, l > 0 ? pre : nullptr, idx_pad, b->d_order,
-                                           b->d_seq_off, meta->seg_off, Hlimg[l], scratch));
+                                           b->d_seq_off, row_off, Hlimg[l], scratch));
             else                                                         // small batch: weights resident in smem, N = 32
                 MDF_TRY(launch_lstm_tc(ctx, m->H, n, tm->lstm_alternate ? tm->lstm_Ralt[l] : tm->lstm_R[l],
                                        l == 0 ? tm->lstm_tab : nullptr, l > 0 ? pre : nullptr, idx_pad, b->d_order,
-                                       b->d_seq_off, meta->seg_off, Hlimg[l], scratch, tm->lstm_alternate));
+                                       b->d_seq_off, row_off, Hlimg[l], scratch, tm->lstm_alternate));
         }
         b->tap_h[l] = nullptr;
     }
@@ -848,9 +876,9 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto)
     if (tm->adj_expand && tm->adj_sparse && !tm->adj_pair && meta->n_adj_tiles > 0) {
         ProfScope ps(ctx, "adj_tile_scan", 0.0);
         MDF_TRY(ctx->alloc_n(&kb_idx, (size_t)meta->n_adj_tiles + 8));
-        MDF_TRY(ctx->alloc_n(&kb_cnt, (size_t)meta->m_tiles));
-        adj_tile_scan_kernel<<<meta->m_tiles, 128, 0, s>>>(meta->m_tiles, meta->tile_info, b->d_packed, b->d_packed_off, b->d_seq_off,
-                                                           meta->seg_off, kb_idx, kb_cnt);
+        MDF_TRY(ctx->alloc_n(&kb_cnt, (size_t)meta->adj_m_tiles));
+        adj_tile_scan_kernel<<<meta->adj_m_tiles, 128, 0, s>>>(meta->adj_m_tiles, meta->tile_info, b->d_packed, b->d_packed_off, b->d_seq_off,
+                                                               meta->seg_off, compact ? 1 : 0, kb_idx, kb_cnt);
         MDF_LAUNCH_CHECK(ctx);
     }
     MDF_CUDA(cudaMemsetAsync(b->d_pooled, 0, (size_t)n * m->G * sizeof(float), s));
@@ -894,11 +922,12 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto)
                 g.wide_b = tm->adj_wide;
             }
             const int bn = gd % 256 == 0 ? 256 : 128;
-            g.m_tiles = meta->m_tiles; g.n_tiles = gd / bn;
+            g.m_tiles = meta->adj_m_tiles; g.n_tiles = gd / bn;
+            g.adj_compact = compact ? 1 : 0;
             g.out_img = Xout; g.KB_out = gd / TILE_K;
             // the last layer's activations are only summed (fused sum-pool): no image unless a tap or the separate pool kernel reads it
             if (l == m->n_gc - 1 && tm->pool_fused && !ctx->debug_taps && tm->adj_lean) g.out_img = nullptr;
-            g.skip_pad_rows = tm->adj_lean;
+            g.skip_pad_rows = tm->adj_lean || compact;    // compact axis: a pad row of the tile would land on another protein's row
             g.rowscale = deg_pad; g.bias = m->gc_b[l]; g.act = m->act; g.alpha = m->alpha;
             if (tm->pool_fused) { g.pool = b->d_pooled; g.pool_ld = m->G; g.pool_off = goff; }   // readout from the fp32 accumulators
             static const bool want_trace = getenv("MDF_GEMM_TRACE") != nullptr;
