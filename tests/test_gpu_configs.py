@@ -178,3 +178,34 @@ def test_block_sparse_adjacency_equals_dense_walk(tmp_path, monkeypatch):
     assert np.array_equal(out["1"][0], out["0"][0])
     assert np.allclose(out["1"][1], out["0"][1], rtol=1e-5, atol=1e-4)
     assert np.abs(out["1"][2] - out["0"][2]).max() < 1e-5
+
+
+def test_compact_axis_many_tiny_proteins(tmp_path):
+    """On the compact residue axis one 64-residue k-block of Y^T can hold dozens of proteins: a batch of 300 proteins of 1-25
+    residues (plus a few long ones in between) through the tensor-core engine must agree with the exact-fp32 SIMT engine, and
+    with itself when the padded axis is selected."""
+    import os
+    path = str(tmp_path / "mf.onnx")
+    synth.write_gcn_model(path, synth.GCNConfig())
+    tiny = synth.make_workload(300, 1, 25, seed=41, threshold=10.0)
+    big = synth.make_workload(5, 200, 700, seed=42, threshold=10.0)
+    seqs, gq, gt, co_ = list(tiny.query_seqs), list(tiny.gapped_query), list(tiny.gapped_target), list(tiny.coords)
+    for k in range(len(big)):                                   # long proteins interleaved at positions 0, 61, 122, ...
+        at = 61 * k
+        seqs.insert(at, big.query_seqs[k]); gq.insert(at, big.gapped_query[k]); gt.insert(at, big.gapped_target[k]); co_.insert(at, big.coords[k])
+    pred = predict.Predictor(path)
+    pred.set_engine("simt")
+    want = pred.forward_structures(seqs, gq, gt, co_, threshold=10.0, generated_contacts=2)
+    pred.set_engine("tc")
+    got = pred.forward_structures(seqs, gq, gt, co_, threshold=10.0, generated_contacts=2)
+    pred.close()
+    assert_scores(got, want)
+    os.environ["MDF_COMPACT"] = "0"
+    try:
+        padded = predict.Predictor(path)
+        padded.set_engine("tc")
+        ref = padded.forward_structures(seqs, gq, gt, co_, threshold=10.0, generated_contacts=2)
+        padded.close()
+    finally:
+        del os.environ["MDF_COMPACT"]
+    assert np.abs(got - ref).max() < 2e-5
