@@ -633,7 +633,7 @@ int launch_lstm_fused(mdf_ctx *ctx, int H, int n, const __half *W, int phases, c
         // members' lengths; longest-processing-time-first over the groups keeps them within one sub-batch of each other
         // (round-robin leaves the first group ~20 % more ticks than the last on a metagenomic length distribution).
         int used = 0;
-        std::vector<long long> load(a.n_groups, 0);
+        std::vector<long long> load(a.n_groups, 0), cost(a.n_sub, 0);
         std::vector<std::vector<int>> lists(a.n_groups);
         for (int j = 0; j < a.n_sub; ++j) {
             const int p0 = h_order[(size_t)j * sub_n];
@@ -641,9 +641,42 @@ int launch_lstm_fused(mdf_ctx *ctx, int H, int n, const __half *W, int phases, c
             if (L <= 0) break;                                 // sorted descending: nothing left
             const int gmin = (int)(std::min_element(load.begin(), load.end()) - load.begin());
             lists[gmin].push_back(j);
-            load[gmin] += L + 1 + 8;                           // + sub-batch switch overhead
+            cost[j] = L + 1 + 8;                               // + sub-batch switch overhead
+            load[gmin] += cost[j];
             ++used;
         }
+        // ... then local search on the critical group: move one of its sub-batches to, or swap it with a shorter one of, another
+        // group whenever that lowers the maximum (a few dozen items: LPT 2295 -> 2245 ticks against an ideal 2242 on a
+        // 16,384-protein metagenomic batch)
+        for (int iter = 0; iter < 4096; ++iter) {
+            const int gmax = (int)(std::max_element(load.begin(), load.end()) - load.begin());
+            bool improved = false;
+            for (size_t ia = 0; ia < lists[gmax].size() && !improved; ++ia) {
+                const int ja = lists[gmax][ia];
+                for (int go = 0; go < a.n_groups && !improved; ++go) {
+                    if (go == gmax) continue;
+                    if (load[go] + cost[ja] < load[gmax]) {
+                        lists[go].push_back(ja);
+                        lists[gmax].erase(lists[gmax].begin() + (long)ia);
+                        load[go] += cost[ja]; load[gmax] -= cost[ja];
+                        improved = true;
+                        break;
+                    }
+                    for (size_t ib = 0; ib < lists[go].size(); ++ib) {
+                        const int jb = lists[go][ib];
+                        const long long d = cost[ja] - cost[jb];
+                        if (d > 0 && load[go] + d < load[gmax]) {
+                            std::swap(lists[gmax][ia], lists[go][ib]);
+                            load[go] += d; load[gmax] -= d;
+                            improved = true;
+                            break;
+                        }
+                    }
+                }
+            }
+            if (!improved) break;
+        }
+        for (auto &l : lists) std::sort(l.begin(), l.end());   // longest sub-batch first inside a group, as before
         size_t stride = 1;
         for (auto &l : lists) stride = std::max(stride, l.size() + 1);
         if ((size_t)a.n_groups * stride * sizeof(int) > LF_SCRATCH_HEAD - 8192) { set_error("lstm_fused: schedule does not fit"); return MDF_EUNSUPPORTED; }
