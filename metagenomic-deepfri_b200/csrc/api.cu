@@ -1,5 +1,6 @@
 // C-ABI entry points of libmdf_b200 (include/mdf_b200.h).
 #include <chrono>
+#include <functional>
 #include <stdarg.h>
 #include <algorithm>
 #include <numeric>
@@ -114,6 +115,8 @@ extern "C" int mdf_ctx_create(int device, void *arena, size_t arena_bytes, void 
         c->arena_bytes = arena_bytes;
         c->own_arena = false;
     }
+    MDF_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    MDF_CUDA(cudaEventCreateWithFlags(&c->copy_done, cudaEventDisableTiming));
     MDF_CUDA(cudaMalloc((void **)&c->d_err, 256));
     MDF_CUDA(cudaMemset(c->d_err, 0, 256));
     MDF_CUDA(cudaMallocHost((void **)&c->h_err, 256));
@@ -130,6 +133,8 @@ extern "C" int mdf_ctx_destroy(mdf_ctx *c)
     if (c->own_arena && c->arena) cudaFree(c->arena);
     if (c->d_err) cudaFree(c->d_err);
     if (c->h_err) cudaFreeHost(c->h_err);
+    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    if (c->copy_done) cudaEventDestroy(c->copy_done);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
     return MDF_OK;
@@ -423,13 +428,20 @@ static int batch_build(mdf_ctx *ctx, mdf_batch *b, bool persistent, int n, const
         MDF_LAUNCH_CHECK(ctx);
     }
     if (b->has_structure) {
-        if (ncoord) MDF_CUDA(cudaMemcpyAsync(b->d_coords, coords, ncoord * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
-        MDF_CUDA(cudaMemcpyAsync(b->d_coord_off, coord_off, (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+        // transient batches (mdf_path_forward): coordinates and alignments - nine tenths of the input bytes - travel on the copy
+        // stream and are only awaited by the contact-map stage, which run_path enqueues after the LSTM language model
+        cudaStream_t cs = (!persistent && ctx->copy_stream) ? ctx->copy_stream : s;
+        if (ncoord) MDF_CUDA(cudaMemcpyAsync(b->d_coords, coords, ncoord * 3 * sizeof(float), cudaMemcpyHostToDevice, cs));
+        MDF_CUDA(cudaMemcpyAsync(b->d_coord_off, coord_off, (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, cs));
         if (alnb) {
-            MDF_CUDA(cudaMemcpyAsync(b->d_qaln, q_aln, alnb, cudaMemcpyHostToDevice, s));
-            MDF_CUDA(cudaMemcpyAsync(b->d_taln, t_aln, alnb, cudaMemcpyHostToDevice, s));
+            MDF_CUDA(cudaMemcpyAsync(b->d_qaln, q_aln, alnb, cudaMemcpyHostToDevice, cs));
+            MDF_CUDA(cudaMemcpyAsync(b->d_taln, t_aln, alnb, cudaMemcpyHostToDevice, cs));
         }
-        MDF_CUDA(cudaMemcpyAsync(b->d_aln_off, aln_off, (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+        MDF_CUDA(cudaMemcpyAsync(b->d_aln_off, aln_off, (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, cs));
+        if (cs != s) {
+            MDF_CUDA(cudaEventRecord(ctx->copy_done, cs));
+            b->copy_pending = true;
+        }
     } else if (packed_host && b->h_packed_off[n]) {
         MDF_CUDA(cudaMemcpyAsync(b->d_packed, packed_host, (size_t)b->h_packed_off[n] * 4, cudaMemcpyHostToDevice, s));
     }
@@ -451,6 +463,10 @@ static double cmap_algorithmic_bytes(const mdf_batch *b, int64_t ncoord_rows, in
 
 static int run_cmap(mdf_ctx *ctx, mdf_batch *b, float thr2, int gen)
 {
+    if (b->copy_pending) {                      // structure inputs were sent on the copy stream
+        MDF_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->copy_done, 0));
+        b->copy_pending = false;
+    }
     ProfScope ps(ctx, "cmap_build_transfer", ctx->profiling ? cmap_algorithmic_bytes(b, b->n_coord_rows, b->n_aln_cols) : 0.0);
     MDF_TRY(launch_aln_transfer(ctx, b->n, b->d_qaln, b->d_taln, b->d_aln_off, b->d_seq_off, b->d_coords,
                                 b->d_coord_off, b->d_qc));
@@ -471,17 +487,24 @@ static int run_path(mdf_model *m, mdf_batch *b, float thr2, int gen, int upto, b
     // a persistent batch that already holds the maps for this (threshold, generated contacts) keeps them for the next head
     const bool maps_cached = with_cmap && b->owns_memory && b->reuse && b->cmap_valid && b->cmap_thr2 == thr2 && b->cmap_gen == gen &&
                              b->cmap_eps == m->eps && upto >= 2;
-    if (with_cmap && !maps_cached) {
+    // Transient batches on the tensor-core engine: the LSTM language model and the embedding only need the sequences, so they are
+    // enqueued first and the contact-map stage (which waits for the coordinates still travelling on the copy stream) follows
+    const bool defer_cmap = with_cmap && !maps_cached && b->copy_pending && m->engine == 1 && upto >= 3;
+    std::function<int()> cmap_stage = [&]() -> int {
+        MDF_TRY(run_cmap(ctx, b, thr2, gen));
+        return launch_prep_adjacency(ctx, b, m->eps);
+    };
+    if (with_cmap && !maps_cached && !defer_cmap) {
         MDF_TRY(run_cmap(ctx, b, thr2, gen));
         b->cmap_valid = false;
     }
     if (upto < 2) return MDF_OK;
     MDF_TRY(launch_seq_to_idx(ctx, b->T, b->d_seq, b->d_idx));
-    if (!maps_cached) {
+    if (!maps_cached && !defer_cmap) {
         MDF_TRY(launch_prep_adjacency(ctx, b, m->eps));
         if (with_cmap && b->owns_memory) { b->cmap_valid = true; b->cmap_thr2 = thr2; b->cmap_gen = gen; b->cmap_eps = m->eps; }
     }
-    if (m->engine == 1) return tc_forward(m, b, upto);
+    if (m->engine == 1) return tc_forward(m, b, upto, defer_cmap ? &cmap_stage : nullptr);
     return simt_forward(m, b, upto);
 }
 

@@ -30,6 +30,7 @@ struct mdf_batch {
     int maxL = 0;
     int nwork = 0;          // 32-row blocks over all proteins
     bool has_structure = false;
+    bool copy_pending = false;   // structure inputs are still in flight on ctx->copy_stream (wait for ctx->copy_done before reading them)
     bool owns_memory = false;
     void *block = nullptr;  // one allocation holding everything below
     void *out_block = nullptr;  // pooled + scores of persistent batches (sized by the model head)

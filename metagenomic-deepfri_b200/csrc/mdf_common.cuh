@@ -59,6 +59,10 @@ struct mdf_ctx {
     // device-side error flag (invalid residue, non-0/1 cmap, Lq mismatch ...)
     int *d_err = nullptr;
     int *h_err = nullptr;  // pinned
+    // second stream for the structure inputs of mdf_path_forward: their host->device copy runs beside the LSTM language model,
+    // which only needs the sequences; the contact-map stage waits for `copy_done`
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t copy_done = nullptr;
 
     // optional per-stage CUDA-event profiling (bench.py roofline leg)
     struct ProfEntry { const char *name; cudaEvent_t start, stop; double units; };

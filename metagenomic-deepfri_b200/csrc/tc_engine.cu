@@ -720,7 +720,7 @@ size_t tc_workspace_bytes(const mdf_model *m, int n, const int64_t *seq_off)
 }
 
 // ------------------------------------------------------------------------------------------- forward
-int tc_forward(mdf_model *m, mdf_batch *b, int upto)
+int tc_forward(mdf_model *m, mdf_batch *b, int upto, const std::function<int()> *before_graphconv)
 {
     mdf_ctx *ctx = m->ctx;
     TcModel *tm = static_cast<TcModel *>(m->tc);
@@ -863,6 +863,12 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto)
         b->tap_x0 = tap;
     }
     if (upto < 3) return MDF_OK;
+    if (before_graphconv) {
+        // deferred contact-map stage: the maps and degrees exist from here on; the degree vector over image rows is (re)built
+        MDF_TRY((*before_graphconv)());
+        pad_vectors_kernel<<<(unsigned)cdiv64(Tp, 256), 256, 0, s>>>(Tp, meta->rowmap, b->d_deg, b->d_idx, deg_pad, idx_pad);
+        MDF_LAUNCH_CHECK(ctx);
+    }
     // ---- adjacency operand tiles
     if (meta->n_adj_tiles > 0 && !tm->adj_expand) {
         ProfScope ps(ctx, "expand_adjacency", 0.0);
