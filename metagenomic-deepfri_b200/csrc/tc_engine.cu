@@ -730,7 +730,8 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto, const std::function<int()> 
     cudaStream_t s = ctx->stream;
 
     // ---- residue-axis metadata (compact axis needs the list-walking adjacency GEMM)
-    const bool want_compact = tm->compact && tm->adj_expand && tm->adj_sparse && !tm->adj_pair;
+    // (the separate pooling kernel of MDF_POOL_FUSED=0 walks per-protein 128-row tiles of the image: padded axis only)
+    const bool want_compact = tm->compact && tm->adj_expand && tm->adj_sparse && !tm->adj_pair && tm->pool_fused;
     TcBatchMeta local_meta;
     TcBatchMeta *meta = &local_meta;
     if (b->owns_memory) {
