@@ -217,6 +217,27 @@ cmap_pair_sym_kernel(const int2 *__restrict__ work, const float4 *__restrict__ q
     const int ntile = (L + 127) >> 7, dt = rb >> 2;              // dt = the tile that holds this block's own columns
     for (int tile = dt + warp; tile < ntile; tile += PAIR_WARPS) {
         const int jlo = tile << 7;
+        const int kend = min(4, (L - jlo + 31) >> 5);             // 32-column groups of this tile that hold a column < L
+        if (kend < 4) {
+            // partly filled last tile: one column group at a time (the full-tile body below would spend up to three quarters of
+            // its work on padding columns); the row words of the groups past L are padding and must read as zero
+            for (int k = 0; k < kend; ++k) {
+                const int j = jlo + 32 * k + lane;
+                const float4 v = j < L ? q[j] : make_float4(qnan, qnan, qnan, 0.f);
+                uint32_t t1 = 0u;
+#pragma unroll
+                for (int r = 0; r < 32; ++r) {
+                    const float4 a = rows[r];
+                    if (sqdist3(a.x, a.y, a.z, v.x, v.y, v.z) < thr2) t1 |= 1u << r;
+                }
+                if (tile > dt && j < L) out[(size_t)j * rw + rb] = t1;
+                const uint32_t rowword = warp_transpose32(t1, lane);
+                if (rb * 32 + lane < L) out[(size_t)(rb * 32 + lane) * rw + tile * 4 + k] = rowword;
+            }
+            if (rb * 32 + lane < L)
+                for (int k = kend; k < 4; ++k) out[(size_t)(rb * 32 + lane) * rw + tile * 4 + k] = 0u;
+            continue;
+        }
         float cx[4], cy[4], cz[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
