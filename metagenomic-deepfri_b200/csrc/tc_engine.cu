@@ -360,7 +360,7 @@ __global__ void pad_vectors_kernel(int64_t Tp, const int *__restrict__ rowmap, c
     const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (r >= Tp) return;
     const int s = rowmap[r];
-    deg_pad[r] = s >= 0 ? deg[s] : 0.0f;
+    if (deg) deg_pad[r] = s >= 0 ? deg[s] : 0.0f;        // deg == nullptr: the degrees do not exist yet (deferred contact-map stage)
     idx_pad[r] = s >= 0 ? idx[s] : (uint8_t)0;
 }
 
@@ -769,7 +769,8 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto, const std::function<int()> 
     MDF_TRY(ctx->alloc_n(&Xa, (size_t)Tp * gmax));
     MDF_TRY(ctx->alloc_n(&Xb, (size_t)Tp * gmax));
     MDF_TRY(ctx->alloc((void **)&Aimg, tm->adj_expand ? 256 : (size_t)meta->n_adj_tiles * TILE_BYTES + 256));
-    pad_vectors_kernel<<<(unsigned)cdiv64(Tp, 256), 256, 0, s>>>(Tp, meta->rowmap, b->d_deg, b->d_idx, deg_pad, idx_pad);
+    pad_vectors_kernel<<<(unsigned)cdiv64(Tp, 256), 256, 0, s>>>(Tp, meta->rowmap, before_graphconv ? nullptr : b->d_deg, b->d_idx, deg_pad,
+                                                                 idx_pad);
     MDF_LAUNCH_CHECK(ctx);
 
     // ---- LSTM language model.  A persistent batch keeps the last layer's output image: another head with the same LM
