@@ -79,10 +79,18 @@ def make_weights(cfg: GCNConfig, seed: int = 1234, lm_seed: int = 99) -> Dict[st
 
 
 def build_gcn_model(cfg: GCNConfig, weights: Optional[Dict[str, np.ndarray]] = None,
-                    seed: int = 1234) -> ox.Model:
+                    seed: int = 1234, style: str = "compact") -> ox.Model:
     """DeepFRI GCN head as an ONNX graph. Inputs are ordered (cmap, seq) as the reference
     feeds them (`predict.pyx:87-90`); output is [1, C, 2] with the score in channel 0
-    (`predict.pyx:100`)."""
+    (`predict.pyx:100`).
+
+    `style="compact"`: the adjacency is normalised once (D.A.D as two broadcast Muls) and shared by the layers.
+    `style="tf2onnx"`: closer to what tf2onnx makes of upstream's Keras layers - every GraphConv layer carries its own
+    copy of `GraphConv._normalize` with D_hat an explicit diagonal MATRIX and `matmul(matmul(D_hat, A_hat), D_hat)`
+    (three data-dependent MatMuls per layer), `eps + sqrt(.)` with the constant on the left, and the LSTM nodes carry an
+    empty sequence_lens, constant-zero initial_h / initial_c and the Y_h / Y_c outputs.  Same function, same weights."""
+    if style not in ("compact", "tf2onnx"):
+        raise ValueError(style)
     w = dict(weights) if weights is not None else make_weights(cfg, seed)
     g = ox.Graph(name="DeepFRI_GraphConv")
     g.inputs = [ox.ValueInfo("cmap", ox.FLOAT, ("unk__b", "unk__l", "unk__l")),
@@ -106,9 +114,15 @@ def build_gcn_model(cfg: GCNConfig, weights: Optional[Dict[str, np.ndarray]] = N
     # ---- LSTM language model (tf2onnx: Transpose -> LSTM -> Squeeze, time-major)
     H = cfg.lstm_hidden
     x = add("Transpose", ["seq"], ["lm/seq_tm"], perm=[1, 0, 2])
+    if style == "tf2onnx":
+        init["lm/zero_state"] = np.zeros((1, 1, H), np.float32)
     for l in (1, 2):
-        y = add("LSTM", [x, f"lstm{l}_W", f"lstm{l}_R", f"lstm{l}_B"],
-                [f"lm/LSTM{l}_Y"], hidden_size=H, direction="forward")
+        if style == "tf2onnx":
+            y = add("LSTM", [x, f"lstm{l}_W", f"lstm{l}_R", f"lstm{l}_B", "", "lm/zero_state", "lm/zero_state"],
+                    [f"lm/LSTM{l}_Y", f"lm/LSTM{l}_Yh", f"lm/LSTM{l}_Yc"], hidden_size=H, direction="forward")
+        else:
+            y = add("LSTM", [x, f"lstm{l}_W", f"lstm{l}_R", f"lstm{l}_B"],
+                    [f"lm/LSTM{l}_Y"], hidden_size=H, direction="forward")
         x = add("Squeeze", [y, "const_axes_1"], [f"lm/LSTM{l}_out"])
     lm_out = add("Transpose", [x], ["lm/LSTM2_bm"], perm=[1, 0, 2])
     x_lm = add("MatMul", [lm_out, "LM_embedding_W"], ["LM_embedding/MatMul"])
@@ -118,24 +132,33 @@ def build_gcn_model(cfg: GCNConfig, weights: Optional[Dict[str, np.ndarray]] = N
     x = add("Relu", [x], ["activation/Relu"])
 
     # ---- adjacency normalisation (GraphConv._normalize upstream)
-    a2 = add("Squeeze", ["cmap", "const_axes_0"], ["norm/A2d"])
-    eye = add("EyeLike", [a2], ["norm/eye2d"])
-    eye = add("Unsqueeze", [eye, "const_axes_0"], ["norm/eye"])
-    dg = add("Mul", ["cmap", eye], ["norm/diagA"])
-    a0 = add("Sub", ["cmap", dg], ["norm/A_nodiag"])
-    ah = add("Add", [a0, eye], ["norm/A_hat"])
-    rs = add("ReduceSum", [ah, "const_axes_2"], ["norm/rowsum"], keepdims=0)
-    sq = add("Sqrt", [rs], ["norm/sqrt"])
-    dn = add("Add", [sq, "const_eps"], ["norm/denom"])
-    d = add("Div", ["const_one", dn], ["norm/d"])
-    dc = add("Unsqueeze", [d, "const_axes_2"], ["norm/d_col"])
-    dr = add("Unsqueeze", [d, "const_axes_1"], ["norm/d_row"])
-    an = add("Mul", [dc, ah], ["norm/DA"])
-    an = add("Mul", [an, dr], ["norm/DAD"])
+    def normalize(pfx: str, matrix_form: bool) -> str:
+        a2 = add("Squeeze", ["cmap", "const_axes_0"], [pfx + "A2d"])
+        eye = add("EyeLike", [a2], [pfx + "eye2d"])
+        eye = add("Unsqueeze", [eye, "const_axes_0"], [pfx + "eye"])
+        dg = add("Mul", ["cmap", eye], [pfx + "diagA"])
+        a0 = add("Sub", ["cmap", dg], [pfx + "A_nodiag"])
+        ah = add("Add", [a0, eye], [pfx + "A_hat"])
+        rs = add("ReduceSum", [ah, "const_axes_2"], [pfx + "rowsum"], keepdims=0)
+        sq = add("Sqrt", [rs], [pfx + "sqrt"])
+        dn = add("Add", ["const_eps", sq] if matrix_form else [sq, "const_eps"], [pfx + "denom"])
+        d = add("Div", ["const_one", dn], [pfx + "d"])
+        dc = add("Unsqueeze", [d, "const_axes_2"], [pfx + "d_col"])
+        if matrix_form:
+            dm = add("Mul", [dc, eye], [pfx + "D_hat"])                       # tf.linalg.diag(d)
+            da = add("MatMul", [dm, ah], [pfx + "DA"])
+            return add("MatMul", [da, dm], [pfx + "DAD"])
+        dr = add("Unsqueeze", [d, "const_axes_1"], [pfx + "d_row"])
+        da = add("Mul", [dc, ah], [pfx + "DA"])
+        return add("Mul", [da, dr], [pfx + "DAD"])
+
+    an = normalize("norm/", False) if style == "compact" else None
 
     # ---- GraphConv stack: act((A_n . X) . W [+ b])
     outs = []
     for l, gdim in enumerate(cfg.gc_dims, 1):
+        if style == "tf2onnx":
+            an = normalize(f"GraphConv_{l}/norm/", True)
         t = add("MatMul", [an, x], [f"GraphConv_{l}/batch_dot"])
         t = add("MatMul", [t, f"GraphConv_{l}_W"], [f"GraphConv_{l}/MatMul"])
         if cfg.gc_bias:
@@ -158,8 +181,8 @@ def build_gcn_model(cfg: GCNConfig, weights: Optional[Dict[str, np.ndarray]] = N
                     producer_version="1")
 
 
-def write_gcn_model(path: str, cfg: GCNConfig, seed: int = 1234) -> None:
-    ox.save(build_gcn_model(cfg, seed=seed), path)
+def write_gcn_model(path: str, cfg: GCNConfig, seed: int = 1234, style: str = "compact") -> None:
+    ox.save(build_gcn_model(cfg, seed=seed, style=style), path)
 
 
 # ----------------------------------------------------------------------------- sequence-only DeepCNN heads
