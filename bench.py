@@ -1,58 +1,36 @@
 #!/usr/bin/env python
-"""bench.py — proteins/s of the structure-branch hot path (contact-map build + alignment transfer +
-DeepFRI GCN MF forward) on N B200s of one node, one process per GPU.
+"""bench.py — throughput of the structure-branch hot path (contact-map build + alignment transfer + DeepFRI GCN forward) on
+N B200s of one node, one process per GPU.
 
   python bench.py --gpus 1 --steps K --warmup W            # this repo's CUDA path
-  python bench.py --impl reference ...                     # the reference's CPU path (oracle) on host cores
+  python bench.py --impl reference ...                     # the reference's CPU path (oracle) on the host cores
 
-One "step" = one pass of the whole path over one batch of synthetic proteins.  The default workload is
-the configuration BASELINE.json's metric is quoted on, configs[4] (the 1M-protein metagenomic MF job,
-L ~ LogNormal(median 250, sigma 0.6) clipped to [50, 1000]), processed the way the sharded job runs it:
-in batches of 16,384 proteins per GPU (Markov-gapped alignments, random-walk C-alpha structures, 10 A
-contact maps, random-init MF head C=489 in the reference's ONNX layout).  `--workload config0` selects
-configs[0] (1,000 proteins, L~U{100..500}), the reference's own CPU-runnable case.  Weak scaling: every
-rank processes its own copy of the batch (same seed, so per-GPU work is exactly fixed); no collective on the
-compute path, one final gather of the score matrices.
+Workloads (`--workload`, BASELINE.json `configs[i]`):
+  config4 (default)  the 1M-protein metagenomic MF job, L ~ LogNormal(median 250, sigma 0.6) clipped to [50, 1000], Markov-gapped
+                     alignments, random-walk C-alpha structures, 10 A maps, random-init MF head C = 489 in the reference's
+                     ONNX layout.  The job's proteins (protein i = a pure function of (seed 5, i)) are partitioned over the
+                     ranks by length-balanced LPT bins (`sharding.lpt_bins`) and every rank streams its bin in chunks of
+                     <= 16,384 proteins.  One timed "step" = the whole path over one chunk per GPU:
+                       value  = inputs of the chunk resident in HBM, CUDA events;
+                       e2e    = the chunks of the rank's bin, one per step, from PYTHON LISTS of str / ndarray through
+                                `Predictor.submit_structures` / `wait` (C packing into pinned memory, H2D, kernels, D2H; two jobs
+                                in flight), then the single result gather;
+                     then (not a step-contract number) `sharded_job`: the whole 1M-protein job end to end, strong scaling.
+  config0            1,000 proteins L~U{100..500}, MF head: one step = all 1,000 proteins.
+  config1            contact-map build + alignment transfer only, 100k pairs at 6 A: one step = one chunk of 16,384 pairs;
+                     metric pairs/s; roofline against HBM for both output layouts (bit-packed, and the reference's dense int32).
+  config2            the four heads (MF, BP, CC, EC) on 10k proteins (maps and LM shared): one step = all heads on all proteins.
+  config3            2,000 proteins L 1000-2500: one step = all of them.
 
 Prints ONE JSON line on rank 0 (contract in the task statement).
 """
 import argparse
 import json
 import os
-import statistics
-import subprocess
 import sys
-import tempfile
-import threading
-import time
-
-import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, ROOT)
-import mdf_pkg  # noqa: E402
-
-mdf_pkg.load()
-from metagenomic_deepfri_b200 import synth  # noqa: E402
-
-THRESHOLD, GEN = 10.0, 2
-WORKLOADS = {
-    # name: (description, default proteins per step per GPU, generator)
-    "config4": ("BASELINE configs[4]: 1M-protein metagenomic MF job, L~LogNormal(250, 0.6) clipped [50,1000], run in "
-                "batches of {n} proteins per GPU per step; gapped alignments, 10A maps, MF head C=489", 16384,
-                lambda n, seed: synth.make_workload(n, 50, 1000, seed=seed, dist="lognormal", threshold=THRESHOLD)),
-    "config0": ("BASELINE configs[0]: {n} synthetic proteins L~U{{100..500}}, gapped alignments, 10A maps, MF head C=489", 1000,
-                lambda n, seed: synth.make_workload(n, 100, 500, seed=seed, threshold=THRESHOLD)),
-}
-
-
-def make_batch(args, rank):
-    desc, default_n, gen = WORKLOADS[args.workload]
-    n = args.proteins or default_n
-    base_seed = 5 if args.workload == "config4" else 1
-    # every rank draws the same batch: per-GPU work is exactly fixed as N grows (weak scaling); ranks differ in nothing but
-    # the device they run on
-    return gen(n, base_seed), desc.format(n=n)
+WORKLOAD_NAMES = ("config0", "config1", "config2", "config3", "config4")
 
 
 def parse():
@@ -61,13 +39,50 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="config4", choices=sorted(WORKLOADS))
-    ap.add_argument("--proteins", type=int, default=0, help="proteins per step per GPU (0 = the workload's default)")
+    ap.add_argument("--workload", default="config4", choices=WORKLOAD_NAMES)
+    ap.add_argument("--proteins", type=int, default=0, help="proteins per chunk (0 = the workload's default)")
+    ap.add_argument("--job-proteins", type=int, default=-1,
+                    help="config4: size of the sharded job (default 1,000,000; 0 skips the sharded_job leg)")
     ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tc"])
-    ap.add_argument("--cpu-sample", type=int, default=400, help="proteins in the cpu_baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=400, help="proteins (pairs) in the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-lanes", type=int, default=1, help="concurrent contexts per GPU in the end-to-end leg (1 or 2)")
     return ap.parse_args()
+
+
+ARGS = parse()
+if ARGS.impl == "reference":
+    # the CPU arm uses every host core; torch.distributed.run exports OMP_NUM_THREADS=1 to its workers, which would otherwise
+    # pin the BLAS / OpenMP pools of this process to one thread
+    for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+        os.environ[k] = str(os.cpu_count() or 1)
+
+import statistics  # noqa: E402
+import subprocess  # noqa: E402
+import tempfile  # noqa: E402
+import threading  # noqa: E402
+import time  # noqa: E402
+
+import numpy as np  # noqa: E402
+
+sys.path.insert(0, ROOT)
+import mdf_pkg  # noqa: E402
+
+mdf_pkg.load()
+from metagenomic_deepfri_b200 import synth  # noqa: E402
+
+GEN = 2
+HEADS = {"mf": 489, "bp": 1943, "cc": 320, "ec": 538}
+CHUNK = 16384
+DESCRIPTIONS = {
+    "config4": "BASELINE configs[4]: metagenomic MF job, L~LogNormal(250, 0.6) clipped [50,1000], protein i keyed by (seed 5, i), LPT bins "
+               "over the ranks, chunks of <= {n} proteins per GPU per step; gapped alignments, 10A maps, MF head C=489",
+    "config0": "BASELINE configs[0]: {n} synthetic proteins L~U{{100..500}}, gapped alignments, 10A maps, MF head C=489",
+    "config1": "BASELINE configs[1]: contact-map build + alignment transfer only, chunks of {n} of 100,000 query/target pairs "
+               "(L~U{{50..1000}}, Markov-gapped alignments, 6A, generated contacts 2)",
+    "config2": "BASELINE configs[2]: MF, BP, CC and EC heads on {n} proteins, L~LogNormal(250, 0.6) clipped [50,1000], maps + LM shared",
+    "config3": "BASELINE configs[3]: {n} proteins L~U{{1000..2500}}, 10A maps, MF head C=489",
+}
+THRESHOLDS = {"config0": 10.0, "config1": 6.0, "config2": 10.0, "config3": 10.0, "config4": 10.0}
 
 
 def measured_peaks():
@@ -88,70 +103,160 @@ def ncu_traffic(stage):
     return None
 
 
+def sub(wl, idx):
+    return synth.Workload([wl.query_seqs[i] for i in idx], [wl.gapped_query[i] for i in idx], [wl.gapped_target[i] for i in idx],
+                          [wl.coords[i] for i in idx], wl.threshold, wl.generated_contacts, wl.name)
+
+
+# ------------------------------------------------------------------------------------------ workloads
+def small_workload(name, n_override):
+    """configs[0..3] -> (list of chunks, description).  Same seeds as synth.config_workload."""
+    idx = int(name[-1])
+    full = {0: 1000, 1: 100_000, 2: 10_000, 3: 2000}[idx]
+    if idx == 1:
+        n = n_override or CHUNK
+        wl = synth.config_workload(1, min(1.0, 4 * n / full))          # four different chunks are enough for the step loop
+        chunks = [sub(wl, range(lo, min(len(wl), lo + n))) for lo in range(0, len(wl), n)]
+        return chunks, DESCRIPTIONS[name].format(n=n)
+    n = n_override or full
+    wl = synth.config_workload(idx, n / full)
+    return [wl], DESCRIPTIONS[name].format(n=len(wl))
+
+
+def config4_plan(args, world):
+    """Lengths of the whole job, LPT bins, chunks: identical on every rank (pure function of the seed)."""
+    from metagenomic_deepfri_b200 import distributed, sharding
+    n_chunk = args.proteins or CHUNK
+    job_n = 1_000_000 if args.job_proteins < 0 else args.job_proteins
+    # the step legs need at least `chunks_wanted` chunks per rank even when the sharded_job leg is off or small
+    plan_n = max(job_n, world * n_chunk * 2)
+    lengths = synth.keyed_lengths(np.arange(plan_n), 5)
+    shards = distributed.shard_job(lengths, world, max_proteins=n_chunk)
+    bins = [np.concatenate(s) if s else np.zeros(0, np.int64) for s in shards]
+    pred_imb = sharding.imbalance(bins, lengths)
+    return lengths, shards, job_n, plan_n, pred_imb
+
+
 # ------------------------------------------------------------------------------------------ CPU arm
-def cpu_path_proteins_per_s(wl, model_path, idx):
-    """The reference's CPU path on `idx`: compiled contact_map_utils.pyx (oracle/_ref) when present,
-    else the C port, + NumPy glue of bio_utils.py:214-223, then the fp32 ONNX interpreter standing in
-    for onnxruntime (absent from this image), one protein per call like pipeline.py:301-319."""
+def cpu_predictor(model_path):
+    """The GCN half of the CPU arm: the `.onnx` file executed on PyTorch's CPU kernels (oracle/torch_ref.py: torch.nn.LSTM
+    / oneDNN GEMMs - the fastest stand-in for onnxruntime this image has; onnxruntime itself is absent), batch = 1 per call
+    like pipeline.py:301-319, all host threads."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch
+    import torch_ref
+    torch.set_num_threads(os.cpu_count() or 1)
+    return torch_ref.Predictor(model_path), torch.get_num_threads()
+
+
+def cpu_cmap(wl, i, thr):
+    import cmap_oracle as co
+    ref = co.ref_module()
+    if ref is not None:
+        D = ref.pairwise_sqeuclidean(wl.coords[i])
+        sp = np.argwhere((D < thr ** 2).astype(np.int32) == 1).astype(np.int32)        # bio_utils.py:220-223
+        return ref.align_contact_map(wl.gapped_query[i], wl.gapped_target[i], sp, GEN)
+    return co.build_align_contact_map(wl.gapped_query[i], wl.gapped_target[i], wl.coords[i], thr, GEN)
+
+
+_POOL_WL = None
+
+
+def _pool_cmap(args):
+    i, thr = args
+    return cpu_cmap(_POOL_WL, i, thr).shape[0]
+
+
+def cpu_path(wl, thr, idx, model_paths, pool=None):
+    """The reference's CPU path on proteins `idx`: compiled contact_map_utils.pyx (oracle/_ref; the C port when it is not
+    built) + the NumPy glue of bio_utils.py:214-223, then one forward_pass per protein and head.  -> (units/s, seconds, cores, what)"""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import cmap_oracle as co
-    import gcn_oracle as go
-    ref = co.ref_module()
-    pred = go.Predictor(model_path)
+    cm_impl = "reference contact_map_utils.pyx" if co.ref_module() is not None else "C port"
+    if not model_paths:                               # configs[1]: maps only, a process pool like pipeline.py:476-481
+        t0 = time.perf_counter()
+        if pool is not None:
+            pool.map(_pool_cmap, [(int(i), thr) for i in idx], chunksize=4)
+        else:
+            for i in idx:
+                cpu_cmap(wl, int(i), thr)
+        dt = time.perf_counter() - t0
+        return len(idx) / dt, dt, (pool._processes if pool is not None else 1), f"cmap: {cm_impl}, process pool"
+    preds, threads = [], 1
+    for p in model_paths:
+        pr, threads = cpu_predictor(p)
+        preds.append(pr)
     t0 = time.perf_counter()
     for i in idx:
-        c = wl.coords[i]
-        if ref is not None:
-            D = ref.pairwise_sqeuclidean(c)
-            sp = np.argwhere((D < THRESHOLD ** 2).astype(np.int32) == 1).astype(np.int32)
-            cm = ref.align_contact_map(wl.gapped_query[i], wl.gapped_target[i], sp, GEN)
-        else:
-            cm = co.build_align_contact_map(wl.gapped_query[i], wl.gapped_target[i], c, THRESHOLD, GEN)
-        pred.forward_pass(wl.query_seqs[i], cm)
+        cm = cpu_cmap(wl, int(i), thr)
+        for pr in preds:
+            pr.forward_pass(wl.query_seqs[int(i)], cm)
     dt = time.perf_counter() - t0
-    kind = "port"   # the GCN half is a port (onnxruntime unavailable); the cmap half runs the reference itself when built
-    return len(idx) / dt, dt, kind, ("reference .pyx" if ref is not None else "C port")
+    return len(idx) / dt, dt, threads, (f"cmap: {cm_impl}; GCN: torch-CPU executor of the .onnx file standing in for onnxruntime "
+                                       f"({threads} threads), batch=1 per call")
 
 
-def blas_threads():
-    try:
-        from threadpoolctl import threadpool_info
-        n = [d.get("num_threads", 1) for d in threadpool_info() if d.get("user_api") == "blas"]
-        return max(n) if n else 1
-    except Exception:
-        return os.cpu_count() or 1
+def write_models(tmp, workload):
+    if workload == "config1":
+        p = os.path.join(tmp, "mf.onnx")
+        synth.write_gcn_model(p, synth.GCNConfig())
+        return {"mf": p}
+    heads = HEADS if workload == "config2" else {"mf": 489}
+    out = {}
+    for h, C in heads.items():
+        out[h] = os.path.join(tmp, f"{h}.onnx")
+        synth.write_gcn_model(out[h], synth.GCNConfig(n_terms=C), seed=1234 if h == "mf" else 77 + C)
+    return out
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    wl, workload = make_batch(args, 0)
-    per_step = 6
+    global _POOL_WL
+    thr = THRESHOLDS[args.workload]
+    if args.workload == "config4":
+        n = args.proteins or CHUNK
+        wl, workload = synth.keyed_workload_parallel(np.arange(2048), 5, min(8, os.cpu_count() or 1)), DESCRIPTIONS["config4"].format(n=n)
+    else:
+        chunks, workload = small_workload(args.workload, min(args.proteins or 2048, 2048) if args.workload == "config1" else args.proteins)
+        wl = chunks[0]
+    maps_only = args.workload == "config1"
+    per_step = 64 if maps_only else (2 if args.workload in ("config2", "config3") else 6)
+    pool = None
+    if maps_only:
+        import multiprocessing as mp
+        _POOL_WL = wl
+        pool = mp.get_context("fork").Pool(os.cpu_count() or 1)
     with tempfile.TemporaryDirectory() as d:
-        path = os.path.join(d, "mf.onnx")
-        synth.write_gcn_model(path, synth.GCNConfig())
+        models = [] if maps_only else list(write_models(d, args.workload).values())
         rng = np.random.default_rng(0)
-        times = []
+        times, cores, what = [], 1, ""
         for s in range(args.warmup + args.steps):
-            idx = rng.choice(len(wl), per_step, replace=False)
-            pps, dt, kind, cm_impl = cpu_path_proteins_per_s(wl, path, idx)
+            idx = rng.choice(len(wl), min(per_step, len(wl)), replace=False)
+            _, dt, cores, what = cpu_path(wl, thr, idx, models, pool)
             if s >= args.warmup:
                 times.append(dt)
+    if pool is not None:
+        pool.close()
     total = sum(times)
     value = per_step * args.steps / total
-    cores = blas_threads()
+    unit = "pairs/s" if maps_only else "proteins/s"
     line = {
-        "impl": "reference", "metric": "proteins/sec (GCN MF fwd incl. cmap)", "value": value, "unit": "proteins/s",
+        "impl": "reference", "metric": metric_name(args.workload), "value": value, "unit": unit,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload, "sample": f"{per_step} proteins per step drawn from one {len(wl)}-protein batch",
-                   "cmap": cm_impl, "gcn": "fp32 NumPy ONNX interpreter (onnxruntime absent)"},
-        "cpu_baseline": {"value": value, "unit": "proteins/s", "cores": cores, "kind": "port",
-                         "sample": f"{per_step * args.steps} proteins, batch=1 per call, host has {os.cpu_count()} cpus"},
-        "e2e": {"value": value, "unit": "proteins/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": {"workload": workload, "sample": f"{per_step} units per step drawn from {len(wl)} of the workload's proteins", "cpu_path": what},
+        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port",
+                         "sample": f"{per_step * args.steps} units; {what}; host has {os.cpu_count()} cpus"},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def metric_name(workload):
+    return {"config1": "pairs/sec (contact-map build + alignment transfer)",
+            "config2": "proteins/sec (GCN MF+BP+CC+EC fwd incl. cmap)"}.get(workload, "proteins/sec (GCN MF fwd incl. cmap)")
 
 
 # ------------------------------------------------------------------------------------------ clocks
@@ -200,36 +305,97 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ B200 arm
-def run_b200(args, rank, world, local_rank):
+def prepare_inputs(args, rank, world):
+    """Host-side inputs of this rank.  Runs before the process group and CUDA exist: the generators fork worker processes."""
+    global _POOL_WL
+    thr = THRESHOLDS[args.workload]
+    maps_only = args.workload == "config1"
+    t_gen = time.perf_counter()
+    sharded = None
+    if args.workload == "config4":
+        lengths, shards, job_n, plan_n, pred_imb = config4_plan(args, world)
+        my_chunks_idx = shards[rank]
+        chunks_wanted = len(my_chunks_idx) if job_n else min(len(my_chunks_idx), 2)
+        procs = max(1, min(16, (os.cpu_count() or 1) // max(1, min(world, 8))))
+        ids = np.concatenate(my_chunks_idx[:chunks_wanted])
+        wl_all = synth.keyed_workload_parallel(ids, 5, procs, threshold=thr)
+        chunks, lo = [], 0
+        for ci in my_chunks_idx[:chunks_wanted]:
+            chunks.append(sub(wl_all, range(lo, lo + len(ci))))
+            lo += len(ci)
+        del wl_all
+        workload = DESCRIPTIONS["config4"].format(n=args.proteins or CHUNK)
+        sharded = dict(job_n=job_n, lengths=lengths, my_idx=my_chunks_idx, pred_imb=pred_imb)
+    else:
+        chunks, workload = small_workload(args.workload, args.proteins)
+    gen_s = time.perf_counter() - t_gen
+    cpu_pool = None
+    if maps_only and rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import multiprocessing as mp
+        _POOL_WL = chunks[0]
+        cpu_pool = mp.get_context("fork").Pool(os.cpu_count() or 1)      # forked before the CUDA context exists
+    return dict(chunks=chunks, workload=workload, sharded=sharded, gen_s=gen_s, cpu_pool=cpu_pool)
+
+
+def run_b200(args, rank, world, local_rank, inputs):
+    thr = THRESHOLDS[args.workload]
+    maps_only = args.workload == "config1"
+    multi_head = args.workload == "config2"
+    chunks, workload, sharded, gen_s, cpu_pool = (inputs[k] for k in ("chunks", "workload", "sharded", "gen_s", "cpu_pool"))
+
     import torch
     import torch.distributed as dist
-    from metagenomic_deepfri_b200 import _lib, predict
+    from metagenomic_deepfri_b200 import _lib, bio_utils, distributed, pipeline, predict
     torch.cuda.set_device(local_rank)
     stream = torch.cuda.Stream()             # a real (non-NULL) stream shared by torch and the library
     torch.cuda.set_stream(stream)
     ctx = _lib.Context(local_rank, stream=stream.cuda_stream)
-    wl, workload = make_batch(args, rank)
     tmp = tempfile.mkdtemp()
-    path = os.path.join(tmp, f"mf_{rank}.onnx")
-    synth.write_gcn_model(path, synth.GCNConfig())
-    pred = predict.Predictor(path, context=ctx)
+    models = write_models(tmp, args.workload)
+    preds = {h: predict.Predictor(p, context=ctx) for h, p in models.items()}
+    pred = preds["mf"]
     if args.engine != "auto":
-        pred.set_engine(args.engine)
-    n = len(wl)
-    C = pred.n_terms
-    T = sum(len(s) for s in wl.query_seqs)
+        for p in preds.values():
+            p.set_engine(args.engine)
+    C = sum(p.n_terms for p in preds.values()) if multi_head else pred.n_terms
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def allsum(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t[0])
+
+    def allmax(*xs):
+        t = torch.tensor([float(x) for x in xs], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t]
+
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
+    wl0 = chunks[0]
+    n0 = len(wl0)
+    T0 = sum(len(s) for s in wl0.query_seqs)
+
+    def run_resident(batch):
+        if maps_only:
+            pred.run(batch, thr, GEN, upto=1)
+        elif multi_head:
+            batch.invalidate()                  # nothing computed by an earlier step may be reused: every step builds the maps and runs the LM
+            for p in preds.values():
+                p.run(batch, thr, GEN, share=True)      # within the step the four heads share maps + LM output (pipeline.py:546-655)
+        else:
+            pred.run(batch, thr, GEN)
 
     # ---- resident leg: inputs already in HBM when the timed region starts
-    batch = pred.upload(wl.query_seqs, wl.gapped_query, wl.gapped_target, wl.coords)
+    batch = pred.upload(wl0.query_seqs, wl0.gapped_query, wl0.gapped_target, wl0.coords)
     for _ in range(args.warmup):
-        pred.run(batch, THRESHOLD, GEN)
+        run_resident(batch)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -241,82 +407,128 @@ def run_b200(args, rank, world, local_rank):
     for s in range(args.steps):
         flush.zero_()                           # L2 flush between timed iterations (outside the events)
         ev[s][0].record(stream)
-        pred.run(batch, THRESHOLD, GEN)
+        run_resident(batch)
         ev[s][1].record(stream)
     barrier()
     timed_stages = ctx.profile_report()
     ctx.profile(False)
     launches = ctx.launch_count - launches0
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
-    scores_resident = pred.fetch_scores(batch)
+    dense = None
+    if maps_only:                               # the reference-layout (dense int32) output of the same maps: HBM-bound variant
+        for _ in range(2):
+            cells = pred.unpack_dense(batch)
+        ctx.profile(True)
+        for _ in range(max(3, args.steps)):
+            flush.zero_()
+            pred.unpack_dense(batch)
+        rep = [r for r in ctx.profile_report() if r[0] == "cmap_unpack_dense"]
+        ctx.profile(False)
+        dms = sum(r[1] for r in rep) / len(rep)
+        dense = {"cells": cells, "unpack_ms": dms, "bytes": rep[0][2]}
+    scores_resident = None if maps_only else np.concatenate([p.fetch_scores(batch) for p in preds.values()], axis=1) if multi_head \
+        else pred.fetch_scores(batch)
+    batch.close()
+    del batch
 
-    # ---- end-to-end leg: pinned host buffers -> H2D -> path -> D2H, through the public call
-    inputs = predict.PathInputs(wl.query_seqs, wl.gapped_query, wl.gapped_target, wl.coords, pin=True)
-    out = inputs.output_buffer(C)
-    for _ in range(args.warmup):
-        pred.forward_inputs(inputs, THRESHOLD, GEN, out)
-    barrier()
-    # the job's one collective: the final result gather.  Source = the pinned score buffer of the last step, destination = a
-    # pinned [world, n, C] matrix on rank 0 allocated before the timed region (pageable staging of 8 x 32 MB cost more than a step)
-    gathered = torch.empty((world, n, C), dtype=torch.float32, pin_memory=True) if (world > 1 and rank == 0) else None
-
-    def gather_scores(host_scores):
-        sd = torch.from_numpy(host_scores).cuda(non_blocking=True)
-        gl = [torch.empty_like(sd) for _ in range(world)] if rank == 0 else None
-        dist.gather(sd, gl, dst=0)
-        if rank != 0:
-            return None
-        for r in range(world):
-            gathered[r].copy_(gl[r], non_blocking=True)
-        torch.cuda.synchronize()
-        return gathered.numpy()
-    if world > 1:
-        gather_scores(out)                                      # warm-up: NCCL builds its gather channels lazily
-    barrier()
-    # Two lanes per GPU: a second context (own stream + workspace) and Predictor in a second host thread, so that one
-    # batch's host-side packing, H2D and D2H overlap the other batch's kernels.  Every step still does the full
-    # H2D -> path -> D2H of its own batch through the same public call (ctypes releases the GIL).
-    lanes = [(pred, inputs, out)]
-    if args.e2e_lanes > 1:
-        stream2 = torch.cuda.Stream()
-        ctx2 = _lib.Context(local_rank, stream=stream2.cuda_stream)
-        pred2 = predict.Predictor(path, context=ctx2)
-        if args.engine != "auto":
-            pred2.set_engine(args.engine)
-        inputs2 = predict.PathInputs(wl.query_seqs, wl.gapped_query, wl.gapped_target, wl.coords, pin=True)
-        out2 = inputs2.output_buffer(C)
+    # ---- end-to-end leg: Python lists -> (C packing into pinned memory) -> H2D -> path -> D2H, through the public calls
+    class Aln:
+        def __init__(self, w, i):
+            self.query_name, self.target_name = f"q{i}", f"t{i}"
+            self.gapped_sequence, self.gapped_target, self.coords = w.gapped_query[i], w.gapped_target[i], w.coords[i]
+            self.query_sequence = w.query_seqs[i]
+    steps_chunks = [chunks[s % len(chunks)] for s in range(args.steps)]
+    n_e2e = sum(len(c) for c in steps_chunks)
+    h2d = d2h = 0
+    if maps_only:
+        aln_chunks = [[Aln(c, i) for i in range(len(c))] for c in chunks]
         for _ in range(max(1, args.warmup)):
-            pred2.forward_inputs(inputs2, THRESHOLD, GEN, out2)
-        lanes.append((pred2, inputs2, out2))
-    barrier()
+            bio_utils.build_align_contact_maps(aln_chunks[0], thr, GEN, packed=True)
+        barrier()
+        t0 = time.perf_counter()
+        for s in range(args.steps):
+            maps = bio_utils.build_align_contact_maps(aln_chunks[s % len(chunks)], thr, GEN, packed=True)
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        c = steps_chunks[0]
+        h2d = int(sum(x.nbytes for x in c.coords) + 2 * sum(len(q) for q in c.gapped_query))
+        d2h = int(sum(m.nbytes for m in maps))
+    elif multi_head:
+        alns = [Aln(wl0, i) for i in range(n0)]
+        for _ in range(max(1, args.warmup)):
+            pipeline.predict_structures(preds, alns, thr, GEN)
+        barrier()
+        t0 = time.perf_counter()
+        for s in range(args.steps):
+            out_heads, _, _ = pipeline.predict_structures(preds, alns, thr, GEN)
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        local_scores = np.concatenate([out_heads[h] for h in preds], axis=1)
+        h2d = int(sum(x.nbytes for x in wl0.coords) + 2 * sum(len(q) for q in wl0.gapped_query) + T0)
+        d2h = int(local_scores.nbytes)
+    else:
+        out_host = torch.empty((n_e2e, C), dtype=torch.float32, pin_memory=True).numpy()
 
-    def lane_worker(lane, nsteps):
-        p, i, o = lane
-        for _ in range(nsteps):
-            p.forward_inputs(i, THRESHOLD, GEN, o)              # synchronous: returns with scores on the host
-    split = [args.steps // len(lanes) + (1 if k < args.steps % len(lanes) else 0) for k in range(len(lanes))]
-    threads = [threading.Thread(target=lane_worker, args=(lanes[k], split[k])) for k in range(1, len(lanes))]
-    t0 = time.perf_counter()
-    for th in threads:
-        th.start()
-    lane_worker(lanes[0], split[0])
-    for th in threads:
-        th.join()
-    local_scores = out                                          # nothing writes the pinned buffer after the last step
-    for _, _, o in lanes[1:]:
-        assert np.abs(o - local_scores).max() < 1e-5, "the two end-to-end lanes disagree"
-    if world > 1:
-        all_scores = gather_scores(local_scores)
-    barrier()
-    e2e_s = time.perf_counter() - t0
+        def submit(c, rows):
+            return pred.submit_structures(c.query_seqs, c.gapped_query, c.gapped_target, c.coords, thr, GEN, out=rows)
+        for _ in range(max(1, args.warmup)):
+            distributed.stream_chunks(submit, [(chunks[0], n0)], out_host[:n0])
+        if world > 1:                                           # warm-up: NCCL builds its gather channels lazily
+            distributed.gather_scores(np.arange(8) + 8 * rank, out_host[:8], 8 * world, C)
+        barrier()
+        t0 = time.perf_counter()
+        distributed.stream_chunks(submit, [(c, len(c)) for c in steps_chunks], out_host)
+        local_scores = out_host
+        if world > 1:       # the job's one collective: the final result gather (scores of every step of every rank on rank 0)
+            counts = np.zeros(world + 1, np.int64)
+            tcount = torch.tensor([n_e2e], dtype=torch.int64, device="cuda")
+            lst = [torch.zeros_like(tcount) for _ in range(world)]
+            dist.all_gather(lst, tcount)
+            counts[1:] = np.cumsum([int(x.item()) for x in lst])
+            distributed.gather_scores(np.arange(counts[rank], counts[rank + 1]), local_scores, int(counts[-1]), C)
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        c = steps_chunks[0]
+        h2d = int(sum(x.nbytes for x in c.coords) + 2 * sum(len(q) for q in c.gapped_query) + sum(len(q) for q in c.query_seqs))
+        d2h = int(len(c) * C * 4)
+        if len(chunks) == 1 or args.steps >= 1:
+            assert np.abs(local_scores[:n0] - scores_resident).max() < 1e-5, "resident and end-to-end legs disagree"
     clocks = sampler.stop() if rank == 0 else None
-    assert np.abs(local_scores - scores_resident).max() < 1e-5, "resident and end-to-end legs disagree"
+
+    # ---- config4: the whole sharded job, end to end (strong scaling): every rank streams ALL chunks of its LPT bin from Python
+    # lists, rank 0 gathers the [job_n, C] score matrix in protein order
+    job = None
+    if sharded and sharded["job_n"] > 0:
+        my_idx = [ci[ci < sharded["job_n"]] for ci in sharded["my_idx"]]
+        my_chunks = [(sub(c, range(len(ix))) if len(ix) != len(c) else c) for c, ix in zip(chunks, my_idx) if len(ix)]
+        my_ids = np.concatenate([ix for ix in my_idx if len(ix)]) if my_chunks else np.zeros(0, np.int64)
+        job_out = torch.empty((len(my_ids), C), dtype=torch.float32, pin_memory=True).numpy()
+
+        def submit(c, rows):
+            return pred.submit_structures(c.query_seqs, c.gapped_query, c.gapped_target, c.coords, thr, GEN, out=rows)
+        barrier()
+        t0 = time.perf_counter()
+        distributed.stream_chunks(submit, [(c, len(c)) for c in my_chunks], job_out)
+        t_rank = time.perf_counter() - t0
+        final = distributed.gather_scores(my_ids, job_out, sharded["job_n"], C)
+        barrier()
+        job_s = time.perf_counter() - t0
+        busy = allsum(t_rank) / world
+        job_s, t_rank_max = allmax(job_s, t_rank)
+        if rank == 0:
+            assert final is not None and final.shape == (sharded["job_n"], C) and np.isfinite(final[::997]).all()
+            assert np.abs(final[my_ids[:64]] - job_out[:64]).max() == 0.0
+        job = {"proteins": sharded["job_n"], "residues": int(sharded["lengths"][:sharded["job_n"]].sum()), "seconds": job_s,
+               "proteins_per_s": sharded["job_n"] / job_s, "scaling": "strong",
+               "chunks_per_rank": len(my_chunks), "imbalance_measured": t_rank_max / busy if busy else None,
+               "imbalance_predicted_lpt": sharded["pred_imb"], "gather_and_tail_s": job_s - t_rank_max,
+               "input": "Python lists of str / ndarray per protein -> Predictor.submit_structures (two jobs in flight)",
+               "generator_s": round(gen_s, 1)}
 
     # max over ranks
-    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    dev_ms, e2e_ms = allmax(dev_ms, e2e_s * 1e3)
+    units_resident = allsum(n0 * args.steps)
+    units_e2e = allsum(n_e2e)
 
     # ---- per-stage profile for the roofline object: the stage events recorded live inside the timed steps, averaged per step
     PROF_PASSES = max(1, args.steps)
@@ -328,8 +540,7 @@ def run_b200(args, rank, world, local_rank):
         a[2] //= PROF_PASSES
     peaks = measured_peaks()
     stage_total = sum(a[0] for a in agg.values())
-    dom = max(agg.items(), key=lambda kv: kv[1][0])
-    dname, (dms, dunits, dcount) = dom
+    dname, (dms, dunits, dcount) = max(agg.items(), key=lambda kv: kv[1][0])
     if dname == "cmap_build_transfer":
         roof = {"bound": "hbm", "achieved": dunits / (dms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s"}
     else:
@@ -341,38 +552,54 @@ def run_b200(args, rank, world, local_rank):
     roof["share_of_step"] = dms / stage_total if stage_total else None
     roof["peak_source"] = peaks["source"] + (" sustained bf16" if roof["bound"] == "tensor" else "")
     roof["stages_ms"] = {k: round(v[0], 4) for k, v in agg.items()}
+    if maps_only:
+        lq = np.array([len(s) for s in wl0.query_seqs], np.float64)
+        flops = float((9 * lq * (lq - 1) / 2).sum())            # 9 non-fusable FP32 ops per unordered residue pair
+        roof["fp32_issue"] = {"achieved_Tops": flops / (dms * 1e-3) / 1e12, "peak_Tops": 37.0, "frac": flops / (dms * 1e-3) / 1e12 / 37.0,
+                              "note": "bit-packed output makes the kernel FP32-issue-bound, not HBM-bound (SURVEY 8d)"}
+        roof["dense_output_variant"] = {"kernel": "unpack_dense_kernel", "bound": "hbm", "bytes_per_launch": dense["bytes"],
+                                        "ms": dense["unpack_ms"], "achieved": dense["bytes"] / (dense["unpack_ms"] * 1e-3) / 1e9,
+                                        "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                        "frac": dense["bytes"] / (dense["unpack_ms"] * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                        "note": "reference layout: int32 [Lq, Lq] per pair written to HBM (4 bytes per cell)"}
 
     if rank != 0:
         return
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        idx = np.random.default_rng(0).choice(n, min(args.cpu_sample, n), replace=False)
-        pps, dt, kind, cm_impl = cpu_path_proteins_per_s(wl, path, idx)
-        cpu = {"value": pps, "unit": "proteins/s", "cores": blas_threads(), "kind": kind,
-               "sample": f"{len(idx)} of the {n} proteins of one step ({dt:.1f} s), batch=1 per call; cmap: {cm_impl}; "
-                         f"GCN: fp32 NumPy ONNX interpreter standing in for onnxruntime; host has {os.cpu_count()} cpus"}
-    total_proteins = n * world * args.steps
+        idx = np.random.default_rng(0).choice(n0, min(args.cpu_sample if not multi_head else max(8, args.cpu_sample // 8), n0), replace=False)
+        pps, dt, cores, what = cpu_path(wl0, thr, idx, [] if maps_only else list(models.values()), cpu_pool)
+        if cpu_pool is not None:
+            cpu_pool.close()
+        cpu = {"value": pps, "unit": "pairs/s" if maps_only else "proteins/s", "cores": cores, "kind": "port",
+               "sample": f"{len(idx)} of the {n0} units of one step ({dt:.1f} s); {what}; host has {os.cpu_count()} cpus"}
+    unit = "pairs/s" if maps_only else "proteins/s"
     line = {
-        "metric": "proteins/sec (GCN MF fwd incl. cmap)", "value": total_proteins / (dev_ms * 1e-3), "unit": "proteins/s",
+        "metric": metric_name(args.workload), "value": units_resident / (dev_ms * 1e-3), "unit": unit,
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32" if pred.engine == "simt" else "f16 (hi/lo split weights) with f32 accumulate",
+        "dtype": "f32" if maps_only or pred.engine == "simt" else "f16 (hi/lo split weights) with f32 accumulate",
         "data": "synthetic",
-        "config": {"workload": workload, "proteins_per_step_per_gpu": n, "residues_per_step_per_gpu": T,
-                   "threshold_A": THRESHOLD, "generated_contacts": GEN, "engine": pred.engine,
+        "config": {"workload": workload, "units_per_step_per_gpu": n0, "residues_per_step_per_gpu": T0,
+                   "threshold_A": thr, "generated_contacts": GEN, "engine": "cmap kernels" if maps_only else pred.engine,
+                   "heads": list(preds) if not maps_only else [],
                    "l2": "flushed between timed iterations (256 MiB memset outside the event pairs)",
-                   "timing": "per-step CUDA events on the launch stream, summed over steps, max over ranks"},
-        "e2e": {"value": total_proteins / (e2e_ms * 1e-3), "unit": "proteins/s",
-                "h2d_bytes_per_step": inputs.h2d_bytes, "d2h_bytes_per_step": int(out.nbytes),
-                "ms_per_step": e2e_ms / args.steps,
-                "lanes_per_gpu": len(lanes),
-                "note": "Predictor.forward_inputs: pinned host buffers -> H2D -> all kernels -> D2H scores, wall clock; "
-                        "lanes_per_gpu contexts run such calls concurrently so copies overlap kernels"},
+                   "timing": "per-step CUDA events on the launch stream, summed over steps, max over ranks",
+                   "generator_s": round(gen_s, 1)},
+        "e2e": {"value": units_e2e / (e2e_ms * 1e-3), "unit": unit,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
+                "distinct_chunks": len(chunks),
+                "note": ("bio_utils.build_align_contact_maps(packed=True) from Python lists of alignments" if maps_only else
+                         "pipeline.predict_structures from Python lists (one upload, all heads)" if multi_head else
+                         "Predictor.submit_structures / wait from Python lists of str / ndarray: C packing into pinned memory -> H2D -> all "
+                         "kernels -> D2H scores, two jobs in flight per GPU, + the final result gather; wall clock")},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roof,
         "cpu_baseline": cpu,
     }
+    if job:
+        line["sharded_job"] = job
     print(json.dumps(line), flush=True)
 
 
@@ -381,20 +608,21 @@ def main():
     real_stdout = os.dup(1)
     os.dup2(2, 1)
     sys.stdout = os.fdopen(real_stdout, "w")
-    args = parse()
+    args = ARGS
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+    inputs = prepare_inputs(args, rank, world)
     if world > 1:
-        import torch.distributed as dist
         import torch
+        import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
-        run_b200(args, rank, world, local_rank)
+        run_b200(args, rank, world, local_rank, inputs)
     finally:
         if world > 1:
             import torch.distributed as dist

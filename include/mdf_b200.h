@@ -28,6 +28,8 @@ extern "C" {
 #define MDF_ECUDA        -2   /* CUDA runtime error (see mdf_last_error) */
 #define MDF_ENOMEM       -3   /* workspace arena exhausted */
 #define MDF_EUNSUPPORTED -4   /* model graph not supported by the fused pipeline */
+#define MDF_ENOENT       -5   /* model / structure file cannot be opened */
+#define MDF_EPARSE       -6   /* file is not what it should be (ONNX protobuf, coordinate cache ...) */
 
 typedef struct mdf_ctx   mdf_ctx;    /* one per device: stream + workspace arena */
 typedef struct mdf_model mdf_model;  /* one per loaded GCN head: weights resident in HBM */
@@ -119,6 +121,23 @@ typedef struct mdf_model_desc {
 
 int mdf_model_create(mdf_ctx *ctx, const mdf_model_desc *desc, mdf_model **out);
 int mdf_model_destroy(mdf_model *model);
+
+/* ---- predict.pyx:62-73  Predictor._load_model: straight from the `.onnx` file the reference hands to onnxruntime -----
+ * The file is decoded (protobuf wire format, no library) and the graph RECOGNISED as a DeepFRI GCN head: weights are found by
+ * dataflow role, hyper-parameters read from shapes / op types, and the adjacency-normalisation sub-graph is verified by
+ * evaluating it on two small probe maps at load time (it must equal D (A - diag A + I) D, d = 1 / (eps + sqrt(rowsum))).
+ * MDF_ENOENT: cannot open; MDF_EPARSE: not an ONNX protobuf; MDF_EUNSUPPORTED: not a graph the fused pipeline computes
+ * (mdf_last_error says why).  There is no fallback executor. */
+int mdf_model_load(mdf_ctx *ctx, const char *onnx_path, mdf_model **out);
+/* head sizes of a loaded model; any out pointer may be NULL.  gc_dims: room for 8 ints */
+int mdf_model_info(const mdf_model *model, int *n_terms, int *lstm_hidden, int *lm_dim, int *n_gc, int *gc_dims, int *fc_dim);
+/* Host-only (no GPU needed): parse + recognise `onnx_path` and describe it as one JSON object in `buf`:
+ * {"kind": "gcn" | "cnn", "input_names": [...], "n_terms": C, hyper-parameters ..., "roles": {role: initialiser name}}. */
+int mdf_onnx_inspect(const char *onnx_path, char *buf, size_t capacity);
+/* Host-only: the recognised weight playing `role` ("lstm1_W", "lm_W", "gc2_W", "fc_b", "out_W", "conv3_W", "scale", "shift" ...)
+ * exactly as the pipeline will use it (Gemm transposes undone, conv bias + BatchNormalization folded).  buf == NULL only
+ * reports *count (0 for an absent optional bias). */
+int mdf_onnx_tensor(const char *onnx_path, const char *role, float *buf, int64_t capacity, int64_t *count);
 /* 0 = fp32 SIMT reference engine, 1 = tcgen05 tensor-core engine */
 int mdf_model_set_engine(mdf_model *model, int engine);
 int mdf_model_get_engine(const mdf_model *model);
@@ -141,6 +160,28 @@ int mdf_path_forward(mdf_model *model, int n,
                      const char *q_aln, const char *t_aln, const int64_t *aln_off,
                      float thr2, int generated_contacts, float *scores);
 
+/* Asynchronous form: mdf_path_submit enqueues the host->device copies, every kernel and the device->host copy of the scores
+ * and returns; mdf_path_wait blocks until `scores` is complete and reports device-side input errors.  Up to TWO jobs may be in
+ * flight per context (each owns one of the context's two job slots): while job k computes, the inputs of job k + 1 are copied
+ * into the other slot, so H2D / D2H and host-side packing overlap the kernels.  Flat input buffers and `scores` must stay valid
+ * until mdf_path_wait returns (pinned memory makes the copies truly asynchronous).  mdf_path_forward == submit + wait. */
+typedef struct mdf_job mdf_job;
+int mdf_path_submit(mdf_model *model, int n,
+                    const char *seq, const int64_t *seq_off,
+                    const float *coords, const int64_t *coord_off,
+                    const char *q_aln, const char *t_aln, const int64_t *aln_off,
+                    float thr2, int generated_contacts, float *scores, mdf_job **job);
+/* Ragged form: protein p is given by its own pointers - seq[p] (seq_len[p] residues, no gaps), coords[p] (float32
+ * [coord_rows[p], 3]), q_aln[p] / t_aln[p] (aln_len[p] alignment columns each) - exactly what pipeline.py:476-481 holds per
+ * alignment.  The library packs them into pinned staging memory on `MDF_HOST_THREADS` (default 4) host threads; the
+ * caller's input buffers may be released as soon as the call returns. */
+int mdf_path_submit_ragged(mdf_model *model, int n,
+                           const char *const *seq, const int *seq_len,
+                           const float *const *coords, const int *coord_rows,
+                           const char *const *q_aln, const char *const *t_aln, const int *aln_len,
+                           float thr2, int generated_contacts, float *scores, mdf_job **job);
+int mdf_path_wait(mdf_job *job);
+
 /* Same path split into upload / run / fetch so that the compute can be timed with inputs
  * already resident in HBM (bench.py `value`). */
 int mdf_batch_upload(mdf_ctx *ctx, int n,
@@ -154,6 +195,8 @@ int mdf_path_run(mdf_model *model, mdf_batch *batch, float thr2, int generated_c
  * (same thr2 / generated_contacts / eps) and the LSTM-LM output (same LM weights).  pipeline.py:546-655 runs the MF / BP /
  * CC / EC heads one after the other over the same proteins; mdf_path_run itself always recomputes everything. */
 int mdf_path_run_shared(mdf_model *model, mdf_batch *batch, float thr2, int generated_contacts);
+/* forget what earlier runs left on this batch for mdf_path_run_shared (the next shared run recomputes maps and LM output) */
+int mdf_batch_invalidate(mdf_batch *batch);
 /* stage selector for profiling / unit parity: 1 = cmap only, 2 = + LSTM-LM, 3 = + GraphConv, 4 = all */
 int mdf_path_run_stages(mdf_model *model, mdf_batch *batch, float thr2, int generated_contacts, int upto);
 int mdf_batch_fetch_scores(mdf_model *model, mdf_batch *batch, float *scores /* host [n,C] */);
@@ -162,6 +205,11 @@ int mdf_batch_fetch_scores(mdf_model *model, mdf_batch *batch, float *scores /* 
  * 2 = LSTM layer-1 output [T,H], 3 = LSTM layer-2 output [T,H], 4 = X0 [T,E],
  * 5 = pooled [n, sum(gc)], 6 = last GraphConv output [T, g].  fp32 unless noted. */
 int mdf_batch_fetch(mdf_model *model, mdf_batch *batch, int what, void *dst, size_t dst_bytes);
+
+/* Reference-layout output of the contact-map stage of the last run: dense int32 [Lq, Lq] per protein (bio_utils.py:348-385),
+ * protein p at element offset sum_{q<p} Lq^2 of `dense_device` (DEVICE memory; NULL = workspace scratch, for timing the
+ * HBM-bound variant of K1/K2).  *cells_out = total cells. */
+int mdf_batch_unpack_dense(mdf_batch *batch, int32_t *dense_device, int64_t *cells_out);
 
 /* device pointer of the scores of the last mdf_path_run ([n, C] float32) */
 const float *mdf_batch_scores_device(const mdf_batch *batch);
@@ -189,6 +237,8 @@ typedef struct mdf_cnn_model mdf_cnn_model;
 
 int mdf_cnn_model_create(mdf_ctx *ctx, const mdf_cnn_desc *desc, mdf_cnn_model **out);
 int mdf_cnn_model_destroy(mdf_cnn_model *model);
+/* same from a single-input `DeepCNN-*.onnx` file (conv bias + BatchNormalization folded into scale / shift while loading) */
+int mdf_cnn_model_load(mdf_ctx *ctx, const char *onnx_path, mdf_cnn_model **out);
 /* n sequences (ASCII residues, CSR offsets; every sequence needs >= 1 residue) -> scores host float32 [n, C] */
 int mdf_cnn_forward(mdf_cnn_model *model, int n, const char *seq, const int64_t *seq_off, float *scores);
 /* same with the sequences already resident: upload once, run many times (bench `value`), fetch */

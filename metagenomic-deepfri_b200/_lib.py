@@ -15,7 +15,12 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmdf_b200.so")
 
-MDF_OK, MDF_EINVAL, MDF_ECUDA, MDF_ENOMEM, MDF_EUNSUPPORTED = 0, -1, -2, -3, -4
+MDF_OK, MDF_EINVAL, MDF_ECUDA, MDF_ENOMEM, MDF_EUNSUPPORTED, MDF_ENOENT, MDF_EPARSE = 0, -1, -2, -3, -4, -5, -6
+
+
+class UnsupportedModelError(NotImplementedError):
+    """The `.onnx` graph is not one the fused pipeline computes (MDF_EUNSUPPORTED); a RuntimeError, as `predict.pyi:70-72`
+    promises for models that cannot be loaded.  There is no fallback executor."""
 
 c_f32p = C.POINTER(C.c_float)
 c_i32p = C.POINTER(C.c_int32)
@@ -84,6 +89,13 @@ def lib() -> C.CDLL:
                                               C.c_float, C.c_int, c_u32p, c_i64p, c_i32p, c_i64p]
         L.mdf_model_create.argtypes = [vp, C.POINTER(ModelDesc), C.POINTER(vp)]
         L.mdf_model_destroy.argtypes = [vp]
+        L.mdf_model_load.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
+        L.mdf_cnn_model_load.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
+        L.mdf_onnx_inspect.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t]
+        L.mdf_onnx_tensor.argtypes = [C.c_char_p, C.c_char_p, c_f32p, C.c_int64, c_i64p]
+        L.mdf_onnx_tensor.restype = C.c_int
+        ip_ = C.POINTER(C.c_int)
+        L.mdf_model_info.argtypes = [vp, ip_, ip_, ip_, ip_, ip_, ip_]
         L.mdf_model_set_engine.argtypes = [vp, C.c_int]
         L.mdf_model_get_engine.argtypes = [vp]
         L.mdf_model_get_engine.restype = C.c_int
@@ -91,6 +103,11 @@ def lib() -> C.CDLL:
         L.mdf_gcn_forward_packed.argtypes = [vp, C.c_int, C.c_char_p, c_i64p, c_u32p, c_i64p, c_f32p]
         L.mdf_path_forward.argtypes = [vp, C.c_int, vp, c_i64p, vp, c_i64p, vp, vp, c_i64p,
                                        C.c_float, C.c_int, vp]
+        L.mdf_path_submit.argtypes = [vp, C.c_int, vp, c_i64p, vp, c_i64p, vp, vp, c_i64p, C.c_float, C.c_int, vp, C.POINTER(vp)]
+        L.mdf_path_submit_ragged.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, C.c_float, C.c_int, vp, C.POINTER(vp)]
+        L.mdf_path_wait.argtypes = [vp]
+        for name in ("mdf_path_submit", "mdf_path_submit_ragged", "mdf_path_wait"):
+            getattr(L, name).restype = C.c_int
         L.mdf_batch_upload.argtypes = [vp, C.c_int, vp, c_i64p, vp, c_i64p, vp, vp, c_i64p, C.POINTER(vp)]
         L.mdf_batch_destroy.argtypes = [vp]
         L.mdf_path_run.argtypes = [vp, vp, C.c_float, C.c_int]
@@ -98,6 +115,10 @@ def lib() -> C.CDLL:
         L.mdf_path_run_shared.argtypes = [vp, vp, C.c_float, C.c_int]
         L.mdf_batch_fetch_scores.argtypes = [vp, vp, vp]
         L.mdf_batch_fetch.argtypes = [vp, vp, C.c_int, vp, C.c_size_t]
+        L.mdf_batch_invalidate.argtypes = [vp]
+        L.mdf_batch_invalidate.restype = C.c_int
+        L.mdf_batch_unpack_dense.argtypes = [vp, vp, c_i64p]
+        L.mdf_batch_unpack_dense.restype = C.c_int
         L.mdf_batch_scores_device.argtypes = [vp]
         L.mdf_batch_scores_device.restype = vp
         L.mdf_cnn_model_create.argtypes = [vp, C.POINTER(CnnDesc), C.POINTER(vp)]
@@ -106,6 +127,8 @@ def lib() -> C.CDLL:
         L.mdf_cnn_upload.argtypes = [vp, C.c_int, vp, c_i64p]
         L.mdf_cnn_run.argtypes = [vp]
         L.mdf_cnn_fetch.argtypes = [vp, vp, vp]
+        for name in ("mdf_model_load", "mdf_cnn_model_load", "mdf_onnx_inspect", "mdf_model_info"):
+            getattr(L, name).restype = C.c_int
         for name in ("mdf_cnn_model_create", "mdf_cnn_model_destroy", "mdf_cnn_forward", "mdf_cnn_upload", "mdf_cnn_run",
                      "mdf_cnn_fetch"):
             getattr(L, name).restype = C.c_int
@@ -126,8 +149,10 @@ EXPORTED_SYMBOLS = [
     "mdf_align_contact_map", "mdf_cmap_build_transfer", "mdf_model_create", "mdf_model_destroy",
     "mdf_model_set_engine", "mdf_model_get_engine", "mdf_gcn_forward_dense", "mdf_gcn_forward_packed", "mdf_path_forward",
     "mdf_batch_upload", "mdf_batch_destroy", "mdf_path_run", "mdf_path_run_stages", "mdf_path_run_shared",
-    "mdf_batch_fetch_scores", "mdf_batch_fetch", "mdf_batch_scores_device",
+    "mdf_batch_fetch_scores", "mdf_batch_fetch", "mdf_batch_scores_device", "mdf_batch_unpack_dense", "mdf_batch_invalidate",
     "mdf_cnn_model_create", "mdf_cnn_model_destroy", "mdf_cnn_forward", "mdf_cnn_upload", "mdf_cnn_run", "mdf_cnn_fetch",
+    "mdf_path_submit", "mdf_path_submit_ragged", "mdf_path_wait",
+    "mdf_model_load", "mdf_cnn_model_load", "mdf_onnx_inspect", "mdf_onnx_tensor", "mdf_model_info",
 ]
 
 
@@ -140,8 +165,53 @@ def check(rc: int) -> None:
     if rc == MDF_ENOMEM:
         raise MemoryError(msg)
     if rc == MDF_EUNSUPPORTED:
-        raise NotImplementedError(msg)
+        raise UnsupportedModelError(msg)
+    if rc == MDF_ENOENT:
+        raise FileNotFoundError(msg)
     raise RuntimeError(msg)
+
+
+_pyhost = None
+
+
+def pyhost():
+    """The CPython glue module `_mdf_pyhost` (csrc/pyhost.c, built in-tree beside libmdf_b200.so): collects the buffer pointers
+    of lists of str / ndarray in C and calls the ragged entry points with the GIL released."""
+    global _pyhost
+    if _pyhost is None:
+        import importlib.machinery
+        import importlib.util
+        import sysconfig
+        path = os.path.join(_HERE, "_mdf_pyhost" + sysconfig.get_config_var("EXT_SUFFIX"))
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} is missing: build the extension first (python -c 'import __graft_entry__ as g; g.build()')")
+        loader = importlib.machinery.ExtensionFileLoader("_mdf_pyhost", path)
+        spec = importlib.util.spec_from_loader("_mdf_pyhost", loader)
+        mod = importlib.util.module_from_spec(spec)
+        loader.exec_module(mod)
+        _pyhost = mod
+    return _pyhost
+
+
+def fn_addr(name: str) -> int:
+    return C.cast(getattr(lib(), name), C.c_void_p).value
+
+
+def inspect_onnx(path: str) -> dict:
+    """`mdf_onnx_inspect`: what the library recognises in an `.onnx` file (host only, no GPU needed)."""
+    import json
+    buf = C.create_string_buffer(1 << 16)
+    check(lib().mdf_onnx_inspect(os.fsencode(path), buf, len(buf)))
+    return json.loads(buf.value.decode())
+
+
+def onnx_tensor(path: str, role: str) -> np.ndarray:
+    """`mdf_onnx_tensor`: the recognised weight playing `role`, flat float32 (host only)."""
+    n = C.c_int64(0)
+    check(lib().mdf_onnx_tensor(os.fsencode(path), role.encode(), None, 0, C.byref(n)))
+    out = np.empty(n.value, np.float32)
+    check(lib().mdf_onnx_tensor(os.fsencode(path), role.encode(), fp(out), n.value, C.byref(n)))
+    return out
 
 
 def packed_row_words(L: int) -> int:

@@ -4,6 +4,7 @@
 #include <stdarg.h>
 #include <algorithm>
 #include <numeric>
+#include <thread>
 
 #include "cmap_kernels.cuh"
 #include "gcn.cuh"
@@ -121,6 +122,13 @@ extern "C" int mdf_ctx_create(int device, void *arena, size_t arena_bytes, void 
     MDF_CUDA(cudaMemset(c->d_err, 0, 256));
     MDF_CUDA(cudaMallocHost((void **)&c->h_err, 256));
     *c->h_err = 0;
+    for (auto &sl : c->slots) {
+        sl.ctx = c;
+        MDF_CUDA(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+        sl.h_err = c->h_err + 8 + 8 * (int)(&sl - c->slots);
+        sl.h_err[0] = sl.h_err[1] = 0;
+    }
+    if (const char *e = getenv("MDF_HOST_THREADS")) c->host_threads = std::max(1, std::min(64, atoi(e)));
     *out = c;
     return MDF_OK;
 }
@@ -130,6 +138,12 @@ extern "C" int mdf_ctx_destroy(mdf_ctx *c)
     if (!c) return MDF_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    for (auto &sl : c->slots) {
+        if (sl.done) { cudaEventSynchronize(sl.done); cudaEventDestroy(sl.done); }
+        if (sl.dev) cudaFree(sl.dev);
+        if (sl.pin) cudaFreeHost(sl.pin);
+        delete sl.batch;
+    }
     if (c->own_arena && c->arena) cudaFree(c->arena);
     if (c->d_err) cudaFree(c->d_err);
     if (c->h_err) cudaFreeHost(c->h_err);
@@ -365,7 +379,7 @@ __global__ void fill_res_prot_kernel(int n, const int64_t *__restrict__ seq_off,
 
 static int batch_build(mdf_ctx *ctx, mdf_batch *b, bool persistent, int n, const char *seq, const int64_t *seq_off,
                        const float *coords, const int64_t *coord_off, const char *q_aln, const char *t_aln,
-                       const int64_t *aln_off, const uint32_t *packed_host, int G, int C, size_t extra_reserve)
+                       const int64_t *aln_off, const uint32_t *packed_host, int G, int C, size_t extra_reserve, mdf_job *slot = nullptr)
 {
     MDF_REQUIRE(n >= 0 && seq_off && (n == 0 || seq), "batch: sequences missing");
     b->ctx = ctx;
@@ -409,6 +423,18 @@ static int batch_build(mdf_ctx *ctx, mdf_batch *b, bool persistent, int n, const
     if (persistent) {
         MDF_CUDA(cudaMalloc((void **)&base, bytes));
         b->owns_memory = true;
+    } else if (slot) {
+        // job slot: a device block of its own, so the inputs of this job may arrive while the previous job still computes
+        if (slot->dev_bytes < bytes) {
+            if (slot->dev) MDF_CUDA(cudaFree(slot->dev));
+            slot->dev = nullptr; slot->dev_bytes = 0;
+            const size_t want = align_up(bytes + bytes / 4, 2u << 20);
+            cudaError_t e = cudaMalloc((void **)&slot->dev, want);
+            if (e != cudaSuccess) { cudaGetLastError(); set_error("cudaMalloc(%zu bytes) for a job slot failed: %s", want, cudaGetErrorString(e)); return MDF_ENOMEM; }
+            slot->dev_bytes = want;
+        }
+        MDF_TRY(ctx->reserve(extra_reserve));
+        base = slot->dev;
     } else {
         MDF_TRY(ctx->reserve(bytes + extra_reserve));
         MDF_TRY(ctx->alloc((void **)&base, bytes));
@@ -431,6 +457,12 @@ static int batch_build(mdf_ctx *ctx, mdf_batch *b, bool persistent, int n, const
         // transient batches (mdf_path_forward): coordinates and alignments - nine tenths of the input bytes - travel on the copy
         // stream and are only awaited by the contact-map stage, which run_path enqueues after the LSTM language model
         cudaStream_t cs = (!persistent && ctx->copy_stream) ? ctx->copy_stream : s;
+        if (cs != s && !slot) {
+            // arena-backed transient batch: the bytes below may still be in use by kernels queued on the compute stream by an
+            // earlier call (the arena is reused in stream order) - the copy stream must not run ahead of them
+            MDF_CUDA(cudaEventRecord(ctx->copy_done, s));
+            MDF_CUDA(cudaStreamWaitEvent(cs, ctx->copy_done, 0));
+        }
         if (ncoord) MDF_CUDA(cudaMemcpyAsync(b->d_coords, coords, ncoord * 3 * sizeof(float), cudaMemcpyHostToDevice, cs));
         MDF_CUDA(cudaMemcpyAsync(b->d_coord_off, coord_off, (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, cs));
         if (alnb) {
@@ -589,11 +621,54 @@ extern "C" int mdf_path_run_shared(mdf_model *m, mdf_batch *b, float thr2, int g
     return r;
 }
 
+// forget what earlier runs on this batch left for sharing (contact maps + degrees, LSTM-LM output)
+extern "C" int mdf_batch_invalidate(mdf_batch *b)
+{
+    MDF_REQUIRE(b, "mdf_batch_invalidate: batch is NULL");
+    b->cmap_valid = false;
+    b->lm_hash = 0;
+    return MDF_OK;
+}
+
 extern "C" int mdf_batch_fetch_scores(mdf_model *m, mdf_batch *b, float *scores)
 {
     MDF_REQUIRE(m && b && scores, "mdf_batch_fetch_scores: bad arguments");
     MDF_CUDA(cudaSetDevice(m->ctx->device));
     return fetch_scores(m, b, scores);
+}
+
+// The reference-layout output of the contact-map stage for a resident batch: dense int32 [Lq, Lq] per protein (what
+// build_align_contact_map returns, bio_utils.py:348-385), written to `dense_device` (device memory, protein p at element offset
+// sum_{q<p} Lq^2) or, with NULL, to workspace scratch - the variant whose roofline is the HBM write rate.
+extern "C" int mdf_batch_unpack_dense(mdf_batch *b, int32_t *dense_device, int64_t *cells_out)
+{
+    MDF_REQUIRE(b && b->ctx, "mdf_batch_unpack_dense: batch is NULL");
+    MDF_REQUIRE(b->owns_memory && b->has_structure, "mdf_batch_unpack_dense: needs an uploaded batch with structures");
+    mdf_ctx *ctx = b->ctx;
+    MDF_CUDA(cudaSetDevice(ctx->device));
+    ArenaScope scope(ctx);
+    std::vector<int64_t> off((size_t)b->n + 1, 0);
+    double packed_bytes = 0.0;
+    for (int p = 0; p < b->n; ++p) {
+        const int64_t L = b->h_seq_off[p + 1] - b->h_seq_off[p];
+        off[(size_t)p + 1] = off[(size_t)p] + L * L;
+        packed_bytes += 4.0 * (double)(L * mdf_packed_row_words((int)L));
+    }
+    const int64_t cells = off[(size_t)b->n];
+    if (cells_out) *cells_out = cells;
+    if (cells == 0) return MDF_OK;
+    MDF_TRY(ctx->reserve((dense_device ? 0 : (size_t)cells * 4) + (size_t)(b->n + 1) * 8 + 4096));
+    int64_t *doff;
+    int32_t *dd = dense_device;
+    MDF_TRY(ctx->alloc_n(&doff, (size_t)b->n + 1));
+    if (!dd) MDF_TRY(ctx->alloc_n(&dd, (size_t)cells));
+    MDF_CUDA(cudaMemcpyAsync(doff, off.data(), off.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    {
+        ProfScope ps(ctx, "cmap_unpack_dense", 4.0 * (double)cells + packed_bytes);
+        MDF_TRY(launch_unpack_dense(ctx, b->nwork, b->d_work, b->d_seq_off, b->d_packed, b->d_packed_off, dd, doff));
+    }
+    MDF_CUDA(cudaStreamSynchronize(ctx->stream));     // `off` is pageable
+    return MDF_OK;
 }
 
 extern "C" const float *mdf_batch_scores_device(const mdf_batch *b) { return b ? b->d_scores : nullptr; }
@@ -623,30 +698,171 @@ extern "C" int mdf_batch_fetch(mdf_model *m, mdf_batch *b, int what, void *dst, 
     return MDF_OK;
 }
 
+// ------------------------------------------------------------------------------------------- jobs: submit / wait
+// A job = one transient batch through the whole path.  mdf_path_submit* enqueue H2D + every kernel + the D2H of the scores and
+// return; mdf_path_wait blocks until the scores are on the host.  Two jobs may be in flight per context: the inputs of job k + 1
+// are packed (pinned slot memory, host threads) and copied (copy stream, the slot's own device block) while job k computes.
+static int slot_acquire(mdf_ctx *ctx, mdf_job **out)
+{
+    mdf_job *sl = &ctx->slots[ctx->next_slot];
+    if (sl->busy) {
+        set_error("mdf_path_submit: both job slots of this context are in flight; call mdf_path_wait on the older job first");
+        return MDF_EINVAL;
+    }
+    MDF_CUDA(cudaEventSynchronize(sl->done));        // a slot is only rewritten after its previous job has completely finished
+    ctx->next_slot ^= 1;
+    delete sl->batch;
+    sl->batch = new mdf_batch();
+    sl->h_err[0] = sl->h_err[1] = 0;
+    sl->rc = MDF_OK;
+    *out = sl;
+    return MDF_OK;
+}
+
+static int slot_pinned(mdf_job *sl, size_t bytes)
+{
+    if (sl->pin_bytes >= bytes) return MDF_OK;
+    if (sl->pin) MDF_CUDA(cudaFreeHost(sl->pin));
+    sl->pin = nullptr; sl->pin_bytes = 0;
+    const size_t want = align_up(bytes + bytes / 4, 2u << 20);
+    cudaError_t e = cudaHostAlloc((void **)&sl->pin, want, cudaHostAllocDefault);
+    if (e != cudaSuccess) { cudaGetLastError(); set_error("cudaHostAlloc(%zu bytes) for a job slot failed: %s", want, cudaGetErrorString(e)); return MDF_ENOMEM; }
+    sl->pin_bytes = want;
+    return MDF_OK;
+}
+
+// enqueue everything for flat inputs (already where they may be read asynchronously: pinned slot memory or caller buffers)
+static int job_enqueue(mdf_model *m, mdf_job *sl, int n, const char *seq, const int64_t *seq_off, const float *coords,
+                       const int64_t *coord_off, const char *q_aln, const char *t_aln, const int64_t *aln_off, float thr2, int gen,
+                       float *scores)
+{
+    mdf_ctx *ctx = m->ctx;
+    ArenaScope scope(ctx);
+    mdf_batch *b = sl->batch;
+    static const bool timing = getenv("MDF_TIMING") != nullptr;       // host-side breakdown of one call on stderr
+    const auto t0 = std::chrono::steady_clock::now();
+    int rc = batch_build(ctx, b, false, n, seq, seq_off, coords, coord_off, q_aln, t_aln, aln_off, nullptr, m->G, m->C,
+                         engine_workspace(m, n, seq_off), sl);
+    const auto t1 = std::chrono::steady_clock::now();
+    if (rc == MDF_OK) rc = run_path(m, b, thr2, gen, 4, true);
+    if (rc == MDF_OK && n > 0) {
+        cudaError_t e = cudaMemcpyAsync(scores, b->d_scores, (size_t)n * m->C * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(sl->h_err, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e != cudaSuccess) { set_error("mdf_path_submit: result copy failed: %s", cudaGetErrorString(e)); rc = MDF_ECUDA; }
+    }
+    if (rc != MDF_OK && ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);   // no input copy may outlive a failed call
+    cudaEventRecord(sl->done, ctx->stream);
+    if (timing) {
+        const auto t2 = std::chrono::steady_clock::now();
+        auto ms = [](auto a, auto b2) { return std::chrono::duration<double, std::milli>(b2 - a).count(); };
+        fprintf(stderr, "[mdf_path_submit] n=%d: batch build + H2D %.2f ms, enqueue (host) %.2f ms\n", n, ms(t0, t1), ms(t1, t2));
+    }
+    return rc;
+}
+
+extern "C" int mdf_path_submit(mdf_model *m, int n, const char *seq, const int64_t *seq_off, const float *coords,
+                               const int64_t *coord_off, const char *q_aln, const char *t_aln, const int64_t *aln_off, float thr2,
+                               int gen, float *scores, mdf_job **job)
+{
+    MDF_REQUIRE(m && coords && scores && job && n >= 0, "mdf_path_submit: bad arguments");
+    mdf_ctx *ctx = m->ctx;
+    MDF_CUDA(cudaSetDevice(ctx->device));
+    mdf_job *sl = nullptr;
+    MDF_TRY(slot_acquire(ctx, &sl));
+    const int rc = job_enqueue(m, sl, n, seq, seq_off, coords, coord_off, q_aln, t_aln, aln_off, thr2, gen, scores);
+    if (rc != MDF_OK) return rc;
+    sl->busy = true;
+    *job = sl;
+    return MDF_OK;
+}
+
+// n proteins given as arrays of per-protein pointers (what a host holding n separate strings and coordinate arrays has): packed
+// into the slot's pinned block by host threads, then as mdf_path_submit.  The caller's buffers are no longer needed on return.
+extern "C" int mdf_path_submit_ragged(mdf_model *m, int n, const char *const *seq, const int *seq_len, const float *const *coords,
+                                      const int *coord_rows, const char *const *q_aln, const char *const *t_aln, const int *aln_len,
+                                      float thr2, int gen, float *scores, mdf_job **job)
+{
+    MDF_REQUIRE(m && scores && job && n >= 0, "mdf_path_submit_ragged: bad arguments");
+    MDF_REQUIRE(n == 0 || (seq && seq_len && coords && coord_rows && q_aln && t_aln && aln_len), "mdf_path_submit_ragged: input arrays missing");
+    mdf_ctx *ctx = m->ctx;
+    MDF_CUDA(cudaSetDevice(ctx->device));
+    const auto t0 = std::chrono::steady_clock::now();
+    int64_t T = 0, R = 0, A = 0;
+    for (int p = 0; p < n; ++p) {
+        MDF_REQUIRE(seq_len[p] >= 0 && coord_rows[p] >= 0 && aln_len[p] >= 0, "mdf_path_submit_ragged: protein %d has a negative length", p);
+        MDF_REQUIRE(seq[p] || seq_len[p] == 0, "mdf_path_submit_ragged: protein %d has no sequence", p);
+        MDF_REQUIRE(coords[p] || coord_rows[p] == 0, "mdf_path_submit_ragged: protein %d has no coordinates (filter structure-less queries first)", p);
+        MDF_REQUIRE((q_aln[p] && t_aln[p]) || aln_len[p] == 0, "mdf_path_submit_ragged: protein %d has no alignment", p);
+        T += seq_len[p]; R += coord_rows[p]; A += aln_len[p];
+    }
+    mdf_job *sl = nullptr;
+    MDF_TRY(slot_acquire(ctx, &sl));
+    const size_t off_b = align_up((size_t)(n + 1) * 8, 256);
+    const size_t seq_at = 3 * off_b, crd_at = seq_at + align_up((size_t)T + 16, 256), qa_at = crd_at + align_up((size_t)R * 12 + 16, 256),
+                 ta_at = qa_at + align_up((size_t)A + 16, 256), total = ta_at + align_up((size_t)A + 16, 256);
+    MDF_TRY(slot_pinned(sl, total));
+    int64_t *so = (int64_t *)sl->pin, *co = (int64_t *)(sl->pin + off_b), *ao = (int64_t *)(sl->pin + 2 * off_b);
+    so[0] = co[0] = ao[0] = 0;
+    for (int p = 0; p < n; ++p) { so[p + 1] = so[p] + seq_len[p]; co[p + 1] = co[p] + coord_rows[p]; ao[p + 1] = ao[p] + aln_len[p]; }
+    char *pseq = sl->pin + seq_at, *pq = sl->pin + qa_at, *pt = sl->pin + ta_at;
+    float *pc = (float *)(sl->pin + crd_at);
+    auto pack = [&](int lo, int hi) {
+        for (int p = lo; p < hi; ++p) {
+            if (seq_len[p]) memcpy(pseq + so[p], seq[p], (size_t)seq_len[p]);
+            if (coord_rows[p]) memcpy(pc + co[p] * 3, coords[p], (size_t)coord_rows[p] * 12);
+            if (aln_len[p]) { memcpy(pq + ao[p], q_aln[p], (size_t)aln_len[p]); memcpy(pt + ao[p], t_aln[p], (size_t)aln_len[p]); }
+        }
+    };
+    const int nt = std::max(1, std::min(ctx->host_threads, n / 256));
+    if (nt == 1) pack(0, n);
+    else {
+        // ranges of equal bytes, not equal protein counts
+        std::vector<std::thread> th;
+        const int64_t per = (T + R * 12 + 2 * A) / nt + 1;
+        int lo = 0;
+        for (int k = 0; k < nt; ++k) {
+            int hi = lo;
+            if (k == nt - 1) hi = n;
+            else while (hi < n && (so[hi] + co[hi] * 12 + 2 * ao[hi]) < per * (k + 1)) ++hi;
+            if (hi > lo) th.emplace_back(pack, lo, hi);
+            lo = hi;
+        }
+        for (auto &t : th) t.join();
+    }
+    static const bool timing = getenv("MDF_TIMING") != nullptr;
+    if (timing)
+        fprintf(stderr, "[mdf_path_submit_ragged] n=%d: packed %.1f MB with %d threads in %.2f ms\n", n, (T + R * 12 + 2 * A) / 1e6, nt,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    const int rc = job_enqueue(m, sl, n, pseq, so, pc, co, pq, pt, ao, thr2, gen, scores);
+    if (rc != MDF_OK) return rc;
+    sl->busy = true;
+    *job = sl;
+    return MDF_OK;
+}
+
+extern "C" int mdf_path_wait(mdf_job *job)
+{
+    MDF_REQUIRE(job && job->ctx, "mdf_path_wait: job is NULL");
+    MDF_REQUIRE(job->busy, "mdf_path_wait: this job has already been waited for");
+    MDF_CUDA(cudaSetDevice(job->ctx->device));
+    job->busy = false;
+    MDF_CUDA(cudaEventSynchronize(job->done));
+    const int e = job->h_err[0];
+    if (e == 0) return MDF_OK;
+    set_error("path: %s", e == MDF_DERR_BAD_RESIDUE ? "Invalid character in sequence"
+                        : e == MDF_DERR_BAD_CMAP    ? "contact map holds values other than 0/1"
+                        : e == MDF_DERR_LQ_MISMATCH ? "query sequence length does not match the gap-stripped query alignment"
+                                                    : "unknown device error");
+    return MDF_EINVAL;
+}
+
 extern "C" int mdf_path_forward(mdf_model *m, int n, const char *seq, const int64_t *seq_off, const float *coords,
                                 const int64_t *coord_off, const char *q_aln, const char *t_aln,
                                 const int64_t *aln_off, float thr2, int gen, float *scores)
 {
-    MDF_REQUIRE(m && coords && scores, "mdf_path_forward: bad arguments");
-    mdf_ctx *ctx = m->ctx;
-    MDF_CUDA(cudaSetDevice(ctx->device));
-    ArenaScope scope(ctx);
-    mdf_batch b;
-    static const bool timing = getenv("MDF_TIMING") != nullptr;       // host-side breakdown of one call on stderr
-    const auto t0 = std::chrono::steady_clock::now();
-    MDF_TRY(batch_build(ctx, &b, false, n, seq, seq_off, coords, coord_off, q_aln, t_aln, aln_off, nullptr, m->G, m->C,
-                        engine_workspace(m, n, seq_off)));
-    const auto t1 = std::chrono::steady_clock::now();
-    MDF_TRY(run_path(m, &b, thr2, gen, 4, true));
-    const auto t2 = std::chrono::steady_clock::now();
-    const int rc = fetch_scores(m, &b, scores);
-    if (timing) {
-        const auto t3 = std::chrono::steady_clock::now();
-        auto ms = [](auto a, auto b2) { return std::chrono::duration<double, std::milli>(b2 - a).count(); };
-        fprintf(stderr, "[mdf_path_forward] n=%d: batch build + H2D %.2f ms, enqueue (host) %.2f ms, wait + D2H %.2f ms\n", n, ms(t0, t1),
-                ms(t1, t2), ms(t2, t3));
-    }
-    return rc;
+    mdf_job *job = nullptr;
+    MDF_TRY(mdf_path_submit(m, n, seq, seq_off, coords, coord_off, q_aln, t_aln, aln_off, thr2, gen, scores, &job));
+    return mdf_path_wait(job);
 }
 
 extern "C" int mdf_gcn_forward_packed(mdf_model *m, int n, const char *seq, const int64_t *seq_off,
@@ -724,9 +940,16 @@ extern "C" int mdf_cmap_build_transfer(mdf_ctx *ctx, int n, const float *coords,
                         dense_total * 4 + (size_t)(n + 1) * 8 + 8192));
     if (packed_off)
         for (int p = 0; p <= n; ++p)
-            MDF_REQUIRE(packed_off[p] == b.h_packed_off[p], "mdf_cmap_build_transfer: packed_off[%d] is not canonical", p);
+            if (packed_off[p] != b.h_packed_off[p]) {
+                if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+                set_error("mdf_cmap_build_transfer: packed_off[%d] is not canonical", p);
+                return MDF_EINVAL;
+            }
     MDF_CUDA(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
-    MDF_TRY(run_cmap(ctx, &b, thr2, gen));
+    {
+        const int rc = run_cmap(ctx, &b, thr2, gen);
+        if (rc != MDF_OK) { if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream); return rc; }
+    }
     if (packed_out) {
         if (b.h_packed_off[n])
             MDF_CUDA(cudaMemcpyAsync(packed_out, b.d_packed, (size_t)b.h_packed_off[n] * 4, cudaMemcpyDeviceToHost, ctx->stream));

@@ -18,3 +18,12 @@ for f in *.cu; do
 done
 $NVCC -shared -gencode arch=compute_100a,code=sm_100a "${objs[@]}" -o $OUT -lcuda
 echo "built $OUT"
+# CPython glue (lists of str / ndarray -> pointer arrays for the ragged entry points); no CUDA in it
+PY=${PYTHON:-python3}
+PYINC=$($PY -c "import sysconfig; print(sysconfig.get_paths()['include'])")
+PYEXT=$($PY -c "import sysconfig; print(sysconfig.get_config_var('EXT_SUFFIX'))")
+HOSTSO=../_mdf_pyhost$PYEXT
+if [ ! -f "$HOSTSO" ] || [ pyhost.c -nt "$HOSTSO" ]; then
+  ${CC:-gcc} -O2 -Wall -shared -fPIC -I"$PYINC" pyhost.c -o "$HOSTSO"
+  echo "built $HOSTSO"
+fi

@@ -293,21 +293,35 @@ __global__ void cmap_band_kernel(int n, const float4 *__restrict__ qc, const int
 }
 
 
-// packed -> dense int32 [L, L] (the reference's layout; bio_utils.py:220 / contact_map_utils.pyx:82)
-__global__ void unpack_dense_kernel(const int2 *__restrict__ work, const int64_t *__restrict__ seq_off,
-                                    const uint32_t *__restrict__ packed, const int64_t *__restrict__ packed_off,
-                                    int32_t *__restrict__ dense, const int64_t *__restrict__ dense_off)
+// packed -> dense int32 [L, L] (the reference's layout; bio_utils.py:220 / contact_map_utils.pyx:82).  HBM-bound by its 4 bytes
+// per cell of output: one warp per row, 16-byte stores from the first 16-byte boundary of the row on (rows of an L x L int32
+// block start at arbitrary 4-byte offsets), four bits per store cut out of two packed words with one funnel shift.
+__global__ void __launch_bounds__(256) unpack_dense_kernel(const int2 *__restrict__ work, const int64_t *__restrict__ seq_off,
+                                                           const uint32_t *__restrict__ packed, const int64_t *__restrict__ packed_off,
+                                                           int32_t *__restrict__ dense, const int64_t *__restrict__ dense_off)
 {
     const int p = work[blockIdx.x].x, rb = work[blockIdx.x].y;
     const int L = (int)(seq_off[p + 1] - seq_off[p]);
     const int rw = packed_row_words(L);
     const uint32_t *src = packed + packed_off[p];
     int32_t *dst = dense + dense_off[p];
-    for (int r = 0; r < 32; ++r) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int r = warp; r < 32; r += 8) {
         const int i = rb * 32 + r;
         if (i >= L) break;
-        for (int j = threadIdx.x; j < L; j += blockDim.x)
-            dst[(size_t)i * L + j] = (src[(size_t)i * rw + (j >> 5)] >> (j & 31)) & 1u;
+        const uint32_t *row = src + (size_t)i * rw;
+        int32_t *out = dst + (size_t)i * L;
+        int head = (int)(((16u - (unsigned)((uintptr_t)out & 15u)) & 15u) >> 2);
+        if (head > L) head = L;
+        if (lane < head) out[lane] = (int32_t)((row[0] >> lane) & 1u);
+        const int nvec = (L - head) >> 2;
+        int4 *ov = reinterpret_cast<int4 *>(out + head);
+        for (int v = lane; v < nvec; v += 32) {
+            const int j = head + 4 * v, w = j >> 5;
+            const uint32_t bits = __funnelshift_r(row[w], row[min(w + 1, rw - 1)], j & 31);
+            ov[v] = make_int4((int)(bits & 1u), (int)((bits >> 1) & 1u), (int)((bits >> 2) & 1u), (int)((bits >> 3) & 1u));
+        }
+        for (int j = head + 4 * nvec + lane; j < L; j += 32) out[j] = (int32_t)((row[j >> 5] >> (j & 31)) & 1u);
     }
 }
 

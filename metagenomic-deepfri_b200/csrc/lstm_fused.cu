@@ -548,6 +548,23 @@ size_t lstm_fused_scratch_bytes(const mdf_ctx *ctx, int H)
     return (size_t)covers * 4 * LF_M * H * 2 + LF_SCRATCH_HEAD;
 }
 
+// Nsight Compute cannot profile a cooperative launch that also carries a cluster dimension (it aborts the capture), and it
+// serialises kernels anyway, so under an injected profiler the kernel is launched plainly: the grid never exceeds one CTA per
+// SM, which makes it co-resident whenever the stream owns the GPU.
+static bool profiler_injected()
+{
+    static int cached = -1;
+    if (cached < 0) {
+        cached = 0;
+        extern char **environ;
+        for (char **e = environ; e && *e; ++e)
+            if (!strncmp(*e, "NV_NSIGHT_INJECTION", 19) || !strncmp(*e, "CUDA_INJECTION64_PATH=", 22) || !strncmp(*e, "NV_COMPUTE_PROFILER", 19) ||
+                !strncmp(*e, "NVTX_INJECTION64_PATH=", 22) || !strncmp(*e, "NSIGHT_COMPUTE", 14))
+                cached = 1;
+    }
+    return cached == 1;
+}
+
 template <bool PAIR, int MODE>
 static int launch_variant(mdf_ctx *ctx, LstmFusedArgs &a, size_t smem)
 {
@@ -563,20 +580,32 @@ static int launch_variant(mdf_ctx *ctx, LstmFusedArgs &a, size_t smem)
     // Co-residency: the CTAs spin on each other's release counters.  The grid never exceeds one CTA per SM, so a plain
     // launch is co-resident too whenever the stream owns the GPU; MDF_LSTM_COOP=0 drops the attribute because Nsight
     // Compute cannot profile a cooperative launch that also carries a cluster dimension.
-    static const int coop_env = getenv("MDF_LSTM_COOP") ? atoi(getenv("MDF_LSTM_COOP")) : 1;
-    if (coop_env) {
-        attrs[na].id = cudaLaunchAttributeCooperative;
-        attrs[na].val.cooperative = 1;
-        ++na;
+    static const int coop_env = getenv("MDF_LSTM_COOP") ? atoi(getenv("MDF_LSTM_COOP")) : (profiler_injected() ? 0 : 1);
+    static bool coop_ok = coop_env != 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        na = 0;
+        if (coop_ok) {
+            attrs[na].id = cudaLaunchAttributeCooperative;
+            attrs[na].val.cooperative = 1;
+            ++na;
+        }
+        if (PAIR) {
+            attrs[na].id = cudaLaunchAttributeClusterDimension;
+            attrs[na].val.clusterDim.x = 2 * a.spc; attrs[na].val.clusterDim.y = 1; attrs[na].val.clusterDim.z = 1;
+            ++na;
+        }
+        cfg.attrs = attrs;
+        cfg.numAttrs = na;
+        const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a);
+        if (e == cudaSuccess) break;
+        if (coop_ok && attempt == 0) {          // a refused cooperative launch (profiler, MPS ...): retry plainly, once and for all
+            cudaGetLastError();
+            coop_ok = false;
+            continue;
+        }
+        set_error("%s:%d: lstm_fused launch failed: %s", __FILE__, __LINE__, cudaGetErrorString(e));
+        return MDF_ECUDA;
     }
-    if (PAIR) {
-        attrs[na].id = cudaLaunchAttributeClusterDimension;
-        attrs[na].val.clusterDim.x = 2 * a.spc; attrs[na].val.clusterDim.y = 1; attrs[na].val.clusterDim.z = 1;
-        ++na;
-    }
-    cfg.attrs = attrs;
-    cfg.numAttrs = na;
-    MDF_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
     ctx->launches++;
     return MDF_OK;
 }

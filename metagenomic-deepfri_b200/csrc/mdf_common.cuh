@@ -45,6 +45,22 @@ static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 }  // namespace mdf
 
+// One of the two job slots of a context (mdf_path_submit* / mdf_path_wait): the device block that holds a transient batch's inputs,
+// contact maps and scores, and the pinned host block its inputs are packed into.  While job k computes out of slot k & 1, job
+// k + 1 is packed and copied into the other slot; the engine workspace (arena) is shared in stream order.
+struct mdf_batch;
+struct mdf_model;
+struct mdf_job {
+    struct mdf_ctx *ctx = nullptr;
+    char *dev = nullptr;  size_t dev_bytes = 0;     // cudaMalloc
+    char *pin = nullptr;  size_t pin_bytes = 0;     // cudaHostAlloc
+    int *h_err = nullptr;                           // pinned [2]: device error flag of this job
+    cudaEvent_t done = nullptr;                     // recorded after the scores have reached the host
+    bool busy = false;                              // submitted, not yet waited for
+    mdf_batch *batch = nullptr;
+    int rc = 0;                                     // deferred submit status
+};
+
 // Device workspace: one big allocation, bump-allocated, reset per API call (stack discipline).
 struct mdf_ctx {
     int device = 0;
@@ -63,6 +79,9 @@ struct mdf_ctx {
     // which only needs the sequences; the contact-map stage waits for `copy_done`
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t copy_done = nullptr;
+    mdf_job slots[2];
+    int next_slot = 0;
+    int host_threads = 4;     // packing threads of mdf_path_submit_ragged (MDF_HOST_THREADS)
 
     // optional per-stage CUDA-event profiling (bench.py roofline leg)
     struct ProfEntry { const char *name; cudaEvent_t start, stop; double units; };

@@ -4,8 +4,8 @@
 (`model_path`, `threads`, `session`, `input_names`, `predict.pyx:50-60`) and
 `forward_pass(seqres, cmap)` keeps its contract (`predict.pyx:75-102`): a float32 vector with
 one score per GO term (channel 0 of the [1, C, 2] softmax output).  Instead of an onnxruntime
-session, the `.onnx` file is recognised by `onnx_plan` and executed by the fused CUDA pipeline
-behind the C ABI.  Batched entry points (`forward_batch`, `forward_structures`) run the same
+session, the `.onnx` file is decoded and recognised by the library itself (`mdf_model_load`, `csrc/onnx_load.cu`) and
+executed by the fused CUDA pipeline behind the C ABI.  Batched entry points (`forward_batch`, `forward_structures`) run the same
 kernels over many proteins per launch; `forward_pass` is a batch of one.
 
 A single-input `.onnx` file (the `DeepCNN-MERGED_*` models) is the reference's sequence-only CNN
@@ -16,13 +16,13 @@ CPU or library fallback on either branch.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Optional, Sequence
 
 import numpy as np
 
 from . import _lib
 from .batching import pack_structures, packed_offsets
-from .onnx_plan import CNNPlan, GCNPlan, load_plan
 
 _ALPHABET = b"-DGULNTKHYWCPVSOIEFXQABZRM"          # predict.pyx:26
 _LUT = np.full(256, -1, np.int16)
@@ -70,7 +70,7 @@ class _Session:
         def __init__(self, name):
             self.name = name
 
-    def __init__(self, plan: GCNPlan, handle, ctx: _lib.Context):
+    def __init__(self, plan, handle, ctx: _lib.Context):
         self.plan = plan
         self.handle = handle
         self.ctx = ctx
@@ -80,6 +80,20 @@ class _Session:
 
     def get_providers(self):
         return ["B200ExecutionProvider"]
+
+
+class ModelInfo:
+    """What `mdf_onnx_inspect` reports about the loaded file: head sizes, hyper-parameters, which initialiser plays which role."""
+
+    def __init__(self, info: dict):
+        self.info = info
+        self.input_names = list(info["input_names"])
+        self.n_terms = int(info["n_terms"])
+        self.roles = dict(info.get("roles", {}))
+        for k in ("lstm_hidden", "lm_dim", "fc_dim", "gc_dims", "gc_activation", "gc_alpha", "eps", "lm_fingerprint", "n_lstm",
+                  "conv_filters", "conv_width", "conv_pad_left"):
+            if k in info:
+                setattr(self, k, info[k])
 
 
 class PathInputs:
@@ -145,6 +159,10 @@ class PathBatch:
         self.h2d_bytes = (len(seq_bytes) + ps.coords.nbytes + 2 * len(ps.q_aln)
                           + 8 * (seq_off.size + ps.coord_off.size + ps.aln_off.size))
 
+    def invalidate(self) -> None:
+        """Drop what `run(share=True)` keeps between heads (contact maps, LSTM-LM output): the next run recomputes them."""
+        _lib.check(_lib.lib().mdf_batch_invalidate(self.handle))
+
     def close(self):
         if getattr(self, "handle", None):
             _lib.lib().mdf_batch_destroy(self.handle)
@@ -155,6 +173,32 @@ class PathBatch:
             self.close()
         except Exception:
             pass
+
+
+class PathJob:
+    """An in-flight `Predictor.submit_structures` call."""
+
+    def __init__(self, pred: "Predictor", handle: int, out: np.ndarray, inputs):
+        self._pred, self._handle, self._out, self._inputs = pred, handle, out, inputs
+
+    def wait(self) -> np.ndarray:
+        if self._handle is None:
+            return self._out
+        h, self._handle = self._handle, None
+        try:
+            _lib.check(_lib.lib().mdf_path_wait(C.c_void_p(h)))
+        except ValueError as e:
+            # the device only flags THAT an input was bad; name it the way the reference does (predict.pyx:45-46)
+            seqs, gq, _ = self._inputs
+            if "Invalid character" in str(e):
+                for s in seqs:
+                    _encode(s)
+            if "does not match" in str(e):
+                raise ValueError("query sequences do not match the gap-stripped query alignments") from None
+            raise
+        finally:
+            self._inputs = None
+        return self._out
 
 
 class Predictor:
@@ -169,66 +213,21 @@ class Predictor:
 
     # -- predict.pyx:62-73
     def _load_model(self):
-        plan = load_plan(self.model_path)        # FileNotFoundError / RuntimeError on bad files
-        self.is_cnn = isinstance(plan, CNNPlan)
+        L = _lib.lib()
+        path = os.fsencode(self.model_path)
+        info = _lib.inspect_onnx(self.model_path)     # FileNotFoundError / RuntimeError / UnsupportedModelError on bad files
+        self.is_cnn = info["kind"] == "cnn"
+        h = C.c_void_p()
         if self.is_cnn:
-            return self._load_cnn(plan)
-        d = _lib.ModelDesc()
-        keep = []
-
-        def ptr(a):
-            if a is None:
-                return None
-            a = np.ascontiguousarray(a, np.float32)
-            keep.append(a)
-            return _lib.fp(a)
-
-        d.n_channels, d.lstm_hidden, d.n_lstm = plan.n_channels, plan.lstm_hidden, len(plan.lstm_W)
-        if d.n_lstm > 4 or len(plan.gc_W) > 8:
-            raise NotImplementedError("model deeper than the fused pipeline supports")
-        for l in range(d.n_lstm):
-            d.lstm_W[l], d.lstm_R[l], d.lstm_B[l] = ptr(plan.lstm_W[l]), ptr(plan.lstm_R[l]), ptr(plan.lstm_B[l])
-        d.lm_dim, d.aa_W, d.lm_W, d.lm_b = plan.lm_dim, ptr(plan.aa_W), ptr(plan.lm_W), ptr(plan.lm_b)
-        d.n_gc = len(plan.gc_W)
-        for l, w in enumerate(plan.gc_W):
-            d.gc_dims[l], d.gc_W[l], d.gc_b[l] = w.shape[1], ptr(w), ptr(plan.gc_b[l])
-        d.gc_activation, d.gc_alpha, d.eps = plan.gc_activation, plan.gc_alpha, plan.eps
-        d.fc_dim, d.fc_W, d.fc_b = plan.fc_W.shape[1], ptr(plan.fc_W), ptr(plan.fc_b)
-        d.n_terms, d.out_W, d.out_b = plan.n_terms, ptr(plan.out_W), ptr(plan.out_b)
-        h = C.c_void_p()
-        _lib.check(_lib.lib().mdf_model_create(self._ctx.handle, C.byref(d), C.byref(h)))
+            _lib.check(L.mdf_cnn_model_load(self._ctx.handle, path, C.byref(h)))
+            self.n_pooled = int(sum(info["conv_filters"]))
+        else:
+            _lib.check(L.mdf_model_load(self._ctx.handle, path, C.byref(h)))
         self._handle = h
-        self.n_terms = plan.n_terms
-        self.plan = plan
-        self.session = _Session(plan, h, self._ctx)
-        self.input_names = list(plan.input_names)
-
-    def _load_cnn(self, plan: CNNPlan):
-        d = _lib.CnnDesc()
-        keep = []
-
-        def ptr(a):
-            if a is None:
-                return None
-            a = np.ascontiguousarray(a, np.float32)
-            keep.append(a)
-            return _lib.fp(a)
-
-        if len(plan.conv_W) > _lib.MAX_CONV:
-            raise NotImplementedError("DeepCNN model has more parallel Conv layers than the kernel supports")
-        d.n_channels, d.n_conv = plan.n_channels, len(plan.conv_W)
-        for l, (w, pl) in enumerate(zip(plan.conv_W, plan.conv_pad_left)):
-            d.conv_filters[l], d.conv_width[l], d.conv_pad_left[l], d.conv_W[l] = w.shape[0], w.shape[2], pl, ptr(w)
-        d.scale, d.shift = ptr(plan.scale), ptr(plan.shift)
-        d.n_terms, d.out_W, d.out_b = plan.n_terms, ptr(plan.out_W), ptr(plan.out_b)
-        h = C.c_void_p()
-        _lib.check(_lib.lib().mdf_cnn_model_create(self._ctx.handle, C.byref(d), C.byref(h)))
-        self._handle = h
-        self.n_terms = plan.n_terms
-        self.n_pooled = int(plan.scale.size)
-        self.plan = plan
-        self.session = _Session(plan, h, self._ctx)
-        self.input_names = list(plan.input_names)
+        self.n_terms = int(info["n_terms"])
+        self.plan = ModelInfo(info)
+        self.session = _Session(self.plan, h, self._ctx)
+        self.input_names = list(info["input_names"])
 
     # -- predict.pyx:91-95, batched: the sequence-only branch for n sequences
     def forward_sequences(self, seqs: Sequence[str], out: Optional[np.ndarray] = None) -> np.ndarray:
@@ -261,12 +260,19 @@ class Predictor:
         _lib.check(_lib.lib().mdf_cnn_fetch(self._handle, out.ctypes.data, pl.ctypes.data if pooled else None))
         return (out, pl) if pooled else out
 
+    def _require_gcn(self, what: str) -> None:
+        # the C handle of a DeepCNN Predictor is an mdf_cnn_model*: never hand it to an entry point that takes mdf_model*
+        if self.is_cnn:
+            raise ValueError(f"{what} needs a GCN head (cmap, seq); this Predictor holds a sequence-only DeepCNN model")
+
     def set_engine(self, engine: str) -> None:
         """'simt' = exact-fp32 CUDA-core engine, 'tc' = tcgen05 tensor-core engine."""
+        self._require_gcn("set_engine")
         _lib.check(_lib.lib().mdf_model_set_engine(self._handle, {"simt": 0, "tc": 1}[engine]))
 
     @property
     def engine(self) -> str:
+        self._require_gcn("engine")
         return {0: "simt", 1: "tc"}[_lib.lib().mdf_model_get_engine(self._handle)]
 
     # -- predict.pyx:75-102
@@ -299,6 +305,7 @@ class Predictor:
 
     def forward_batch(self, seqs: Sequence[str], packed_cmaps: Sequence[np.ndarray]) -> np.ndarray:
         """GCN forward for n proteins with bit-packed maps (uint32 [L, row_words] each)."""
+        self._require_gcn("forward_batch")
         n = len(seqs)
         seq_bytes, seq_off = _pack_checked(seqs)
         poff = packed_offsets(np.diff(seq_off))
@@ -311,29 +318,50 @@ class Predictor:
                                                      _lib.lp(poff), _lib.fp(out)))
         return out
 
+    def submit_structures(self, seqs: Sequence[str], gapped_query: Sequence[str], gapped_target: Sequence[str],
+                          coords: Sequence[np.ndarray], threshold: float = 6, generated_contacts: int = 2,
+                          out: Optional[np.ndarray] = None) -> "PathJob":
+        """Asynchronous `forward_structures`: packs the n proteins into pinned staging memory (C, worker threads, GIL released),
+        enqueues H2D + every kernel + the D2H of the scores and returns a `PathJob`; `job.wait()` returns the score matrix.
+        Two jobs may be in flight per context, so the next batch's packing and copies overlap this batch's kernels."""
+        from .bio_utils import threshold_sq
+        self._require_gcn("submit_structures")
+        n = len(seqs)
+        if out is None:
+            out = np.empty((n, self.n_terms), np.float32)
+        if out.shape != (n, self.n_terms) or out.dtype != np.float32 or not out.flags["C_CONTIGUOUS"]:
+            raise ValueError("out must be a C-contiguous float32 array of shape (n, n_terms)")
+        host = _lib.pyhost()
+        args = (_lib.fn_addr("mdf_path_submit_ragged"), self._handle.value, seqs, gapped_query, gapped_target)
+        tail = (float(threshold_sq(threshold)), int(generated_contacts), out.ctypes.data)
+        try:
+            rc, job = host.submit_ragged(*args, coords, *tail)
+        except TypeError:
+            # some structure is not a C-contiguous float32 [Lt, 3] array (lists, float64 ...): convert like the reference's
+            # astype(np.float32) (contact_map.py:25) and retry once
+            conv = []
+            for i, c in enumerate(coords):
+                c = np.ascontiguousarray(c, dtype=np.float32)
+                if c.ndim != 2 or c.shape[1] != 3:
+                    raise ValueError(f"structure {i}: coordinates must have shape (Lt, 3)")
+                conv.append(c)
+            rc, job = host.submit_ragged(*args, conv, *tail)
+        _lib.check(rc)
+        return PathJob(self, job, out, (seqs, gapped_query, gapped_target))
+
     def forward_structures(self, seqs: Sequence[str], gapped_query: Sequence[str], gapped_target: Sequence[str],
                            coords: Sequence[np.ndarray], threshold: float = 6, generated_contacts: int = 2,
                            out: Optional[np.ndarray] = None) -> np.ndarray:
         """The whole path for n proteins (contact map build + alignment transfer + GCN), host
         buffers in, host scores out: what `pipeline.py:476-481` + `:301-319` compute together."""
-        from .bio_utils import threshold_sq
-        n = len(seqs)
-        ps = pack_structures(gapped_query, gapped_target, coords)
-        seq_bytes, seq_off = _pack_checked(seqs)
-        if not np.array_equal(seq_off, ps.seq_off):
-            raise ValueError("query sequences do not match the gap-stripped query alignments")
-        if out is None:
-            out = np.empty((n, self.n_terms), np.float32)
-        _lib.check(_lib.lib().mdf_path_forward(
-            self._handle, n, seq_bytes, _lib.lp(seq_off), ps.coords.ctypes.data, _lib.lp(ps.coord_off), ps.q_aln,
-            ps.t_aln, _lib.lp(ps.aln_off), float(threshold_sq(threshold)), int(generated_contacts), out.ctypes.data))
-        return out
+        return self.submit_structures(seqs, gapped_query, gapped_target, coords, threshold, generated_contacts, out).wait()
 
     def forward_inputs(self, inputs: PathInputs, threshold: float = 6, generated_contacts: int = 2,
                        out: Optional[np.ndarray] = None) -> np.ndarray:
         """`forward_structures` on pre-packed (optionally pinned) host buffers: per call this does
         the host->device copies, every kernel of the path and the device->host copy of the scores."""
         from .bio_utils import threshold_sq
+        self._require_gcn("forward_inputs")
         if out is None:
             out = inputs.output_buffer(self.n_terms)
         _lib.check(_lib.lib().mdf_path_forward(
@@ -344,6 +372,7 @@ class Predictor:
 
     # -- resident-batch interface (bench / multi-head reuse)
     def upload(self, seqs, gapped_query, gapped_target, coords) -> PathBatch:
+        self._require_gcn("upload")
         return PathBatch(self._ctx, seqs, gapped_query, gapped_target, coords)
 
     def run(self, batch: PathBatch, threshold: float = 6, generated_contacts: int = 2, upto: int = 4,
@@ -351,6 +380,7 @@ class Predictor:
         """Run the path on an uploaded batch.  `share=True` keeps what an earlier run of ANOTHER head on this batch
         already computed and this head shares (contact maps, LSTM-LM output); the default recomputes everything."""
         from .bio_utils import threshold_sq
+        self._require_gcn("run")
         if share:
             if upto != 4:
                 raise ValueError("run(share=True) runs the whole path")
@@ -361,21 +391,30 @@ class Predictor:
                                                   int(generated_contacts), upto))
 
     def fetch_scores(self, batch: PathBatch, out: Optional[np.ndarray] = None) -> np.ndarray:
+        self._require_gcn("fetch_scores")
         if out is None:
             out = np.empty((batch.n, self.n_terms), np.float32)
         _lib.check(_lib.lib().mdf_batch_fetch_scores(self._handle, batch.handle, out.ctypes.data))
         return out
 
+    def unpack_dense(self, batch: PathBatch) -> int:
+        """Writes the contact maps of the last run in the reference's dense int32 [Lq, Lq] layout to workspace scratch
+        (the HBM-bound variant of the contact-map stage, timed by bench.py / tools/cmap_bench.py); returns the cell count."""
+        cells = C.c_int64(0)
+        _lib.check(_lib.lib().mdf_batch_unpack_dense(batch.handle, None, C.byref(cells)))
+        return int(cells.value)
+
     _TAPS = {"packed": 0, "deg": 1, "lstm1": 2, "lstm2": 3, "x0": 4, "pooled": 5, "gc_last": 6}
 
     def fetch(self, batch: PathBatch, what: str) -> np.ndarray:
+        self._require_gcn("fetch")
         T = int(batch.seq_off[-1])
         p = self.plan
         shape, dt = {
             "packed": ((int(batch.packed_off[-1]),), np.uint32), "deg": ((T,), np.float32),
             "lstm1": ((T, p.lstm_hidden), np.float32), "lstm2": ((T, p.lstm_hidden), np.float32),
-            "x0": ((T, p.lm_dim), np.float32), "pooled": ((batch.n, sum(w.shape[1] for w in p.gc_W)), np.float32),
-            "gc_last": ((T, p.gc_W[-1].shape[1]), np.float32)}[what]
+            "x0": ((T, p.lm_dim), np.float32), "pooled": ((batch.n, sum(p.gc_dims)), np.float32),
+            "gc_last": ((T, p.gc_dims[-1]), np.float32)}[what]
         out = np.empty(shape, dt)
         _lib.check(_lib.lib().mdf_batch_fetch(self._handle, batch.handle, self._TAPS[what], out.ctypes.data, out.nbytes))
         return out

@@ -11,8 +11,10 @@ from typing import List, Sequence
 
 import numpy as np
 
-# fitted on B200 (tensor-core engine): the linear term (LSTM + dense) dominates below L ~ 1000
-ALPHA, BETA = 3.0e-4, 1.0
+# seconds per protein = ALPHA L^2 + BETA L, fitted to the per-stage CUDA-event profile of one 16,384-protein configs[4] batch on a
+# B200 (tools/fit_cost.py on profiles/r02_bench_base_before.json: T = 4,901,679 residues, sum L^2 = 2.033e9; quadratic stages =
+# contact maps + tile scan + adjacency product 13.03 ms, linear stages = LSTM-LM + embedding + X.W + head 54.74 ms)
+ALPHA, BETA = 6.41e-12, 1.117e-8
 
 
 def cost(lengths: Sequence[int], alpha: float = ALPHA, beta: float = BETA) -> np.ndarray:
@@ -21,17 +23,19 @@ def cost(lengths: Sequence[int], alpha: float = ALPHA, beta: float = BETA) -> np
 
 
 def lpt_bins(lengths: Sequence[int], n_bins: int, alpha: float = ALPHA, beta: float = BETA) -> List[np.ndarray]:
-    """Greedy LPT: heaviest protein first onto the currently lightest bin.  Returns, per bin, the
-    protein indices sorted by descending length (the order the LSTM kernel wants)."""
+    """Greedy LPT: heaviest protein first onto the currently lightest bin (heap: a million proteins in about a second).
+    Returns, per bin, the protein indices in ascending index order - a random mix of lengths, which is what a chunk of the
+    bin should look like (the LSTM kernel sorts each chunk itself)."""
+    import heapq
     c = cost(lengths, alpha, beta)
     order = np.argsort(-c, kind="stable")
-    loads = np.zeros(n_bins)
-    bins: List[List[int]] = [[] for _ in range(n_bins)]
-    for i in order:
-        b = int(np.argmin(loads))
-        bins[b].append(int(i))
-        loads[b] += c[i]
-    return [np.asarray(b, dtype=np.int64) for b in bins]
+    heap = [(0.0, b) for b in range(n_bins)]
+    owner = np.empty(len(c), np.int32)
+    for i, ci in zip(order.tolist(), c[order].tolist()):
+        load, b = heap[0]
+        owner[i] = b
+        heapq.heapreplace(heap, (load + ci, b))
+    return [np.flatnonzero(owner == b).astype(np.int64) for b in range(n_bins)]
 
 
 def chunks_by_residues(indices: np.ndarray, lengths: Sequence[int], max_residues: int,

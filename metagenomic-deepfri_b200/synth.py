@@ -383,6 +383,146 @@ def make_workload(n: int, lmin: int, lmax: int, seed: int, *, gapped: bool = Tru
                     name or f"n{n}_L{lmin}-{lmax}_{dist}_seed{seed}")
 
 
+# ----------------------------------------------------------------------------- keyed generator (the sharded 1M-protein job)
+# Protein i of a job is a pure function of (seed, i): any rank can generate exactly its own shard of BASELINE configs[4] without
+# generating (or receiving) the rest, whatever the number of ranks.  Counter-based: every random number is a splitmix64 hash of
+# (seed, protein, position, channel).  Same model as make_workload: L ~ LogNormal(median 250, sigma 0.6) clipped, uniform
+# residues, Markov-gapped alignments (gap open 0.02 + 0.02, extension 0.5, 5 % leading / trailing gaps, 60 % identity),
+# C-alpha random walks with 3.8 A steps and 0.5 direction persistence, coordinates rounded to 3 decimals.
+_G = np.uint64(0x9E3779B97F4A7C15)
+_M1, _M2 = np.uint64(0xBF58476D1CE4E5B9), np.uint64(0x94D049BB133111EB)
+_K1, _K2 = np.uint64(0xD6E8FEB86659FD93), np.uint64(0xA24BAED4963EE407)
+
+
+def _mix64(x: np.ndarray) -> np.ndarray:
+    x = (x ^ (x >> np.uint64(30))) * _M1
+    x = (x ^ (x >> np.uint64(27))) * _M2
+    return x ^ (x >> np.uint64(31))
+
+
+def _hash(base: np.ndarray, t, c: int) -> np.ndarray:
+    """base = per-protein key (uint64), t = position (scalar or array), c = channel."""
+    with np.errstate(over="ignore"):
+        return _mix64(base + np.uint64(t) * _K1 + np.uint64(c) * _K2) if np.isscalar(t) else \
+            _mix64(base + t.astype(np.uint64) * _K1 + np.uint64(c) * _K2)
+
+
+def _u01(h: np.ndarray) -> np.ndarray:
+    return ((h >> np.uint64(11)).astype(np.float64) + 0.5) * (2.0 ** -53)
+
+
+def _protein_keys(ids: np.ndarray, seed: int) -> np.ndarray:
+    with np.errstate(over="ignore"):
+        return _mix64(np.asarray(ids, np.uint64) * _G + np.uint64(seed) * _K2 + _K1)
+
+
+def keyed_lengths(ids: Sequence[int], seed: int, lmin: int = 50, lmax: int = 1000) -> np.ndarray:
+    """Query lengths of the proteins `ids` of job `seed` (cheap: the LPT partition needs all of them on every rank)."""
+    k = _protein_keys(np.asarray(ids, np.int64), seed)
+    z = np.sqrt(-2.0 * np.log(_u01(_hash(k, 0, 101)))) * np.cos(2.0 * np.pi * _u01(_hash(k, 0, 102)))
+    return np.clip(np.exp(np.log(250.0) + 0.6 * z), lmin, lmax).astype(np.int64)
+
+
+def keyed_workload(ids: Sequence[int], seed: int, lmin: int = 50, lmax: int = 1000, threshold: float = 10.0,
+                   generated_contacts: int = 2, name: str = "") -> Workload:
+    ids = np.asarray(ids, np.int64)
+    n = len(ids)
+    if n == 0:
+        return Workload([], [], [], [], threshold, generated_contacts, name)
+    key = _protein_keys(ids, seed)
+    L = keyed_lengths(ids, seed, lmin, lmax)
+    aa = np.frombuffer(AA20.encode(), np.uint8)
+    # ---- alignment columns: state 0 = M, 1 = I ('-' in the query), 2 = D ('-' in the target); one column per step for all proteins
+    cap = int(L.max() * 1.25) + 64
+    state = np.full((n, cap), 3, np.int8)                  # 3 = past the end
+    qpos = np.zeros(n, np.int64)                           # query residues consumed so far
+    cur = np.where(_u01(_hash(key, 0, 1)) < 0.05, np.where(_hash(key, 0, 2) & np.uint64(1), 1, 2), 0).astype(np.int8)   # leading gap
+    ncols = np.zeros(n, np.int64)
+    alive = np.arange(n)
+    for col in range(cap):
+        if alive.size == 0:
+            break
+        k, c = key[alive], cur[alive]
+        state[alive, col] = c
+        qpos[alive] += c != 1
+        ncols[alive] = col + 1
+        u = _u01(_hash(k, col, 3))
+        gap_type = np.where(_hash(k, col, 4) & np.uint64(1), 1, 2).astype(np.int8)
+        nxt = np.where(c == 0, np.where(u < 0.04, gap_type, 0), np.where(u < 0.5, c, 0)).astype(np.int8)
+        cur[alive] = nxt
+        done = qpos[alive] >= L[alive]
+        alive = alive[~done]
+    if alive.size:
+        raise RuntimeError("keyed_workload: alignment did not terminate (raise the column capacity)")
+    # trailing query gap (5 %): 1-3 extra I columns
+    trail = np.where(_u01(_hash(key, 0, 5)) < 0.05, 1 + (_hash(key, 0, 6) % np.uint64(3)).astype(np.int64), 0)
+    for extra in range(3):
+        m = trail > extra
+        state[m, ncols[m] + extra] = 1
+    ncols = ncols + trail
+    cols = np.arange(cap)
+    valid = cols[None, :] < ncols[:, None]
+    consumes_q = valid & (state != 1)
+    qi = np.cumsum(consumes_q, axis=1) - 1
+    tt = np.broadcast_to(cols[None, :], (n, cap))
+    qres = aa[(_hash(key[:, None], np.clip(qi, 0, None), 7) % np.uint64(20)).astype(np.int64)]      # residue qi of the query
+    rnd = aa[(_hash(key[:, None], tt, 8) % np.uint64(20)).astype(np.int64)]
+    keep = _u01(_hash(key[:, None], tt, 9)) < 0.6
+    gq = np.where(state == 1, ord("-"), qres).astype(np.uint8)
+    gt = np.where(state == 2, ord("-"), np.where((state == 0) & keep, qres, rnd)).astype(np.uint8)
+    Lt = (valid & (state != 2)).sum(axis=1)
+    gapped_q = [gq[i, :ncols[i]].tobytes().decode() for i in range(n)]
+    gapped_t = [gt[i, :ncols[i]].tobytes().decode() for i in range(n)]
+    seqs = [s.replace("-", "") for s in gapped_q]
+    # ---- structures: random walk over the target residues, longest first so that every step only touches the live prefix
+    order = np.argsort(-Lt, kind="stable")
+    ko, Lo = key[order], Lt[order]
+    Lmax = int(Lo[0]) if n else 0
+    pos = np.zeros((n, 3))
+    vprev = np.zeros((n, 3))
+    out = np.zeros((Lmax, n, 3), np.float32)
+    live = n
+    for t in range(Lmax):
+        while live > 0 and Lo[live - 1] <= t:
+            live -= 1
+        if t:
+            kk = ko[:live]
+            r1 = np.sqrt(-2.0 * np.log(_u01(_hash(kk, t, 10))))
+            r2 = np.sqrt(-2.0 * np.log(_u01(_hash(kk, t, 11))))
+            a1, a2 = 2.0 * np.pi * _u01(_hash(kk, t, 12)), 2.0 * np.pi * _u01(_hash(kk, t, 13))
+            v = np.stack([r1 * np.cos(a1), r1 * np.sin(a1), r2 * np.cos(a2)], axis=1)
+            v /= np.linalg.norm(v, axis=1, keepdims=True) + 1e-12
+            v += 0.5 * vprev[:live]
+            v /= np.linalg.norm(v, axis=1, keepdims=True) + 1e-12
+            pos[:live] += 3.8 * v
+            vprev[:live] = v
+        out[t, :live] = np.round(pos[:live], 3)
+    inv = np.empty(n, np.int64)
+    inv[order] = np.arange(n)
+    coords = [np.ascontiguousarray(out[:Lt[i], inv[i]]) for i in range(n)]
+    return Workload(seqs, gapped_q, gapped_t, coords, threshold, generated_contacts, name or f"keyed_seed{seed}_n{n}")
+
+
+def keyed_workload_parallel(ids: Sequence[int], seed: int, procs: int, block: int = 4096, **kw) -> Workload:
+    """`keyed_workload` over a process pool (fork; call before CUDA is initialised in this process)."""
+    ids = np.asarray(ids, np.int64)
+    parts = [ids[i:i + block] for i in range(0, len(ids), block)]
+    if procs <= 1 or len(parts) <= 1:
+        ws = [keyed_workload(p, seed, **kw) for p in parts]
+    else:
+        import multiprocessing as mp
+        from functools import partial
+        with mp.get_context("fork").Pool(min(procs, len(parts))) as pool:
+            ws = pool.map(partial(keyed_workload, seed=seed, **kw), parts)
+    out = Workload([], [], [], [], kw.get("threshold", 10.0), kw.get("generated_contacts", 2), f"keyed_seed{seed}_n{len(ids)}")
+    for w in ws:
+        out.query_seqs += w.query_seqs
+        out.gapped_query += w.gapped_query
+        out.gapped_target += w.gapped_target
+        out.coords += w.coords
+    return out
+
+
 def config_workload(idx: int, scale: float = 1.0) -> Workload:
     """BASELINE.json `configs[idx]`; `scale` shrinks the protein count for tests."""
     if idx == 0:

@@ -45,9 +45,9 @@ def seq2onehot(seq: str) -> np.ndarray:
     return F.one_hot(torch.tensor(idx), 26).to(torch.float32).numpy()
 
 
-def _onnx_lstm(X, W, R, B, H, init_h, init_c, dtype):
-    """ONNX LSTM (forward, layout 0): X [T, b, I], W [1, 4H, I], R [1, 4H, H], B [1, 8H] = [Wb | Rb], gates i, o, f, c.
-    torch.nn.LSTM stacks its rows as i, f, g(cell), o and keeps the two bias halves apart as bias_ih / bias_hh."""
+def _torch_lstm_module(W, R, B, H, dtype):
+    """torch.nn.LSTM holding the weights of one ONNX LSTM node: W [1, 4H, I], R [1, 4H, H], B [1, 8H] = [Wb | Rb], ONNX gate
+    order i, o, f, c.  torch stacks its rows as i, f, g(cell), o and keeps the two bias halves apart as bias_ih / bias_hh."""
     if W.shape[0] != 1:
         raise NotImplementedError("bidirectional LSTM")
     perm = torch.cat([torch.arange(0, H), torch.arange(2 * H, 3 * H), torch.arange(3 * H, 4 * H), torch.arange(H, 2 * H)])
@@ -61,6 +61,17 @@ def _onnx_lstm(X, W, R, B, H, init_h, init_c, dtype):
         else:
             lstm.bias_ih_l0.zero_()
             lstm.bias_hh_l0.zero_()
+    return lstm
+
+
+def _onnx_lstm(X, W, R, B, H, init_h, init_c, dtype, cache=None, key=None):
+    """ONNX LSTM (forward, layout 0) on X [T, b, I] -> (Y [T, 1, b, H], Y_h, Y_c)."""
+    lstm = cache.get(key) if cache is not None else None
+    if lstm is None:
+        lstm = _torch_lstm_module(W, R, B, H, dtype)
+        if cache is not None:
+            cache[key] = lstm
+    with torch.no_grad():
         b = X.shape[1]
         h0 = torch.zeros(1, b, H, dtype=dtype) if init_h is None else init_h.to(dtype)
         c0 = torch.zeros(1, b, H, dtype=dtype) if init_c is None else init_c.to(dtype)
@@ -92,6 +103,7 @@ class TorchOnnx:
         self.input_names = [v.name for v in self.graph.inputs]
         self.output_names = [v.name for v in self.graph.outputs]
         self.const = {k: self._t(v) for k, v in self.graph.initializers.items()}
+        self._lstm_modules = {}       # one torch.nn.LSTM per LSTM node, built on first use (constant weights)
 
     def _t(self, a) -> torch.Tensor:
         t = torch.from_numpy(np.array(a, copy=True)) if isinstance(a, np.ndarray) else torch.as_tensor(a)
@@ -211,7 +223,9 @@ class TorchOnnx:
             X = inp(0)
             if inp(4) is not None and any(int(s) != X.shape[0] for s in inp(4).reshape(-1).tolist()):
                 raise NotImplementedError("LSTM sequence_lens shorter than the sequence")
-            return list(_onnx_lstm(X, inp(1), inp(2), inp(3), int(a["hidden_size"]), inp(5), inp(6), self.dtype))
+            const_w = all(k in self.const for k in n.inputs[1:4] if k)
+            return list(_onnx_lstm(X, inp(1), inp(2), inp(3), int(a["hidden_size"]), inp(5), inp(6), self.dtype,
+                                   self._lstm_modules if const_w else None, n.outputs[0]))
         raise NotImplementedError(f"torch_ref: ONNX op {op} not implemented")
 
     def run(self, output_names: Optional[List[str]], feeds: Dict[str, np.ndarray]) -> List[np.ndarray]:

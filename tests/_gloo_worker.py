@@ -24,6 +24,27 @@ def fake_forward(idx):      # a deterministic stand-in for Predictor.forward_str
 
 
 out = distributed.predict_sharded(fake_forward, lengths, C, rank, world, max_residues=20000)
+
+# the streaming form bench.py uses: chunks of this rank's bin through submit / wait jobs (two in flight), rows in chunk order
+class FakeJob:
+    def __init__(self, idx, rows):
+        self.idx, self.rows, self.done = idx, rows, False
+
+    def wait(self):
+        assert not self.done
+        self.rows[...] = fake_forward(self.idx)
+        self.done = True
+
+
+mine = distributed.shard_job(lengths, world, max_proteins=40, max_residues=20000)[rank]
+assert all(len(c) <= 40 and lengths[c].sum() <= 20000 for c in mine)
+local = np.zeros((sum(len(c) for c in mine), C), np.float32)
+jobs = []
+distributed.stream_chunks(lambda ch, rows: jobs.append(FakeJob(ch, rows)) or jobs[-1], ((c, len(c)) for c in mine), local)
+assert all(j.done for j in jobs)
+out2 = distributed.gather_scores(np.concatenate(mine), local, len(lengths), C)
+if rank == 0:
+    assert np.array_equal(out2, fake_forward(np.arange(len(lengths))))
 if rank == 0:
     want = fake_forward(np.arange(len(lengths)))
     assert out is not None and np.array_equal(out, want)

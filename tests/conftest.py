@@ -77,3 +77,43 @@ class Aln:
         self.gapped_target = gt
         self.query_sequence = gq.replace("-", "")
         self.coords = coords
+
+
+class Recognised:
+    """What the library's loader (`mdf_onnx_inspect` / `mdf_onnx_tensor`, host only) makes of an `.onnx` file."""
+
+    def __init__(self, path, temporary=False):
+        from metagenomic_deepfri_b200 import _lib
+        self.path = path
+        self.temporary = temporary
+        try:
+            self.info = _lib.inspect_onnx(path)
+        except Exception:
+            self.__del__()
+            raise
+
+    def __del__(self):
+        if self.__dict__.get("temporary") and os.path.exists(self.path):
+            os.unlink(self.path)
+
+    def __getattr__(self, k):
+        try:
+            return self.__dict__["info"][k]
+        except KeyError:
+            raise AttributeError(k)
+
+    def tensor(self, role, shape=None):
+        from metagenomic_deepfri_b200 import _lib
+        a = _lib.onnx_tensor(self.path, role)
+        return a.reshape(shape) if shape is not None else a
+
+
+def recognise(model):
+    """`model`: a path, or an onnx_lite.Model (written to a temporary file first)."""
+    import tempfile
+    from metagenomic_deepfri_b200 import onnx_lite
+    if isinstance(model, str):
+        return Recognised(model)
+    with tempfile.NamedTemporaryFile(suffix=".onnx", delete=False) as fh:
+        fh.write(onnx_lite.dumps(model))
+    return Recognised(fh.name, temporary=True)

@@ -8,7 +8,9 @@ import pytest
 
 import gcn_oracle as go
 from metagenomic_deepfri_b200 import onnx_lite as ox
-from metagenomic_deepfri_b200 import onnx_plan, synth
+from metagenomic_deepfri_b200 import synth
+from metagenomic_deepfri_b200._lib import UnsupportedModelError
+from conftest import recognise
 import spec
 
 ALPHABET = "-DGULNTKHYWCPVSOIEFXQABZRM"
@@ -60,33 +62,37 @@ def test_oracle_matches_independent_restatement(tag, tmp_path):
 def test_cnn_plan_reads_graph():
     cfg = synth.CNNConfig(filter_lens=(5, 8, 16), num_filters=(128, 256, 128), n_terms=17)
     w = synth.make_cnn_weights(cfg, 3)
-    plan = onnx_plan.cnn_plan_from_model(ox.loads(ox.dumps(synth.build_cnn_model(cfg, w))))
-    assert plan.input_names == ["seq"] and plan.n_terms == 17
-    assert [x.shape for x in plan.conv_W] == [(128, 26, 5), (256, 26, 8), (128, 26, 16)]
+    plan = recognise(synth.build_cnn_model(cfg, w))
+    assert plan.kind == "cnn" and plan.input_names == ["seq"] and plan.n_terms == 17
+    assert plan.conv_filters == [128, 256, 128] and plan.conv_width == [5, 8, 16]
     assert plan.conv_pad_left == [2, 3, 7]
+    for l in (1, 2, 3):
+        assert np.array_equal(plan.tensor(f"conv{l}_W"), w[f"conv1d_{l}_W"].reshape(-1))      # [F, 26, 1, w] == [F, 26, w] flat
     s = w["bn_gamma"].astype(np.float64) / np.sqrt(w["bn_var"].astype(np.float64) + cfg.bn_epsilon)
     b = np.concatenate([w[f"conv1d_{l}_b"] for l in (1, 2, 3)])
-    assert np.allclose(plan.scale, s, rtol=1e-6) and np.allclose(plan.shift, (b - w["bn_mean"]) * s + w["bn_beta"], rtol=1e-5, atol=1e-6)
-    assert np.array_equal(plan.out_W, w["labels_W"]) and np.array_equal(plan.out_b, w["labels_b"])
+    assert np.allclose(plan.tensor("scale"), s, rtol=1e-6)
+    assert np.allclose(plan.tensor("shift"), (b - w["bn_mean"]) * s + w["bn_beta"], rtol=1e-5, atol=1e-6)
+    assert np.array_equal(plan.tensor("out_W"), w["labels_W"].reshape(-1)) and np.array_equal(plan.tensor("out_b"), w["labels_b"])
 
 
 def test_cnn_plan_rejects_foreign_graphs():
     cfg = synth.CNNConfig(filter_lens=(5, 8), num_filters=(128, 128), n_terms=9)
     m = synth.build_cnn_model(cfg)
     g = m.graph
-    with pytest.raises(onnx_plan.UnsupportedModelError):            # a GCN head is not a DeepCNN
-        onnx_plan.cnn_plan_from_model(synth.build_gcn_model(synth.GCNConfig(**spec.SMALL)))
+    gcn = synth.build_gcn_model(synth.GCNConfig(**spec.SMALL)).graph   # a GCN body behind a single input is not a DeepCNN
+    with pytest.raises(UnsupportedModelError):
+        recognise(ox.Model(ox.Graph(nodes=gcn.nodes, initializers=gcn.initializers, inputs=[gcn.inputs[1]], outputs=gcn.outputs)))
     nodes = [n for n in g.nodes if n.op_type != "Relu"]
-    with pytest.raises(onnx_plan.UnsupportedModelError):
-        onnx_plan.cnn_plan_from_model(ox.Model(ox.Graph(nodes=nodes, initializers=g.initializers, inputs=g.inputs, outputs=g.outputs)))
+    with pytest.raises(UnsupportedModelError):
+        recognise(ox.Model(ox.Graph(nodes=nodes, initializers=g.initializers, inputs=g.inputs, outputs=g.outputs)))
     import copy
     g2 = copy.deepcopy(g)
     for n in g2.nodes:
         if n.op_type == "Conv":
             n.attrs["pads"] = [0, 0, 0, 0]                         # 'valid' padding changes the output length
             break
-    with pytest.raises(onnx_plan.UnsupportedModelError, match="same"):
-        onnx_plan.cnn_plan_from_model(ox.Model(g2))
+    with pytest.raises(UnsupportedModelError, match="same"):
+        recognise(ox.Model(g2))
 
 
 def test_cnn_golden_matches_oracle(cnn_golden, cnn_model_dir):
@@ -107,7 +113,7 @@ def test_cnn_plan_accepts_equivalent_lowerings(tmp_path):
     import copy
     cfg = synth.CNNConfig(filter_lens=(4, 9), num_filters=(128, 128), n_terms=7, logit_scale=0.5)
     base = synth.build_cnn_model(cfg, seed=8)
-    ref_plan = onnx_plan.cnn_plan_from_model(ox.loads(ox.dumps(base)))
+    ref_plan = recognise(base)
 
     def variant(edit):
         m = ox.loads(ox.dumps(base))
@@ -133,10 +139,10 @@ def test_cnn_plan_accepts_equivalent_lowerings(tmp_path):
     ox.save(base, p0)
     want = [go.Predictor(p0).forward_pass(s) for s in seqs]
     for tag, m in variants.items():
-        plan = onnx_plan.cnn_plan_from_model(m)
+        plan = recognise(m)
         assert plan.conv_pad_left == ref_plan.conv_pad_left and plan.n_terms == ref_plan.n_terms, tag
-        assert np.array_equal(plan.scale, ref_plan.scale) and np.array_equal(plan.shift, ref_plan.shift), tag
-        assert np.array_equal(plan.out_W, ref_plan.out_W) and np.array_equal(plan.out_b, ref_plan.out_b), tag
+        for role in ("scale", "shift", "out_W", "out_b"):
+            assert np.array_equal(plan.tensor(role), ref_plan.tensor(role)), (tag, role)
         pth = str(tmp_path / f"{tag}.onnx")
         ox.save(m, pth)
         orc = go.Predictor(pth)
