@@ -35,6 +35,8 @@
 #include "gemm_tc.cuh"
 #include "lstm_tc.cuh"
 
+extern "C" char **environ;
+
 namespace mdf {
 namespace tc {
 
@@ -556,7 +558,6 @@ static bool profiler_injected()
     static int cached = -1;
     if (cached < 0) {
         cached = 0;
-        extern char **environ;
         for (char **e = environ; e && *e; ++e)
             if (!strncmp(*e, "NV_NSIGHT_INJECTION", 19) || !strncmp(*e, "CUDA_INJECTION64_PATH=", 22) || !strncmp(*e, "NV_COMPUTE_PROFILER", 19) ||
                 !strncmp(*e, "NVTX_INJECTION64_PATH=", 22) || !strncmp(*e, "NSIGHT_COMPUTE", 14))
