@@ -27,7 +27,8 @@ def mf(model_dir):
 
 def test_loader_styles_give_identical_scores(tmp_path):
     """Same weights lowered two ways (shared broadcast-Mul normalisation vs per-layer matmul(matmul(D, A), D), LSTM nodes with
-    zero initial states): the C loader recognises both and the pipeline computes bit-identical scores."""
+    zero initial states): the C loader recognises both and the pipeline computes the same scores (up to the order of the
+    floating-point atomics of the fused sum-pool, which differs from run to run)."""
     cfg = synth.GCNConfig(**spec.GCN_CASES["tc_small"][0])
     w = synth.make_weights(cfg, seed=8)
     pa, pb = str(tmp_path / "a.onnx"), str(tmp_path / "b.onnx")
@@ -36,7 +37,7 @@ def test_loader_styles_give_identical_scores(tmp_path):
     wl = golden_workload("tc_small")
     ya = predict.Predictor(pa).forward_structures(wl.query_seqs, wl.gapped_query, wl.gapped_target, wl.coords, 10.0, 2)
     yb = predict.Predictor(pb).forward_structures(wl.query_seqs, wl.gapped_query, wl.gapped_target, wl.coords, 10.0, 2)
-    assert np.array_equal(ya, yb)
+    assert np.abs(ya - yb).max() < 1e-5
     want = np.stack([go.Predictor(pb).forward_pass(s, co.build_align_contact_map(q, t, c, 10.0, 2))
                      for s, q, t, c in zip(wl.query_seqs, wl.gapped_query, wl.gapped_target, wl.coords)])
     assert np.abs(yb - want).max() <= TOL
