@@ -246,6 +246,30 @@ int mdf_cnn_upload(mdf_cnn_model *model, int n, const char *seq, const int64_t *
 int mdf_cnn_run(mdf_cnn_model *model);
 int mdf_cnn_fetch(mdf_cnn_model *model, float *scores /* host [n, C] */, float *pooled /* host [n, sum filters] or NULL */);
 
+/* ---- pdb.py:130-162 extract_calpha_coords / bio_utils.py:230-302 extract_residues_coordinates: coordinate ingest (host only) ----
+ * C-alpha coordinates of one PDB text with biotite's selection as the reference applies it: first model, ATOM records (HETATM =
+ * hetero, excluded), chain `chain`, atom name "CA", first alternate location per residue.  coords float32 [capacity, 3];
+ * residues (one-letter, ProteinSequence alphabet; a name outside it -> MDF_EINVAL "non-standard residue XXX") and resnames3
+ * (3 chars per atom, not terminated) may be NULL.  All three NULL: only count (*n_out).  A structure without the chain ->
+ * MDF_EINVAL "Chain A not found in structure." (bio_utils.py:243-244). */
+int mdf_pdb_calpha(const char *text, size_t len, char chain, float *coords, char *residues, char *resnames3, int capacity, int *n_out);
+/* n texts on `threads` host threads.  rows[p] = C-alpha count (-1: chain not found, no rows); coords = flat float32
+ * [sum rows, 3] (NULL: only count into rows / *total_rows). */
+int mdf_pdb_calpha_batch(int n, const char *const *texts, const int64_t *lens, char chain, int threads, int *rows, float *coords,
+                         int64_t capacity_rows, int64_t *total_rows);
+
+/* C-alpha cache: one mmap-able file per structure database (ids, float32 [L, 3] blocks, id hash table), written once.
+ * Lookups return pointers INTO the mapping (valid until close) - the (pointer, rows) arrays mdf_path_submit_ragged takes. */
+typedef struct mdf_coords_cache mdf_coords_cache;
+int mdf_coords_cache_create(const char *path, int64_t n, const char *const *ids, const int *rows, const float *const *coords);
+int mdf_coords_cache_open(const char *path, mdf_coords_cache **out);
+int mdf_coords_cache_close(mdf_coords_cache *cache);
+int64_t mdf_coords_cache_size(const mdf_coords_cache *cache);
+/* unknown id -> coords_out[p] = NULL, rows_out[p] = -1; *missing (may be NULL) = how many */
+int mdf_coords_cache_lookup(const mdf_coords_cache *cache, int64_t n, const char *const *ids, const float **coords_out, int *rows_out,
+                            int64_t *missing);
+int mdf_coords_cache_entry(const mdf_coords_cache *cache, int64_t index, char *id_buf, size_t capacity, int *rows);
+
 #ifdef __cplusplus
 }
 #endif

@@ -127,6 +127,18 @@ def lib() -> C.CDLL:
         L.mdf_cnn_upload.argtypes = [vp, C.c_int, vp, c_i64p]
         L.mdf_cnn_run.argtypes = [vp]
         L.mdf_cnn_fetch.argtypes = [vp, vp, vp]
+        L.mdf_pdb_calpha.argtypes = [vp, C.c_size_t, C.c_char, vp, vp, vp, C.c_int, C.POINTER(C.c_int)]
+        L.mdf_pdb_calpha_batch.argtypes = [C.c_int, vp, c_i64p, C.c_char, C.c_int, vp, vp, C.c_int64, c_i64p]
+        L.mdf_coords_cache_create.argtypes = [C.c_char_p, C.c_int64, vp, vp, vp]
+        L.mdf_coords_cache_open.argtypes = [C.c_char_p, C.POINTER(vp)]
+        L.mdf_coords_cache_close.argtypes = [vp]
+        L.mdf_coords_cache_size.argtypes = [vp]
+        L.mdf_coords_cache_size.restype = C.c_int64
+        L.mdf_coords_cache_lookup.argtypes = [vp, C.c_int64, vp, vp, vp, c_i64p]
+        L.mdf_coords_cache_entry.argtypes = [vp, C.c_int64, C.c_char_p, C.c_size_t, C.POINTER(C.c_int)]
+        for name in ("mdf_pdb_calpha", "mdf_pdb_calpha_batch", "mdf_coords_cache_create", "mdf_coords_cache_open", "mdf_coords_cache_close",
+                     "mdf_coords_cache_lookup", "mdf_coords_cache_entry"):
+            getattr(L, name).restype = C.c_int
         for name in ("mdf_model_load", "mdf_cnn_model_load", "mdf_onnx_inspect", "mdf_model_info"):
             getattr(L, name).restype = C.c_int
         for name in ("mdf_cnn_model_create", "mdf_cnn_model_destroy", "mdf_cnn_forward", "mdf_cnn_upload", "mdf_cnn_run",
@@ -152,6 +164,8 @@ EXPORTED_SYMBOLS = [
     "mdf_batch_fetch_scores", "mdf_batch_fetch", "mdf_batch_scores_device", "mdf_batch_unpack_dense", "mdf_batch_invalidate",
     "mdf_cnn_model_create", "mdf_cnn_model_destroy", "mdf_cnn_forward", "mdf_cnn_upload", "mdf_cnn_run", "mdf_cnn_fetch",
     "mdf_path_submit", "mdf_path_submit_ragged", "mdf_path_wait",
+    "mdf_pdb_calpha", "mdf_pdb_calpha_batch", "mdf_coords_cache_create", "mdf_coords_cache_open", "mdf_coords_cache_close",
+    "mdf_coords_cache_size", "mdf_coords_cache_lookup", "mdf_coords_cache_entry",
     "mdf_model_load", "mdf_cnn_model_load", "mdf_onnx_inspect", "mdf_onnx_tensor", "mdf_model_info",
 ]
 
@@ -168,6 +182,8 @@ def check(rc: int) -> None:
         raise UnsupportedModelError(msg)
     if rc == MDF_ENOENT:
         raise FileNotFoundError(msg)
+    if rc == MDF_EPARSE:
+        raise RuntimeError(msg)
     raise RuntimeError(msg)
 
 

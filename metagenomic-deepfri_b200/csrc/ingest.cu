@@ -15,6 +15,8 @@
 #include <sys/stat.h>
 #include <unistd.h>
 #include <algorithm>
+#include <functional>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -35,20 +37,40 @@ char three_to_one(const char *r)
     return 0;
 }
 
-// float(line[a:b]) the way Python parses it: surrounding blanks ignored, the value rounded to double, then stored as float32
+// float(line[a:b]) the way Python parses it: surrounding blanks ignored, the value rounded to double, then stored as float32.
+// Plain fixed-point fields ("%8.3f", what every PDB writer emits) take the fast path: the digits as one integer m (< 2^53) divided
+// by 10^k - both exact in double, and IEEE division rounds correctly, so the result equals strtod's.  Anything else goes to strtod.
 bool field_to_float(const char *p, int width, float *out)
 {
-    char buf[16];
-    int n = 0;
-    for (int i = 0; i < width && p[i] != '\n' && p[i] != '\r' && p[i] != 0; ++i) buf[n++] = p[i];
+    static const double p10[16] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15};
+    int a = 0, b = 0;
+    while (b < width && p[b] != '\n' && p[b] != '\r' && p[b] != 0) ++b;
+    while (a < b && p[a] == ' ') ++a;
+    while (b > a && p[b - 1] == ' ') --b;
+    if (a == b) return false;
+    int i = a;
+    bool neg = false;
+    if (p[i] == '-' || p[i] == '+') { neg = p[i] == '-'; ++i; }
+    unsigned long long m = 0;
+    int digits = 0, frac = -1;
+    for (; i < b; ++i) {
+        const char c = p[i];
+        if (c >= '0' && c <= '9') { m = m * 10 + (unsigned)(c - '0'); ++digits; if (frac >= 0) ++frac; }
+        else if (c == '.' && frac < 0) frac = 0;
+        else break;
+    }
+    if (i == b && digits > 0 && digits <= 15) {
+        const double v = (double)m / p10[frac < 0 ? 0 : frac];
+        *out = (float)(neg ? -v : v);
+        return true;
+    }
+    char buf[24];
+    const int n = std::min(b - a, 23);
+    memcpy(buf, p + a, (size_t)n);
     buf[n] = 0;
-    char *s = buf;
-    while (*s == ' ') ++s;
-    if (!*s) return false;
     char *end = nullptr;
-    const double v = strtod(s, &end);
-    while (*end == ' ') ++end;
-    if (*end) return false;
+    const double v = strtod(buf, &end);
+    if (end == buf || *end) return false;
     *out = (float)v;
     return true;
 }

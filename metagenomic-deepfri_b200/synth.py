@@ -523,6 +523,56 @@ def keyed_workload_parallel(ids: Sequence[int], seed: int, procs: int, block: in
     return out
 
 
+ONE_TO_THREE = {"A": "ALA", "R": "ARG", "N": "ASN", "D": "ASP", "C": "CYS", "Q": "GLN", "E": "GLU", "G": "GLY", "H": "HIS", "I": "ILE",
+                "L": "LEU", "K": "LYS", "M": "MET", "F": "PHE", "P": "PRO", "S": "SER", "T": "THR", "W": "TRP", "Y": "TYR", "V": "VAL"}
+
+
+def pdb_text(seq: str, ca: np.ndarray, rng: Optional[np.random.Generator] = None, chain: str = "A", *, backbone: bool = True,
+             extra_chain: bool = False, hetatm: bool = False, altloc_every: int = 0, models: int = 1, crlf: bool = False,
+             first_res: int = 1) -> str:
+    """A PDB file (fixed-column ATOM records, the text FoldComp decompresses to, `pdb.py:150-156`) holding `seq` with C-alpha
+    atoms at `ca` [L, 3] - plus, optionally, what a parser has to skip: N / C / O backbone atoms, a second chain, HETATM records
+    (a calcium ion named "CA", a modified residue), alternate locations, further models, CRLF line ends."""
+    rng = rng or np.random.default_rng(0)
+    lines: List[str] = ["HEADER    SYNTHETIC STRUCTURE", "CRYST1    1.000    1.000    1.000  90.00  90.00  90.00 P 1           1"]
+    serial = [0]
+
+    def atom(rec, name, alt, res, ch, num, xyz, elem):
+        serial[0] += 1
+        nm = f" {name:<3s}" if len(name) < 4 and len(elem) == 1 else f"{name:<4s}"
+        lines.append(f"{rec:<6s}{serial[0] % 100000:5d} {nm}{alt}{res:>3s} {ch}{num:4d}    {xyz[0]:8.3f}{xyz[1]:8.3f}{xyz[2]:8.3f}{1.0:6.2f}{rng.uniform(20, 90):6.2f}"
+                     f"          {elem:>2s}")
+
+    def write_chain(ch, residues, cas, shift):
+        for i, (r, c) in enumerate(zip(residues, cas)):
+            res, num = ONE_TO_THREE[r], first_res + i
+            c = np.asarray(c, np.float64) + shift
+            alts = ["A", "B"] if altloc_every and i % altloc_every == altloc_every - 1 else [" "]
+            if backbone:
+                atom("ATOM", "N", " ", res, ch, num, c + [-1.2, 0.4, 0.3], "N")
+            for k, alt in enumerate(alts):
+                atom("ATOM", "CA", alt, res, ch, num, c + 0.25 * k, "C")
+            if backbone:
+                atom("ATOM", "C", " ", res, ch, num, c + [1.1, 0.7, -0.2], "C")
+                atom("ATOM", "O", " ", res, ch, num, c + [1.6, 1.8, -0.4], "O")
+        lines.append(f"TER   {serial[0] + 1:5d}      {ONE_TO_THREE[residues[-1]]:>3s} {ch}{first_res + len(residues) - 1:4d}" if residues else "TER")
+
+    for m in range(models):
+        if models > 1:
+            lines.append(f"MODEL     {m + 1:4d}")
+        if extra_chain and chain != "B":
+            write_chain("B", seq[:max(1, len(seq) // 3)], ca[:max(1, len(seq) // 3)], np.array([50.0, 0.0, 0.0]))
+        write_chain(chain, seq, ca, np.zeros(3) + 0.5 * m)
+        if hetatm:
+            atom("HETATM", "CA", " ", "CA", chain, first_res + len(seq) + 1, np.array([1.0, 2.0, 3.0]), "CA")      # a calcium ion
+            atom("HETATM", "CA", " ", "MSE", chain, first_res + len(seq) + 2, np.array([4.0, 5.0, 6.0]), "C")       # modified residue
+            atom("HETATM", "O", " ", "HOH", chain, first_res + len(seq) + 3, np.array([7.0, 8.0, 9.0]), "O")
+        if models > 1:
+            lines.append("ENDMDL")
+    lines.append("END")
+    return ("\r\n" if crlf else "\n").join(lines) + ("\r\n" if crlf else "\n")
+
+
 def config_workload(idx: int, scale: float = 1.0) -> Workload:
     """BASELINE.json `configs[idx]`; `scale` shrinks the protein count for tests."""
     if idx == 0:

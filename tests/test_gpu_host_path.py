@@ -177,3 +177,24 @@ def test_notebook_harness_nonsymmetric_maps(mf, model_dir):
         assert np.array_equal((got >= 0.1)[~band], (want >= 0.1)[~band])
     print(f"notebook harness: max |score - torch-CPU| = {worst:.2e}; {in_band} scores within 1e-3 of the 0.1 threshold, {flips} of them flip")
     assert worst <= TOL
+
+
+def test_calpha_cache_feeds_the_path(mf, tmp_path):
+    """§8f row 3: structures parsed from PDB text once, cached, and handed to the batched path as views into the mapping give the
+    same scores as the coordinate arrays themselves."""
+    from metagenomic_deepfri_b200 import ingest
+    wl = synth.keyed_workload(np.arange(200, 328), 5)
+    rng = np.random.default_rng(1)
+    targets = [t.replace("-", "") for t in wl.gapped_target]
+    texts = [synth.pdb_text(t, c, rng, hetatm=(i % 3 == 0), extra_chain=(i % 5 == 0)) for i, (t, c) in enumerate(zip(targets, wl.coords))]
+    ids = [f"target_{i}" for i in range(len(wl))]
+    path = str(tmp_path / "targets.mdfca")
+    assert ingest.write_cache_from_pdb_texts(path, ids, texts, "A", threads=4) == []
+    cache = ingest.CoordsCache(path)
+    views = cache.get(ids)
+    for v, c in zip(views, wl.coords):
+        assert np.array_equal(v, c)                       # keyed coordinates carry 3 decimals: the PDB text is lossless for them
+    want = mf.forward_structures(wl.query_seqs, wl.gapped_query, wl.gapped_target, wl.coords, 10.0, 2)
+    got = mf.forward_structures(wl.query_seqs, wl.gapped_query, wl.gapped_target, views, 10.0, 2)
+    assert np.abs(got - want).max() < 1e-5
+    cache.close()
