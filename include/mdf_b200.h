@@ -270,6 +270,18 @@ int mdf_coords_cache_lookup(const mdf_coords_cache *cache, int64_t n, const char
                             int64_t *missing);
 int mdf_coords_cache_entry(const mdf_coords_cache *cache, int64_t index, char *id_buf, size_t capacity, int *rows);
 
+/* ---- alignment.py:163-221  best_hit_database / align_pairwise: batched global alignment (NW, affine gaps) on the GPU --------
+ * What the reference asks of PyOpal: pyopal.Aligner(scoring_matrix, gap_open, gap_extend).align(query, db, algorithm="nw",
+ * mode="full" | "score").  query[p] / target[p]: q_len[p] / t_len[p] letters of `alphabet` (anything else -> MDF_EINVAL);
+ * matrix: A x A int8 row-major in the order of `alphabet`, A <= 32 (VTML80 by default in the reference: the caller passes the
+ * values of scoring_matrices.ScoringMatrix.from_name(...)); a gap of length k costs gap_open + (k - 1) * gap_extend, end gaps
+ * included.  scores[p] = optimal score.  ops != NULL: the alignment string of pair p over M (equal residues) / X (mismatch) /
+ * I ('-' in the query) / D ('-' in the target) - the dialect mDeepFRI.alignment.insert_gaps reads - at ops + ops_off[p] (room
+ * for q_len[p] + t_len[p] columns), ops_len[p] columns long, not terminated.  ops == NULL: scores only. */
+int mdf_nw_align(mdf_ctx *ctx, int n, const char *const *query, const int *q_len, const char *const *target, const int *t_len,
+                 const int8_t *matrix, const char *alphabet, int A, int gap_open, int gap_extend,
+                 int32_t *scores, char *ops, const int64_t *ops_off, int *ops_len);
+
 #ifdef __cplusplus
 }
 #endif

@@ -139,6 +139,8 @@ def lib() -> C.CDLL:
         for name in ("mdf_pdb_calpha", "mdf_pdb_calpha_batch", "mdf_coords_cache_create", "mdf_coords_cache_open", "mdf_coords_cache_close",
                      "mdf_coords_cache_lookup", "mdf_coords_cache_entry"):
             getattr(L, name).restype = C.c_int
+        L.mdf_nw_align.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, C.c_char_p, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]
+        L.mdf_nw_align.restype = C.c_int
         for name in ("mdf_model_load", "mdf_cnn_model_load", "mdf_onnx_inspect", "mdf_model_info"):
             getattr(L, name).restype = C.c_int
         for name in ("mdf_cnn_model_create", "mdf_cnn_model_destroy", "mdf_cnn_forward", "mdf_cnn_upload", "mdf_cnn_run",
@@ -166,6 +168,7 @@ EXPORTED_SYMBOLS = [
     "mdf_path_submit", "mdf_path_submit_ragged", "mdf_path_wait",
     "mdf_pdb_calpha", "mdf_pdb_calpha_batch", "mdf_coords_cache_create", "mdf_coords_cache_open", "mdf_coords_cache_close",
     "mdf_coords_cache_size", "mdf_coords_cache_lookup", "mdf_coords_cache_entry",
+    "mdf_nw_align",
     "mdf_model_load", "mdf_cnn_model_load", "mdf_onnx_inspect", "mdf_onnx_tensor", "mdf_model_info",
 ]
 
