@@ -65,6 +65,7 @@ import time  # noqa: E402
 import numpy as np  # noqa: E402
 
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))      # the CPU arm (cpu_baseline / --impl reference) is the only user
 import mdf_pkg  # noqa: E402
 
 mdf_pkg.load()
@@ -426,8 +427,8 @@ def run_b200(args, rank, world, local_rank, inputs):
         ctx.profile(False)
         dms = sum(r[1] for r in rep) / len(rep)
         dense = {"cells": cells, "unpack_ms": dms, "bytes": rep[0][2]}
-    scores_resident = None if maps_only else np.concatenate([p.fetch_scores(batch) for p in preds.values()], axis=1) if multi_head \
-        else pred.fetch_scores(batch)
+    # (the batch holds the scores of the head that ran last)
+    scores_resident = None if maps_only else list(preds.values())[-1].fetch_scores(batch)
     batch.close()
     del batch
 
@@ -464,6 +465,7 @@ def run_b200(args, rank, world, local_rank, inputs):
         barrier()
         e2e_s = time.perf_counter() - t0
         local_scores = np.concatenate([out_heads[h] for h in preds], axis=1)
+        assert np.abs(out_heads[list(preds)[-1]] - scores_resident).max() < 1e-5, "resident and end-to-end legs disagree"
         h2d = int(sum(x.nbytes for x in wl0.coords) + 2 * sum(len(q) for q in wl0.gapped_query) + T0)
         d2h = int(local_scores.nbytes)
     else:

@@ -142,6 +142,7 @@ extern "C" int mdf_ctx_destroy(mdf_ctx *c)
         if (sl.done) { cudaEventSynchronize(sl.done); cudaEventDestroy(sl.done); }
         if (sl.dev) cudaFree(sl.dev);
         if (sl.pin) cudaFreeHost(sl.pin);
+        if (sl.meta) cudaFreeHost(sl.meta);
         delete sl.batch;
     }
     if (c->own_arena && c->arena) cudaFree(c->arena);
@@ -444,11 +445,20 @@ static int batch_build(mdf_ctx *ctx, mdf_batch *b, bool persistent, int n, const
     carve.base = base;
     carve_batch(b, carve, (size_t)b->T, ncoord, alnb, (size_t)b->h_packed_off[n], G, C);
     cudaStream_t s = ctx->stream;
+    b->slot = slot;
+    // small metadata: through the slot's pinned staging when there is one (asynchronous), else from the pageable vectors (+ sync below)
+    bool staged = slot != nullptr;
+    auto src_of = [&](const void *p, size_t bytes) -> const void * {
+        if (!staged) return p;
+        const void *q = slot->stage(p, bytes);
+        if (!q) { staged = false; return p; }
+        return q;
+    };
     if (b->T) MDF_CUDA(cudaMemcpyAsync(b->d_seq, seq, (size_t)b->T, cudaMemcpyHostToDevice, s));
-    MDF_CUDA(cudaMemcpyAsync(b->d_seq_off, b->h_seq_off.data(), (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
-    MDF_CUDA(cudaMemcpyAsync(b->d_packed_off, b->h_packed_off.data(), (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
-    if (b->nwork) MDF_CUDA(cudaMemcpyAsync(b->d_work, work.data(), work.size() * sizeof(int2), cudaMemcpyHostToDevice, s));
-    if (n) MDF_CUDA(cudaMemcpyAsync(b->d_order, b->h_order.data(), n * sizeof(int), cudaMemcpyHostToDevice, s));
+    MDF_CUDA(cudaMemcpyAsync(b->d_seq_off, src_of(b->h_seq_off.data(), (n + 1) * sizeof(int64_t)), (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+    MDF_CUDA(cudaMemcpyAsync(b->d_packed_off, src_of(b->h_packed_off.data(), (n + 1) * sizeof(int64_t)), (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+    if (b->nwork) MDF_CUDA(cudaMemcpyAsync(b->d_work, src_of(work.data(), work.size() * sizeof(int2)), work.size() * sizeof(int2), cudaMemcpyHostToDevice, s));
+    if (n) MDF_CUDA(cudaMemcpyAsync(b->d_order, src_of(b->h_order.data(), n * sizeof(int)), n * sizeof(int), cudaMemcpyHostToDevice, s));
     if (b->T) {                                     // [T] protein of each residue: filled on the device (20 MB for 16k proteins)
         fill_res_prot_kernel<<<std::min(n, 8 * ctx->sm_count), 128, 0, s>>>(n, b->d_seq_off, b->d_res_prot);
         MDF_LAUNCH_CHECK(ctx);
@@ -477,8 +487,8 @@ static int batch_build(mdf_ctx *ctx, mdf_batch *b, bool persistent, int n, const
     } else if (packed_host && b->h_packed_off[n]) {
         MDF_CUDA(cudaMemcpyAsync(b->d_packed, packed_host, (size_t)b->h_packed_off[n] * 4, cudaMemcpyHostToDevice, s));
     }
-    // work/res_prot/order vectors are pageable: the async copies above have already staged them
-    MDF_CUDA(cudaStreamSynchronize(s));
+    // pageable sources (work / order vectors) must be consumed before they go out of scope; pinned staging needs no wait
+    if (!staged) MDF_CUDA(cudaStreamSynchronize(s));
     return MDF_OK;
 }
 
@@ -633,6 +643,7 @@ extern "C" int mdf_batch_invalidate(mdf_batch *b)
 extern "C" int mdf_batch_fetch_scores(mdf_model *m, mdf_batch *b, float *scores)
 {
     MDF_REQUIRE(m && b && scores, "mdf_batch_fetch_scores: bad arguments");
+    MDF_REQUIRE(b->out_C == m->C && b->d_scores, "mdf_batch_fetch_scores: the batch holds the scores of another head (run this head first)");
     MDF_CUDA(cudaSetDevice(m->ctx->device));
     return fetch_scores(m, b, scores);
 }
@@ -715,7 +726,21 @@ static int slot_acquire(mdf_ctx *ctx, mdf_job **out)
     sl->batch = new mdf_batch();
     sl->h_err[0] = sl->h_err[1] = 0;
     sl->rc = MDF_OK;
+    sl->meta_top = 0;
     *out = sl;
+    return MDF_OK;
+}
+
+// room for the metadata of an n-protein / T-residue batch in the slot's pinned staging (only grows while the slot is idle)
+static int slot_meta_reserve(mdf_job *sl, int n, int64_t T)
+{
+    const size_t want = (size_t)n * 96 + (size_t)T + (2u << 20);
+    if (sl->meta_bytes >= want) return MDF_OK;
+    if (sl->meta) MDF_CUDA(cudaFreeHost(sl->meta));
+    sl->meta = nullptr; sl->meta_bytes = 0;
+    cudaError_t e = cudaHostAlloc((void **)&sl->meta, want + want / 4, cudaHostAllocDefault);
+    if (e != cudaSuccess) { cudaGetLastError(); return MDF_OK; }      // without it the copies fall back to pageable sources + a sync
+    sl->meta_bytes = want + want / 4;
     return MDF_OK;
 }
 
@@ -741,6 +766,7 @@ static int job_enqueue(mdf_model *m, mdf_job *sl, int n, const char *seq, const 
     mdf_batch *b = sl->batch;
     static const bool timing = getenv("MDF_TIMING") != nullptr;       // host-side breakdown of one call on stderr
     const auto t0 = std::chrono::steady_clock::now();
+    slot_meta_reserve(sl, n, n > 0 ? seq_off[n] : 0);
     int rc = batch_build(ctx, b, false, n, seq, seq_off, coords, coord_off, q_aln, t_aln, aln_off, nullptr, m->G, m->C,
                          engine_workspace(m, n, seq_off), sl);
     const auto t1 = std::chrono::steady_clock::now();

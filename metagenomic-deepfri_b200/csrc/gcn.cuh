@@ -32,6 +32,7 @@ struct mdf_batch {
     bool has_structure = false;
     bool copy_pending = false;   // structure inputs are still in flight on ctx->copy_stream (wait for ctx->copy_done before reading them)
     bool owns_memory = false;
+    mdf_job *slot = nullptr;     // transient batch of an asynchronous job: its metadata is staged through the slot's pinned memory
     void *block = nullptr;  // one allocation holding everything below
     void *out_block = nullptr;  // pooled + scores of persistent batches (sized by the model head)
     int out_G = 0, out_C = 0;

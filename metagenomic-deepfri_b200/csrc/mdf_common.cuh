@@ -59,6 +59,17 @@ struct mdf_job {
     bool busy = false;                              // submitted, not yet waited for
     mdf_batch *batch = nullptr;
     int rc = 0;                                     // deferred submit status
+    // pinned staging for the small per-batch metadata (work lists, offsets, tile tables): copied from here the H2D copies are
+    // truly asynchronous, so a submit never blocks on the previous job and the GPU does not idle between jobs
+    char *meta = nullptr; size_t meta_bytes = 0, meta_top = 0;
+    const void *stage(const void *src, size_t bytes)
+    {
+        const size_t at = (meta_top + 63) & ~(size_t)63;
+        if (!meta || at + bytes > meta_bytes) return nullptr;
+        memcpy(meta + at, src, bytes);
+        meta_top = at + bytes;
+        return meta + at;
+    }
 };
 
 // Device workspace: one big allocation, bump-allocated, reset per API call (stack discipline).

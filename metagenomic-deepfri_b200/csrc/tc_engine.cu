@@ -669,19 +669,27 @@ static int build_meta(mdf_ctx *ctx, mdf_batch *b, TcBatchMeta &meta, bool want_e
     meta.seg_off = (int64_t *)base; base += align_up((size_t)(n + 1) * 8, 256);
     meta.pairs = (int4 *)base;
     cudaStream_t s = ctx->stream;
+    // asynchronous jobs stage these tables through the slot's pinned memory: the copies then never block the submitting thread
+    bool staged = b->slot != nullptr;
+    auto src_of = [&](const void *p, size_t bytes) -> const void * {
+        if (!staged) return p;
+        const void *q = b->slot->stage(p, bytes);
+        if (!q) { staged = false; return p; }
+        return q;
+    };
     // the [Tp] row map (24 MB for a 16k-protein batch) is filled on the device; only the per-tile / per-protein arrays travel
-    MDF_CUDA(cudaMemcpyAsync(meta.seg_off, seg_off.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, s));
+    MDF_CUDA(cudaMemcpyAsync(meta.seg_off, src_of(seg_off.data(), (size_t)(n + 1) * 8), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, s));
     MDF_CUDA(cudaMemsetAsync(meta.rowmap, 0xFF, (size_t)Tp * 4, s));
     if (n > 0) {
         // compact axis: the row map is the identity on [0, T) (and -1 on the tail padding)
         fill_rowmap_kernel<<<std::min(n, 8 * ctx->sm_count), 128, 0, s>>>(n, b->d_seq_off, compact ? b->d_seq_off : meta.seg_off, meta.rowmap);
         MDF_LAUNCH_CHECK(ctx);
     }
-    MDF_CUDA(cudaMemcpyAsync(meta.tile_info, tile_info.data(), tile_info.size() * 16, cudaMemcpyHostToDevice, s));
+    MDF_CUDA(cudaMemcpyAsync(meta.tile_info, src_of(tile_info.data(), tile_info.size() * 16), tile_info.size() * 16, cudaMemcpyHostToDevice, s));
     if (!exp_tiles.empty())
-        MDF_CUDA(cudaMemcpyAsync(meta.exp_tiles, exp_tiles.data(), exp_tiles.size() * 16, cudaMemcpyHostToDevice, s));
-    if (!pairs.empty()) MDF_CUDA(cudaMemcpyAsync(meta.pairs, pairs.data(), pairs.size() * 16, cudaMemcpyHostToDevice, s));
-    MDF_CUDA(cudaStreamSynchronize(s));      // host vectors are pageable
+        MDF_CUDA(cudaMemcpyAsync(meta.exp_tiles, src_of(exp_tiles.data(), exp_tiles.size() * 16), exp_tiles.size() * 16, cudaMemcpyHostToDevice, s));
+    if (!pairs.empty()) MDF_CUDA(cudaMemcpyAsync(meta.pairs, src_of(pairs.data(), pairs.size() * 16), pairs.size() * 16, cudaMemcpyHostToDevice, s));
+    if (!staged) MDF_CUDA(cudaStreamSynchronize(s));      // host vectors are pageable
     return MDF_OK;
 }
 
