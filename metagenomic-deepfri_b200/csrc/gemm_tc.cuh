@@ -26,14 +26,6 @@ struct GemmArgs {
     int m_tiles = 0, n_tiles = 0;    // output tiles (128 rows x BN columns)
     int nkb = 0;                     // k-blocks per output tile (regular case)
     int m_fastest = 0;               // tile order: consecutive CTAs walk M first (B tile shared in L2) instead of N first
-    // Dithered single-term weights (tc_engine.cu build_dither_images_host): the weight operand exists as `phases`
-    // roundings whose mean is exact; the phase follows the 128-row residue tile, so the rounding error cancels
-    // across the tiles of a protein instead of accumulating in the sum-pool (half the MMAs of a hi+lo split).
-    //   b_phases > 0: B = weights, phase = m-tile % b_phases           (B[0] + phase * b_phase_stride bytes)
-    //   a_phases > 0: A = weights, phase = (nt*NSUB + j) % a_phases per 128-column sub-tile j: the stage holds one
-    //                 A tile per sub-tile and MMA j pairs A_j with B sub-tile j   (A[0] + phase * a_phase_stride bytes)
-    int a_phases = 0, b_phases = 0;
-    size_t a_phase_stride = 0, b_phase_stride = 0;
     // grouped case (adjacency product): per m-tile {A tile index of its first k-block, first k-block
     // on the B side, number of k-blocks, unused}
     const int4 *tile_info = nullptr;
@@ -48,9 +40,6 @@ struct GemmArgs {
     // block-sparse adjacency (tc_engine.cu adj_tile_scan_kernel): the k-blocks of an m-tile whose 128 x 64 A tile holds at
     // least one contact, as a compact list adj_kb_idx[tile_info[mt].x + j], j < adj_kb_cnt[mt].  All-zero tiles contribute
     // nothing to A_hat . Y, so the producer, the expanders and the MMA issuer walk this list instead of 0..nkb-1.
-    // BN = 256 only: land the two 128-row B sub-tiles of a stage interleaved by k-group ([k-group][256 rows], 16 copies of 2 KiB)
-    // so that ONE M128 x N256 MMA per k-step reads them (LBO = 4096) instead of two N = 128 MMAs that each re-read the A tile
-    int wide_b = 0;
     int adj_compact = 0;             // adjacency product on the compact residue axis (tc_engine.cu build_meta)
     const unsigned short *adj_kb_idx = nullptr;
     const int *adj_kb_cnt = nullptr;
@@ -94,9 +83,6 @@ int launch_gemm_tc(mdf_ctx *ctx, int epi, int bn, int a_terms, int b_terms, cons
 // 256-row / 256-column tiles, a_bytes / b_bytes are the byte sizes of the term images (for the tensor maps).
 int launch_gemm_pair(mdf_ctx *ctx, int epi, int a_terms, int b_terms, const GemmArgs &args, const size_t a_bytes[2], const size_t b_bytes[2]);
 
-// CTA-pair form of the grouped adjacency GEMM (bit-packed A): pairs = device [n_pairs] int4 {m-tile of rank 0, m-tile of
-// rank 1 or -1, first k-block on the B side, k-blocks}; n_tiles in `args` counts 256-column tiles; y_bytes = size of Y^T
-int launch_gemm_adj_pair(mdf_ctx *ctx, const GemmArgs &args, const int4 *pairs, int n_pairs, size_t y_bytes);
 
 // flat [bytes/512][256] u16 tensor map whose [32 x 256] boxes are the 16 KiB operand tiles of an image
 int make_tile_map(CUtensorMap *map, const void *base, size_t bytes);

@@ -36,22 +36,13 @@ struct TcModel {
     unsigned long long lm_hash = 0;                        // FNV-1a of the LSTM weights: heads that share the LM share its output
     int head_tc = 1;                                       // head GEMMs on tensor cores (activations and weights both split hi + lo)
     int single_term_mask = 0;                              // MDF_SINGLE_TERM (experiment): bit 0 embedding, bit 1+l GraphConv layer l use the hi weight term only
-    int adj_pair = 0;                                      // MDF_ADJ_PAIR=1: CTA-pair (cta_group::2) form of the adjacency GEMM.  Measured
-                                                           // 4.7-5.0 ms vs 4.5 ms per layer: halving the shared-memory operand traffic does
-                                                           // not help, the kernel is paced by draining its short-K accumulators
     int pool_fused = 1;                                    // sum-pool readout inside the adjacency GEMM epilogue (fp32, no X re-read)
-    int adj_wide = 0;                                      // MDF_ADJ_WIDE=1 (measured, not default: stage 10.7 -> 11.1 ms): one N = 256 MMA per k-step, B sub-tiles interleaved by k-group
     int compact = 1;                                       // compact residue axis (MDF_COMPACT=0: per-protein segments padded to 128 rows)
     int embed_staged = 1;                                  // embedding GEMM gathers W_aa + b from a per-tile shared-memory slice (MDF_EMBED_STAGED=0: from global memory)
     int adj_lean = 1;                                      // adjacency GEMM stores no pad rows and no image of the last layer (MDF_ADJ_LEAN=0: store all)
     int adj_sparse = 1;                                    // adjacency GEMM skips all-zero 128 x 64 A tiles (MDF_ADJ_SPARSE=0: dense walk)
     int adj_expand = 1;                                    // adjacency GEMM expands its A tiles from the bit-packed map on the fly
     int gemm_pair = 1;                                     // CTA-pair (cta_group::2) kernels for the embedding and X.W GEMMs
-    int gemm_phases = 0;                                   // > 0 (MDF_GEMM_PHASES, experiment): single-term dithered weights, phase = residue tile
-                                                           // % phases.  Measured and rejected as default: a short protein spans 1-3 tiles, so
-                                                           // the rounding error does not cancel (6.7e-4 at L~128) and scores depend on the batch
-    __half *lm_Wd = nullptr;                               // [phases][E rows x H k]
-    __half *gc_Wd[MDF_MAX_GC] = {nullptr};                 // [phases][g rows x k_in]
     __half *lstm_R[MDF_MAX_LSTM] = {nullptr};              // [H/16][2][64 x H] resident recurrent slices (hi, lo)
     __half *lstm_Ralt[MDF_MAX_LSTM] = {nullptr};           // same, time-dithered pair (R_a, R_b = fp16(2R - R_a))
     int lstm_alternate = 1;
@@ -76,8 +67,6 @@ struct TcBatchMeta {
     int *rowmap = nullptr;      // [Tp] padded row -> packed residue index, -1 on pads
     int4 *tile_info = nullptr;  // [m_tiles] grouped-GEMM info per 128-row tile
     int4 *exp_tiles = nullptr;  // [n_adj_tiles] {protein, local m-tile, k-block, first tile of protein}
-    int4 *pairs = nullptr;      // [n_pairs] CTA-pair work list of the adjacency GEMM {m-tile 0, m-tile 1 or -1, first B k-block, k-blocks}
-    int n_pairs = 0;
     int64_t *seg_off = nullptr; // [n+1] padded row offsets
     void *block = nullptr;
     bool persistent = false;
@@ -145,15 +134,12 @@ int tc_model_init(mdf_model *m, const mdf_model_desc *d)
     if (const char *e = getenv("MDF_GEMM_PAIR")) t->gemm_pair = atoi(e);
     if (const char *e = getenv("MDF_ADJ_EXPAND")) t->adj_expand = atoi(e);
     if (const char *e = getenv("MDF_POOL_FUSED")) t->pool_fused = atoi(e);
-    if (const char *e = getenv("MDF_ADJ_PAIR")) t->adj_pair = atoi(e);
     if (const char *e = getenv("MDF_ADJ_SPARSE")) t->adj_sparse = atoi(e);
-    if (const char *e = getenv("MDF_ADJ_WIDE")) t->adj_wide = atoi(e);
     if (const char *e = getenv("MDF_ADJ_LEAN")) t->adj_lean = atoi(e);
     if (const char *e = getenv("MDF_EMBED_STAGED")) t->embed_staged = atoi(e);
     if (const char *e = getenv("MDF_COMPACT")) t->compact = atoi(e);
     if (const char *e = getenv("MDF_SINGLE_TERM")) t->single_term_mask = atoi(e);
     if (const char *e = getenv("MDF_HEAD_TC")) t->head_tc = atoi(e);
-    if (const char *e = getenv("MDF_GEMM_PHASES")) t->gemm_phases = std::min(64, std::max(0, atoi(e)));   // 0: hi+lo split on every tile
     // shape constraints of the tile-image GEMMs
     bool ok = m->H % 64 == 0 && m->E % 128 == 0;
     for (int l = 0; l < m->n_gc; ++l) ok = ok && m->gc[l] % 128 == 0;
@@ -177,21 +163,11 @@ int tc_model_init(mdf_model *m, const mdf_model_desc *d)
         m->owned.push_back(t->out_b_pad);
         MDF_CUDA(cudaMemcpy(t->out_b_pad, bp.data(), bp.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
-    auto upload_dithered = [&](const float *src_kn, int rows, int K, __half **dst) -> int {   // src[k][row] -> [phases][rows x K] images
-        std::vector<float> tr((size_t)rows * K);
-        for (int r = 0; r < rows; ++r)
-            for (int k = 0; k < K; ++k) tr[(size_t)r * K + k] = src_kn[(size_t)k * rows + r];
-        std::vector<__half> all((size_t)t->gemm_phases * cdiv(rows, TILE_ROWS) * cdiv(K, TILE_K) * (TILE_BYTES / 2));
-        build_dither_images_host(tr.data(), rows, K, t->gemm_phases, all.data());
-        return upload_half(m, dst, all);
-    };
-    if (t->gemm_phases > 0) MDF_TRY(upload_dithered(d->lm_W, m->E, m->H, &t->lm_Wd));
     int prev = m->E;
     for (int l = 0; l < m->n_gc; ++l) {
         build_image_host(d->gc_W[l], m->gc[l], prev, true, m->gc[l], hi, lo);   // rows = out, k = in : W[k][out]
         MDF_TRY(upload_half(m, &t->gc_W[l][0], hi));
         MDF_TRY(upload_half(m, &t->gc_W[l][1], lo));
-        if (t->gemm_phases > 0) MDF_TRY(upload_dithered(d->gc_W[l], m->gc[l], prev, &t->gc_Wd[l]));
         prev = m->gc[l];
     }
     {
@@ -628,7 +604,7 @@ static int build_meta(mdf_ctx *ctx, mdf_batch *b, TcBatchMeta &meta, bool want_e
     const int64_t Tp = ((compact ? b->h_seq_off[n] : seg_off[n]) + 255) / 256 * 256;
     const int64_t adj_rows = (seg_off[n] + 255) / 256 * 256;
     std::vector<int4> tile_info((size_t)(adj_rows / 128), make_int4(0, 0, 0, 0));
-    std::vector<int4> exp_tiles, pairs;
+    std::vector<int4> exp_tiles;
     int tile_base = 0;
     for (int p = 0; p < n; ++p) {
         const int L = (int)(b->h_seq_off[p + 1] - b->h_seq_off[p]);
@@ -640,21 +616,16 @@ static int build_meta(mdf_ctx *ctx, mdf_batch *b, TcBatchMeta &meta, bool want_e
             tile_info[(size_t)mt0 + mt] = make_int4(tile_base + mt * KBp, (int)((compact ? s0 : seg_off[p]) / TILE_K), KBp, p);
             if (want_exp_tiles)
                 for (int kb = 0; kb < KBp; ++kb) exp_tiles.push_back(make_int4(p, mt, kb, tile_base));
-            if ((mt & 1) == 0) pairs.push_back(make_int4(mt0 + mt, mt + 1 < MT ? mt0 + mt + 1 : -1, (int)(seg_off[p] / TILE_K), KBp));
         }
         tile_base += MT * KBp;
     }
-    // longest k-range first: the pairs are dealt round-robin to the CTA pairs, and the big ones should not end the kernel
-    std::stable_sort(pairs.begin(), pairs.end(), [](const int4 &x, const int4 &y) { return x.w > y.w; });
     meta.Tp = Tp;
     meta.m_tiles = (int)(Tp / 128);
     meta.adj_m_tiles = (int)(adj_rows / 128);
     meta.compact = compact;
     meta.n_adj_tiles = tile_base;
-    meta.n_pairs = (int)pairs.size();
     const size_t bytes = align_up((size_t)Tp * 4, 256) + align_up(tile_info.size() * 16, 256) +
-                         align_up(exp_tiles.size() * 16 + 16, 256) + align_up((size_t)(n + 1) * 8, 256) +
-                         align_up(pairs.size() * 16 + 16, 256);
+                         align_up(exp_tiles.size() * 16 + 16, 256) + align_up((size_t)(n + 1) * 8, 256);
     char *base = nullptr;
     if (b->owns_memory) {
         MDF_CUDA(cudaMalloc((void **)&base, bytes));
@@ -666,8 +637,7 @@ static int build_meta(mdf_ctx *ctx, mdf_batch *b, TcBatchMeta &meta, bool want_e
     meta.rowmap = (int *)base; base += align_up((size_t)Tp * 4, 256);
     meta.tile_info = (int4 *)base; base += align_up(tile_info.size() * 16, 256);
     meta.exp_tiles = (int4 *)base; base += align_up(exp_tiles.size() * 16 + 16, 256);
-    meta.seg_off = (int64_t *)base; base += align_up((size_t)(n + 1) * 8, 256);
-    meta.pairs = (int4 *)base;
+    meta.seg_off = (int64_t *)base;
     cudaStream_t s = ctx->stream;
     // asynchronous jobs stage these tables through the slot's pinned memory: the copies then never block the submitting thread
     bool staged = b->slot != nullptr;
@@ -688,7 +658,6 @@ static int build_meta(mdf_ctx *ctx, mdf_batch *b, TcBatchMeta &meta, bool want_e
     MDF_CUDA(cudaMemcpyAsync(meta.tile_info, src_of(tile_info.data(), tile_info.size() * 16), tile_info.size() * 16, cudaMemcpyHostToDevice, s));
     if (!exp_tiles.empty())
         MDF_CUDA(cudaMemcpyAsync(meta.exp_tiles, src_of(exp_tiles.data(), exp_tiles.size() * 16), exp_tiles.size() * 16, cudaMemcpyHostToDevice, s));
-    if (!pairs.empty()) MDF_CUDA(cudaMemcpyAsync(meta.pairs, src_of(pairs.data(), pairs.size() * 16), pairs.size() * 16, cudaMemcpyHostToDevice, s));
     if (!staged) MDF_CUDA(cudaStreamSynchronize(s));      // host vectors are pageable
     return MDF_OK;
 }
@@ -739,7 +708,7 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto, const std::function<int()> 
 
     // ---- residue-axis metadata (compact axis needs the list-walking adjacency GEMM)
     // (the separate pooling kernel of MDF_POOL_FUSED=0 walks per-protein 128-row tiles of the image: padded axis only)
-    const bool want_compact = tm->compact && tm->adj_expand && tm->adj_sparse && !tm->adj_pair && tm->pool_fused;
+    const bool want_compact = tm->compact && tm->adj_expand && tm->adj_sparse && tm->pool_fused;
     TcBatchMeta local_meta;
     TcBatchMeta *meta = &local_meta;
     if (b->owns_memory) {
@@ -851,11 +820,7 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto, const std::function<int()> 
         g.m_tiles = meta->m_tiles; g.n_tiles = m->E / 128; g.nkb = m->H / TILE_K;
         g.out_img = X0img; g.KB_out = m->E / TILE_K;
         g.bias = m->lm_b; g.gtab = m->aa_W; g.gidx = idx_pad; g.ldg = m->E;
-        if (tm->lm_Wd) {                                  // single-term weights, dither phase = residue tile
-            g.B[0] = tm->lm_Wd; g.B[1] = nullptr;
-            g.b_phases = tm->gemm_phases; g.b_phase_stride = (size_t)m->E * m->H * 2;
-            MDF_TRY(launch_gemm_tc(ctx, EPI_IMG_EMBED, 128, 1, 1, g));
-        } else if (tm->gemm_pair && Tp % 256 == 0 && m->E % 256 == 0) {   // CTA pairs: 256 x 256 tiles
+        if (tm->gemm_pair && Tp % 256 == 0 && m->E % 256 == 0) {   // CTA pairs: 256 x 256 tiles
             g.m_tiles = (int)(Tp / 256); g.n_tiles = m->E / 256;
             g.embed_staged = tm->embed_staged;
             const size_t ab[2] = {(size_t)Tp * m->H * 2, 0}, bb[2] = {(size_t)m->E * m->H * 2, (size_t)m->E * m->H * 2};
@@ -889,7 +854,7 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto, const std::function<int()> 
     // ---- block-sparse walk lists of the adjacency GEMM (per run: they follow the contact maps of this threshold)
     unsigned short *kb_idx = nullptr;
     int *kb_cnt = nullptr;
-    if (tm->adj_expand && tm->adj_sparse && !tm->adj_pair && meta->n_adj_tiles > 0) {
+    if (tm->adj_expand && tm->adj_sparse && meta->n_adj_tiles > 0) {
         ProfScope ps(ctx, "adj_tile_scan", 0.0);
         MDF_TRY(ctx->alloc_n(&kb_idx, (size_t)meta->n_adj_tiles + 8));
         MDF_TRY(ctx->alloc_n(&kb_cnt, (size_t)meta->adj_m_tiles));
@@ -914,11 +879,7 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto, const std::function<int()> 
             g.out_img = Yt; g.KB_out = (int)(Tp / TILE_K);
             g.colscale = deg_pad;
             g.m_fastest = 1;                              // the 4 feature tiles of one residue block run back to back: X is read once
-            if (tm->gc_Wd[l]) {                           // single-term weights, dither phase = residue tile
-                g.A[0] = tm->gc_Wd[l]; g.A[1] = nullptr;
-                g.a_phases = tm->gemm_phases; g.a_phase_stride = (size_t)gd * kin * 2;
-                MDF_TRY(launch_gemm_tc(ctx, EPI_IMG_COLSCALE, 256, 1, 1, g));
-            } else if (tm->gemm_pair && gd % 256 == 0 && Tp % 256 == 0) {   // CTA pairs: 256 features x 256 residues
+            if (tm->gemm_pair && gd % 256 == 0 && Tp % 256 == 0) {   // CTA pairs: 256 features x 256 residues
                 g.m_tiles = gd / 256; g.n_tiles = (int)(Tp / 256);
                 const size_t ab[2] = {(size_t)gd * kin * 2, (size_t)gd * kin * 2}, bb[2] = {(size_t)Tp * kin * 2, 0};
                 MDF_TRY(launch_gemm_pair(ctx, EPI_IMG_COLSCALE, (tm->single_term_mask & (2 << l)) ? 1 : 2, 1, g, ab, bb));
@@ -935,7 +896,6 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto, const std::function<int()> 
             if (tm->adj_expand) {                         // A tiles built in shared memory from the bit-packed map
                 g.adj_packed = b->d_packed; g.adj_packed_off = b->d_packed_off; g.adj_seq_off = b->d_seq_off; g.adj_seg_off = meta->seg_off;
                 g.adj_kb_idx = kb_idx; g.adj_kb_cnt = kb_cnt;
-                g.wide_b = tm->adj_wide;
             }
             const int bn = gd % 256 == 0 ? 256 : 128;
             g.m_tiles = meta->adj_m_tiles; g.n_tiles = gd / bn;
@@ -953,12 +913,7 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto, const std::function<int()> 
                 MDF_CUDA(cudaMemsetAsync(d_trace, 0, 64, s));
                 g.trace = d_trace;
             }
-            if (tm->adj_pair && tm->adj_expand && gd % 256 == 0 && !want_trace) {
-                g.n_tiles = gd / 256;
-                MDF_TRY(launch_gemm_adj_pair(ctx, g, meta->pairs, meta->n_pairs, (size_t)Tp * gd * sizeof(__half)));
-            } else {
-                MDF_TRY(launch_gemm_tc(ctx, EPI_IMG_ROWSCALE, bn, 1, 1, g));
-            }
+            MDF_TRY(launch_gemm_tc(ctx, EPI_IMG_ROWSCALE, bn, 1, 1, g));
             if (want_trace) {
                 long long h[8];
                 MDF_CUDA(cudaStreamSynchronize(s));

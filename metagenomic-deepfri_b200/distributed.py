@@ -37,48 +37,70 @@ def stream_chunks(submit: Callable[[object, np.ndarray], object], chunks: Iterab
         jobs.popleft().wait()
 
 
+class ScoreGather:
+    """The job's one collective, with every buffer allocated up front (page-locking 2 GB of host memory or growing the CUDA
+    caching allocator inside the gather costs more than the gather itself).  Tensors, not pickles: one `gather` of the padded
+    score blocks and one of the index vectors - NCCL: over NVLink, the scatter into protein order done on the GPU and ONE
+    device->host copy into pinned memory; gloo: on the host."""
+
+    def __init__(self, n_local: int, n_total: int, n_terms: int, dst: int = 0):
+        import torch
+        import torch.distributed as dist
+        self.n_local, self.n_total, self.n_terms, self.dst = int(n_local), int(n_total), int(n_terms), dst
+        self.dist_on = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        if not self.dist_on:
+            return
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.cuda = dist.get_backend() == "nccl"
+        dev = torch.device("cuda", torch.cuda.current_device()) if self.cuda else torch.device("cpu")
+        mine = torch.tensor([self.n_local], dtype=torch.int64, device=dev)
+        counts = [torch.zeros_like(mine) for _ in range(self.world)]
+        dist.all_gather(counts, mine)
+        self.counts = [int(c.item()) for c in counts]
+        self.nmax = max(max(self.counts), 1)
+        self.sc = torch.zeros((self.nmax, n_terms), dtype=torch.float32, device=dev)
+        self.ix = torch.zeros(self.nmax, dtype=torch.int64, device=dev)
+        self.sc_all = self.ix_all = self.final = self.host = None
+        if self.rank == dst:
+            self.sc_all = [torch.empty_like(self.sc) for _ in range(self.world)]
+            self.ix_all = [torch.empty_like(self.ix) for _ in range(self.world)]
+            self.final = torch.zeros((n_total, n_terms), dtype=torch.float32, device=dev)
+            self.host = torch.empty((n_total, n_terms), dtype=torch.float32, pin_memory=self.cuda)
+
+    def gather(self, local_idx: np.ndarray, local_scores: np.ndarray) -> Optional[np.ndarray]:
+        """-> [n_total, C] float32 in original protein order on `dst` (a view of this object's host buffer), None elsewhere."""
+        import torch
+        import torch.distributed as dist
+        if len(local_idx) != self.n_local:
+            raise ValueError("ScoreGather.gather: local size differs from the one announced at construction")
+        if not self.dist_on:
+            if len(local_idx) == self.n_total and (len(local_idx) == 0 or (local_idx[0] == 0 and local_idx[-1] == self.n_total - 1
+                                                                          and np.all(np.diff(local_idx) == 1))):
+                return local_scores
+            out = np.zeros((self.n_total, self.n_terms), np.float32)
+            out[local_idx] = local_scores
+            return out
+        n = self.n_local
+        if n:
+            self.sc[:n].copy_(torch.from_numpy(np.ascontiguousarray(local_scores, np.float32)), non_blocking=True)
+            self.ix[:n].copy_(torch.from_numpy(np.ascontiguousarray(local_idx, np.int64)), non_blocking=True)
+        dist.gather(self.sc, self.sc_all, dst=self.dst)
+        dist.gather(self.ix, self.ix_all, dst=self.dst)
+        if self.rank != self.dst:
+            return None
+        for r in range(self.world):
+            if self.counts[r]:
+                self.final.index_copy_(0, self.ix_all[r][:self.counts[r]], self.sc_all[r][:self.counts[r]])
+        self.host.copy_(self.final, non_blocking=self.cuda)
+        if self.cuda:
+            torch.cuda.synchronize()
+        return self.host.numpy()
+
+
 def gather_scores(local_idx: np.ndarray, local_scores: np.ndarray, n_total: int, n_terms: int,
                   dst: int = 0) -> Optional[np.ndarray]:
-    """Collect every rank's (indices, scores) on `dst` as one [n_total, C] float32 matrix in original protein order.
-    Tensors, not pickles: one `gather` of the padded score blocks and one of the index vectors (NCCL: over NVLink, with the
-    scatter into protein order done on the GPU and one device->host copy into pinned memory; gloo: on the host)."""
-    import torch
-    import torch.distributed as dist
-    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
-        if len(local_idx) == n_total and np.array_equal(local_idx, np.arange(n_total)):
-            return local_scores
-        out = np.zeros((n_total, n_terms), np.float32)
-        out[local_idx] = local_scores
-        return out
-    rank, world = dist.get_rank(), dist.get_world_size()
-    cuda = dist.get_backend() == "nccl"
-    dev = torch.device("cuda", torch.cuda.current_device()) if cuda else torch.device("cpu")
-    n_local = torch.tensor([len(local_idx)], dtype=torch.int64, device=dev)
-    counts = [torch.zeros_like(n_local) for _ in range(world)]
-    dist.all_gather(counts, n_local)
-    counts = [int(c.item()) for c in counts]
-    nmax = max(max(counts), 1)
-    sc = torch.zeros((nmax, n_terms), dtype=torch.float32, device=dev)
-    ix = torch.zeros(nmax, dtype=torch.int64, device=dev)
-    if len(local_idx):
-        sc[:len(local_idx)].copy_(torch.from_numpy(np.ascontiguousarray(local_scores, np.float32)), non_blocking=True)
-        ix[:len(local_idx)].copy_(torch.from_numpy(np.ascontiguousarray(local_idx, np.int64)), non_blocking=True)
-    sc_all = [torch.empty_like(sc) for _ in range(world)] if rank == dst else None
-    ix_all = [torch.empty_like(ix) for _ in range(world)] if rank == dst else None
-    dist.gather(sc, sc_all, dst=dst)
-    dist.gather(ix, ix_all, dst=dst)
-    if rank != dst:
-        return None
-    final = torch.zeros((n_total, n_terms), dtype=torch.float32, device=dev)
-    for r in range(world):
-        if counts[r]:
-            final.index_copy_(0, ix_all[r][:counts[r]], sc_all[r][:counts[r]])
-    if cuda:
-        host = torch.empty((n_total, n_terms), dtype=torch.float32, pin_memory=True)
-        host.copy_(final, non_blocking=True)
-        torch.cuda.synchronize()
-        return host.numpy()
-    return final.numpy()
+    """One-shot form of `ScoreGather` (allocates its buffers on every call)."""
+    return ScoreGather(len(local_idx), n_total, n_terms, dst).gather(np.asarray(local_idx, np.int64), local_scores)
 
 
 def predict_sharded(forward: Callable[[np.ndarray], np.ndarray], lengths: Sequence[int], n_terms: int,
