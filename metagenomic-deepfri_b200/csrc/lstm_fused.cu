@@ -85,6 +85,8 @@ struct LstmFusedArgs {
     unsigned *flags;          // [n_groups][halves][2 layers][LF_MAX_KB] release counters, one per operand tile
     long long *trace;         // optional clock64 stamps of CTA 0 (MDF_LSTM_TRACE=1)
     int trace_items;
+    int ablate;               // MDF_LSTM_ABLATE (timing experiments only, results are wrong): 1 no cell math, 2 no operand loads,
+                              //   4 no weight loads, 8 no h / image stores, 16 loader ignores the release counters, 32 no MMAs, 64 generic (slow) issuer loop
     // PAIR mode: flat [bytes/512][256] u16 tensor maps (one 16 KiB tile = a [32 x 256] box) over the six weight
     // images and the exchange buffer - tensor-map TMA is the form that can credit the leader CTA's barrier
     alignas(64) CUtensorMap tmW;
@@ -163,7 +165,7 @@ __device__ __forceinline__ LfSub lf_next(int &cursor, int g, const LstmFusedArgs
 // one layer's cell update for this thread's LF_UPT units: TMEM (gates) + pre-activations -> c, h -> exchange tile (+ image)
 template <int MODE>
 __device__ __forceinline__ void lf_epilogue(uint32_t tgates, bool have_gates, bool active, const float4 *pre4, float (&cst)[LF_UPT],
-                                            uint8_t *xd, uint8_t *id)
+                                            uint8_t *xd, uint8_t *id, int ablate)
 {
 #pragma unroll
     for (int c0 = 0; c0 < LF_UPT; c0 += 8) {
@@ -184,6 +186,10 @@ __device__ __forceinline__ void lf_epilogue(uint32_t tgates, bool have_gates, bo
             for (int j = 0; j < 8; ++j) {
                 const float4 pre = pre4[c0 + j];
                 float c;
+                if (ablate & 1) {
+                    c = __uint_as_float(gi[j]) + pre.x + __uint_as_float(go[j]) + pre.y;
+                    hv[j] = __uint_as_float(gf[j]) + pre.z + __uint_as_float(gc[j]) + pre.w + cst[c0 + j];
+                } else
                 lf_cell<MODE>(__uint_as_float(gi[j]) + pre.x, __uint_as_float(go[j]) + pre.y, __uint_as_float(gf[j]) + pre.z,
                               __uint_as_float(gc[j]) + pre.w, cst[c0 + j], c, hv[j]);
                 cst[c0 + j] = c;
@@ -191,8 +197,10 @@ __device__ __forceinline__ void lf_epilogue(uint32_t tgates, bool have_gates, bo
             uint4 pk;
             pk.x = pack_half2(hv[0], hv[1]); pk.y = pack_half2(hv[2], hv[3]);
             pk.z = pack_half2(hv[4], hv[5]); pk.w = pack_half2(hv[6], hv[7]);
+            if (!(ablate & 8) || pk.x == 0x12345678u) {
             *reinterpret_cast<uint4 *>(xd + (c0 >> 3) * 2048) = pk;
             if (id) *reinterpret_cast<uint4 *>(id + (c0 >> 3) * 2048) = pk;
+            }
         }
     }
 }
@@ -260,7 +268,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
 
     if (warp == LF_W_PROD) {
         // =========================================================== weight producer
-        if (lane == 0) {
+        if (lane == 0 && !(a.ablate & 4)) {
             int st = 0; uint32_t ph = 0;
             const int tiles_per_img = 4 * H / TILE_ROWS * KB;
             bool precise = false;
@@ -307,10 +315,12 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
                 const bool trh = a.trace && blockIdx.x < 2 && layer == 0 && item < a.trace_items;
                 // the slices that produce my chunks have published them (PAIR: I fetch chunks kb = si, si + spc, ... for the
                 // whole cluster; otherwise all of them for myself) ...
+                if (!(a.ablate & 16))
                 for (int kb = si; kb < KB; kb += spc) {
                     const unsigned *f = flags + layer * LF_MAX_KB + kb;
                     while (lf_ld_acquire(f) < target) __nanosleep(100);
                 }
+                if (a.ablate & 2) return;
                 if (trh) th[item * 16 + blockIdx.x * 8 + 1] = lf_gtime();
                 // ... and ONE proxy fence orders those generic-proxy stores before the async-proxy reads below (a fence
                 // per chunk serialises the chunk loads: it waits for this thread's TMA copies already in flight)
@@ -342,6 +352,97 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
         // =========================================================== MMA issuer (PAIR: leader CTA only).  The whole warp walks the
         // loops converged and the single-thread instructions are predicated on elect.sync inside their asm blocks: under
         // `if (lane == 0)` the compiler wraps each tcgen05.mma / commit in a per-lane waterfall loop.
+        if (PAIR && leader && !(a.ablate & 64)) {
+            // ---- CTA-pair fast path: every address and descriptor is hoisted, a k-block is ONE elected asm block (re-arm, 4 MMAs,
+            // commits) and the weight / operand barriers are polled together.  The generic loop below spends ~500 issue cycles per
+            // k-block on ELECT / VOTEU / R2UR / S2UR bookkeeping against 512 cycles of tensor work: the issuing warp, not the
+            // tensor pipe, paced the tick (a tick with every load, MMA and cell update removed still took 12.4 k cycles).
+            constexpr uint32_t idesc = umma_idesc_f16(256, 256);
+            const uint32_t full0 = smem_u32(&bar_full[0]), empty0 = smem_u32(&bar_empty[0]);
+            const uint32_t hfull0 = smem_u32(&bar_hfull[0]), hfree0 = smem_u32(&bar_hfree[0]);
+            const uint32_t gfull0 = smem_u32(&bar_gfull[0]), gfree0 = smem_u32(&bar_gfree[0]);
+            const uint64_t hdesc0 = umma_smem_desc(smem_u32(sH), TILE_LBO, TILE_SBO);
+            const uint64_t wdesc0 = umma_smem_desc(smem_u32(sW), TILE_LBO, TILE_SBO);
+            const bool skip_h = (a.ablate & 2) != 0, skip_w = (a.ablate & 4) != 0;
+            int st = 0; uint32_t ph = 0, hph = 0;
+            uint32_t rounds[2] = {0, 0};
+            int item = 0;
+            const bool trw = a.trace && blockIdx.x == 0;                       // uniform: every lane reads the clock, lane 0 stores
+            long long *tw = a.trace + (size_t)a.trace_items * 8;
+            long long acc_h = 0, acc_w = 0, acc_g = 0;
+            int nterms = 1;
+            auto pass = [&](uint32_t d0, bool accumulate, bool wait_h, bool release_chunks) {
+                for (int kb = 0; kb < KB; ++kb) {
+                    for (int term = 0; term < nterms; ++term) {
+                        const bool need_h = wait_h && term == 0 && !skip_h;
+                        const long long c0 = trw ? clock64() : 0;
+                        if (need_h) {
+                            if (!skip_w) mbar_wait2_addr(hfull0 + 8u * kb, hph, full0 + 8u * st, ph);
+                            else mbar_wait_addr(hfull0 + 8u * kb, hph);
+                        } else if (!skip_w) {
+                            mbar_wait_addr(full0 + 8u * st, ph);
+                        }
+                        if (trw) { const long long dt = clock64() - c0; if (need_h) acc_h += dt; else acc_w += dt; }
+                        const uint32_t rearm = need_h ? hfull0 + 8u * kb : 0u, wfree = skip_w ? 0u : empty0 + 8u * st;
+                        const uint32_t cfree = (release_chunks && term == nterms - 1) ? hfree0 + 8u * kb : 0u;
+                        const uint16_t cmask = (uint16_t)(3u << (2 * (kb % spc)));
+                        if (a.ablate & 32)
+                            umma_pair_kblock_nomma_elect(rearm, 2 * TILE_BYTES, wfree, pair_mask, cfree, cmask);
+                        else
+                            umma_f16_pair_kblock_elect(tmem_base + d0, hdesc0 + (uint64_t)(kb * (TILE_BYTES >> 4)), wdesc0 + (uint64_t)(st * (TILE_BYTES >> 4)),
+                                                       idesc, (accumulate || (kb | term) != 0) ? 1u : 0u, rearm, 2 * TILE_BYTES, wfree, pair_mask, cfree, cmask);
+                        if (++st == LF_STAGES) { st = 0; ph ^= 1; }
+                    }
+                }
+            };
+            auto wait_gfree = [&](int acc) {
+                const long long c0 = trw ? clock64() : 0;
+                mbar_wait_addr(gfree0 + 8u * acc, (rounds[acc] & 1) ^ 1);
+                if (trw) acc_g += clock64() - c0;
+                tcgen05_fence_after();
+            };
+            auto commit_gfull = [&](int acc) {
+                umma_commit_pair_elect(&bar_gfull[acc], pair_mask);
+                ++rounds[acc];
+            };
+            (void)gfull0;
+            int cursor = 0;
+            for (LfSub sbt = lf_next<PAIR>(cursor, g, a); sbt.sb >= 0; sbt = lf_next<PAIR>(cursor, g, a)) {
+                nterms = sbt.Lmax > a.precise_len ? 2 : 1;
+                for (int tau = 1; tau <= sbt.Lmax; ++tau, ++item) {
+                    const bool tr = trw && item < a.trace_items;
+                    long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+                    if (tr) t0 = clock64();
+                    const bool p1 = tau < sbt.Lmax;
+                    if (p1) {                                             // P1
+                        wait_gfree(0);
+                        pass(0u, false, true, false);
+                        commit_gfull(0);
+                    }
+                    const long long ah1 = acc_h;
+                    if (tr) t1 = clock64();
+                    wait_gfree(1);                                        // P2
+                    pass(256u, false, !p1, true);
+                    hph ^= 1;
+                    if (tr) t2 = clock64();
+                    if (tau >= 2) {                                       // P3
+                        pass(256u, true, true, true);
+                        hph ^= 1;
+                    }
+                    commit_gfull(1);
+                    if (tr) {
+                        t3 = clock64();
+                        if (lane == 0) {
+                            a.trace[item * 8 + 0] = t0; a.trace[item * 8 + 1] = t1; a.trace[item * 8 + 2] = t2; a.trace[item * 8 + 3] = t3;
+                            a.trace[(size_t)a.trace_items * 12 + item * 16 + 3] = lf_gtime();
+                            tw[item * 4 + 0] = ah1; tw[item * 4 + 1] = acc_h; tw[item * 4 + 2] = acc_w; tw[item * 4 + 3] = acc_g;
+                        }
+                        __syncwarp();
+                    }
+                    acc_h = acc_w = acc_g = 0;
+                }
+            }
+        } else
         if (leader) {
             constexpr uint32_t idesc = PAIR ? umma_idesc_f16(256, 256) : umma_idesc_f16(128, 128);
             int st = 0; uint32_t ph = 0, hph = 0;
@@ -355,7 +456,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
             int nterms = 1;
             auto pass = [&](uint32_t d0, bool accumulate, bool wait_h, bool release_chunks) {
                 for (int kb = 0; kb < KB; ++kb) {
-                    if (wait_h) {
+                    if (wait_h && !(a.ablate & 2)) {
                         const long long c0 = trw ? clock64() : 0;
                         mbar_wait(&bar_hfull[kb], hph);
                         if (PAIR) mbar_arrive_expect_tx_elect(&bar_hfull[kb], 2 * TILE_BYTES);     // arm the next operand's phase
@@ -367,15 +468,17 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
                     const uint64_t hd = umma_smem_desc(sh_addr + kb * TILE_BYTES, TILE_LBO, TILE_SBO);   // A: proteins x 64 k
                     for (int tj = 0; tj < nterms * TPK; ++tj) {
                         const int term = tj / TPK, jj = tj % TPK;
-                        {
+                        if (!(a.ablate & 4)) {
                             const long long c0 = trw ? clock64() : 0;
                             mbar_wait(&bar_full[st], ph);
                             if (trw) acc_w += clock64() - c0;
                         }
                         tcgen05_fence_after();
                         const uint64_t wd = umma_smem_desc(smem_u32(sW + (size_t)st * TILE_BYTES), TILE_LBO, TILE_SBO);   // B: gate rows x 64 k
+                        const int nks = (a.ablate & 32) ? 0 : TILE_K / 16;
 #pragma unroll
                         for (int ks = 0; ks < TILE_K / 16; ++ks) {
+                            if (ks >= nks) break;
                             if (PAIR)
                                 umma_f16_pair_elect(tmem_base + d0, hd + (uint64_t)(ks * 256), wd + (uint64_t)(ks * 256), idesc,
                                                     accumulate || (kb | ks | term) != 0);
@@ -383,7 +486,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
                                 umma_f16_elect(tmem_base + d0 + (uint32_t)(jj * 128), hd + (uint64_t)(ks * 256), wd + (uint64_t)(ks * 256), idesc,
                                                accumulate || (kb | ks | term) != 0);
                         }
-                        if (PAIR) umma_commit_pair_elect(&bar_empty[st], pair_mask); else umma_commit_elect(&bar_empty[st]);
+                        if (!(a.ablate & 4)) { if (PAIR) umma_commit_pair_elect(&bar_empty[st], pair_mask); else umma_commit_elect(&bar_empty[st]); }
                         if (++st == LF_STAGES) { st = 0; ph ^= 1; }
                     }
                     if (release_chunks) {
@@ -486,7 +589,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
                         id = reinterpret_cast<uint8_t *>(a.H1img) + ((size_t)(row >> 7) * KB + s) * TILE_BYTES +
                              (size_t)((ub >> 3) * 2048 + (((int)row & 127) >> 3) * 128 + ((int)row & 7) * 16);
                     }
-                    lf_epilogue<MODE>(trow, tau >= 1, active, pre4, c1, x1 + (size_t)(tau & 1) * h_bytes, id);
+                    lf_epilogue<MODE>(trow, tau >= 1, active, pre4, c1, x1 + (size_t)(tau & 1) * h_bytes, id, a.ablate);
                     if (tr) a.trace[item * 8 + 5] = clock64();
                     if (tau >= 1) {
                         tcgen05_fence_before();
@@ -511,7 +614,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
                     uint8_t *id = reinterpret_cast<uint8_t *>(a.H2img) + ((size_t)(row >> 7) * KB + s) * TILE_BYTES +
                                   (size_t)((ub >> 3) * 2048 + (((int)row & 127) >> 3) * 128 + ((int)row & 7) * 16);
                     lf_epilogue<MODE>(trow + 256, true, active, reinterpret_cast<const float4 *>(b2S + ub * 4), c2,
-                                      x2 + (size_t)(t2 & 1) * h_bytes, id);
+                                      x2 + (size_t)(t2 & 1) * h_bytes, id, a.ablate);
                     tcgen05_fence_before();
                     __syncwarp();
                     if (lane == 0) {                                      // g2 drained by this warp
@@ -723,6 +826,8 @@ int launch_lstm_fused(mdf_ctx *ctx, int H, int n, const __half *W, int phases, c
         MDF_TRY(make_tile_map(&a.tmW, a.W, (size_t)3 * (phases + 2) * 4 * H * H * 2));
         MDF_TRY(make_tile_map(&a.tmH, a.hbuf, (size_t)a.n_groups * 2 * 4 * LF_M * H * 2));
     }
+    static const int ablate_env = getenv("MDF_LSTM_ABLATE") ? atoi(getenv("MDF_LSTM_ABLATE")) : 0;
+    a.ablate = ablate_env;
     a.trace = nullptr; a.trace_items = 0;
     const bool want_trace = getenv("MDF_LSTM_TRACE") != nullptr;
     if (want_trace) {

@@ -219,6 +219,83 @@ __device__ __forceinline__ void umma_commit_pair_elect(uint64_t *bar, uint16_t c
         "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
         ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
 }
+// One k-block of a CTA-pair pass issued by a converged warp under ONE elect.sync: [re-arm the operand barrier] + the four
+// K = 16 MMAs of a 64-wide k-block + commit -> weight stage free [+ commit -> operand chunk free].  Barrier arguments are
+// shared-window addresses (0 = skip).  The per-instruction elect forms above cost ~50 issue cycles per MMA (ELECT, VOTEU,
+// R2UR of every descriptor); a single issuing warp then needs longer to issue a k-block than the tensor pipe needs to run it.
+__device__ __forceinline__ void umma_f16_pair_kblock_elect(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc_first,
+                                                           uint32_t rearm_bar, uint32_t rearm_bytes, uint32_t empty_bar, uint16_t empty_mask,
+                                                           uint32_t free_bar, uint16_t free_mask)
+{
+    asm volatile(
+        "{\n\t.reg .pred q, p0, pt, pr, pe, pf;\n\t"
+        ".reg .b64 a1, a2, a3, b1, b2, b3;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p0, %4, 0;\n\t"
+        "setp.eq.b32 pt, 0, 0;\n\t"
+        "setp.ne.b32 pr, %5, 0;\n\t"
+        "and.pred pr, pr, q;\n\t"
+        "setp.ne.b32 pe, %7, 0;\n\t"
+        "and.pred pe, pe, q;\n\t"
+        "setp.ne.b32 pf, %9, 0;\n\t"
+        "and.pred pf, pf, q;\n\t"
+        "add.s64 a1, %1, 256;\n\t"
+        "add.s64 a2, %1, 512;\n\t"
+        "add.s64 a3, %1, 768;\n\t"
+        "add.s64 b1, %2, 256;\n\t"
+        "add.s64 b2, %2, 512;\n\t"
+        "add.s64 b3, %2, 768;\n\t"
+        "@pr mbarrier.arrive.expect_tx.shared::cta.b64 _, [%5], %6;\n\t"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p0;\n\t"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], a1, b1, %3, pt;\n\t"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], a2, b2, %3, pt;\n\t"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], a3, b3, %3, pt;\n\t"
+        "@pe tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%7], %8;\n\t"
+        "@pf tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%9], %10;\n\t}"
+        ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc_first), "r"(rearm_bar), "r"(rearm_bytes), "r"(empty_bar), "h"(empty_mask),
+          "r"(free_bar), "h"(free_mask) : "memory");
+}
+// the same block without its MMAs (timing experiments)
+__device__ __forceinline__ void umma_pair_kblock_nomma_elect(uint32_t rearm_bar, uint32_t rearm_bytes, uint32_t empty_bar, uint16_t empty_mask,
+                                                             uint32_t free_bar, uint16_t free_mask)
+{
+    asm volatile(
+        "{\n\t.reg .pred q, pr, pe, pf;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 pr, %0, 0;\n\t"
+        "and.pred pr, pr, q;\n\t"
+        "setp.ne.b32 pe, %2, 0;\n\t"
+        "and.pred pe, pe, q;\n\t"
+        "setp.ne.b32 pf, %4, 0;\n\t"
+        "and.pred pf, pf, q;\n\t"
+        "@pr mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t"
+        "@pe tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%2], %3;\n\t"
+        "@pf tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%4], %5;\n\t}"
+        ::"r"(rearm_bar), "r"(rearm_bytes), "r"(empty_bar), "h"(empty_mask), "r"(free_bar), "h"(free_mask) : "memory");
+}
+// try_wait on a shared-window address; two barriers polled together (their latencies overlap)
+__device__ __forceinline__ bool mbar_try_wait_addr(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_addr(uint32_t bar, uint32_t parity)
+{
+    while (!mbar_try_wait_addr(bar, parity)) { }
+}
+__device__ __forceinline__ void mbar_wait2_addr(uint32_t bar_a, uint32_t parity_a, uint32_t bar_b, uint32_t parity_b)
+{
+    bool a = mbar_try_wait_addr(bar_a, parity_a), b = mbar_try_wait_addr(bar_b, parity_b);
+    while (!(a & b)) {
+        if (!a) a = mbar_try_wait_addr(bar_a, parity_a);
+        if (!b) b = mbar_try_wait_addr(bar_b, parity_b);
+    }
+}
 // arrive + expect_tx by the elected lane of a converged warp
 __device__ __forceinline__ void mbar_arrive_expect_tx_elect(uint64_t *bar, uint32_t bytes)
 {
