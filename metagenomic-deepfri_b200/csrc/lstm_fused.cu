@@ -48,13 +48,13 @@ constexpr int LF_STAGES = 4;         // weight ring (16 KiB tiles: 128 gate rows
 #endif
 constexpr int LF_EW = LF_EPI_WARPS;                  // epilogue warps (8 or 16): 4 TMEM lane quarters x LF_EW/4 unit ranges
 constexpr int LF_UPT = LF_U / (LF_EW / 4);           // units per epilogue thread (per layer)
-constexpr int LF_THREADS = (3 + LF_EW) * 32;         // warps 0..LF_EW-1: epilogue, then weight producer, operand loader, MMA issuer
+constexpr int LF_THREADS = (4 + LF_EW) * 32;         // warps 0..LF_EW-1: epilogue, then weight producer, operand loader, MMA issuer, publisher
 #ifndef LF_ROLES_LOW
-constexpr int LF_W_PROD = LF_EW, LF_W_LOAD = LF_EW + 1, LF_W_MMA = LF_EW + 2;   // single-thread roles on the highest warp ids: the
+constexpr int LF_W_PROD = LF_EW, LF_W_LOAD = LF_EW + 1, LF_W_MMA = LF_EW + 2, LF_W_PUB = LF_EW + 3;   // single-thread roles on the highest warp ids: the
                                                      // arbiter prefers them over the epilogue warps of their scheduler
 constexpr int LF_W_EPI0 = 0;
 #else
-constexpr int LF_W_PROD = 0, LF_W_LOAD = 1, LF_W_MMA = 2, LF_W_EPI0 = 3;
+constexpr int LF_W_PROD = 0, LF_W_LOAD = 1, LF_W_MMA = 2, LF_W_PUB = 3, LF_W_EPI0 = 4;
 #endif
 constexpr int LF_TAB_STRIDE = 260;   // floats per residue row of the layer-1 table slice (64 units x 4 gates + pad)
 constexpr int LF_MAX_KB = 8;
@@ -82,7 +82,7 @@ struct LstmFusedArgs {
     __half *H1img;            // [Tp x H] layer-1 output image (debug taps only) or nullptr
     __half *H2img;            // [Tp x H] layer-2 output image
     __half *hbuf;             // [n_groups][halves][2 layers][2 parities][128 x H] exchange buffers (operand tile images)
-    unsigned *flags;          // [n_groups][halves][2 layers][LF_MAX_KB] release counters, one per operand tile
+    unsigned *flags;          // [n_groups][halves][2 layers][LF_MAX_KB] release counters: slot 0 of each layer counts the published tiles
     long long *trace;         // optional clock64 stamps of CTA 0 (MDF_LSTM_TRACE=1)
     int trace_items;
     int ablate;               // MDF_LSTM_ABLATE (timing experiments only, results are wrong): 1 no cell math, 2 no operand loads,
@@ -163,9 +163,11 @@ __device__ __forceinline__ LfSub lf_next(int &cursor, int g, const LstmFusedArgs
 }
 
 // one layer's cell update for this thread's LF_UPT units: TMEM (gates) + pre-activations -> c, h -> exchange tile (+ image)
-template <int MODE>
+// `drained()` runs once the last gate values have left TMEM (before their cell math): the accumulator is handed back to the MMA
+// issuer half an epilogue earlier than after the stores
+template <int MODE, class Drained>
 __device__ __forceinline__ void lf_epilogue(uint32_t tgates, bool have_gates, bool active, const float4 *pre4, float (&cst)[LF_UPT],
-                                            uint8_t *xd, uint8_t *id, int ablate)
+                                            uint8_t *xd, uint8_t *id, int ablate, Drained drained)
 {
 #pragma unroll
     for (int c0 = 0; c0 < LF_UPT; c0 += 8) {
@@ -176,6 +178,7 @@ __device__ __forceinline__ void lf_epilogue(uint32_t tgates, bool have_gates, bo
             tmem_ld_32x32b_x8(tgates + 2 * 64 + c0, gf);
             tmem_ld_32x32b_x8(tgates + 3 * 64 + c0, gc);
             tmem_ld_wait();
+            if (c0 + 8 >= LF_UPT) drained();
         } else {
 #pragma unroll
             for (int j = 0; j < 8; ++j) gi[j] = go[j] = gf[j] = gc[j] = 0u;
@@ -212,6 +215,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
     __shared__ uint64_t bar_full[LF_STAGES], bar_empty[LF_STAGES];     // weight ring
     __shared__ uint64_t bar_hfull[LF_MAX_KB], bar_hfree[LF_MAX_KB];    // operand chunks
     __shared__ uint64_t bar_gfull[2], bar_gfree[2];                    // TMEM accumulators g1, g2
+    __shared__ uint64_t bar_pub[2];                                    // h1 / h2 stores of this CTA issued -> publisher
     __shared__ uint32_t tmem_slot;
 
     constexpr int HALVES = PAIR ? 2 : 1;
@@ -250,7 +254,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
         // PAIR: chunk kb is fetched by slice kb % spc of the cluster for all its pairs: that CTA's hfree collects one commit
         // per pair, and every leader arms its own hfull (bytes of both halves) itself
         for (int i = 0; i < LF_MAX_KB; ++i) { mbar_init(&bar_hfull[i], 1); mbar_init(&bar_hfree[i], spc); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&bar_gfull[i], 1); mbar_init(&bar_gfree[i], LF_EW * HALVES); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&bar_gfull[i], 1); mbar_init(&bar_gfree[i], LF_EW * HALVES); mbar_init(&bar_pub[i], 1); }
         fence_mbar_init();
         if (PAIR && leader)
             for (int i = 0; i < KB; ++i) mbar_arrive_expect_tx(&bar_hfull[i], 2 * TILE_BYTES);
@@ -315,10 +319,10 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
                 const bool trh = a.trace && blockIdx.x < 2 && layer == 0 && item < a.trace_items;
                 // the slices that produce my chunks have published them (PAIR: I fetch chunks kb = si, si + spc, ... for the
                 // whole cluster; otherwise all of them for myself) ...
-                if (!(a.ablate & 16))
-                for (int kb = si; kb < KB; kb += spc) {
-                    const unsigned *f = flags + layer * LF_MAX_KB + kb;
-                    while (lf_ld_acquire(f) < target) __nanosleep(100);
+                // (ONE counter per layer, bumped by all KB slices: eight acquire loads in a row are eight L2 round trips)
+                if (!(a.ablate & 16)) {
+                    const unsigned *f = flags + layer * LF_MAX_KB;
+                    while (lf_ld_acquire(f) < target * (unsigned)KB) __nanosleep(40);
                 }
                 if (a.ablate & 2) return;
                 if (trh) th[item * 16 + blockIdx.x * 8 + 1] = lf_gtime();
@@ -352,81 +356,81 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
         // =========================================================== MMA issuer (PAIR: leader CTA only).  The whole warp walks the
         // loops converged and the single-thread instructions are predicated on elect.sync inside their asm blocks: under
         // `if (lane == 0)` the compiler wraps each tcgen05.mma / commit in a per-lane waterfall loop.
-        if (PAIR && leader && !(a.ablate & 64)) {
-            // ---- CTA-pair fast path: every address and descriptor is hoisted, a k-block is ONE elected asm block (re-arm, 4 MMAs,
-            // commits) and the weight / operand barriers are polled together.  The generic loop below spends ~500 issue cycles per
-            // k-block on ELECT / VOTEU / R2UR / S2UR bookkeeping against 512 cycles of tensor work: the issuing warp, not the
-            // tensor pipe, paced the tick (a tick with every load, MMA and cell update removed still took 12.4 k cycles).
+        if (PAIR && leader && KB == 8 && LF_STAGES == 4 && !(a.ablate & (2 | 4 | 32 | 64))) {
+            // ---- CTA-pair fast path (H = 512).  The generic loop below spends ~500 issue cycles per k-block on ELECT / VOTEU / R2UR /
+            // S2UR bookkeeping against 512 cycles of tensor work: the issuing warp, not the tensor pipe, paced the tick (a tick with every
+            // load, MMA and cell update removed still took 12.4 k cycles).  Here a pass is eight straight-line k-blocks: every barrier
+            // address and descriptor is a pinned base plus a constant (8 k-blocks = two turns of the 4-stage ring, so stage and parity are
+            // static), a k-block is one combined wait + ONE elected asm block (re-arm, 4 MMAs, commits).
             constexpr uint32_t idesc = umma_idesc_f16(256, 256);
-            const uint32_t full0 = smem_u32(&bar_full[0]), empty0 = smem_u32(&bar_empty[0]);
-            const uint32_t hfull0 = smem_u32(&bar_hfull[0]), hfree0 = smem_u32(&bar_hfree[0]);
-            const uint32_t gfull0 = smem_u32(&bar_gfull[0]), gfree0 = smem_u32(&bar_gfree[0]);
-            const uint64_t hdesc0 = umma_smem_desc(smem_u32(sH), TILE_LBO, TILE_SBO);
-            const uint64_t wdesc0 = umma_smem_desc(smem_u32(sW), TILE_LBO, TILE_SBO);
-            const bool skip_h = (a.ablate & 2) != 0, skip_w = (a.ablate & 4) != 0;
-            int st = 0; uint32_t ph = 0, hph = 0;
+            const uint32_t full0 = pin_u32(smem_u32(&bar_full[0])), empty0 = pin_u32(smem_u32(&bar_empty[0]));
+            const uint32_t hfull0 = pin_u32(smem_u32(&bar_hfull[0])), hfree0 = pin_u32(smem_u32(&bar_hfree[0]));
+            const uint32_t gfull0 = pin_u32(smem_u32(&bar_gfull[0])), gfree0 = pin_u32(smem_u32(&bar_gfree[0]));
+            const uint64_t hdesc0 = pin_u64(umma_smem_desc(smem_u32(sH), TILE_LBO, TILE_SBO));
+            const uint64_t wdesc0 = pin_u64(umma_smem_desc(smem_u32(sW), TILE_LBO, TILE_SBO));
+            const uint32_t spc_mask = (uint32_t)spc - 1u;                       // spc is 1 or 4
+            uint32_t ph = 0, hph = 0;                                           // ring parity at the start of a pass; operand parity
             uint32_t rounds[2] = {0, 0};
             int item = 0;
             const bool trw = a.trace && blockIdx.x == 0;                       // uniform: every lane reads the clock, lane 0 stores
             long long *tw = a.trace + (size_t)a.trace_items * 8;
-            long long acc_h = 0, acc_w = 0, acc_g = 0;
-            int nterms = 1;
-            auto pass = [&](uint32_t d0, bool accumulate, bool wait_h, bool release_chunks) {
-                for (int kb = 0; kb < KB; ++kb) {
-                    for (int term = 0; term < nterms; ++term) {
-                        const bool need_h = wait_h && term == 0 && !skip_h;
-                        const long long c0 = trw ? clock64() : 0;
-                        if (need_h) {
-                            if (!skip_w) mbar_wait2_addr(hfull0 + 8u * kb, hph, full0 + 8u * st, ph);
-                            else mbar_wait_addr(hfull0 + 8u * kb, hph);
-                        } else if (!skip_w) {
-                            mbar_wait_addr(full0 + 8u * st, ph);
-                        }
-                        if (trw) { const long long dt = clock64() - c0; if (need_h) acc_h += dt; else acc_w += dt; }
-                        const uint32_t rearm = need_h ? hfull0 + 8u * kb : 0u, wfree = skip_w ? 0u : empty0 + 8u * st;
-                        const uint32_t cfree = (release_chunks && term == nterms - 1) ? hfree0 + 8u * kb : 0u;
-                        const uint16_t cmask = (uint16_t)(3u << (2 * (kb % spc)));
-                        if (a.ablate & 32)
-                            umma_pair_kblock_nomma_elect(rearm, 2 * TILE_BYTES, wfree, pair_mask, cfree, cmask);
-                        else
-                            umma_f16_pair_kblock_elect(tmem_base + d0, hdesc0 + (uint64_t)(kb * (TILE_BYTES >> 4)), wdesc0 + (uint64_t)(st * (TILE_BYTES >> 4)),
-                                                       idesc, (accumulate || (kb | term) != 0) ? 1u : 0u, rearm, 2 * TILE_BYTES, wfree, pair_mask, cfree, cmask);
-                        if (++st == LF_STAGES) { st = 0; ph ^= 1; }
+            // one pass of single-term weights: gates[d0] (+)= W_slice . operand
+            auto pass = [&](uint32_t d0, uint32_t accumulate, bool wait_h, bool release_chunks) {
+#pragma unroll
+                for (int kb = 0; kb < 8; ++kb) {
+                    const uint32_t stg = (uint32_t)(kb & 3), par = ph ^ (uint32_t)(kb >> 2);
+                    if (wait_h) mbar_wait2_asm(hfull0 + 8u * kb, hph, full0 + 8u * stg, par);
+                    else mbar_wait1_asm(full0 + 8u * stg, par);
+                    umma_f16_pair_kblock_elect(tmem_base + d0, hdesc0 + (uint64_t)(kb * (TILE_BYTES >> 4)), wdesc0 + (uint64_t)(stg * (TILE_BYTES >> 4)),
+                                               idesc, kb ? 1u : accumulate, wait_h ? hfull0 + 8u * kb : 0u, 2 * TILE_BYTES, empty0 + 8u * stg, pair_mask,
+                                               release_chunks ? hfree0 + 8u * kb : 0u, (uint16_t)(3u << (2 * ((uint32_t)kb & spc_mask))));
+                }
+            };
+            // two-term passes (sub-batches above precise_len): 16 stages per pass, still two... four turns of the ring
+            auto pass2 = [&](uint32_t d0, uint32_t accumulate, bool wait_h, bool release_chunks) {
+#pragma unroll 1
+                for (int kb = 0; kb < 8; ++kb) {
+#pragma unroll
+                    for (int term = 0; term < 2; ++term) {
+                        const uint32_t stg = (uint32_t)((2 * kb + term) & 3), par = ph ^ (uint32_t)(((2 * kb + term) >> 2) & 1);
+                        const bool need_h = wait_h && term == 0;
+                        if (need_h) mbar_wait2_asm(hfull0 + 8u * kb, hph, full0 + 8u * stg, par);
+                        else mbar_wait1_asm(full0 + 8u * stg, par);
+                        umma_f16_pair_kblock_elect(tmem_base + d0, hdesc0 + (uint64_t)(kb * (TILE_BYTES >> 4)), wdesc0 + (uint64_t)(stg * (TILE_BYTES >> 4)),
+                                                   idesc, (kb | term) ? 1u : accumulate, need_h ? hfull0 + 8u * kb : 0u, 2 * TILE_BYTES, empty0 + 8u * stg, pair_mask,
+                                                   (release_chunks && term == 1) ? hfree0 + 8u * kb : 0u, (uint16_t)(3u << (2 * ((uint32_t)kb & spc_mask))));
                     }
                 }
             };
             auto wait_gfree = [&](int acc) {
-                const long long c0 = trw ? clock64() : 0;
-                mbar_wait_addr(gfree0 + 8u * acc, (rounds[acc] & 1) ^ 1);
-                if (trw) acc_g += clock64() - c0;
+                mbar_wait1_asm(gfree0 + 8u * acc, (rounds[acc] & 1) ^ 1);
                 tcgen05_fence_after();
             };
             auto commit_gfull = [&](int acc) {
-                umma_commit_pair_elect(&bar_gfull[acc], pair_mask);
+                umma_pair_kblock_nomma_elect(0u, 0u, gfull0 + 8u * acc, pair_mask, 0u, (uint16_t)0);
                 ++rounds[acc];
             };
-            (void)gfull0;
             int cursor = 0;
             for (LfSub sbt = lf_next<PAIR>(cursor, g, a); sbt.sb >= 0; sbt = lf_next<PAIR>(cursor, g, a)) {
-                nterms = sbt.Lmax > a.precise_len ? 2 : 1;
+                const bool two = sbt.Lmax > a.precise_len;
                 for (int tau = 1; tau <= sbt.Lmax; ++tau, ++item) {
                     const bool tr = trw && item < a.trace_items;
                     long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
                     if (tr) t0 = clock64();
                     const bool p1 = tau < sbt.Lmax;
-                    if (p1) {                                             // P1
+                    if (p1) {                                             // P1 (the operand's parity flips after P2: P2 re-reads it)
                         wait_gfree(0);
-                        pass(0u, false, true, false);
+                        if (two) pass2(0u, 0u, true, false); else pass(0u, 0u, true, false);
                         commit_gfull(0);
                     }
-                    const long long ah1 = acc_h;
                     if (tr) t1 = clock64();
                     wait_gfree(1);                                        // P2
-                    pass(256u, false, !p1, true);
+                    if (p1) { if (two) pass2(256u, 0u, false, true); else pass(256u, 0u, false, true); }
+                    else    { if (two) pass2(256u, 0u, true, true); else pass(256u, 0u, true, true); }
                     hph ^= 1;
                     if (tr) t2 = clock64();
                     if (tau >= 2) {                                       // P3
-                        pass(256u, true, true, true);
+                        if (two) pass2(256u, 1u, true, true); else pass(256u, 1u, true, true);
                         hph ^= 1;
                     }
                     commit_gfull(1);
@@ -435,11 +439,10 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
                         if (lane == 0) {
                             a.trace[item * 8 + 0] = t0; a.trace[item * 8 + 1] = t1; a.trace[item * 8 + 2] = t2; a.trace[item * 8 + 3] = t3;
                             a.trace[(size_t)a.trace_items * 12 + item * 16 + 3] = lf_gtime();
-                            tw[item * 4 + 0] = ah1; tw[item * 4 + 1] = acc_h; tw[item * 4 + 2] = acc_w; tw[item * 4 + 3] = acc_g;
+                            tw[item * 4 + 0] = 0; tw[item * 4 + 1] = 0; tw[item * 4 + 2] = 0; tw[item * 4 + 3] = 0;
                         }
                         __syncwarp();
                     }
-                    acc_h = acc_w = acc_g = 0;
                 }
             }
         } else
@@ -531,6 +534,27 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
                 }
             }
         }
+    } else if (warp == LF_W_PUB) {
+        // =========================================================== publisher: the release at gpu scope waits until the CTA's h
+        // stores have reached L2 (~2 k cycles); done here, the epilogue warps go straight on to their next cell update
+        if (lane == 0 && !(a.ablate & 256)) {
+            uint32_t pph[2] = {0, 0};
+            int cursor = 0;
+            for (LfSub sbt = lf_next<PAIR>(cursor, g, a); sbt.sb >= 0; sbt = lf_next<PAIR>(cursor, g, a)) {
+                for (int tau = 0; tau <= sbt.Lmax; ++tau) {
+                    if (tau < sbt.Lmax) {
+                        mbar_wait(&bar_pub[0], pph[0]);
+                        pph[0] ^= 1;
+                        lf_red_release(flags, 1u);
+                    }
+                    if (tau >= 1) {
+                        mbar_wait(&bar_pub[1], pph[1]);
+                        pph[1] ^= 1;
+                        lf_red_release(flags + LF_MAX_KB, 1u);
+                    }
+                }
+            }
+        }
     } else {
         // =========================================================== epilogue: thread = one protein x LF_UPT units x both layers
         const int et = tid - LF_W_EPI0 * 32;
@@ -544,6 +568,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
         uint8_t *x1 = hb + (size_t)s * TILE_BYTES + xoff;                       // layer 1, parity 0
         uint8_t *x2 = hb + (size_t)2 * h_bytes + (size_t)s * TILE_BYTES + xoff; // layer 2, parity 0
         float c1[LF_UPT], c2[LF_UPT];
+        const bool early = !(a.ablate & 128), use_pub = !(a.ablate & 256);
         unsigned done = 0;
         uint32_t rounds[2] = {0, 0};
         int cursor = 0;
@@ -551,9 +576,9 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
         for (LfSub sbt = lf_next<PAIR>(cursor, g, a); sbt.sb >= 0; sbt = lf_next<PAIR>(cursor, g, a)) {
             // The exchange buffers are reused: every CTA of this half-group must have finished the previous
             // sub-batch (its last operand loads precede its last layer-2 publish) before tick 0 writes them.
-            if (et < KB) {
-                const unsigned *f = flags + LF_MAX_KB + et;
-                while (lf_ld_acquire(f) < done) { }
+            if (et == 0) {
+                const unsigned *f = flags + LF_MAX_KB;
+                while (lf_ld_acquire(f) < done * (unsigned)KB) { }
             }
             lf_bar_sync(1, LF_EW * 32);
             int len = 0;
@@ -589,18 +614,19 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
                         id = reinterpret_cast<uint8_t *>(a.H1img) + ((size_t)(row >> 7) * KB + s) * TILE_BYTES +
                              (size_t)((ub >> 3) * 2048 + (((int)row & 127) >> 3) * 128 + ((int)row & 7) * 16);
                     }
-                    lf_epilogue<MODE>(trow, tau >= 1, active, pre4, c1, x1 + (size_t)(tau & 1) * h_bytes, id, a.ablate);
-                    if (tr) a.trace[item * 8 + 5] = clock64();
-                    if (tau >= 1) {
+                    auto drained1 = [&]() {
                         tcgen05_fence_before();
                         __syncwarp();
                         if (lane == 0) {                                  // g1 drained by this warp
                             if (PAIR && !leader) mbar_arrive_remote(&bar_gfree[0], (uint32_t)(crank & ~1)); else mbar_arrive(&bar_gfree[0]);
                         }
-                    }
+                    };
+                    lf_epilogue<MODE>(trow, tau >= 1, active, pre4, c1, x1 + (size_t)(tau & 1) * h_bytes, id, a.ablate, [&]() { if (early) drained1(); });
+                    if (tau >= 1 && !early) drained1();
+                    if (tr) a.trace[item * 8 + 5] = clock64();
                     lf_bar_sync(1, LF_EW * 32);                                  // all h1_tau stores of this CTA issued
                     if (tr) a.trace[item * 8 + 6] = clock64();
-                    if (et == 0) lf_red_release(flags + s, 1u);
+                    if (et == 0) { if (use_pub) mbar_arrive(&bar_pub[0]); else lf_red_release(flags, 1u); }   // the publisher releases them to the group
                     if (tr) { a.trace[item * 8 + 7] = clock64(); a.trace[(size_t)a.trace_items * 12 + item * 16 + 7] = lf_gtime(); }
                 }
                 // ---------------------------------------------------------------- E2: layer 2, step tau-1
@@ -610,18 +636,21 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
                     mbar_wait_sleep(&bar_gfull[1], rounds[1] & 1, LF_EPI_SLEEP_NS);
                     ++rounds[1];
                     tcgen05_fence_after();
+                    auto drained2 = [&]() {
+                        tcgen05_fence_before();
+                        __syncwarp();
+                        if (lane == 0) {                                  // g2 drained by this warp
+                            if (PAIR && !leader) mbar_arrive_remote(&bar_gfree[1], (uint32_t)(crank & ~1)); else mbar_arrive(&bar_gfree[1]);
+                        }
+                    };
                     const long long row = row0 + t2;
                     uint8_t *id = reinterpret_cast<uint8_t *>(a.H2img) + ((size_t)(row >> 7) * KB + s) * TILE_BYTES +
                                   (size_t)((ub >> 3) * 2048 + (((int)row & 127) >> 3) * 128 + ((int)row & 7) * 16);
                     lf_epilogue<MODE>(trow + 256, true, active, reinterpret_cast<const float4 *>(b2S + ub * 4), c2,
-                                      x2 + (size_t)(t2 & 1) * h_bytes, id, a.ablate);
-                    tcgen05_fence_before();
-                    __syncwarp();
-                    if (lane == 0) {                                      // g2 drained by this warp
-                        if (PAIR && !leader) mbar_arrive_remote(&bar_gfree[1], (uint32_t)(crank & ~1)); else mbar_arrive(&bar_gfree[1]);
-                    }
+                                      x2 + (size_t)(t2 & 1) * h_bytes, id, a.ablate, [&]() { if (early) drained2(); });
+                    if (!early) drained2();
                     lf_bar_sync(1, LF_EW * 32);                                  // all h2 stores of this CTA issued
-                    if (et == 0) lf_red_release(flags + LF_MAX_KB + s, 1u);
+                    if (et == 0) { if (use_pub) mbar_arrive(&bar_pub[1]); else lf_red_release(flags + LF_MAX_KB, 1u); }
                     ++item;
                 }
             }

@@ -255,6 +255,31 @@ __device__ __forceinline__ void umma_f16_pair_kblock_elect(uint32_t tmem_d, uint
         ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc_first), "r"(rearm_bar), "r"(rearm_bytes), "r"(empty_bar), "h"(empty_mask),
           "r"(free_bar), "h"(free_mask) : "memory");
 }
+// Wait for one or two mbarrier phases in one asm block (both polls are issued before either result is consumed; the label is
+// local to the braces, so the block can be inlined any number of times).
+__device__ __forceinline__ void mbar_wait2_asm(uint32_t bar_a, uint32_t parity_a, uint32_t bar_b, uint32_t parity_b)
+{
+    asm volatile(
+        "{\n\t.reg .pred p1, p2;\n\t"
+        "MDF_WAIT2:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p1, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p2, [%2], %3;\n\t"
+        "and.pred p1, p1, p2;\n\t"
+        "@!p1 bra MDF_WAIT2;\n\t}"
+        ::"r"(bar_a), "r"(parity_a), "r"(bar_b), "r"(parity_b) : "memory");
+}
+__device__ __forceinline__ void mbar_wait1_asm(uint32_t bar_a, uint32_t parity_a)
+{
+    asm volatile(
+        "{\n\t.reg .pred p1;\n\t"
+        "MDF_WAIT1:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p1, [%0], %1;\n\t"
+        "@!p1 bra MDF_WAIT1;\n\t}"
+        ::"r"(bar_a), "r"(parity_a) : "memory");
+}
+// keeps a hoisted value in a register: the compiler would otherwise rematerialise shared-window addresses (S2UR + ULEA) at every use
+__device__ __forceinline__ uint32_t pin_u32(uint32_t v) { uint32_t r; asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v)); return r; }
+__device__ __forceinline__ uint64_t pin_u64(uint64_t v) { uint64_t r; asm volatile("mov.u64 %0, %1;" : "=l"(r) : "l"(v)); return r; }
 // the same block without its MMAs (timing experiments)
 __device__ __forceinline__ void umma_pair_kblock_nomma_elect(uint32_t rearm_bar, uint32_t rearm_bytes, uint32_t empty_bar, uint16_t empty_mask,
                                                              uint32_t free_bar, uint16_t free_mask)

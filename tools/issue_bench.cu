@@ -7,12 +7,16 @@
 #include "../metagenomic-deepfri_b200/csrc/tc_ptx.cuh"
 using namespace mdf::tc;
 
+#ifndef NOISE_UNROLL
+#define NOISE_UNROLL 64
+#endif
+// NOISE_UNROLL sets the code footprint of the noise warps' loop body (3 instructions = 48 bytes per step)
 __device__ __forceinline__ float busy(float x, int n)
 {
 #pragma unroll 1
-    for (int i = 0; i < n; ++i) {
+    for (int i = 0; i < n * 64 / NOISE_UNROLL; ++i) {
 #pragma unroll
-        for (int j = 0; j < 64; ++j) x = fmaf(x, 1.0001f, ex2_ftz(x * 0.001f));
+        for (int j = 0; j < NOISE_UNROLL; ++j) x = fmaf(x, 1.0001f, ex2_ftz(x * 0.001f));
     }
     return x;
 }
