@@ -749,7 +749,7 @@ int launch_lstm_fused(mdf_ctx *ctx, int H, int n, const __half *W, int phases, c
 {
     if (n <= 0) return MDF_OK;
     static const int pair_env = getenv("MDF_LSTM_PAIR") ? atoi(getenv("MDF_LSTM_PAIR")) : 1;
-    static const int cell_env = getenv("MDF_LSTM_CELL") ? atoi(getenv("MDF_LSTM_CELL")) : 0;
+    static const int cell_env = getenv("MDF_LSTM_CELL") ? atoi(getenv("MDF_LSTM_CELL")) : 1;   // 1: tanh.approx cell (default), 0: exp/rcp cell
     const bool pair = pair_env != 0;
     LstmFusedArgs a;
     a.H = H; a.n = n;
