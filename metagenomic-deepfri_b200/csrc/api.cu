@@ -118,6 +118,8 @@ extern "C" int mdf_ctx_create(int device, void *arena, size_t arena_bytes, void 
     }
     MDF_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     MDF_CUDA(cudaEventCreateWithFlags(&c->copy_done, cudaEventDisableTiming));
+    MDF_CUDA(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) MDF_CUDA(cudaEventCreateWithFlags(&c->path_done[i], cudaEventDisableTiming));
     MDF_CUDA(cudaMalloc((void **)&c->d_err, 256));
     MDF_CUDA(cudaMemset(c->d_err, 0, 256));
     MDF_CUDA(cudaMallocHost((void **)&c->h_err, 256));
@@ -150,6 +152,8 @@ extern "C" int mdf_ctx_destroy(mdf_ctx *c)
     if (c->h_err) cudaFreeHost(c->h_err);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     if (c->copy_done) cudaEventDestroy(c->copy_done);
+    if (c->d2h_stream) { cudaStreamSynchronize(c->d2h_stream); cudaStreamDestroy(c->d2h_stream); }
+    for (int i = 0; i < 2; ++i) if (c->path_done[i]) cudaEventDestroy(c->path_done[i]);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
     return MDF_OK;
@@ -756,6 +760,29 @@ static int slot_pinned(mdf_job *sl, size_t bytes)
     return MDF_OK;
 }
 
+// After a job has been enqueued from slot `sl`, bring the idle peer slot to the same buffer sizes while the GPU is busy with that
+// job: page-locking ~100 MB and a first cudaMalloc cost 50-75 ms of host time, which the second job of a stream of chunks would
+// otherwise pay in front of an idle GPU.
+static void slot_match_peer(mdf_ctx *ctx, mdf_job *sl)
+{
+    mdf_job *peer = &ctx->slots[(sl - ctx->slots) ^ 1];
+    if (peer->busy || (peer->done && cudaEventQuery(peer->done) != cudaSuccess)) { cudaGetLastError(); return; }
+    if (peer->pin_bytes < sl->pin_bytes) {
+        if (peer->pin) cudaFreeHost(peer->pin);
+        peer->pin = nullptr; peer->pin_bytes = 0;
+        if (cudaHostAlloc((void **)&peer->pin, sl->pin_bytes, cudaHostAllocDefault) == cudaSuccess) peer->pin_bytes = sl->pin_bytes;
+    }
+    if (peer->meta_bytes < sl->meta_bytes) {
+        if (peer->meta) cudaFreeHost(peer->meta);
+        peer->meta = nullptr; peer->meta_bytes = 0;
+        if (cudaHostAlloc((void **)&peer->meta, sl->meta_bytes, cudaHostAllocDefault) == cudaSuccess) peer->meta_bytes = sl->meta_bytes;
+    }
+    if (peer->dev_bytes < sl->dev_bytes && peer->dev == nullptr) {     // (growing an existing block would need a cudaFree = a device sync)
+        if (cudaMalloc((void **)&peer->dev, sl->dev_bytes) == cudaSuccess) peer->dev_bytes = sl->dev_bytes;
+    }
+    cudaGetLastError();
+}
+
 // enqueue everything for flat inputs (already where they may be read asynchronously: pinned slot memory or caller buffers)
 static int job_enqueue(mdf_model *m, mdf_job *sl, int n, const char *seq, const int64_t *seq_off, const float *coords,
                        const int64_t *coord_off, const char *q_aln, const char *t_aln, const int64_t *aln_off, float thr2, int gen,
@@ -771,13 +798,23 @@ static int job_enqueue(mdf_model *m, mdf_job *sl, int n, const char *seq, const 
                          engine_workspace(m, n, seq_off), sl);
     const auto t1 = std::chrono::steady_clock::now();
     if (rc == MDF_OK) rc = run_path(m, b, thr2, gen, 4, true);
+    cudaStream_t out_stream = ctx->stream;
     if (rc == MDF_OK && n > 0) {
-        cudaError_t e = cudaMemcpyAsync(scores, b->d_scores, (size_t)n * m->C * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(sl->h_err, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+        // the scores (and the job's error word, parked in a per-slot device word because the next job resets d_err) leave on the
+        // device-to-host stream behind an event: the next job's kernels do not queue behind this job's 32 MB result copy
+        const int slot = (int)(sl - ctx->slots);
+        cudaError_t e = cudaMemcpyAsync(ctx->d_err + 2 + slot, ctx->d_err, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream);
+        if (e == cudaSuccess && ctx->d2h_stream) {
+            e = cudaEventRecord(ctx->path_done[slot], ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->d2h_stream, ctx->path_done[slot], 0);
+            if (e == cudaSuccess) out_stream = ctx->d2h_stream;
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(scores, b->d_scores, (size_t)n * m->C * sizeof(float), cudaMemcpyDeviceToHost, out_stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(sl->h_err, ctx->d_err + 2 + slot, sizeof(int), cudaMemcpyDeviceToHost, out_stream);
         if (e != cudaSuccess) { set_error("mdf_path_submit: result copy failed: %s", cudaGetErrorString(e)); rc = MDF_ECUDA; }
     }
     if (rc != MDF_OK && ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);   // no input copy may outlive a failed call
-    cudaEventRecord(sl->done, ctx->stream);
+    cudaEventRecord(sl->done, out_stream);
     if (timing) {
         const auto t2 = std::chrono::steady_clock::now();
         auto ms = [](auto a, auto b2) { return std::chrono::duration<double, std::milli>(b2 - a).count(); };
@@ -799,6 +836,7 @@ extern "C" int mdf_path_submit(mdf_model *m, int n, const char *seq, const int64
     if (rc != MDF_OK) return rc;
     sl->busy = true;
     *job = sl;
+    slot_match_peer(ctx, sl);
     return MDF_OK;
 }
 
@@ -863,6 +901,7 @@ extern "C" int mdf_path_submit_ragged(mdf_model *m, int n, const char *const *se
     if (rc != MDF_OK) return rc;
     sl->busy = true;
     *job = sl;
+    slot_match_peer(ctx, sl);
     return MDF_OK;
 }
 
