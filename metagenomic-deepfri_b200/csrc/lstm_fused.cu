@@ -202,7 +202,7 @@ __device__ __forceinline__ void lf_epilogue(uint32_t tgates, bool have_gates, bo
             pk.z = pack_half2(hv[4], hv[5]); pk.w = pack_half2(hv[6], hv[7]);
             if (!(ablate & 8) || pk.x == 0x12345678u) {
             *reinterpret_cast<uint4 *>(xd + (c0 >> 3) * 2048) = pk;
-            if (id) *reinterpret_cast<uint4 *>(id + (c0 >> 3) * 2048) = pk;
+            if (id) __stcs(reinterpret_cast<uint4 *>(id + (c0 >> 3) * 2048), pk);      // streamed out once: evict-first, the weight images stay in L2
             }
         }
     }

@@ -50,7 +50,10 @@ struct TcModel {
     float *lstm_tab_full = nullptr;                        // [26][H][4] layer-1 table over all units
     int lstm_stream_min = 2048;                            // proteins per batch from which the streamed kernel is used
     __half *lstm_fused_W = nullptr;                        // fused kernel: [R1, W2, R2][phase][4H rows (slice, gate, unit) x H] images
-    int lstm_phases = 8;                                   // time-dither period of the fused kernel's weights (sigma-delta rounding)
+    int lstm_phases = 5;                                   // time-dither period of the fused kernel's weights (sigma-delta rounding).  Measured:
+                                                           // 8 phases (48 MB) do not stay in L2 between their uses - one 6 MB phase came from DRAM
+                                                           // every tick (13.5 GB per launch, also with an evict_last hint); 5 phases (30 MB) do:
+                                                           // 3.1 GB, kernel -3.7 %, score error unchanged (3.4e-4 -> 3.8e-4; 4 phases 5.2e-4)
     int lstm_fused = 1;                                    // use the fused two-layer wavefront kernel when supported
     float *lstm_tab = nullptr;                             // [H/16][26][16][4] layer-1 input table (bias folded)
     __half *lstm_Win[MDF_MAX_LSTM][2] = {{nullptr}};       // layers >= 2: [4H rows in (unit,gate) order x H k]
