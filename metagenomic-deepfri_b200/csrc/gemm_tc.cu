@@ -62,6 +62,7 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmArgs &g, uint32_t 
                 v[4 * q + 2] = cs.z != 0.0f ? v[4 * q + 2] * cs.z : 0.0f;
                 v[4 * q + 3] = cs.w != 0.0f ? v[4 * q + 3] * cs.w : 0.0f;
             }
+        } else if (EPI == EPI_IMG_ROWSCALE && (g.ablate & 1)) {
         } else if (EPI == EPI_IMG_ROWSCALE) {
             if (g.bias) {
 #pragma unroll
@@ -107,7 +108,7 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmArgs &g, uint32_t 
                 v[4 * q + 3] = fmaxf(v[4 * q + 3] + b.w + a.w, 0.0f);
             }
         }
-        if (EPI == EPI_IMG_ROWSCALE && pool_row) {
+        if (EPI == EPI_IMG_ROWSCALE && pool_row && !(g.ablate & 2)) {
             // fused sum-pool: column sums over the 32 rows of this warp (pad rows masked), butterfly transpose-reduce so
             // that lane l ends with the total of column n0 + l (31 shuffles), then one fp32 atomic per lane
             float c[32];
@@ -129,7 +130,7 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmArgs &g, uint32_t 
         // The adjacency product is bound by HBM bytes (Y^T in, X out), not by the tensor pipe: it never stores pad rows (nothing
         // reads them as values: rows are independent in X.W and its column scale zeroes their Y^T columns), and stores no image
         // at all when only the fused sum-pool consumes the layer (out_img == nullptr: the last GraphConv layer)
-        if (EPI == EPI_IMG_ROWSCALE && (g.out_img == nullptr || (rs == 0.0f && g.skip_pad_rows))) return;
+        if (EPI == EPI_IMG_ROWSCALE && (g.out_img == nullptr || (rs == 0.0f && g.skip_pad_rows) || ((g.ablate & 4) && v[0] != 1234.5f))) return;
         uint8_t *dst = row_ptr + (size_t)(n0 >> 6) * TILE_BYTES + (((n0 & 63) >> 3) * 2048);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -212,6 +213,9 @@ gemm_tc_kernel(GemmArgs g, int a_terms, int b_terms, int stages)
             int st = 0; uint32_t ph = 0;
             int acc = 0; uint32_t acc_ph = 0;
             const bool tr = g.trace && blockIdx.x == 0;
+            const uint32_t full_bar0 = pin_u32(smem_u32(&bars.full[0])), empty_bar0 = pin_u32(smem_u32(&bars.empty[0]));
+            const uint32_t tfull_bar0 = pin_u32(smem_u32(&bars.tmem_full[0]));
+            const uint64_t desc0 = pin_u64(umma_smem_desc(smem_u32(smem), TILE_LBO, TILE_SBO));
             long long t_info = 0, t_acc = 0, t_full = 0, n_tiles_done = 0;
             const long long t_begin = tr ? clock64() : 0;
             for (int grp = blockIdx.x; grp < outer; grp += gridDim.x)
@@ -224,6 +228,28 @@ gemm_tc_kernel(GemmArgs g, int a_terms, int b_terms, int stages)
                 if (tr) { const long long c1 = clock64(); t_acc += c1 - c0; ++n_tiles_done; }
                 tcgen05_fence_after();
                 const uint32_t d0 = tmem_base + (uint32_t)(acc * BN);
+                if (EPI == EPI_IMG_ROWSCALE && BN == 256 && a_terms == 1 && b_terms == 1) {
+                    // adjacency product: one wait + ONE elected asm block per k-block (eight MMAs + commits; bases pinned, descriptors
+                    // = base + stage offset).  With an elect per MMA the issuing warp needed ~1 k cycles per k-block against 512 of
+                    // tensor work (same finding as in the fused LSTM kernel).
+                    for (int kb = 0; kb < nkb; ++kb) {
+                        c0 = tr ? clock64() : 0;
+                        mbar_wait1_asm(full_bar0 + 8u * st, ph);
+                        if (tr) t_full += clock64() - c0;
+                        const uint64_t ad = desc0 + (uint64_t)(st * (stage_bytes >> 4));
+                        if (g.ablate & 16) {
+                            umma_commit_elect(&bars.empty[st]);
+                            if (kb == nkb - 1) umma_commit_elect(&bars.tmem_full[acc]);
+                        } else
+                        umma_f16_kblock_2n128_elect(d0, ad, ad + (uint64_t)(TILE_BYTES >> 4), ad + (uint64_t)(2 * TILE_BYTES >> 4), idesc, kb ? 1u : 0u,
+                                                    empty_bar0 + 8u * st, kb == nkb - 1 ? tfull_bar0 + 8u * acc : 0u);
+                        if (++st == stages) { st = 0; ph ^= 1; }
+                    }
+                    if (nkb == 0) umma_commit_elect(&bars.tmem_full[acc]);
+                    __syncwarp();
+                    if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+                    continue;
+                }
                 for (int kb = 0; kb < nkb; ++kb) {
                     c0 = tr ? clock64() : 0;
                     mbar_wait(&bars.full[st], ph);
@@ -294,6 +320,7 @@ gemm_tc_kernel(GemmArgs g, int a_terms, int b_terms, int stages)
                     __syncwarp();
                     const uint32_t dst = smem_u32(smem + (size_t)st * stage_bytes) + (uint32_t)((et >> 3) * 128 + (et & 7) * 16);
                     const uint32_t one = 0x3C00u;
+                    if (!(g.ablate & 8))
 #pragma unroll
                     for (int k8 = 0; k8 < 8; ++k8) {
                         const uint32_t b8 = (w[k8 >> 2] >> (8 * (k8 & 3))) & 0xFFu;
@@ -379,7 +406,7 @@ gemm_tc_kernel(GemmArgs g, int a_terms, int b_terms, int stages)
 #pragma unroll 1
             for (int c0 = ch * (BN * 4 / EW); c0 < (ch + 1) * (BN * 4 / EW); c0 += 32) {
                 uint32_t r[32];
-                if (nkb > 0) {
+                if (nkb > 0 && !(g.ablate & 32)) {
                     tmem_ld_32x32b_x32(trow + c0, r);
                     tmem_ld_wait();
                 } else {

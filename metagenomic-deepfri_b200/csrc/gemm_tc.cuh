@@ -61,6 +61,8 @@ struct GemmArgs {
     int act = 0;
     float alpha = 1.0f;
     int m_valid = 0, n_valid = 0;    // bounds for the fp32 epilogue
+    int ablate = 0;                  // MDF_ADJ_ABLATE (timing experiments, wrong results): 1 no epilogue math, 2 no pool, 4 no image stores,
+                                     //   8 expanders skip the expansion, 16 no MMAs, 32 no TMEM loads
 };
 
 // bits j0 .. j0 + 63 of a bit-packed contact-map row (rw words, padding bits zero); j0 may be negative (> -64): the bits

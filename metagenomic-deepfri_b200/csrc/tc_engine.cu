@@ -908,6 +908,8 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto, const std::function<int()> 
             if (l == m->n_gc - 1 && tm->pool_fused && !ctx->debug_taps && tm->adj_lean) g.out_img = nullptr;
             g.skip_pad_rows = tm->adj_lean || compact;    // compact axis: a pad row of the tile would land on another protein's row
             g.rowscale = deg_pad; g.bias = m->gc_b[l]; g.act = m->act; g.alpha = m->alpha;
+            static const int adj_ablate = getenv("MDF_ADJ_ABLATE") ? atoi(getenv("MDF_ADJ_ABLATE")) : 0;
+            g.ablate = adj_ablate;
             if (tm->pool_fused) { g.pool = b->d_pooled; g.pool_ld = m->G; g.pool_off = goff; }   // readout from the fp32 accumulators
             static const bool want_trace = getenv("MDF_GEMM_TRACE") != nullptr;
             long long *d_trace = nullptr;

@@ -280,6 +280,42 @@ __device__ __forceinline__ void mbar_wait1_asm(uint32_t bar_a, uint32_t parity_a
 // keeps a hoisted value in a register: the compiler would otherwise rematerialise shared-window addresses (S2UR + ULEA) at every use
 __device__ __forceinline__ uint32_t pin_u32(uint32_t v) { uint32_t r; asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v)); return r; }
 __device__ __forceinline__ uint64_t pin_u64(uint64_t v) { uint64_t r; asm volatile("mov.u64 %0, %1;" : "=l"(r) : "l"(v)); return r; }
+// Single-CTA variant for a 128 x 256 tile held as two N = 128 accumulators (the adjacency product): eight MMAs of one 64-wide k-block
+// (A . B0 -> d0, A . B1 -> d0 + 128) + commit -> stage free [+ commit -> accumulator full] under one elect.sync.
+__device__ __forceinline__ void umma_f16_kblock_2n128_elect(uint32_t tmem_d, uint64_t a_desc, uint64_t b0_desc, uint64_t b1_desc, uint32_t idesc,
+                                                            uint32_t acc_first, uint32_t empty_bar, uint32_t full_bar)
+{
+    asm volatile(
+        "{\n\t.reg .pred q, p0, pt, pf;\n\t"
+        ".reg .b64 a1, a2, a3, b1, b2, b3, c1, c2, c3;\n\t"
+        ".reg .b32 d1;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p0, %5, 0;\n\t"
+        "setp.eq.b32 pt, 0, 0;\n\t"
+        "setp.ne.b32 pf, %7, 0;\n\t"
+        "and.pred pf, pf, q;\n\t"
+        "add.u32 d1, %0, 128;\n\t"
+        "add.s64 a1, %1, 256;\n\t"
+        "add.s64 a2, %1, 512;\n\t"
+        "add.s64 a3, %1, 768;\n\t"
+        "add.s64 b1, %2, 256;\n\t"
+        "add.s64 b2, %2, 512;\n\t"
+        "add.s64 b3, %2, 768;\n\t"
+        "add.s64 c1, %3, 256;\n\t"
+        "add.s64 c2, %3, 512;\n\t"
+        "add.s64 c3, %3, 768;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %4, p0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [d1], %1, %3, %4, p0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %4, pt;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [d1], a1, c1, %4, pt;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %4, pt;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [d1], a2, c2, %4, pt;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %4, pt;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [d1], a3, c3, %4, pt;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n\t"
+        "@pf tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n\t}"
+        ::"r"(tmem_d), "l"(a_desc), "l"(b0_desc), "l"(b1_desc), "r"(idesc), "r"(acc_first), "r"(empty_bar), "r"(full_bar) : "memory");
+}
 // the same block without its MMAs (timing experiments)
 __device__ __forceinline__ void umma_pair_kblock_nomma_elect(uint32_t rearm_bar, uint32_t rearm_bytes, uint32_t empty_bar, uint16_t empty_mask,
                                                              uint32_t free_bar, uint16_t free_mask)
