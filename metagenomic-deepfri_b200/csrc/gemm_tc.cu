@@ -125,7 +125,7 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmArgs &g, uint32_t 
                     c[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
                 }
             }
-            atomicAdd(pool_row + n0 + lane, c[0]);
+            if (!(g.ablate & 64) || c[0] == 1234.5f) atomicAdd(pool_row + n0 + lane, c[0]);
         }
         // The adjacency product is bound by HBM bytes (Y^T in, X out), not by the tensor pipe: it never stores pad rows (nothing
         // reads them as values: rows are independent in X.W and its column scale zeroes their Y^T columns), and stores no image
