@@ -11,10 +11,11 @@ from typing import List, Sequence
 
 import numpy as np
 
-# seconds per protein = ALPHA L^2 + BETA L, fitted to the per-stage CUDA-event profile of one 16,384-protein configs[4] batch on a
-# B200 (tools/fit_cost.py on profiles/r02_bench_base_before.json: T = 4,901,679 residues, sum L^2 = 2.033e9; quadratic stages =
-# contact maps + tile scan + adjacency product 13.03 ms, linear stages = LSTM-LM + embedding + X.W + head 54.74 ms)
-ALPHA, BETA = 6.41e-12, 1.117e-8
+# seconds per protein = ALPHA L^2 + BETA L, fitted to the per-stage CUDA-event profile of one 16,384-protein configs[4] chunk on a
+# B200 (`python tools/fit_cost.py profiles/r02b_bench_config4.json`: T = 4,813,437 residues, sum L^2 = 1.97e9; quadratic stages =
+# contact maps + tile scan + adjacency product 13.05 ms, linear stages = LSTM-LM + embedding + X.W + head 47.22 ms; before the
+# round-2 LSTM work the linear stages took 54.74 ms: BETA 1.117e-8)
+ALPHA, BETA = 6.62e-12, 9.81e-9
 
 
 def cost(lengths: Sequence[int], alpha: float = ALPHA, beta: float = BETA) -> np.ndarray:

@@ -17,11 +17,14 @@ from metagenomic_deepfri_b200 import batching, predict, synth  # noqa: E402
 import cmap_oracle as co  # noqa: E402
 import spec  # noqa: E402
 
-kw = spec.GCN_CASES["tc_small"][0]
+# MDF_TEST_FULL_MODEL=1: the full-size head (H = 512: the fused LSTM kernel's straight-line CTA-pair issuer), else the smallest tc shape
+kw = {} if os.environ.get("MDF_TEST_FULL_MODEL") else spec.GCN_CASES["tc_small"][0]
 path = os.path.join(tempfile.mkdtemp(), "m.onnx")
 synth.write_gcn_model(path, synth.GCNConfig(**kw), seed=8)
 pred = predict.Predictor(path)
 wl = synth.make_workload(300, 1, 330, seed=21, threshold=10.0)
+if os.environ.get("MDF_TEST_FULL_MODEL"):
+    wl = synth.make_workload(300, 20, 260, seed=21, threshold=10.0)
 pred.set_engine("simt")
 want = pred.forward_structures(wl.query_seqs, wl.gapped_query, wl.gapped_target, wl.coords, 10.0, 2)
 pred.set_engine("tc")
