@@ -45,6 +45,25 @@ assert all(j.done for j in jobs)
 out2 = distributed.gather_scores(np.concatenate(mine), local, len(lengths), C)
 if rank == 0:
     assert np.array_equal(out2, fake_forward(np.arange(len(lengths))))
+# the node-local shared result matrix: scatter per chunk while "computing", the final gather is a barrier
+board = distributed.ScoreBoard(len(lengths), C)
+local3 = np.zeros_like(local)
+distributed.stream_chunks(lambda ch, rows: FakeJob(ch, rows), ((c, len(c)) for c in mine), local3,
+                          on_done=lambda k, rows: board.put(mine[k], rows))
+final = board.finish()
+if rank == 0:
+    assert final is not None and np.array_equal(final, fake_forward(np.arange(len(lengths))))
+else:
+    assert final is None
+board.close()
+# contiguous row ranges written in place (the step-contract end-to-end leg of bench.py)
+counts = np.cumsum([0] + [37 + r for r in range(world)])
+board2 = distributed.ScoreBoard(int(counts[-1]), C)
+board2.rows(counts[rank], counts[rank + 1])[...] = fake_forward(np.arange(counts[rank], counts[rank + 1]))
+final2 = board2.finish()
+if rank == 0:
+    assert np.array_equal(final2, fake_forward(np.arange(counts[-1])))
+board2.close()
 if rank == 0:
     want = fake_forward(np.arange(len(lengths)))
     assert out is not None and np.array_equal(out, want)
