@@ -222,6 +222,18 @@ def predict_sharded(forward: Callable[[np.ndarray], np.ndarray], lengths: Sequen
     """`forward(indices) -> scores[len(indices), C]` is run on this rank's LPT bin chunk by chunk; rank 0 returns the
     [len(lengths), C] matrix in input order, the other ranks None."""
     mine = shard_job(lengths, world, max_proteins, max_residues)[rank]
+    try:
+        board = ScoreBoard(len(lengths), n_terms, pin=False) if world > 1 else None
+    except RuntimeError:            # ranks on several hosts: one collective at the end instead
+        board = None
+    if board is not None:
+        for ch in mine:
+            board.put(ch, forward(ch))
+        final = board.finish()
+        out = None if final is None else np.array(final)
+        final = None
+        board.close()
+        return out
     parts = [forward(ch) for ch in mine]
     local_idx = np.concatenate(mine) if mine else np.zeros(0, np.int64)
     local_sc = np.concatenate(parts) if parts else np.zeros((0, n_terms), np.float32)
