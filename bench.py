@@ -487,15 +487,22 @@ def run_b200(args, rank, world, local_rank, inputs):
             lst = [torch.zeros_like(tcount) for _ in range(world)]
             dist.all_gather(lst, tcount)
             counts[1:] = np.cumsum([int(x.item()) for x in lst])
-            board = distributed.ScoreBoard(int(counts[-1]), C)
-            out_host = board.rows(int(counts[rank]), int(counts[rank + 1]))
-            distributed.stream_chunks(submit, [(chunks[0], n0)], out_host[:n0])      # warm-up into the shared rows
+            gatherer = my_rows = None
+            try:
+                board = distributed.ScoreBoard(int(counts[-1]), C)
+                out_host = board.rows(int(counts[rank]), int(counts[rank + 1]))
+                distributed.stream_chunks(submit, [(chunks[0], n0)], out_host[:n0])      # warm-up into the shared rows
+            except RuntimeError:        # (agreed on by all ranks) no usable /dev/shm: one NCCL gather at the end instead
+                board = None
+                gatherer = distributed.ScoreGather(n_e2e, int(counts[-1]), C)
+                my_rows = np.arange(counts[rank], counts[rank + 1])
+                gatherer.gather(my_rows, out_host)                  # warm-up: NCCL builds its gather channels lazily
         barrier()
         t0 = time.perf_counter()
         distributed.stream_chunks(submit, [(c, len(c)) for c in steps_chunks], out_host)
         local_scores = out_host
         if world > 1:       # scores of every step of every rank are now readable on rank 0
-            all_scores = board.finish()
+            all_scores = board.finish() if board is not None else gatherer.gather(my_rows, local_scores)
             if rank == 0:
                 assert all_scores.shape == (int(counts[-1]), C)
         barrier()
@@ -522,19 +529,22 @@ def run_b200(args, rank, world, local_rank, inputs):
         def submit(c, rows):
             return pred.submit_structures(c.query_seqs, c.gapped_query, c.gapped_target, c.coords, thr, GEN, out=rows)
         chunk_ids = [ix for ix in my_idx if len(ix)]
+        job_board = job_gather = on_done = None
         if world > 1:
             # result matrix in protein order: shared, page-locked, allocated before the clock starts; every rank scatters a chunk's
             # rows into it while the next chunks compute
-            job_board = distributed.ScoreBoard(sharded["job_n"], C)
-            on_done = lambda k, rows: job_board.put(chunk_ids[k], rows)             # noqa: E731
-        else:
+            try:
+                job_board = distributed.ScoreBoard(sharded["job_n"], C)
+                on_done = lambda k, rows: job_board.put(chunk_ids[k], rows)         # noqa: E731
+            except RuntimeError:
+                job_board = None
+        if job_board is None:
             job_gather = distributed.ScoreGather(len(my_ids), sharded["job_n"], C)
-            on_done = None
         barrier()
         t0 = time.perf_counter()
         distributed.stream_chunks(submit, [(c, len(c)) for c in my_chunks], job_out, on_done=on_done)
         t_rank = time.perf_counter() - t0
-        final = job_board.finish() if world > 1 else job_gather.gather(my_ids, job_out)
+        final = job_board.finish() if job_board is not None else job_gather.gather(my_ids, job_out)
         barrier()
         job_s = time.perf_counter() - t0
         busy = allsum(t_rank) / world
@@ -542,7 +552,7 @@ def run_b200(args, rank, world, local_rank, inputs):
         if rank == 0:
             assert final is not None and final.shape == (sharded["job_n"], C) and np.isfinite(final[::997]).all()
             assert np.abs(final[my_ids[:64]] - job_out[:64]).max() == 0.0
-        if world > 1:
+        if job_board is not None:
             final = None
             job_board.close()
         job = {"proteins": sharded["job_n"], "residues": int(sharded["lengths"][:sharded["job_n"]].sum()), "seconds": job_s,

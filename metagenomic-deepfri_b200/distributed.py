@@ -74,18 +74,39 @@ class ScoreBoard:
             dist.all_gather_object(hosts, socket.gethostname())
             if len(set(hosts)) != 1:
                 raise RuntimeError("ScoreBoard: ranks on several hosts (%s); use ScoreGather" % sorted(set(hosts)))
+            # every failure is agreed on by all ranks before anybody raises (a rank that raised alone would leave the others in
+            # the next collective): the caller can then fall back to ScoreGather on all ranks
             name = [None]
             if self.rank == dst:
-                self._shm = shared_memory.SharedMemory(create=True, size=nbytes)
-                name[0] = self._shm.name
+                try:
+                    self._shm = shared_memory.SharedMemory(create=True, size=nbytes)
+                    name[0] = self._shm.name
+                except OSError:
+                    name[0] = None
             dist.broadcast_object_list(name, src=dst)
-            if self.rank != dst:
-                self._shm = shared_memory.SharedMemory(name=name[0])
-                try:        # Python < 3.13 registers attached segments with this process's resource tracker, which would unlink
-                    from multiprocessing import resource_tracker      # (and warn about) the creator's segment at exit
-                    resource_tracker.unregister(self._shm._name, "shared_memory")
-                except Exception:
-                    pass
+            ok = name[0] is not None
+            if ok and self.rank != dst:
+                try:
+                    self._shm = shared_memory.SharedMemory(name=name[0])
+                    try:    # Python < 3.13 registers attached segments with this process's resource tracker, which would unlink
+                        from multiprocessing import resource_tracker  # (and warn about) the creator's segment at exit
+                        resource_tracker.unregister(self._shm._name, "shared_memory")
+                    except Exception:
+                        pass
+                except OSError:
+                    ok = False
+            oks = [None] * self.world
+            dist.all_gather_object(oks, bool(ok))
+            if not all(oks):
+                if self._shm is not None:
+                    try:
+                        if self.rank == dst:
+                            self._shm.unlink()
+                        self._shm.close()
+                    except Exception:
+                        pass
+                    self._shm = None
+                raise RuntimeError("ScoreBoard: node-local shared memory is unavailable (/dev/shm too small?); use ScoreGather")
         else:
             self._shm = shared_memory.SharedMemory(create=True, size=nbytes)
         self.array = np.ndarray((self.n_total, self.n_terms), np.float32, buffer=self._shm.buf)
