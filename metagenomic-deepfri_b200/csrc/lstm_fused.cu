@@ -114,30 +114,31 @@ __device__ __forceinline__ void lf_bar_sync(int id, int nthreads)
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// LSTM cell, ONNX gate order (i, o, f, g).
+// LSTM cell, ONNX gate order (i, o, f, g).  The pre-activations of the three sigmoid gates arrive HALVED (xi = i/2 ...): their
+// weight rows, table and bias entries are stored halved (tc_engine.cu), because sigmoid(x) = 1/2 + 1/2 tanh(x/2).
+// MODE 1 (default): 5 tanh.approx; absolute error ~2^-11 per activation.
 // MODE 0: shared denominators, 5 ex2 + 2 rcp, errors ~1e-7:
 //   c' = sigmoid(f) c + sigmoid(i) tanh(g) = [c B C + (C - 2) A] / (A B C),  A = 1+e^-f, B = 1+e^-i, C = e^2g + 1
 //   h  = sigmoid(o) tanh(c')             = (E - 2) / (D E),                  D = 1+e^-o, E = e^2c' + 1
 //   The exponents are capped at 2^40 so that the triple products stay finite (sigmoid/tanh change by < 1e-12).
-// MODE 1: 5 tanh.approx (sigmoid(x) = 0.5 + 0.5 tanh(x/2)); absolute error ~2^-11 per activation.
 template <int MODE>
 __device__ __forceinline__ void lf_cell(float xi, float xo, float xf, float xg, float c_prev, float &c_out, float &h_out)
 {
     if (MODE == 0) {
         constexpr float L2E = 1.4426950408889634f;
-        const float A = 1.0f + ex2_ftz(fminf(xf * -L2E, 40.0f));
-        const float B = 1.0f + ex2_ftz(fminf(xi * -L2E, 40.0f));
+        const float A = 1.0f + ex2_ftz(fminf(xf * (-2.0f * L2E), 40.0f));
+        const float B = 1.0f + ex2_ftz(fminf(xi * (-2.0f * L2E), 40.0f));
         const float C = 1.0f + ex2_ftz(fminf(xg * (2.0f * L2E), 40.0f));
         const float BC = B * C;
         const float c = fmaf(C - 2.0f, A, c_prev * BC) * rcp_ftz(A * BC);
-        const float D = 1.0f + ex2_ftz(fminf(xo * -L2E, 40.0f));
+        const float D = 1.0f + ex2_ftz(fminf(xo * (-2.0f * L2E), 40.0f));
         const float E = 1.0f + ex2_ftz(fminf(c * (2.0f * L2E), 40.0f));
         c_out = c;
         h_out = (E - 2.0f) * rcp_ftz(D * E);
     } else {
-        const float si = fmaf(tanh_approx(0.5f * xi), 0.5f, 0.5f);
-        const float sf = fmaf(tanh_approx(0.5f * xf), 0.5f, 0.5f);
-        const float so = fmaf(tanh_approx(0.5f * xo), 0.5f, 0.5f);
+        const float si = fmaf(tanh_approx(xi), 0.5f, 0.5f);
+        const float sf = fmaf(tanh_approx(xf), 0.5f, 0.5f);
+        const float so = fmaf(tanh_approx(xo), 0.5f, 0.5f);
         const float c = fmaf(sf, c_prev, si * tanh_approx(xg));
         c_out = c;
         h_out = so * tanh_approx(c);

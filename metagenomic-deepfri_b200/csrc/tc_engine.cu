@@ -48,6 +48,7 @@ struct TcModel {
     int lstm_alternate = 1;
     __half *lstm_Rstream[MDF_MAX_LSTM][2] = {{nullptr}};   // streamed kernel: [4H rows (cta,gate,unit) x H], (R_a, R_b)
     float *lstm_tab_full = nullptr;                        // [26][H][4] layer-1 table over all units
+    float *lstm_fused_tab = nullptr, *lstm_fused_b2 = nullptr;   // fused kernel: the same table / layer-2 bias with the i, o, f entries halved (see lstm_fused_W)
     int lstm_stream_min = 2048;                            // proteins per batch from which the streamed kernel is used
     __half *lstm_fused_W = nullptr;                        // fused kernel: [R1, W2, R2][phase][4H rows (slice, gate, unit) x H] images
     int lstm_phases = 5;                                   // time-dither period of the fused kernel's weights (sigma-delta rounding).  Measured:
@@ -265,6 +266,9 @@ int tc_model_init(mdf_model *m, const mdf_model_desc *d)
         // TMEM column = gate*64 + unit: image row s*256 + gate*64 + u <- ONNX row gate*H + s*64 + u.
         // Per matrix, contiguous: P time-dither roundings, then the exact split (hi, lo) that long proteins use:
         // [R1, W2, R2][P + 2][4H x H].
+        // The rows of the sigmoid gates (ONNX order i, o, f = gates 0..2) are stored HALVED, and so are their table / bias entries:
+        // sigmoid(x) = 1/2 + 1/2 tanh(x/2), so the kernel's tanh-form cell receives x/2 straight from the accumulator (an exact
+        // power-of-two scaling; three multiplies less per cell - at the power cap the cell update's instructions are paid in clock).
         const float *src[3] = {d->lstm_R[0], d->lstm_W[1], d->lstm_R[1]};
         const int P = t->lstm_phases;
         const size_t img_elems = (size_t)H4 * H;
@@ -274,14 +278,35 @@ int tc_model_init(mdf_model *m, const mdf_model_desc *d)
             for (int s = 0; s < H / 64; ++s)
                 for (int gate = 0; gate < 4; ++gate)
                     for (int u = 0; u < 64; ++u)
-                        std::copy(src[mi] + (size_t)(gate * H + s * 64 + u) * H, src[mi] + (size_t)(gate * H + s * 64 + u + 1) * H,
-                                  Wp.begin() + (size_t)(s * 256 + gate * 64 + u) * H);
+                    {
+                        const float *row = src[mi] + (size_t)(gate * H + s * 64 + u) * H;
+                        float *dst = Wp.data() + (size_t)(s * 256 + gate * 64 + u) * H;
+                        const float sc = gate < 3 ? 0.5f : 1.0f;
+                        for (int k = 0; k < H; ++k) dst[k] = row[k] * sc;
+                    }
             build_dither_images_host(Wp.data(), H4, H, P, all.data() + (size_t)mi * (P + 2) * img_elems);
             build_image_host(Wp.data(), H4, H, false, H, hi, lo);
             std::copy(hi.begin(), hi.end(), all.begin() + ((size_t)mi * (P + 2) + P) * img_elems);
             std::copy(lo.begin(), lo.end(), all.begin() + ((size_t)mi * (P + 2) + P + 1) * img_elems);
         }
         MDF_TRY(upload_half(m, &t->lstm_fused_W, all));
+        std::vector<float> ftab((size_t)26 * H * 4), fb2((size_t)H * 4, 0.0f);
+        std::vector<float> b1(H4, 0.0f), b2(H4, 0.0f);
+        if (d->lstm_B[0]) for (int r = 0; r < H4; ++r) b1[r] = d->lstm_B[0][r] + d->lstm_B[0][H4 + r];
+        if (d->lstm_B[1]) for (int r = 0; r < H4; ++r) b2[r] = d->lstm_B[1][r] + d->lstm_B[1][H4 + r];
+        for (int unit = 0; unit < H; ++unit)
+            for (int gate = 0; gate < 4; ++gate) {
+                const float sc = gate < 3 ? 0.5f : 1.0f;
+                for (int aa = 0; aa < 26; ++aa)
+                    ftab[((size_t)aa * H + unit) * 4 + gate] = (d->lstm_W[0][(size_t)(gate * H + unit) * m->I + aa] + b1[gate * H + unit]) * sc;
+                fb2[(size_t)unit * 4 + gate] = b2[gate * H + unit] * sc;
+            }
+        MDF_CUDA(cudaMalloc((void **)&t->lstm_fused_tab, ftab.size() * sizeof(float)));
+        m->owned.push_back(t->lstm_fused_tab);
+        MDF_CUDA(cudaMemcpy(t->lstm_fused_tab, ftab.data(), ftab.size() * sizeof(float), cudaMemcpyHostToDevice));
+        MDF_CUDA(cudaMalloc((void **)&t->lstm_fused_b2, fb2.size() * sizeof(float)));
+        m->owned.push_back(t->lstm_fused_b2);
+        MDF_CUDA(cudaMemcpy(t->lstm_fused_b2, fb2.data(), fb2.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
     if (lstm_tc_smem_bytes(H) > 227 * 1024) return MDF_OK;   // cannot keep the slices resident: engine unavailable
     t->ok = true;
@@ -773,7 +798,7 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto, const std::function<int()> 
     } else if (fused) {
         // both layers + the layer-2 input projection in one persistent wavefront kernel (lstm_fused.cu)
         ProfScope ps(ctx, "lstm_fused", 3.0 * 2.0 * T * 4 * m->H * m->H);
-        MDF_TRY(launch_lstm_fused(ctx, m->H, n, tm->lstm_fused_W, tm->lstm_phases, tm->lstm_tab_full, tm->lstm_bperm[1], idx_pad, b->d_order,
+        MDF_TRY(launch_lstm_fused(ctx, m->H, n, tm->lstm_fused_W, tm->lstm_phases, tm->lstm_fused_tab, tm->lstm_fused_b2, idx_pad, b->d_order,
                                   b->d_seq_off, row_off, ctx->debug_taps ? Hlimg[0] : nullptr, Hlimg[1], scratch, b->h_order.data(),
                                   b->h_seq_off.data()));
         b->tap_h[0] = b->tap_h[1] = nullptr;
