@@ -505,6 +505,9 @@ gemm_pair_kernel(const __grid_constant__ PairGemmArgs pa)
         // ===================== MMA issuer (leader CTA): converged warp, elected lane issues
         if (leader) {
             constexpr uint32_t idesc = umma_idesc_f16(256, 256);
+            const uint32_t full_bar0 = pin_u32(smem_u32(&bars.full[0])), empty_bar0 = pin_u32(smem_u32(&bars.empty[0]));
+            const uint32_t tfull_bar0 = pin_u32(smem_u32(&bars.tmem_full[0]));
+            const uint64_t desc0 = pin_u64(umma_smem_desc(smem_u32(smem), TILE_LBO, TILE_SBO));
             int st = 0; uint32_t ph = 0;
             int acc = 0; uint32_t acc_ph = 0;
             for (int grp = pair; grp < outer; grp += n_pairs)
@@ -513,20 +516,18 @@ gemm_pair_kernel(const __grid_constant__ PairGemmArgs pa)
                 tcgen05_fence_after();
                 const uint32_t d0 = tmem_base + (uint32_t)(acc * BN);
                 for (int kb = 0; kb < g.nkb; ++kb) {
-                    mbar_wait(&bars.full[st], ph);
-                    tcgen05_fence_after();
-                    const uint32_t sa = smem_u32(smem + (size_t)st * stage_bytes);
-                    const uint32_t sb = sa + a_bytes;
-                    for (int ta = 0; ta < a_terms; ++ta)
-                        for (int tb = 0; tb < b_terms; ++tb)
-#pragma unroll
-                            for (int ks = 0; ks < TILE_K / 16; ++ks) {
-                                const uint64_t ad = umma_smem_desc(sa + ta * TILE_BYTES + ks * 2 * TILE_LBO, TILE_LBO, TILE_SBO);
-                                const uint64_t bd = umma_smem_desc(sb + tb * TILE_BYTES + ks * 2 * TILE_LBO, TILE_LBO, TILE_SBO);
-                                umma_f16_pair_elect(d0, ad, bd, idesc, (kb | ks | ta | tb) != 0);
-                            }
-                    umma_commit_pair_elect(&bars.empty[st], 3);    // frees the stage in both CTAs when the MMAs retire
-                    if (kb == g.nkb - 1) umma_commit_pair_elect(&bars.tmem_full[acc], 3);
+                    // one wait + one elected asm block per (A term, B term) pair: four K = 16 MMAs, the last pair also carries the
+                    // commits (stage free in both CTAs; accumulator full after the last k-block)
+                    mbar_wait1_asm(full_bar0 + 8u * st, ph);
+                    const uint64_t sdesc = desc0 + (uint64_t)(st * (stage_bytes >> 4));
+                    const int npairs = a_terms * b_terms;
+                    for (int tp = 0; tp < npairs; ++tp) {
+                        const int ta = tp / b_terms, tb = tp % b_terms;
+                        const bool last = tp == npairs - 1;
+                        umma_f16_pair_kblock_elect(d0, sdesc + (uint64_t)(ta * (TILE_BYTES >> 4)), sdesc + (uint64_t)((a_bytes + tb * TILE_BYTES) >> 4), idesc,
+                                                   (kb | tp) ? 1u : 0u, 0u, 0u, last ? empty_bar0 + 8u * st : 0u, (uint16_t)3,
+                                                   (last && kb == g.nkb - 1) ? tfull_bar0 + 8u * acc : 0u, (uint16_t)3);
+                    }
                     if (++st == stages) { st = 0; ph ^= 1; }
                 }
                 if (++acc == 2) { acc = 0; acc_ph ^= 1; }
