@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lstm_fused_kernel(const __grid_
                                                release_chunks ? hfree0 + 8u * kb : 0u, (uint16_t)(3u << (2 * ((uint32_t)kb & spc_mask))));
                 }
             };
-            // two-term passes (sub-batches above precise_len): 16 stages per pass, still two... four turns of the ring
+            // two-term passes (sub-batches above precise_len): 16 stages per pass = four turns of the ring, parity unchanged as well
             auto pass2 = [&](uint32_t d0, uint32_t accumulate, bool wait_h, bool release_chunks) {
 #pragma unroll 1
                 for (int kb = 0; kb < 8; ++kb) {
@@ -899,8 +899,11 @@ int launch_lstm_fused(mdf_ctx *ctx, int H, int n, const __half *W, int phases, c
                 for (int j = 0; j < 4; ++j) w[j] += tw[i * 4 + j];
                 ++k;
             }
-            if (k) fprintf(stderr, "[lstm fused trace] issuer waits per tick: operand chunks %.0f cyc (of which in P1 %.0f), weights %.0f, accumulator drain %.0f\n",
-                           w[1] / k, w[0] / k, w[2] / k, w[3] / k);
+            // (the straight-line issuer does not time its waits: the clock reads cost more than the waits; MDF_LSTM_ABLATE=64 selects the
+            // generic loop, which does)
+            if (k && (w[1] + w[2] + w[3]) > 0)
+                fprintf(stderr, "[lstm fused trace] issuer waits per tick: operand chunks %.0f cyc (of which in P1 %.0f), weights %.0f, accumulator drain %.0f\n",
+                        w[1] / k, w[0] / k, w[2] / k, w[3] / k);
         }
         {
             // layer-1 operand of tick i (h1_{i-1}), relative to the issuer's start of tick i (ns, globaltimer):
