@@ -90,6 +90,19 @@ int mdf_cmap_build_transfer(mdf_ctx *ctx, int n,
                             uint32_t *packed_out, const int64_t *packed_off,
                             int32_t *dense_out, const int64_t *dense_off);
 
+/* The same for n alignments given as arrays of per-alignment pointers (what `pipeline.py:476-481` holds: one gapped query, one
+ * gapped target and one [Lt,3] float32 array per hit).  The library counts the query lengths (characters of q_aln[p] other than
+ * '-'), writes the canonical offsets seq_off_out[n+1] (residues) and packed_off_out[n+1] (uint32 words, row p: Lq *
+ * mdf_packed_row_words(Lq)), packs the inputs into pinned staging memory on MDF_HOST_THREADS host threads and runs the fused
+ * kernels.  packed_out == NULL: sizes only (no GPU work) - call once to size the output, once to fill it;
+ * packed_capacity_words < packed_off_out[n] is MDF_EINVAL.  packed_out may be pageable or pinned. */
+int mdf_cmap_build_transfer_ragged(mdf_ctx *ctx, int n,
+                                   const float *const *coords, const int *coord_rows,
+                                   const char *const *q_aln, const char *const *t_aln, const int *aln_len,
+                                   float thr2, int generated_contacts,
+                                   uint32_t *packed_out, size_t packed_capacity_words,
+                                   int64_t *packed_off_out, int64_t *seq_off_out);
+
 /* ---- predict.pyx:50-73  Predictor.__init__ / _load_model --------------------------------------
  * The host side parses the .onnx file and hands the initialisers over as fp32 host arrays in
  * ONNX layout. */

@@ -148,7 +148,7 @@ def lib() -> C.CDLL:
             getattr(L, name).restype = C.c_int
         for name in ("mdf_ctx_create", "mdf_ctx_destroy", "mdf_ctx_synchronize", "mdf_pairwise_sqeuclidean",
                      "mdf_contact_map_dense", "mdf_contact_map_sparse", "mdf_align_contact_map",
-                     "mdf_cmap_build_transfer", "mdf_model_create", "mdf_model_destroy", "mdf_model_set_engine",
+                     "mdf_cmap_build_transfer", "mdf_cmap_build_transfer_ragged", "mdf_model_create", "mdf_model_destroy", "mdf_model_set_engine",
                      "mdf_gcn_forward_dense", "mdf_gcn_forward_packed", "mdf_path_forward", "mdf_batch_upload",
                      "mdf_batch_destroy", "mdf_path_run", "mdf_path_run_stages", "mdf_path_run_shared",
                      "mdf_batch_fetch_scores", "mdf_batch_fetch"):
@@ -165,7 +165,7 @@ EXPORTED_SYMBOLS = [
     "mdf_batch_upload", "mdf_batch_destroy", "mdf_path_run", "mdf_path_run_stages", "mdf_path_run_shared",
     "mdf_batch_fetch_scores", "mdf_batch_fetch", "mdf_batch_scores_device", "mdf_batch_unpack_dense", "mdf_batch_invalidate",
     "mdf_cnn_model_create", "mdf_cnn_model_destroy", "mdf_cnn_forward", "mdf_cnn_upload", "mdf_cnn_run", "mdf_cnn_fetch",
-    "mdf_path_submit", "mdf_path_submit_ragged", "mdf_path_wait",
+    "mdf_path_submit", "mdf_path_submit_ragged", "mdf_path_wait", "mdf_cmap_build_transfer_ragged",
     "mdf_pdb_calpha", "mdf_pdb_calpha_batch", "mdf_coords_cache_create", "mdf_coords_cache_open", "mdf_coords_cache_close",
     "mdf_coords_cache_size", "mdf_coords_cache_lookup", "mdf_coords_cache_entry",
     "mdf_nw_align",

@@ -153,6 +153,7 @@ extern "C" int mdf_ctx_destroy(mdf_ctx *c)
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     if (c->copy_done) cudaEventDestroy(c->copy_done);
     if (c->d2h_stream) { cudaStreamSynchronize(c->d2h_stream); cudaStreamDestroy(c->d2h_stream); }
+    if (c->rag_pin) cudaFreeHost(c->rag_pin);
     for (int i = 0; i < 2; ++i) if (c->path_done[i]) cudaEventDestroy(c->path_done[i]);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -1030,6 +1031,73 @@ extern "C" int mdf_cmap_build_transfer(mdf_ctx *ctx, int n, const float *coords,
     MDF_CUDA(cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     MDF_CUDA(cudaStreamSynchronize(ctx->stream));
     return ctx->check_device_error("mdf_cmap_build_transfer");
+}
+
+// n alignments as arrays of per-alignment pointers: count the query lengths, pack into pinned staging (host threads), then the flat
+// entry point above.  packed_out == nullptr: offsets only.
+extern "C" int mdf_cmap_build_transfer_ragged(mdf_ctx *ctx, int n, const float *const *coords, const int *coord_rows,
+                                              const char *const *q_aln, const char *const *t_aln, const int *aln_len, float thr2, int gen,
+                                              uint32_t *packed_out, size_t packed_capacity_words, int64_t *packed_off_out,
+                                              int64_t *seq_off_out)
+{
+    MDF_REQUIRE(ctx && n >= 0 && packed_off_out && seq_off_out, "mdf_cmap_build_transfer_ragged: bad arguments");
+    MDF_REQUIRE(n == 0 || (q_aln && aln_len), "mdf_cmap_build_transfer_ragged: alignment arrays missing");
+    const int nt = std::max(1, std::min(ctx->host_threads, n / 256));
+    auto run_threads = [&](auto &&fn) {
+        if (nt == 1) { fn(0, n); return; }
+        std::vector<std::thread> th;
+        for (int k = 0; k < nt; ++k) th.emplace_back(fn, (int)((int64_t)n * k / nt), (int)((int64_t)n * (k + 1) / nt));
+        for (auto &t : th) t.join();
+    };
+    for (int p = 0; p < n; ++p) MDF_REQUIRE(aln_len[p] >= 0 && (q_aln[p] || aln_len[p] == 0), "mdf_cmap_build_transfer_ragged: alignment %d is missing", p);
+    std::vector<int> lq((size_t)n, 0);
+    run_threads([&](int lo, int hi) {
+        for (int p = lo; p < hi; ++p) {
+            const char *q = q_aln[p];
+            int c = 0;
+            for (int i = 0; i < aln_len[p]; ++i) c += q[i] != '-';
+            lq[p] = c;
+        }
+    });
+    seq_off_out[0] = packed_off_out[0] = 0;
+    for (int p = 0; p < n; ++p) {
+        seq_off_out[p + 1] = seq_off_out[p] + lq[p];
+        packed_off_out[p + 1] = packed_off_out[p] + (int64_t)lq[p] * mdf_packed_row_words(lq[p]);
+    }
+    if (!packed_out) return MDF_OK;
+    MDF_REQUIRE(coords && coord_rows && t_aln, "mdf_cmap_build_transfer_ragged: input arrays missing");
+    MDF_REQUIRE((int64_t)packed_capacity_words >= packed_off_out[n], "mdf_cmap_build_transfer_ragged: output holds %zu words, %lld needed",
+                packed_capacity_words, (long long)packed_off_out[n]);
+    MDF_CUDA(cudaSetDevice(ctx->device));
+    int64_t R = 0, A = 0;
+    for (int p = 0; p < n; ++p) {
+        MDF_REQUIRE(coord_rows[p] >= 0 && (coords[p] || coord_rows[p] == 0), "mdf_cmap_build_transfer_ragged: alignment %d has no coordinates", p);
+        MDF_REQUIRE(t_aln[p] || aln_len[p] == 0, "mdf_cmap_build_transfer_ragged: alignment %d has no target string", p);
+        R += coord_rows[p]; A += aln_len[p];
+    }
+    const size_t off_b = align_up((size_t)(n + 1) * 8, 256);
+    const size_t crd_at = 2 * off_b, qa_at = crd_at + align_up((size_t)R * 12 + 16, 256), ta_at = qa_at + align_up((size_t)A + 16, 256),
+                 total = ta_at + align_up((size_t)A + 16, 256);
+    if (ctx->rag_pin_bytes < total) {
+        if (ctx->rag_pin) MDF_CUDA(cudaFreeHost(ctx->rag_pin));
+        ctx->rag_pin = nullptr; ctx->rag_pin_bytes = 0;
+        const size_t want = align_up(total + total / 4, 2u << 20);
+        cudaError_t e = cudaHostAlloc((void **)&ctx->rag_pin, want, cudaHostAllocDefault);
+        if (e != cudaSuccess) { cudaGetLastError(); set_error("cudaHostAlloc(%zu bytes) failed: %s", want, cudaGetErrorString(e)); return MDF_ENOMEM; }
+        ctx->rag_pin_bytes = want;
+    }
+    int64_t *co = (int64_t *)ctx->rag_pin, *ao = (int64_t *)(ctx->rag_pin + off_b);
+    co[0] = ao[0] = 0;
+    for (int p = 0; p < n; ++p) { co[p + 1] = co[p] + coord_rows[p]; ao[p + 1] = ao[p] + aln_len[p]; }
+    float *pc = (float *)(ctx->rag_pin + crd_at);
+    char *pq = ctx->rag_pin + qa_at, *pt = ctx->rag_pin + ta_at;
+    run_threads([&](int lo, int hi) {
+        for (int p = lo; p < hi; ++p) {
+            if (coord_rows[p]) memcpy(pc + co[p] * 3, coords[p], (size_t)coord_rows[p] * 12);
+            if (aln_len[p]) { memcpy(pq + ao[p], q_aln[p], (size_t)aln_len[p]); memcpy(pt + ao[p], t_aln[p], (size_t)aln_len[p]); }
+        }
+    });
+    return mdf_cmap_build_transfer(ctx, n, pc, co, pq, pt, ao, seq_off_out, thr2, gen, packed_out, packed_off_out, nullptr, nullptr);
 }
 
 // ------------------------------------------------------------------------------------------- model

@@ -89,6 +89,7 @@ struct mdf_ctx {
     // second stream for the structure inputs of mdf_path_forward: their host->device copy runs beside the LSTM language model,
     // which only needs the sequences; the contact-map stage waits for `copy_done`
     cudaStream_t copy_stream = nullptr;
+    char *rag_pin = nullptr; size_t rag_pin_bytes = 0;   // pinned staging of the synchronous ragged entry points (grow-only)
     cudaStream_t d2h_stream = nullptr;       // scores of asynchronous jobs leave on their own stream: the next job's kernels start at once
     cudaEvent_t path_done[2] = {nullptr, nullptr};   // per job slot: kernels of the job finished (compute stream)
     cudaEvent_t copy_done = nullptr;
