@@ -94,7 +94,7 @@ int mdf_cmap_build_transfer(mdf_ctx *ctx, int n,
  * gapped target and one [Lt,3] float32 array per hit).  The library counts the query lengths (characters of q_aln[p] other than
  * '-'), writes the canonical offsets seq_off_out[n+1] (residues) and packed_off_out[n+1] (uint32 words, row p: Lq *
  * mdf_packed_row_words(Lq)), packs the inputs into pinned staging memory on MDF_HOST_THREADS host threads and runs the fused
- * kernels.  packed_out == NULL: sizes only (no GPU work) - call once to size the output, once to fill it;
+ * kernels.  packed_out == NULL: sizes only (host work, no GPU, ctx may be NULL) - call once to size the output, once to fill it;
  * packed_capacity_words < packed_off_out[n] is MDF_EINVAL.  packed_out may be pageable or pinned. */
 int mdf_cmap_build_transfer_ragged(mdf_ctx *ctx, int n,
                                    const float *const *coords, const int *coord_rows,

@@ -1040,9 +1040,9 @@ extern "C" int mdf_cmap_build_transfer_ragged(mdf_ctx *ctx, int n, const float *
                                               uint32_t *packed_out, size_t packed_capacity_words, int64_t *packed_off_out,
                                               int64_t *seq_off_out)
 {
-    MDF_REQUIRE(ctx && n >= 0 && packed_off_out && seq_off_out, "mdf_cmap_build_transfer_ragged: bad arguments");
+    MDF_REQUIRE((ctx || !packed_out) && n >= 0 && packed_off_out && seq_off_out, "mdf_cmap_build_transfer_ragged: bad arguments");
     MDF_REQUIRE(n == 0 || (q_aln && aln_len), "mdf_cmap_build_transfer_ragged: alignment arrays missing");
-    const int nt = std::max(1, std::min(ctx->host_threads, n / 256));
+    const int nt = std::max(1, std::min(ctx ? ctx->host_threads : 4, n / 256));         // (sizes only: host work, no context needed)
     auto run_threads = [&](auto &&fn) {
         if (nt == 1) { fn(0, n); return; }
         std::vector<std::thread> th;

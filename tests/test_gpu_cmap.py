@@ -138,3 +138,38 @@ def test_full_size_properties():
         assert not a[i].view(np.uint8).reshape(L, -1)[:, (L + 7) // 8 + 1:].any()      # padding bits stay 0
         if i % 16 == 0:
             assert np.array_equal(d, co.build_align_contact_map(al.gapped_sequence, al.gapped_target, al.coords, 6, 2))
+
+
+def test_build_align_contact_maps_into_caller_arena():
+    """`build_align_contact_maps(packed=True, out=arena)` (lists -> `mdf_cmap_build_transfer_ragged`): maps are views of the
+    caller's buffer, identical to the oracle; an arena that is too small is refused before any GPU work."""
+    import cmap_oracle as co
+    from metagenomic_deepfri_b200 import batching, bio_utils, synth
+
+    class Aln:
+        pass
+    wl = synth.make_workload(60, 1, 420, seed=5, threshold=6.0)
+    alns = []
+    for i in range(len(wl)):
+        a = Aln()
+        a.target_name = f"t{i}"
+        a.coords, a.gapped_sequence, a.gapped_target = wl.coords[i], wl.gapped_query[i], wl.gapped_target[i]
+        alns.append(a)
+    alns[4].coords = None
+    alns[7].coords = alns[7].coords.astype(np.float64)                 # converted like the reference's astype
+    alns[9].coords = alns[9].coords[: max(1, len(alns[9].coords) // 2)]
+    words = sum(len(q) * ((len(q) + 127) // 128 * 4) for q in wl.query_seqs)
+    arena = np.zeros(words + 7, np.uint32)
+    for thr, gen in ((6.0, 2), (10.0, 0)):
+        maps = bio_utils.build_align_contact_maps(alns, thr, gen, packed=True, out=arena)
+        plain = bio_utils.build_align_contact_maps(alns, thr, gen, packed=True)
+        for i, a in enumerate(alns):
+            want = co.build_align_contact_map(a.gapped_sequence, a.gapped_target, a.coords, thr, gen)
+            if want is None:
+                assert maps[i] is None and plain[i] is None
+                continue
+            assert np.shares_memory(maps[i], arena)
+            assert np.array_equal(batching.unpack_bits(maps[i], want.shape[0]), want), i
+            assert np.array_equal(maps[i], plain[i])
+    with pytest.raises(ValueError):
+        bio_utils.build_align_contact_maps(alns, 6.0, 2, packed=True, out=np.zeros(8, np.uint32))

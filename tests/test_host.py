@@ -93,3 +93,21 @@ def test_pack_checked_matches_per_sequence_encoding():
         predict._pack_checked(["aCD"])
     with pytest.raises(UnicodeEncodeError):
         predict._pack_checked(["ACé"])
+
+
+def test_cmap_ragged_sizes_only_needs_no_gpu():
+    """`mdf_cmap_build_transfer_ragged(packed_out=NULL)`: query lengths and canonical offsets from the gapped query strings, on
+    the host (this is what sizes the output arena of `bio_utils.build_align_contact_maps(out=...)`)."""
+    import numpy as np
+    from metagenomic_deepfri_b200 import _lib
+    host = _lib.pyhost()
+    fn = _lib.fn_addr("mdf_cmap_build_transfer_ragged")
+    gq = ["AC-DE", "----", "", "M" * 129 + "-" * 3 + "K", "A-" * 300]
+    rc, poff, soff = host.cmap_ragged(fn, 0, gq, None, None, 36.0, 2, 0, 0)
+    assert rc == 0
+    lens = [len(q) - q.count("-") for q in gq]
+    assert np.frombuffer(soff, np.int64).tolist() == np.concatenate([[0], np.cumsum(lens)]).tolist()
+    words = [L * _lib.packed_row_words(L) for L in lens]
+    assert np.frombuffer(poff, np.int64).tolist() == np.concatenate([[0], np.cumsum(words)]).tolist()
+    with pytest.raises(UnicodeEncodeError):
+        host.cmap_ragged(fn, 0, ["AC\u00e9"], None, None, 36.0, 2, 0, 0)
