@@ -544,6 +544,10 @@ def run_b200(args, rank, world, local_rank, inputs):
                 job_board = None
         if job_board is None:
             job_gather = distributed.ScoreGather(len(my_ids), sharded["job_n"], C)
+        result_gather = ("none (one rank)" if world == 1 else
+                         "NCCL gather + one device->host copy on rank 0" if job_board is None else
+                         "node-local shared result matrix (%s), rows scattered per chunk, barrier" %
+                         ("page-locked" if job_board._registered else "pageable"))
         barrier()
         t0 = time.perf_counter()
         distributed.stream_chunks(submit, [(c, len(c)) for c in my_chunks], job_out, on_done=on_done)
@@ -564,7 +568,7 @@ def run_b200(args, rank, world, local_rank, inputs):
                "chunks_per_rank": len(my_chunks), "imbalance_measured": t_rank_max / busy if busy else None,
                "imbalance_predicted_lpt": sharded["pred_imb"], "gather_and_tail_s": job_s - t_rank_max,
                "input": "Python lists of str / ndarray per protein -> Predictor.submit_structures (two jobs in flight)",
-               "generator_s": round(gen_s, 1)}
+               "result_gather": result_gather, "generator_s": round(gen_s, 1)}
 
     # max over ranks
     dev_ms, e2e_ms = allmax(dev_ms, e2e_s * 1e3)
