@@ -195,7 +195,7 @@ __device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, int lane)
     return x;
 }
 
-__global__ void __launch_bounds__(PAIR_WARPS * 32, 6)
+__global__ void __launch_bounds__(PAIR_WARPS * 32, 8)
 cmap_pair_sym_kernel(const int2 *__restrict__ work, const float4 *__restrict__ qc,
                      const int64_t *__restrict__ seq_off, float thr2,
                      uint32_t *__restrict__ packed, const int64_t *__restrict__ packed_off)
