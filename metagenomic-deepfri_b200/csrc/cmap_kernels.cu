@@ -267,6 +267,110 @@ cmap_pair_sym_kernel(const int2 *__restrict__ work, const float4 *__restrict__ q
     }
 }
 
+// a volatile shared-memory row load: the optimiser must not hoist the 32 (loop-invariant) rows out of the unit loop into
+// 96 registers per lane
+__device__ __forceinline__ float4 lds_row(uint32_t addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
+// Diagonal and generated contacts (contact_map_utils.pyx:82-97) of one 32 x 32 block in column orientation (lane = column c,
+// bit r = row i0 + r; dg = (group of c) - (group of the rows) >= 0):  out[i][i] = diag_val ? 1 : computed;  out[i][c] = 1 for
+// 0 < |c - i| <= gen when residue i or residue c was generated (a query residue facing a target gap).
+__device__ __forceinline__ uint32_t band_bits(int dg, int lane, int gen, int diag_val, bool col_ok, bool col_gen,
+                                              uint32_t row_gen /* bit r = row r generated */, uint32_t row_ok /* bit r = row < L */)
+{
+    const int ctr = 32 * dg + lane;                                          // c - i0: the row bit that faces column c
+    const int lo = max(ctr - gen, 0), hi = min(ctr + gen, 31);
+    uint32_t m = 0u;
+    if (col_ok && lo <= hi) {
+        m = (0xffffffffu >> (31 - hi)) & (0xffffffffu << lo);
+        const uint32_t dbit = dg == 0 ? 1u << lane : 0u;
+        m &= ~dbit;
+        m = col_gen ? (m & row_ok) : (m & row_gen);
+        if (diag_val) m |= dbit & row_ok;
+    }
+    return m;
+}
+
+// Triangular form (the default).  One warp per (protein, 32-row block rb): the warp walks the 32-column groups rb .. nb-1 of its
+// rows (exactly the upper triangle at 32 x 32 granularity; the diagonal block in full) in units of four groups that start AT its
+// own group, the last unit group by group, and writes every block twice: as row words (word cb of its 32 rows, after a 32 x 32 bit
+// transpose across the warp) and, right of the diagonal, transposed (word rb of the group's 32 rows).  Every word of the map is
+// written exactly once: words >= group(row) by the row's own warp, words < group(row) by the transposed stores of warp (word),
+// row padding words (nb .. rw-1) by the row's own warp.  Diagonal and generated contacts are OR-ed into the blocks next to the
+// diagonal before both stores (no second pass over the map).  Single-warp CTAs: no warp of a CTA waits for another one's tail.
+__global__ void __launch_bounds__(32, 32)
+cmap_pair_tri_kernel(const int2 *__restrict__ work, const float4 *__restrict__ qc,
+                     const int64_t *__restrict__ seq_off, float thr2, int gen, int diag_val,
+                     uint32_t *__restrict__ packed, const int64_t *__restrict__ packed_off)
+{
+    __shared__ float4 rows[32];
+    const int p = work[blockIdx.x].x, rb = work[blockIdx.x].y;
+    const int64_t s0 = seq_off[p];
+    const int L = (int)(seq_off[p + 1] - s0);
+    const int rw = packed_row_words(L);
+    const float4 *__restrict__ q = qc + s0;
+    const float qnan = __int_as_float(0x7fc00000);
+    const int lane = threadIdx.x;
+    const int i = rb * 32 + lane;
+    const bool rowok = i < L;
+    const float4 mine = rowok ? q[i] : make_float4(qnan, qnan, qnan, 0.f);
+    rows[lane] = mine;
+    const uint32_t row_ok = __ballot_sync(0xffffffffu, rowok);
+    const uint32_t row_gen = __ballot_sync(0xffffffffu, rowok && (__float_as_int(mine.w) & 1));
+    __syncwarp();
+    const uint32_t rows_s = (uint32_t)__cvta_generic_to_shared(rows);
+    uint32_t *__restrict__ out = packed + packed_off[p];
+    uint32_t *__restrict__ rowp = out + (size_t)i * rw;                      // lane r stores the words of row rb*32 + r
+    const int nb = (L + 31) >> 5;
+    const int band_groups = (31 + gen) >> 5;                                  // groups rb .. rb + band_groups hold diagonal / generated contacts
+    int cb = rb;
+    for (; cb + 4 <= nb; cb += 4) {
+        float cx[4], cy[4], cz[4];
+        uint32_t tw[4];                                                       // bit r = contact(row rb*32 + r, column (cb+k)*32 + lane)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c = (cb + k) * 32 + lane;
+            const float4 v = c < L ? q[c] : make_float4(qnan, qnan, qnan, 0.f);
+            cx[k] = v.x; cy[k] = v.y; cz[k] = v.z;
+            tw[k] = cb + k - rb <= band_groups ? band_bits(cb + k - rb, lane, gen, diag_val, c < L, __float_as_int(v.w) & 1, row_gen, row_ok) : 0u;
+        }
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+            const float4 a = lds_row(rows_s + 16 * r);                        // rows past L hold NaN -> no contact
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (sqdist3(a.x, a.y, a.z, cx[k], cy[k], cz[k]) < thr2) tw[k] |= 1u << r;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c = (cb + k) * 32 + lane;
+            if (cb + k > rb && c < L) out[(size_t)c * rw + rb] = tw[k];       // transposed copy: word rb of the group's rows
+            const uint32_t rowword = warp_transpose32(tw[k], lane);
+            if (rowok) rowp[cb + k] = rowword;
+        }
+    }
+#pragma unroll 1
+    for (; cb < nb; ++cb) {
+        const int c = cb * 32 + lane;
+        const float4 v = c < L ? q[c] : make_float4(qnan, qnan, qnan, 0.f);
+        uint32_t t1 = cb - rb <= band_groups ? band_bits(cb - rb, lane, gen, diag_val, c < L, __float_as_int(v.w) & 1, row_gen, row_ok) : 0u;
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+            const float4 a = lds_row(rows_s + 16 * r);
+            if (sqdist3(a.x, a.y, a.z, v.x, v.y, v.z) < thr2) t1 |= 1u << r;
+        }
+        if (cb > rb && c < L) out[(size_t)c * rw + rb] = t1;
+        const uint32_t rowword = warp_transpose32(t1, lane);
+        if (rowok) rowp[cb] = rowword;
+    }
+    if (rowok)                                                                // row padding words behind the last group
+        for (int w = nb; w < rw; ++w) rowp[w] = 0u;
+}
+
 // Diagonal and generated contacts (contact_map_utils.pyx:82-97): out[i][i] = diag_val ? 1 : computed; out[i][i +- d] = 1 for
 // d = 1..gen when residue i or residue i +- d was generated (a query residue facing a target gap).  One thread per row, at
 // most 2 gen + 1 bits: OR-ed into the words cmap_pair_kernel wrote.
@@ -499,10 +603,15 @@ int launch_cmap_pair(mdf_ctx *ctx, int n, int nwork, const int2 *work, const flo
 {
     if (nwork <= 0) return MDF_OK;
     static const bool full_square = getenv("MDF_CMAP_SYM") && atoi(getenv("MDF_CMAP_SYM")) == 0;   // A/B switch: evaluate both triangles
+    const bool old_sym = getenv("MDF_CMAP_VAR") && atoi(getenv("MDF_CMAP_VAR")) == 0;              // scratch A/B: round-2 symmetric kernel + band pass
     if (full_square)
         cmap_pair_kernel<<<nwork, PAIR_WARPS * 32, 0, ctx->stream>>>(work, qc, seq_off, thr2, gen < 0 ? 0 : gen,
                                                                      diag_val, packed, packed_off);
-    else
+    else if (!old_sym) {
+        cmap_pair_tri_kernel<<<nwork, 32, 0, ctx->stream>>>(work, qc, seq_off, thr2, gen < 0 ? 0 : gen, diag_val, packed, packed_off);
+        MDF_LAUNCH_CHECK(ctx);
+        return MDF_OK;
+    } else
         cmap_pair_sym_kernel<<<nwork, PAIR_WARPS * 32, 0, ctx->stream>>>(work, qc, seq_off, thr2, packed, packed_off);
     MDF_LAUNCH_CHECK(ctx);
     if (n > 0 && (diag_val || gen > 0)) {
