@@ -327,27 +327,38 @@ cmap_pair_tri_kernel(const int2 *__restrict__ work, const float4 *__restrict__ q
     uint32_t *__restrict__ rowp = out + (size_t)i * rw;                      // lane r stores the words of row rb*32 + r
     const int nb = (L + 31) >> 5;
     const int band_groups = (31 + gen) >> 5;                                  // groups rb .. rb + band_groups hold diagonal / generated contacts
+    // The row loop is unrolled by 8 only (a 5 KB loop body per unit instead of 22 KB of straight-line code: with 32 warps per SM
+    // at different places of a fully unrolled unit, a quarter of all issue slots were lost to instruction-cache misses); each
+    // 8-row chunk collects its bits with constant masks and is funnel-shifted into the word from the top.
     int cb = rb;
     for (; cb + 4 <= nb; cb += 4) {
         float cx[4], cy[4], cz[4];
-        uint32_t tw[4];                                                       // bit r = contact(row rb*32 + r, column (cb+k)*32 + lane)
+        uint32_t tw[4] = {0u, 0u, 0u, 0u};                                    // bit r = contact(row rb*32 + r, column (cb+k)*32 + lane)
+        uint32_t cgen = 0u;                                                   // bit k = column of group cb+k is a generated residue
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int c = (cb + k) * 32 + lane;
             const float4 v = c < L ? q[c] : make_float4(qnan, qnan, qnan, 0.f);
             cx[k] = v.x; cy[k] = v.y; cz[k] = v.z;
-            tw[k] = cb + k - rb <= band_groups ? band_bits(cb + k - rb, lane, gen, diag_val, c < L, __float_as_int(v.w) & 1, row_gen, row_ok) : 0u;
+            cgen |= (uint32_t)(__float_as_int(v.w) & 1) << k;
         }
+#pragma unroll 1
+        for (int o = 0; o < 4; ++o) {
+            uint32_t t8[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-        for (int r = 0; r < 32; ++r) {
-            const float4 a = lds_row(rows_s + 16 * r);                        // rows past L hold NaN -> no contact
+            for (int r = 0; r < 8; ++r) {
+                const float4 a = lds_row(rows_s + 128 * o + 16 * r);          // rows past L hold NaN -> no contact
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (sqdist3(a.x, a.y, a.z, cx[k], cy[k], cz[k]) < thr2) tw[k] |= 1u << r;
+                for (int k = 0; k < 4; ++k)
+                    if (sqdist3(a.x, a.y, a.z, cx[k], cy[k], cz[k]) < thr2) t8[k] |= 1u << r;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tw[k] = __funnelshift_r(tw[k], t8[k], 8);
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int c = (cb + k) * 32 + lane;
+            if (cb + k - rb <= band_groups) tw[k] |= band_bits(cb + k - rb, lane, gen, diag_val, c < L, (cgen >> k) & 1u, row_gen, row_ok);
             if (cb + k > rb && c < L) out[(size_t)c * rw + rb] = tw[k];       // transposed copy: word rb of the group's rows
             const uint32_t rowword = warp_transpose32(tw[k], lane);
             if (rowok) rowp[cb + k] = rowword;
@@ -357,12 +368,18 @@ cmap_pair_tri_kernel(const int2 *__restrict__ work, const float4 *__restrict__ q
     for (; cb < nb; ++cb) {
         const int c = cb * 32 + lane;
         const float4 v = c < L ? q[c] : make_float4(qnan, qnan, qnan, 0.f);
-        uint32_t t1 = cb - rb <= band_groups ? band_bits(cb - rb, lane, gen, diag_val, c < L, __float_as_int(v.w) & 1, row_gen, row_ok) : 0u;
+        uint32_t t1 = 0u;
+#pragma unroll 1
+        for (int o = 0; o < 2; ++o) {
+            uint32_t t16 = 0u;
 #pragma unroll
-        for (int r = 0; r < 32; ++r) {
-            const float4 a = lds_row(rows_s + 16 * r);
-            if (sqdist3(a.x, a.y, a.z, v.x, v.y, v.z) < thr2) t1 |= 1u << r;
+            for (int r = 0; r < 16; ++r) {
+                const float4 a = lds_row(rows_s + 256 * o + 16 * r);
+                if (sqdist3(a.x, a.y, a.z, v.x, v.y, v.z) < thr2) t16 |= 1u << r;
+            }
+            t1 = __funnelshift_r(t1, t16, 16);
         }
+        if (cb - rb <= band_groups) t1 |= band_bits(cb - rb, lane, gen, diag_val, c < L, __float_as_int(v.w) & 1, row_gen, row_ok);
         if (cb > rb && c < L) out[(size_t)c * rw + rb] = t1;
         const uint32_t rowword = warp_transpose32(t1, lane);
         if (rowok) rowp[cb] = rowword;
