@@ -176,96 +176,35 @@ cmap_pair_kernel(const int2 *__restrict__ work, const float4 *__restrict__ qc,
     }
 }
 
-// Symmetric form (the default).  The query-frame map is symmetric bit for bit - dist(a, b) and dist(b, a) square the same
-// differences with opposite signs, the reference mirrors D[i][j] = D[j][i] (contact_map_utils.pyx:30-35) and argwhere lists
-// both orientations - so a 32-row block only evaluates the 128-column tiles at or right of its own tile and writes every
-// strictly-right tile twice: as rows (words 4t..4t+3 of its 32 rows) and transposed (word rb of the tile's 128 rows).
-// Each lane accumulates the predicate of (row r, its column) into bit r of a register: after 32 rows that register IS the
-// transposed word (one predicated OR per pair, no ballot); the row words come from a 32 x 32 bit transpose across the
-// warp (5 shuffle stages per word).  Every word of the map is written exactly once: words of tiles >= tile(row) by the
-// row's own block, words of tiles < tile(row) by the transposed stores of block (word index).
-__device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, int lane)
-{
+// Per-lane constants of the 32 x 32 bit transpose across a warp: stage j (16, 8, 4, 2, 1) swaps the j x j sub-blocks across
+// lanes l and l ^ j; a lane with bit j set takes (o >> j) & m, the other one (o << j) & ~m - both are a rotation of o (by 32 - j
+// or j) under the complementary mask, so with the lane's keep mask and rotation held in registers a stage is one shuffle, one
+// funnel shift and one LOP3.
+struct Transpose32 {
+    uint32_t keep[5], rot[5];
+    __device__ __forceinline__ explicit Transpose32(int lane)
+    {
 #pragma unroll
-    for (int j = 16; j >= 1; j >>= 1) {
-        const uint32_t m = j == 16 ? 0x0000FFFFu : j == 8 ? 0x00FF00FFu : j == 4 ? 0x0F0F0F0Fu : j == 2 ? 0x33333333u : 0x55555555u;
-        const uint32_t o = __shfl_xor_sync(0xffffffffu, x, j);
-        x = (lane & j) ? (((o >> j) & m) | (x & ~m)) : ((x & m) | ((o & m) << j));
+        for (int s = 0; s < 5; ++s) {
+            const int j = 16 >> s;
+            const uint32_t m = j == 16 ? 0x0000FFFFu : j == 8 ? 0x00FF00FFu : j == 4 ? 0x0F0F0F0Fu : j == 2 ? 0x33333333u : 0x55555555u;
+            const bool up = (lane & j) != 0;
+            // opaque moves: the optimiser would otherwise re-derive the masks from the lane bit with two extra LOP3 per stage
+            asm volatile("mov.b32 %0, %1;" : "=r"(keep[s]) : "r"(up ? ~m : m));
+            asm volatile("mov.b32 %0, %1;" : "=r"(rot[s]) : "r"(up ? 32 - j : j));
+        }
     }
-    return x;
-}
-
-__global__ void __launch_bounds__(PAIR_WARPS * 32, 8)
-cmap_pair_sym_kernel(const int2 *__restrict__ work, const float4 *__restrict__ qc,
-                     const int64_t *__restrict__ seq_off, float thr2,
-                     uint32_t *__restrict__ packed, const int64_t *__restrict__ packed_off)
-{
-    __shared__ float4 rows[32];
-    const int p = work[blockIdx.x].x, rb = work[blockIdx.x].y;
-    const int64_t s0 = seq_off[p];
-    const int L = (int)(seq_off[p + 1] - s0);
-    const int rw = packed_row_words(L);
-    const float4 *__restrict__ q = qc + s0;
-    const float qnan = __int_as_float(0x7fc00000);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x < 32) {
-        const int i = rb * 32 + threadIdx.x;
-        rows[threadIdx.x] = i < L ? q[i] : make_float4(qnan, qnan, qnan, 0.f);
+    __device__ __forceinline__ uint32_t operator()(uint32_t x) const
+    {
+#pragma unroll
+        for (int s = 0; s < 5; ++s) {
+            const uint32_t o = __shfl_xor_sync(0xffffffffu, x, 16 >> s);
+            const uint32_t r = __funnelshift_l(o, o, rot[s]);
+            x = (x & keep[s]) | (r & ~keep[s]);
+        }
+        return x;
     }
-    __syncthreads();
-    uint32_t *__restrict__ out = packed + packed_off[p];
-    const int ntile = (L + 127) >> 7, dt = rb >> 2;              // dt = the tile that holds this block's own columns
-    for (int tile = dt + warp; tile < ntile; tile += PAIR_WARPS) {
-        const int jlo = tile << 7;
-        const int kend = min(4, (L - jlo + 31) >> 5);             // 32-column groups of this tile that hold a column < L
-        if (kend < 4) {
-            // partly filled last tile: one column group at a time (the full-tile body below would spend up to three quarters of
-            // its work on padding columns); the row words of the groups past L are padding and must read as zero
-            for (int k = 0; k < kend; ++k) {
-                const int j = jlo + 32 * k + lane;
-                const float4 v = j < L ? q[j] : make_float4(qnan, qnan, qnan, 0.f);
-                uint32_t t1 = 0u;
-#pragma unroll
-                for (int r = 0; r < 32; ++r) {
-                    const float4 a = rows[r];
-                    if (sqdist3(a.x, a.y, a.z, v.x, v.y, v.z) < thr2) t1 |= 1u << r;
-                }
-                if (tile > dt && j < L) out[(size_t)j * rw + rb] = t1;
-                const uint32_t rowword = warp_transpose32(t1, lane);
-                if (rb * 32 + lane < L) out[(size_t)(rb * 32 + lane) * rw + tile * 4 + k] = rowword;
-            }
-            if (rb * 32 + lane < L)
-                for (int k = kend; k < 4; ++k) out[(size_t)(rb * 32 + lane) * rw + tile * 4 + k] = 0u;
-            continue;
-        }
-        float cx[4], cy[4], cz[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int j = jlo + 32 * k + lane;
-            float4 v = j < L ? q[j] : make_float4(qnan, qnan, qnan, 0.f);
-            cx[k] = v.x; cy[k] = v.y; cz[k] = v.z;
-        }
-        uint32_t tw[4] = {0u, 0u, 0u, 0u};                       // bit r = contact(row rb*32 + r, column jlo + 32k + lane)
-#pragma unroll
-        for (int r = 0; r < 32; ++r) {
-            const float4 a = rows[r];                            // rows past L hold NaN -> no contact
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (sqdist3(a.x, a.y, a.z, cx[k], cy[k], cz[k]) < thr2) tw[k] |= 1u << r;
-        }
-        if (tile > dt) {                                         // transposed copy: word rb of rows jlo .. jlo + 127
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int c = jlo + 32 * k + lane;
-                if (c < L) out[(size_t)c * rw + rb] = tw[k];
-            }
-        }
-        uint4 rowv;                                              // lane r: the four words of row rb*32 + r in this tile
-        rowv.x = warp_transpose32(tw[0], lane); rowv.y = warp_transpose32(tw[1], lane);
-        rowv.z = warp_transpose32(tw[2], lane); rowv.w = warp_transpose32(tw[3], lane);
-        if (rb * 32 + lane < L) *reinterpret_cast<uint4 *>(out + (size_t)(rb * 32 + lane) * rw + tile * 4) = rowv;
-    }
-}
+};
 
 // a volatile shared-memory row load: the optimiser must not hoist the 32 (loop-invariant) rows out of the unit loop into
 // 96 registers per lane
@@ -327,6 +266,7 @@ cmap_pair_tri_kernel(const int2 *__restrict__ work, const float4 *__restrict__ q
     uint32_t *__restrict__ rowp = out + (size_t)i * rw;                      // lane r stores the words of row rb*32 + r
     const int nb = (L + 31) >> 5;
     const int band_groups = (31 + gen) >> 5;                                  // groups rb .. rb + band_groups hold diagonal / generated contacts
+    const Transpose32 transpose(lane);
     // The row loop is unrolled by 8 only (a 5 KB loop body per unit instead of 22 KB of straight-line code: with 32 warps per SM
     // at different places of a fully unrolled unit, a quarter of all issue slots were lost to instruction-cache misses); each
     // 8-row chunk collects its bits with constant masks and is funnel-shifted into the word from the top.
@@ -344,23 +284,23 @@ cmap_pair_tri_kernel(const int2 *__restrict__ work, const float4 *__restrict__ q
         }
 #pragma unroll 1
         for (int o = 0; o < 4; ++o) {
-            uint32_t t8[4] = {0u, 0u, 0u, 0u};
+            float f8[4] = {0.f, 0.f, 0.f, 0.f};                              // the chunk's bits as an exact float sum (< 256)
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
                 const float4 a = lds_row(rows_s + 128 * o + 16 * r);          // rows past L hold NaN -> no contact
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    if (sqdist3(a.x, a.y, a.z, cx[k], cy[k], cz[k]) < thr2) t8[k] |= 1u << r;
+                    if (sqdist3(a.x, a.y, a.z, cx[k], cy[k], cz[k]) < thr2) f8[k] = __fadd_rn(f8[k], (float)(1 << r));
             }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) tw[k] = __funnelshift_r(tw[k], t8[k], 8);
+            for (int k = 0; k < 4; ++k) tw[k] = __funnelshift_r(tw[k], __float2uint_rz(f8[k]), 8);
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int c = (cb + k) * 32 + lane;
             if (cb + k - rb <= band_groups) tw[k] |= band_bits(cb + k - rb, lane, gen, diag_val, c < L, (cgen >> k) & 1u, row_gen, row_ok);
             if (cb + k > rb && c < L) out[(size_t)c * rw + rb] = tw[k];       // transposed copy: word rb of the group's rows
-            const uint32_t rowword = warp_transpose32(tw[k], lane);
+            const uint32_t rowword = transpose(tw[k]);
             if (rowok) rowp[cb + k] = rowword;
         }
     }
@@ -381,7 +321,7 @@ cmap_pair_tri_kernel(const int2 *__restrict__ work, const float4 *__restrict__ q
         }
         if (cb - rb <= band_groups) t1 |= band_bits(cb - rb, lane, gen, diag_val, c < L, __float_as_int(v.w) & 1, row_gen, row_ok);
         if (cb > rb && c < L) out[(size_t)c * rw + rb] = t1;
-        const uint32_t rowword = warp_transpose32(t1, lane);
+        const uint32_t rowword = transpose(t1);
         if (rowok) rowp[cb] = rowword;
     }
     if (rowok)                                                                // row padding words behind the last group
@@ -620,16 +560,12 @@ int launch_cmap_pair(mdf_ctx *ctx, int n, int nwork, const int2 *work, const flo
 {
     if (nwork <= 0) return MDF_OK;
     static const bool full_square = getenv("MDF_CMAP_SYM") && atoi(getenv("MDF_CMAP_SYM")) == 0;   // A/B switch: evaluate both triangles
-    const bool old_sym = getenv("MDF_CMAP_VAR") && atoi(getenv("MDF_CMAP_VAR")) == 0;              // scratch A/B: round-2 symmetric kernel + band pass
-    if (full_square)
-        cmap_pair_kernel<<<nwork, PAIR_WARPS * 32, 0, ctx->stream>>>(work, qc, seq_off, thr2, gen < 0 ? 0 : gen,
-                                                                     diag_val, packed, packed_off);
-    else if (!old_sym) {
+    if (!full_square) {
         cmap_pair_tri_kernel<<<nwork, 32, 0, ctx->stream>>>(work, qc, seq_off, thr2, gen < 0 ? 0 : gen, diag_val, packed, packed_off);
         MDF_LAUNCH_CHECK(ctx);
         return MDF_OK;
-    } else
-        cmap_pair_sym_kernel<<<nwork, PAIR_WARPS * 32, 0, ctx->stream>>>(work, qc, seq_off, thr2, packed, packed_off);
+    }
+    cmap_pair_kernel<<<nwork, PAIR_WARPS * 32, 0, ctx->stream>>>(work, qc, seq_off, thr2, gen < 0 ? 0 : gen, diag_val, packed, packed_off);
     MDF_LAUNCH_CHECK(ctx);
     if (n > 0 && (diag_val || gen > 0)) {
         cmap_band_kernel<<<std::min(n, 16 * ctx->sm_count), 128, 0, ctx->stream>>>(n, qc, seq_off, gen < 0 ? 0 : gen, diag_val, packed, packed_off);

@@ -122,6 +122,30 @@ def test_fused_build_transfer_batch(thr, gen):
     assert bio_utils.build_align_contact_map(alns[3], thr, gen) == (alns[3], None)
 
 
+@pytest.mark.parametrize("gen", [0, 1, 31, 32, 33, 70, 600])
+def test_generated_contact_band_widths(gen):
+    """The triangular kernel ORs the diagonal and the generated contacts (contact_map_utils.pyx:82-97) into the 32 x 32 blocks
+    next to the diagonal instead of running a second pass: bands narrower than, equal to and wider than a block, wider than the
+    whole map, query residues facing target gaps at block borders, lengths around the 32 / 128 boundaries."""
+    rng = np.random.default_rng(gen)
+    alns = []
+    for n, L in enumerate([1, 2, 31, 32, 33, 63, 64, 65, 96, 127, 128, 129, 160, 257, 300, 511]):
+        coords = (rng.normal(size=(L, 3)) * 6).astype(np.float32).round(3)
+        q, t, keep = [], [], []
+        for i in range(L):
+            # target gaps (-> generated residues) in runs, so that generated residues sit on both sides of block borders
+            gap = (i // 7 + n) % 5 == 0 or i % 32 in (0, 31) and (i // 32 + n) % 2 == 0
+            q.append("A")
+            t.append("-" if gap else "G")
+            keep.append(not gap)
+        alns.append(Aln("".join(q), "".join(t), np.ascontiguousarray(coords[np.array(keep)]) if any(keep) else np.zeros((0, 3), np.float32), n))
+    for thr in (6.0, 12):
+        packed = bio_utils.build_align_contact_maps(alns, thr, gen, packed=True)
+        for a, pk in zip(alns, packed):
+            want = co.build_align_contact_map(a.gapped_sequence, a.gapped_target, a.coords, thr, gen)
+            assert np.array_equal(batching.unpack_bits(pk, want.shape[0]), want), (a.target_name, thr, gen)
+
+
 def test_full_size_properties():
     """Config-1 sized inputs (L up to 1000): checked through size-independent properties -
     symmetry (symmetric inputs), unit diagonal, idempotence across calls, and a checksum against

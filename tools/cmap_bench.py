@@ -52,7 +52,7 @@ def main():
     dt = float(np.median(times[2:]))
     alg_bytes = float((12 * lt + 2 * la + lq * lq / 8).sum())
     # SURVEY 8d counts the reference's own work, 9 non-fusable FP32 ops per unordered residue pair (it mirrors D[j][i] = D[i][j]);
-    # the symmetric kernel evaluates the 128-column tiles at or right of each 32-row block (56-75 % of the square)
+    # the triangular kernel evaluates the 32 x 32 blocks at or right of each 32-row block's own (52 % of the square)
     flops = float((9 * lq * (lq - 1) / 2).sum())
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0}
     print(json.dumps({"pairs_per_s": len(wl) / dt, "ms": dt * 1e3, "algorithmic_GBps": alg_bytes / dt / 1e9,
