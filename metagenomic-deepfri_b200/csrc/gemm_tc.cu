@@ -29,10 +29,29 @@ __device__ __forceinline__ float act_f(float v, int act, float alpha)
     return v;
 }
 
+__device__ __forceinline__ int lane_id() { return (int)(threadIdx.x & 31); }
+
+// column sums of a 32 x 32 block held one row per lane: butterfly transpose-reduce, lane l returns the total of column l
+__device__ __forceinline__ float warp_column_sums(float (&c)[32], int lane)
+{
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int j = 0; j < off; ++j) {
+            const float send = upper ? c[j] : c[j + off];
+            const float keep = upper ? c[j + off] : c[j];
+            c[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return c[0];
+}
+
 // One 32-column chunk of an output row: fused scale / bias / activation / gather, then fp16 image or fp32 store.
 template <int EPI>
 __device__ __forceinline__ void gemm_epilogue_chunk(const GemmArgs &g, uint32_t (&r)[32], int64_t m, int n0, float rs,
-                                                    const float *grow, uint8_t *row_ptr, float *pool_row = nullptr)
+                                                    const float *grow, uint8_t *row_ptr, float *pool_row = nullptr,
+                                                    int corr_mode = 0, float corr_c = 0.0f)
 {
     if (EPI == EPI_F32_BIAS) {
         if (m < g.m_valid) {
@@ -54,6 +73,19 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmArgs &g, uint32_t 
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
         if (EPI == EPI_IMG_COLSCALE) {
+            // per-protein correction of the weight rounding (tc_engine.cu, mean-corrected single term).  The caller looked the
+            // chunk's columns up one chunk ahead: mode 1 = all 32 columns belong to one protein (corr_c is its value for this
+            // row), mode 2 = the chunk crosses a protein boundary and every column is looked up here
+            if (corr_mode == 1) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] += corr_c;
+            } else if (corr_mode == 2) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {                           // (fully unrolled: v[] must stay in registers)
+                    const int pj = __ldg(g.col_group + min(n0 + j, g.col_valid - 1));
+                    v[j] += __ldg(g.corr + (size_t)pj * g.corr_ld + m) * g.corr_scale;
+                }
+            }
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const float4 cs = __ldg(reinterpret_cast<const float4 *>(g.colscale + n0 + 4 * q));
@@ -114,18 +146,8 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmArgs &g, uint32_t 
             float c[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) c[j] = rs != 0.0f ? v[j] : 0.0f;
-            const int lane = threadIdx.x & 31;
-#pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) {
-                const bool upper = (lane & off) != 0;
-#pragma unroll
-                for (int j = 0; j < off; ++j) {
-                    const float send = upper ? c[j] : c[j + off];
-                    const float keep = upper ? c[j + off] : c[j];
-                    c[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-                }
-            }
-            if (!(g.ablate & 64) || c[0] == 1234.5f) atomicAdd(pool_row + n0 + lane, c[0]);
+            const float tot = warp_column_sums(c, threadIdx.x & 31);
+            if (!(g.ablate & 64) || tot == 1234.5f) atomicAdd(pool_row + n0 + lane_id(), tot);
         }
         // The adjacency product is bound by HBM bytes (Y^T in, X out), not by the tensor pipe: it never stores pad rows (nothing
         // reads them as values: rows are independent in X.W and its column scale zeroes their Y^T columns), and stores no image
@@ -567,18 +589,35 @@ gemm_pair_kernel(const __grid_constant__ PairGemmArgs pa)
                     grow = g.gtab + (size_t)g.gidx[m] * g.ldg;
                 }
             }
-            mbar_wait(&bars.tmem_full[acc], acc_ph);
-            tcgen05_fence_after();
             const uint32_t trow = tmem_base + ((uint32_t)lb << 16) + (uint32_t)(acc * BN);
             if (EPI == EPI_IMG_ROWSCALE) rs = g.rowscale[m];
             uint8_t *row_ptr = reinterpret_cast<uint8_t *>(g.out_img) + (size_t)(m >> 7) * g.KB_out * TILE_BYTES +
                                (size_t)((((int)m & 127) >> 3) * 128 + ((int)m & 7) * 16);
+            // mean-corrected single term: the correction of a chunk (two dependent loads) is fetched one chunk ahead, the first
+            // one before the accumulator is awaited - fetched inside the chunk, the load chain paced the whole kernel
+            int corr_mode_n = 0;
+            float corr_c_n = 0.0f;
+            auto corr_fetch = [&](int n0) {
+                corr_mode_n = 0; corr_c_n = 0.0f;
+                if (EPI == EPI_IMG_COLSCALE && g.corr && n0 < g.col_valid) {
+                    const int p0 = __ldg(g.col_group + n0), p1 = __ldg(g.col_group + min(n0 + 31, g.col_valid - 1));
+                    if (p0 == p1) { corr_mode_n = 1; corr_c_n = __ldg(g.corr + (size_t)p0 * g.corr_ld + m) * g.corr_scale; }
+                    else corr_mode_n = 2;
+                }
+            };
+            constexpr int c_begin_stride = BN * 4 / PAIR_EW;
+            corr_fetch(nt * BN + ch * c_begin_stride);
+            mbar_wait(&bars.tmem_full[acc], acc_ph);
+            tcgen05_fence_after();
 #pragma unroll 1
-            for (int c0 = ch * (BN * 4 / PAIR_EW); c0 < (ch + 1) * (BN * 4 / PAIR_EW); c0 += 32) {
+            for (int c0 = ch * c_begin_stride; c0 < (ch + 1) * c_begin_stride; c0 += 32) {
                 uint32_t r[32];
+                const int corr_mode = corr_mode_n;
+                const float corr_c = corr_c_n;
+                if (c0 + 32 < (ch + 1) * c_begin_stride) corr_fetch(nt * BN + c0 + 32);
                 tmem_ld_32x32b_x32(trow + c0, r);
                 tmem_ld_wait();
-                gemm_epilogue_chunk<EPI>(g, r, m, nt * BN + c0, rs, grow, row_ptr);
+                gemm_epilogue_chunk<EPI>(g, r, m, nt * BN + c0, rs, grow, row_ptr, nullptr, corr_mode, corr_c);
             }
             tcgen05_fence_before();
             __syncwarp();

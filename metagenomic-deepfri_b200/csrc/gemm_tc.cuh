@@ -14,7 +14,7 @@ namespace tc {
 
 enum Epi : int {
     EPI_F32_BIAS = 0,   // out_f32[m * ldc + n] = acc + bias[n]
-    EPI_IMG_COLSCALE,   // out image (rows = m, k = n): colscale[n] != 0 ? acc * colscale[n] : 0
+    EPI_IMG_COLSCALE,   // out image (rows = m, k = n): colscale[n] != 0 ? (acc [+ corr]) * colscale[n] : 0
     EPI_IMG_ROWSCALE,   // out image: act(acc * rowscale[m] + bias[n])
     EPI_IMG_EMBED,      // out image: relu(acc + bias[n] + gtab[gidx[m] * ldg + n])
 };
@@ -54,6 +54,12 @@ struct GemmArgs {
     const float *bias = nullptr;
     const float *rowscale = nullptr;
     const float *colscale = nullptr;
+    // EPI_IMG_COLSCALE with ONE weight term (tc_engine.cu, "mean-corrected single term"): acc + corr_scale * corr[group(n) * corr_ld + m]
+    // before the column scale; col_group[n] = protein of image column n (n < col_valid; columns past it are padding)
+    const float *corr = nullptr;
+    const int *col_group = nullptr;
+    int corr_ld = 0, col_valid = 0;
+    float corr_scale = 1.0f;
     const float *gtab = nullptr;
     const uint8_t *gidx = nullptr;
     int ldg = 0;

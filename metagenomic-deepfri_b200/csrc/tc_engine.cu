@@ -30,6 +30,8 @@ using namespace tc;
 struct TcModel {
     __half *lm_W[2] = {nullptr, nullptr};                  // [E rows x H k]  (B operand of the embed GEMM), hi / lo terms
     __half *gc_W[MDF_MAX_GC][2] = {{nullptr}};             // [g rows x k_in] (A operand of X.W, transposed), hi / lo terms
+    __half *gc_dW[MDF_MAX_GC][2] = {{nullptr}};            // 2^11 (W - fp16(W)) as [g rows x k_in] split images (B operand of the mean correction)
+    int xw_mean = 1;                                       // layers >= 2: ONE weight term + per-protein mean correction (MDF_XW_MEAN=0: two terms)
     __half *fc_W[2] = {nullptr, nullptr};                  // head: [F rows x G k] hi / lo (B operand)
     __half *out_W[2] = {nullptr, nullptr};                 // head: [2C rows x F k] hi / lo
     float *out_b_pad = nullptr;                            // head: output bias padded to a multiple of 4 entries
@@ -144,6 +146,7 @@ int tc_model_init(mdf_model *m, const mdf_model_desc *d)
     if (const char *e = getenv("MDF_COMPACT")) t->compact = atoi(e);
     if (const char *e = getenv("MDF_SINGLE_TERM")) t->single_term_mask = atoi(e);
     if (const char *e = getenv("MDF_HEAD_TC")) t->head_tc = atoi(e);
+    if (const char *e = getenv("MDF_XW_MEAN")) t->xw_mean = atoi(e);
     // shape constraints of the tile-image GEMMs
     bool ok = m->H % 64 == 0 && m->E % 128 == 0;
     for (int l = 0; l < m->n_gc; ++l) ok = ok && m->gc[l] % 128 == 0;
@@ -172,6 +175,14 @@ int tc_model_init(mdf_model *m, const mdf_model_desc *d)
         build_image_host(d->gc_W[l], m->gc[l], prev, true, m->gc[l], hi, lo);   // rows = out, k = in : W[k][out]
         MDF_TRY(upload_half(m, &t->gc_W[l][0], hi));
         MDF_TRY(upload_half(m, &t->gc_W[l][1], lo));
+        if (l > 0 && prev % TILE_K == 0) {
+            // rounding residual of the hi term, for the mean correction of the single-term X.W (tc_forward)
+            std::vector<float> dw((size_t)prev * m->gc[l]);
+            for (size_t i = 0; i < dw.size(); ++i) dw[i] = (d->gc_W[l][i] - __half2float(__float2half_rn(d->gc_W[l][i]))) * 2048.0f;
+            build_image_host(dw.data(), m->gc[l], prev, true, m->gc[l], hi, lo, false, 2048.0f);
+            MDF_TRY(upload_half(m, &t->gc_dW[l][0], hi));
+            MDF_TRY(upload_half(m, &t->gc_dW[l][1], lo));
+        }
         prev = m->gc[l];
     }
     {
@@ -432,6 +443,18 @@ pool_image_kernel(const __half *__restrict__ img, int K, const int *__restrict__
 #pragma unroll
         for (int q = 0; q < 8; ++q) atomicAdd(dst + q, acc[q]);
     }
+}
+
+// mean[p][k] = pooled[p][goff + k] / L_p: the mean input row of protein p for the next layer's X.W (the fused sum-pool of the
+// adjacency epilogue has just written pooled[p][goff ..])
+__global__ void pool_mean_kernel(int n, int K, const float *__restrict__ pooled, int G, int goff, const int64_t *__restrict__ seq_off,
+                                 float *__restrict__ mean)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= (int64_t)n * K) return;
+    const int p = (int)(i / K), k = (int)(i % K);
+    const int L = (int)(seq_off[p + 1] - seq_off[p]);
+    mean[i] = L > 0 ? pooled[(size_t)p * G + goff + k] / (float)L : 0.0f;
 }
 
 // fp32 row-major [n, K] -> hi / lo fp16 images over rows padded to a multiple of 128 (pad rows zero)
@@ -898,6 +921,27 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto, const std::function<int()> 
     __half *Xlast = nullptr;
     for (int l = 0; l < m->n_gc; ++l) {
         const int gd = m->gc[l];
+        // Mean-corrected single weight term (layers >= 2).  The hi + lo split of W exists because the rounding error of an fp16
+        // weight is COHERENT across residues: X_j dW survives the sum-pool, while everything zero-mean averages out.  Its coherent
+        // part is rank one per protein: X_j dW = mean_p dW + (X_j - mean_p) dW, and mean_p = pooled_p / L_p is already there (the
+        // previous layer's fused sum-pool).  So: ONE MMA per k-step with fp16(W), and the epilogue adds corr[p] = mean_p (W - fp16(W))
+        // (a [n x k] x [k x gd] product on the exact-split head GEMM, 40 us) to every column of protein p.  CPU emulation (fp64
+        // reference, L 130 / 1000 / 2400): score error 6e-5 / 1.3e-4 / 1.8e-4 against 5e-5 / 1.2e-4 / 1.6e-4 with two terms and
+        // 3e-4 / 2.9e-3 / 5.3e-3 with the hi term alone.  The first layer keeps its two terms: pooling X0 in the embedding GEMM's
+        // epilogue was built and measured - it costs that kernel 2.2 ms for 1.6 ms saved here.
+        const bool pair_ok = tm->gemm_pair && gd % 256 == 0 && Tp % 256 == 0;
+        const bool mean_corr = l > 0 && tm->xw_mean && tm->pool_fused && compact && pair_ok && tm->gc_dW[l][0] && kin % TILE_K == 0 &&
+                               gd % 4 == 0 && !(tm->single_term_mask & (2 << l));
+        float *corr = nullptr;
+        if (mean_corr) {
+            ProfScope ps(ctx, "xw_mean_corr", 2.0 * n * kin * gd);
+            float *mean = nullptr;
+            MDF_TRY(ctx->alloc_n(&mean, (size_t)n * kin));
+            MDF_TRY(ctx->alloc_n(&corr, (size_t)n * gd));
+            pool_mean_kernel<<<(unsigned)cdiv64((int64_t)n * kin, 256), 256, 0, s>>>(n, kin, b->d_pooled, m->G, goff - kin, b->d_seq_off, mean);
+            MDF_LAUNCH_CHECK(ctx);
+            MDF_TRY(tc_dense_split(ctx, n, mean, kin, tm->gc_dW[l], gd, gd, nullptr, 0, corr));
+        }
         {
             ProfScope ps(ctx, "graphconv_xw_gemm", 2.0 * T * kin * gd);
             GemmArgs g;                                   // Y^T[gd x Tp] = W^T . X^T, columns scaled by d_j
@@ -907,10 +951,11 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto, const std::function<int()> 
             g.out_img = Yt; g.KB_out = (int)(Tp / TILE_K);
             g.colscale = deg_pad;
             g.m_fastest = 1;                              // the 4 feature tiles of one residue block run back to back: X is read once
-            if (tm->gemm_pair && gd % 256 == 0 && Tp % 256 == 0) {   // CTA pairs: 256 features x 256 residues
+            if (pair_ok) {                                // CTA pairs: 256 features x 256 residues
                 g.m_tiles = gd / 256; g.n_tiles = (int)(Tp / 256);
                 const size_t ab[2] = {(size_t)gd * kin * 2, (size_t)gd * kin * 2}, bb[2] = {(size_t)Tp * kin * 2, 0};
-                MDF_TRY(launch_gemm_pair(ctx, EPI_IMG_COLSCALE, (tm->single_term_mask & (2 << l)) ? 1 : 2, 1, g, ab, bb));
+                if (mean_corr) { g.corr = corr; g.corr_ld = gd; g.corr_scale = 1.0f / 2048.0f; g.col_group = b->d_res_prot; g.col_valid = (int)T; }
+                MDF_TRY(launch_gemm_pair(ctx, EPI_IMG_COLSCALE, (mean_corr || (tm->single_term_mask & (2 << l))) ? 1 : 2, 1, g, ab, bb));
             } else {
                 MDF_TRY(launch_gemm_tc(ctx, EPI_IMG_COLSCALE, 256, 2, 1, g));
             }

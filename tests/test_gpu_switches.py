@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 SWITCHES = [{}, {"MDF_LSTM_FUSED": "0"}, {"MDF_LSTM_FUSED": "0", "MDF_LSTM_STREAM_MIN": "1"}, {"MDF_LSTM_FUSED": "0", "MDF_LSTM_HILO": "1"},
             {"MDF_COMPACT": "0"}, {"MDF_ADJ_SPARSE": "0"}, {"MDF_POOL_FUSED": "0"}, {"MDF_ADJ_LEAN": "0"}, {"MDF_ADJ_EXPAND": "0"},
-            {"MDF_GEMM_PAIR": "0"}, {"MDF_EMBED_STAGED": "0"}, {"MDF_HEAD_TC": "0"}, {"MDF_CMAP_SYM": "0"}, {"MDF_LSTM_COOP": "0"},
+            {"MDF_GEMM_PAIR": "0"}, {"MDF_EMBED_STAGED": "0"}, {"MDF_HEAD_TC": "0"}, {"MDF_CMAP_SYM": "0"}, {"MDF_XW_MEAN": "0"}, {"MDF_LSTM_COOP": "0"},
             {"MDF_LSTM_PAIR": "0"}, {"MDF_LSTM_CELL": "0"}, {"MDF_LSTM_ABLATE": "64"}, {"MDF_LSTM_ABLATE": "384"}, {"MDF_LSTM_CLUSTER": "8"}, {"MDF_LSTM_PRECISE_LEN": "100"}, {"MDF_HOST_THREADS": "1"}]
 
 
