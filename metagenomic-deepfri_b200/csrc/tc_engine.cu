@@ -742,6 +742,10 @@ size_t tc_workspace_bytes(const mdf_model *m, int n, const int64_t *seq_off)
     add((size_t)Tp * gmax * 2); add((size_t)Tp * gmax * 2); add((size_t)Tp * gmax * 2);   // Y^T, X_a, X_b images
     if (!(m->tc && static_cast<const TcModel *>(m->tc)->adj_expand)) add((size_t)tiles * TILE_BYTES + 256);   // A_hat images
     if (taps) { add((size_t)T * gmax * 4); add((size_t)T * m->E * 4); }   // fp32 taps of the last GraphConv layer and of X0
+    for (int l = 1; l < m->n_gc; ++l) {               // mean-corrected single term: mean rows, correction rows, split operand images
+        add((size_t)n * gmax * 4); add((size_t)n * gmax * 4);
+        for (int q = 0; q < 3; ++q) add((size_t)(cdiv(n, 128) * 128) * gmax * 2);
+    }
     for (int q = 0; q < 3; ++q) add((size_t)(cdiv(n, 128) * 128) * std::max(m->G, m->F) * 2);   // head operand images
     add((size_t)n * m->F * 4); add((size_t)n * 2 * m->C * 4); add((size_t)n * (2 * m->C + 4) * 4);
     return b + 8192;
