@@ -88,7 +88,10 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmArgs &g, uint32_t 
             }
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-                const float4 cs = __ldg(reinterpret_cast<const float4 *>(g.colscale + n0 + 4 * q));
+                // pair kernel: `grow` points into the shared-memory copy of this tile's 256 column scales (staged one tile ahead:
+                // read from global memory here, the load's L2 latency sat in front of every 32-column chunk)
+                const float4 cs = grow ? *reinterpret_cast<const float4 *>(grow + n0 + 4 * q)
+                                       : __ldg(reinterpret_cast<const float4 *>(g.colscale + n0 + 4 * q));
                 v[4 * q + 0] = cs.x != 0.0f ? v[4 * q + 0] * cs.x : 0.0f;
                 v[4 * q + 1] = cs.y != 0.0f ? v[4 * q + 1] * cs.y : 0.0f;
                 v[4 * q + 2] = cs.z != 0.0f ? v[4 * q + 2] * cs.z : 0.0f;
@@ -560,12 +563,29 @@ gemm_pair_kernel(const __grid_constant__ PairGemmArgs pa)
         const int lb = (warp & 3) * 32;
         const int ch = warp >> 2;
         int acc = 0; uint32_t acc_ph = 0;
+        // EPI_IMG_COLSCALE: the 256 column scales of a tile live in shared memory, double-buffered - thread t fetches column t of
+        // the NEXT tile while the current one is processed and parks it after the last chunk; one named barrier per tile
+        float *cs_tab = reinterpret_cast<float *>(smem + (size_t)stages * stage_bytes);
+        auto tile_nt = [&](int grp_, int in_) { return g.m_fastest ? grp_ : in_; };
+        int tile_no = 0;
+        if (EPI == EPI_IMG_COLSCALE && pair < outer) {
+            if (threadIdx.x < BN) cs_tab[threadIdx.x] = __ldg(g.colscale + (size_t)tile_nt(pair, 0) * BN + threadIdx.x);
+            asm volatile("bar.sync 2, %0;" ::"n"(PAIR_EW * 32) : "memory");
+        }
         for (int grp = pair; grp < outer; grp += n_pairs)
         for (int in = 0; in < inner; ++in) {
             const int mt = g.m_fastest ? in : grp, nt = g.m_fastest ? grp : in;
             const int64_t m = ((int64_t)mt * 2 + rank) * 128 + lb + lane;
             float rs = 1.0f;
             const float *grow = nullptr;
+            float cs_next = 0.0f;
+            bool have_next = false;
+            if (EPI == EPI_IMG_COLSCALE) {
+                const int in2 = in + 1 < inner ? in + 1 : 0, grp2 = in + 1 < inner ? grp : grp + n_pairs;
+                have_next = grp2 < outer;
+                if (have_next && threadIdx.x < BN) cs_next = __ldg(g.colscale + (size_t)tile_nt(grp2, in2) * BN + threadIdx.x);
+                grow = cs_tab + (tile_no & 1) * BN - nt * BN;                                  // the chunk adds n0 = nt * BN + c0
+            }
             if (EPI == EPI_IMG_EMBED) {
                 if (g.embed_staged) {
                     // The one-hot embedding is a gather of W_aa[idx[m]] per ROW, i.e. per lane: from global memory every LDG.128
@@ -625,6 +645,11 @@ gemm_pair_kernel(const __grid_constant__ PairGemmArgs pa)
                 if (leader) mbar_arrive(&bars.tmem_empty[acc]); else mbar_arrive_remote(&bars.tmem_empty[acc], 0);
             }
             if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+            if (EPI == EPI_IMG_COLSCALE) {
+                ++tile_no;
+                if (have_next && threadIdx.x < BN) cs_tab[(tile_no & 1) * BN + threadIdx.x] = cs_next;
+                asm volatile("bar.sync 2, %0;" ::"n"(PAIR_EW * 32) : "memory");
+            }
         }
     }
     tcgen05_fence_before();
@@ -669,6 +694,7 @@ static int launch_pair(mdf_ctx *ctx, int a_terms, int b_terms, const GemmArgs &a
     for (int t = 0; t < a_terms; ++t) MDF_TRY(make_tile_map(&pa.tmA[t], args.A[t], a_bytes[t]));
     for (int t = 0; t < b_terms; ++t) MDF_TRY(make_tile_map(&pa.tmB[t], args.B[t], b_bytes[t]));
     size_t smem = (size_t)pa.stages * stage_bytes + 1024;
+    if (EPI == EPI_IMG_COLSCALE) smem += 2 * 256 * sizeof(float);           // double-buffered column-scale slice
     if (EPI == EPI_IMG_EMBED && pa.g.embed_staged) {
         const size_t tab = (size_t)EMB_ROWS * EMB_LD * sizeof(float);
         while (pa.stages > 2 && smem + tab > 226 * 1024) { --pa.stages; smem -= stage_bytes; }
