@@ -472,6 +472,7 @@ struct PairGemmArgs {
 constexpr int EMB_ROWS = 26, EMB_LD = 256 + 4;            // staged embedding-table slice: 26 residue types x 256 columns, rows padded by 16 B
 constexpr int PAIR_EW = MDF_PAIR_EPI_WARPS;               // epilogue warps per CTA (8 or 16)
 constexpr int PAIR_THREADS = (PAIR_EW + 2) * 32;
+constexpr int CS_SLICE = 256 + 16;                        // EPI_IMG_COLSCALE: 256 column scales + 8 chunk groups (+ pad) per staged tile slice
 
 template <int EPI>
 __global__ void __launch_bounds__(PAIR_THREADS, 1)
@@ -565,11 +566,14 @@ gemm_pair_kernel(const __grid_constant__ PairGemmArgs pa)
         int acc = 0; uint32_t acc_ph = 0;
         // EPI_IMG_COLSCALE: the 256 column scales of a tile live in shared memory, double-buffered - thread t fetches column t of
         // the NEXT tile while the current one is processed and parks it after the last chunk; one named barrier per tile
+        // (+ the tile's eight chunk groups of the mean correction behind the 256 scales: CS_SLICE words per buffer)
         float *cs_tab = reinterpret_cast<float *>(smem + (size_t)stages * stage_bytes);
         auto tile_nt = [&](int grp_, int in_) { return g.m_fastest ? grp_ : in_; };
         int tile_no = 0;
+        const bool cg_thread = EPI == EPI_IMG_COLSCALE && g.chunk_group && threadIdx.x < BN / 32;
         if (EPI == EPI_IMG_COLSCALE && pair < outer) {
             if (threadIdx.x < BN) cs_tab[threadIdx.x] = __ldg(g.colscale + (size_t)tile_nt(pair, 0) * BN + threadIdx.x);
+            if (cg_thread) reinterpret_cast<int *>(cs_tab)[BN + threadIdx.x] = __ldg(g.chunk_group + (size_t)tile_nt(pair, 0) * (BN / 32) + threadIdx.x);
             asm volatile("bar.sync 2, %0;" ::"n"(PAIR_EW * 32) : "memory");
         }
         for (int grp = pair; grp < outer; grp += n_pairs)
@@ -579,12 +583,15 @@ gemm_pair_kernel(const __grid_constant__ PairGemmArgs pa)
             float rs = 1.0f;
             const float *grow = nullptr;
             float cs_next = 0.0f;
+            int cg_next = -2;
             bool have_next = false;
+            const int *cg_cur = reinterpret_cast<const int *>(cs_tab) + (tile_no & 1) * CS_SLICE + BN;
             if (EPI == EPI_IMG_COLSCALE) {
                 const int in2 = in + 1 < inner ? in + 1 : 0, grp2 = in + 1 < inner ? grp : grp + n_pairs;
                 have_next = grp2 < outer;
                 if (have_next && threadIdx.x < BN) cs_next = __ldg(g.colscale + (size_t)tile_nt(grp2, in2) * BN + threadIdx.x);
-                grow = cs_tab + (tile_no & 1) * BN - nt * BN;                                  // the chunk adds n0 = nt * BN + c0
+                if (have_next && cg_thread) cg_next = __ldg(g.chunk_group + (size_t)tile_nt(grp2, in2) * (BN / 32) + threadIdx.x);
+                grow = cs_tab + (tile_no & 1) * CS_SLICE - nt * BN;                            // the chunk adds n0 = nt * BN + c0
             }
             if (EPI == EPI_IMG_EMBED) {
                 if (g.embed_staged) {
@@ -619,10 +626,10 @@ gemm_pair_kernel(const __grid_constant__ PairGemmArgs pa)
             float corr_c_n = 0.0f;
             auto corr_fetch = [&](int n0) {
                 corr_mode_n = 0; corr_c_n = 0.0f;
-                if (EPI == EPI_IMG_COLSCALE && g.corr && n0 < g.col_valid) {
-                    const int p0 = __ldg(g.col_group + n0), p1 = __ldg(g.col_group + min(n0 + 31, g.col_valid - 1));
-                    if (p0 == p1) { corr_mode_n = 1; corr_c_n = __ldg(g.corr + (size_t)p0 * g.corr_ld + m) * g.corr_scale; }
-                    else corr_mode_n = 2;
+                if (EPI == EPI_IMG_COLSCALE && g.corr) {
+                    const int cg = cg_cur[(n0 - nt * BN) >> 5];          // staged with the column scales: no global load in the chain
+                    if (cg >= 0) { corr_mode_n = 1; corr_c_n = __ldg(g.corr + (size_t)cg * g.corr_ld + m) * g.corr_scale; }
+                    else if (cg == -1) corr_mode_n = 2;
                 }
             };
             constexpr int c_begin_stride = BN * 4 / PAIR_EW;
@@ -647,7 +654,8 @@ gemm_pair_kernel(const __grid_constant__ PairGemmArgs pa)
             if (++acc == 2) { acc = 0; acc_ph ^= 1; }
             if (EPI == EPI_IMG_COLSCALE) {
                 ++tile_no;
-                if (have_next && threadIdx.x < BN) cs_tab[(tile_no & 1) * BN + threadIdx.x] = cs_next;
+                if (have_next && threadIdx.x < BN) cs_tab[(tile_no & 1) * CS_SLICE + threadIdx.x] = cs_next;
+                if (have_next && cg_thread) reinterpret_cast<int *>(cs_tab)[(tile_no & 1) * CS_SLICE + BN + threadIdx.x] = cg_next;
                 asm volatile("bar.sync 2, %0;" ::"n"(PAIR_EW * 32) : "memory");
             }
         }
@@ -694,7 +702,7 @@ static int launch_pair(mdf_ctx *ctx, int a_terms, int b_terms, const GemmArgs &a
     for (int t = 0; t < a_terms; ++t) MDF_TRY(make_tile_map(&pa.tmA[t], args.A[t], a_bytes[t]));
     for (int t = 0; t < b_terms; ++t) MDF_TRY(make_tile_map(&pa.tmB[t], args.B[t], b_bytes[t]));
     size_t smem = (size_t)pa.stages * stage_bytes + 1024;
-    if (EPI == EPI_IMG_COLSCALE) smem += 2 * 256 * sizeof(float);           // double-buffered column-scale slice
+    if (EPI == EPI_IMG_COLSCALE) smem += 2 * CS_SLICE * sizeof(float);      // double-buffered column-scale slice
     if (EPI == EPI_IMG_EMBED && pa.g.embed_staged) {
         const size_t tab = (size_t)EMB_ROWS * EMB_LD * sizeof(float);
         while (pa.stages > 2 && smem + tab > 226 * 1024) { --pa.stages; smem -= stage_bytes; }

@@ -58,6 +58,7 @@ struct GemmArgs {
     // before the column scale; col_group[n] = protein of image column n (n < col_valid; columns past it are padding)
     const float *corr = nullptr;
     const int *col_group = nullptr;
+    const int *chunk_group = nullptr;   // per 32 image columns: their protein if all 32 share one, -1 if the chunk straddles proteins, -2 = padding
     int corr_ld = 0, col_valid = 0;
     float corr_scale = 1.0f;
     const float *gtab = nullptr;

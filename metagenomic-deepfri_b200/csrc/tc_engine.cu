@@ -445,6 +445,16 @@ pool_image_kernel(const __half *__restrict__ img, int K, const int *__restrict__
     }
 }
 
+// chunk_group[c] for every 32 image columns (compact residue axis): the protein all 32 belong to, -1 when the chunk straddles a
+// protein boundary, -2 behind the last residue
+__global__ void chunk_group_kernel(int64_t n_chunks, int64_t T, const int *__restrict__ res_prot, int *__restrict__ cg)
+{
+    const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= n_chunks) return;
+    const int64_t a = 32 * c, b = min(a + 31, T - 1);
+    cg[c] = a >= T ? -2 : (res_prot[a] == res_prot[b] ? res_prot[a] : -1);
+}
+
 // mean[p][k] = pooled[p][goff + k] / L_p: the mean input row of protein p for the next layer's X.W (the fused sum-pool of the
 // adjacency epilogue has just written pooled[p][goff ..])
 __global__ void pool_mean_kernel(int n, int K, const float *__restrict__ pooled, int G, int goff, const int64_t *__restrict__ seq_off,
@@ -742,6 +752,7 @@ size_t tc_workspace_bytes(const mdf_model *m, int n, const int64_t *seq_off)
     add((size_t)Tp * gmax * 2); add((size_t)Tp * gmax * 2); add((size_t)Tp * gmax * 2);   // Y^T, X_a, X_b images
     if (!(m->tc && static_cast<const TcModel *>(m->tc)->adj_expand)) add((size_t)tiles * TILE_BYTES + 256);   // A_hat images
     if (taps) { add((size_t)T * gmax * 4); add((size_t)T * m->E * 4); }   // fp32 taps of the last GraphConv layer and of X0
+    add((size_t)Tp / 32 * 4);
     for (int l = 1; l < m->n_gc; ++l) {               // mean-corrected single term: mean rows, correction rows, split operand images
         add((size_t)n * gmax * 4); add((size_t)n * gmax * 4);
         for (int q = 0; q < 3; ++q) add((size_t)(cdiv(n, 128) * 128) * gmax * 2);
@@ -922,6 +933,7 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto, const std::function<int()> 
     for (int p = 0; p < n; ++p) { const double L = (double)(b->h_seq_off[p + 1] - b->h_seq_off[p]); l2 += L * L; }
     const __half *Xin = X0img;
     int kin = m->E, goff = 0;
+    int *chunk_group = nullptr;                          // mean-corrected single term: protein of every 32-column chunk
     __half *Xlast = nullptr;
     for (int l = 0; l < m->n_gc; ++l) {
         const int gd = m->gc[l];
@@ -945,6 +957,11 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto, const std::function<int()> 
             pool_mean_kernel<<<(unsigned)cdiv64((int64_t)n * kin, 256), 256, 0, s>>>(n, kin, b->d_pooled, m->G, goff - kin, b->d_seq_off, mean);
             MDF_LAUNCH_CHECK(ctx);
             MDF_TRY(tc_dense_split(ctx, n, mean, kin, tm->gc_dW[l], gd, gd, nullptr, 0, corr));
+            if (!chunk_group) {
+                MDF_TRY(ctx->alloc_n(&chunk_group, (size_t)(Tp / 32)));
+                chunk_group_kernel<<<(unsigned)cdiv64(Tp / 32, 256), 256, 0, s>>>(Tp / 32, T, b->d_res_prot, chunk_group);
+                MDF_LAUNCH_CHECK(ctx);
+            }
         }
         {
             ProfScope ps(ctx, "graphconv_xw_gemm", 2.0 * T * kin * gd);
@@ -958,7 +975,7 @@ int tc_forward(mdf_model *m, mdf_batch *b, int upto, const std::function<int()> 
             if (pair_ok) {                                // CTA pairs: 256 features x 256 residues
                 g.m_tiles = gd / 256; g.n_tiles = (int)(Tp / 256);
                 const size_t ab[2] = {(size_t)gd * kin * 2, (size_t)gd * kin * 2}, bb[2] = {(size_t)Tp * kin * 2, 0};
-                if (mean_corr) { g.corr = corr; g.corr_ld = gd; g.corr_scale = 1.0f / 2048.0f; g.col_group = b->d_res_prot; g.col_valid = (int)T; }
+                if (mean_corr) { g.chunk_group = chunk_group; g.corr = corr; g.corr_ld = gd; g.corr_scale = 1.0f / 2048.0f; g.col_group = b->d_res_prot; g.col_valid = (int)T; }
                 MDF_TRY(launch_gemm_pair(ctx, EPI_IMG_COLSCALE, (mean_corr || (tm->single_term_mask & (2 << l))) ? 1 : 2, 1, g, ab, bb));
             } else {
                 MDF_TRY(launch_gemm_tc(ctx, EPI_IMG_COLSCALE, 256, 2, 1, g));
