@@ -591,7 +591,7 @@ def run_b200(args, rank, world, local_rank, inputs):
     else:
         roof = {"bound": "tensor", "achieved": dunits / (dms * 1e-3) / 1e12, "peak": peaks["tflops"], "unit": "TFLOP/s"}
     roof["frac"] = roof["achieved"] / roof["peak"]
-    roof["traffic"] = ncu_traffic(dname)
+    roof["traffic"] = ncu_traffic(dname + "_config1" if maps_only else dname) or ncu_traffic(dname)
     roof["kernel"] = dname
     roof["launches_per_step"] = dcount
     roof["share_of_step"] = dms / stage_total if stage_total else None
